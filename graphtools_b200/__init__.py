@@ -1,0 +1,14 @@
+"""graphtools_b200 -- B200-native graph construction behind the graphtools API.
+
+    import graphtools_b200 as graphtools
+    G = graphtools.Graph(X, knn=5, decay=40)
+    G.kernel, G.diff_op
+"""
+from .factory import Graph
+from . import graphs
+from .graphs import (kNNGraph, TraditionalGraph, MNNGraph, LandmarkGraph, kNNLandmarkGraph, MNNLandmarkGraph,
+                     TraditionalLandmarkGraph)
+
+__version__ = "0.1.0"
+__all__ = ["Graph", "graphs", "kNNGraph", "TraditionalGraph", "MNNGraph", "LandmarkGraph", "kNNLandmarkGraph",
+           "MNNLandmarkGraph", "TraditionalLandmarkGraph"]

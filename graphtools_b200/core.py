@@ -1,0 +1,458 @@
+"""Host-side mirror of graphtools' abstract graph machinery, re-plumbed onto the CUDA engine.
+
+Public surface kept from the reference (citations relative to /root/reference/graphtools):
+``Base`` (base.py:25-70), ``Data`` (base.py:72-424), ``BaseGraph`` (base.py:427-988, hot-path part)
+and ``DataGraph`` (base.py:1046-1254): same constructor keywords, lazy cached properties
+``K``/``kernel``, ``P``/``diff_op``, ``kernel_degree``, ``diff_aff``; same validation messages and
+warnings; same result containers (scipy CSR float64/int32 for sparse graphs, ndarray for dense).
+
+What differs: ``build_kernel`` implementations return *device-resident* results
+(``pipeline.DeviceCSR`` / CUDA tensors); symmetrisation, anisotropy and the diffusion operator are
+computed on the GPU in the same sweep and only materialised as scipy/numpy objects when a property
+is read.  There is no CPU compute path.
+"""
+import abc
+import inspect
+import numbers
+import warnings
+
+import numpy as np
+from scipy import sparse
+
+from . import pipeline
+from .logging_util import logger as _logger
+
+
+def _is_dataframe(x):
+    try:
+        import pandas as pd
+        return isinstance(x, pd.DataFrame)
+    except ImportError:  # pragma: no cover
+        return False
+
+
+def _is_anndata(x):
+    try:
+        import anndata
+        return isinstance(x, anndata.AnnData)
+    except ImportError:
+        return False
+
+
+class Base(object):
+    """Keyword-argument sink at the end of the cooperative ``__init__`` chain."""
+
+    def __init__(self):
+        super().__init__()
+
+    @classmethod
+    def _get_param_names(cls):
+        """Names of all constructor keywords of ``cls`` and its bases (used by ``api.Graph``
+        to decide which of its arguments a class accepts; reference base.py:33-63)."""
+        names = set()
+        for klass in cls.__mro__:
+            init = klass.__dict__.get("__init__")
+            if init is None:
+                continue
+            for p in inspect.signature(init).parameters.values():
+                if p.name != "self" and p.kind is not p.VAR_KEYWORD:
+                    names.add(p.name)
+        return names
+
+    def set_params(self, **kwargs):
+        return self
+
+
+class Data(Base):
+    """Data ingestion + optional PCA (host side, unchanged in spirit; reference base.py:72-424).
+
+    PCA is outside the accelerated path: it runs with scikit-learn on the host
+    exactly as in the reference and its output ``data_nu`` is what the GPU kernels consume.
+    """
+
+    def __init__(self, data, n_pca=None, rank_threshold=None, random_state=None, **kwargs):
+        if len(data.shape) != 2:
+            msg = "Expected 2D array, got {}D array instead (shape: {}.) ".format(len(data.shape), data.shape)
+            if len(data.shape) < 2:
+                msg += ("\nReshape your data either using array.reshape(-1, 1) "
+                        "if your data has a single feature or array.reshape(1, -1) if "
+                        "it contains a single sample.")
+            raise ValueError(msg)
+        n_pca, rank_threshold = self._parse_n_pca_threshold(data, n_pca, rank_threshold)
+        if _is_dataframe(data):
+            try:
+                data = data.sparse.to_coo()
+            except AttributeError:
+                data = np.array(data)
+        elif _is_anndata(data):
+            data = data.X
+        self.data = data
+        self.n_pca = n_pca
+        self.rank_threshold = rank_threshold
+        self.random_state = random_state
+        self.data_nu = self._reduce_data()
+        super().__init__(**kwargs)
+
+    def _parse_n_pca_threshold(self, data, n_pca, rank_threshold):
+        bad_type = ("n_pca was not an instance of numbers.Number, could not be cast to False, and not None. "
+                    "Please supply an integer 0 <= n_pca < min(n_samples,n_features) or None")
+        if isinstance(n_pca, str):
+            n_pca = n_pca.lower()
+            if n_pca != "auto":
+                raise ValueError("n_pca must be an integer 0 <= n_pca < min(n_samples,n_features), "
+                                 "or in [None, False, True, 'auto'].")
+        if isinstance(n_pca, numbers.Number) and not isinstance(n_pca, bool):
+            if not float(n_pca).is_integer():
+                rounded = np.round(n_pca).astype(int)
+                warnings.warn("Cannot perform PCA to fractional {} dimensions. Rounding to {}".format(n_pca, rounded),
+                              RuntimeWarning)
+                n_pca = rounded
+            if n_pca < 0:
+                raise ValueError("n_pca cannot be negative. Please supply an integer "
+                                 "0 <= n_pca < min(n_samples,n_features) or None")
+            elif np.min(data.shape) <= n_pca:
+                warnings.warn("Cannot perform PCA to {} dimensions on data with min(n_samples, n_features) = {}"
+                              .format(n_pca, np.min(data.shape)), RuntimeWarning)
+                n_pca = 0
+        if n_pca is True:
+            n_pca = "auto"
+            _logger.log_info("Estimating n_pca from matrix rank. Supply an integer n_pca for fixed amount.")
+        elif n_pca is None or n_pca is False or (isinstance(n_pca, numbers.Number) and n_pca == 0):
+            n_pca = None
+        if not (n_pca is None or n_pca == "auto" or isinstance(n_pca, numbers.Number)):
+            raise ValueError(bad_type)
+        if rank_threshold is not None and n_pca != "auto":
+            warnings.warn("n_pca = {}, therefore rank_threshold of {} will not be used. To use rank thresholding, "
+                          "set n_pca = True".format(n_pca, rank_threshold), RuntimeWarning)
+        if n_pca == "auto":
+            if isinstance(rank_threshold, str):
+                rank_threshold = rank_threshold.lower()
+            if rank_threshold is None:
+                rank_threshold = "auto"
+            ok = (isinstance(rank_threshold, numbers.Number) and rank_threshold > 0) or rank_threshold == "auto"
+            if not ok:
+                raise ValueError("rank_threshold must be positive float or 'auto'. ")
+        return n_pca, rank_threshold
+
+    def _reduce_data(self):
+        wants_pca = self.n_pca is not None and (self.n_pca == "auto" or self.n_pca < self.data.shape[1])
+        if not wants_pca:
+            data_nu = self.data
+            if sparse.issparse(data_nu) and not isinstance(
+                    data_nu, (sparse.csr_matrix, sparse.csc_matrix, sparse.bsr_matrix)):
+                data_nu = data_nu.tocsr()
+            return data_nu
+        from sklearn.decomposition import PCA, TruncatedSVD
+        with _logger.log_task("PCA"):
+            k = self.data.shape[1] - 1 if self.n_pca == "auto" else self.n_pca
+            if sparse.issparse(self.data):
+                if isinstance(self.data, (sparse.coo_matrix, sparse.lil_matrix, sparse.dok_matrix)):
+                    self.data = self.data.tocsr()
+                self.data_pca = TruncatedSVD(k, random_state=self.random_state)
+            else:
+                self.data_pca = PCA(k, svd_solver="randomized", random_state=self.random_state)
+            self.data_pca.fit(self.data)
+            if self.n_pca == "auto":
+                s = self.data_pca.singular_values_
+                if self.rank_threshold == "auto":
+                    self.rank_threshold = s.max() * np.finfo(self.data.dtype).eps * max(self.data.shape)
+                gate = np.where(s >= self.rank_threshold)[0]
+                self.n_pca = gate.shape[0]
+                if self.n_pca == 0:
+                    raise ValueError("Supplied threshold {} was greater than maximum singular value {} "
+                                     "for the data matrix".format(self.rank_threshold, s.max()))
+                _logger.log_info("Using rank estimate of {} as n_pca".format(self.n_pca))
+                op = self.data_pca
+                op.components_ = op.components_[gate, :]
+                op.explained_variance_ = op.explained_variance_[gate]
+                op.explained_variance_ratio_ = op.explained_variance_ratio_[gate]
+                op.singular_values_ = op.singular_values_[gate]
+            return self.data_pca.transform(self.data)
+
+    def get_params(self):
+        return {"n_pca": self.n_pca, "random_state": self.random_state}
+
+    def set_params(self, **params):
+        if "n_pca" in params and params["n_pca"] != self.n_pca:
+            raise ValueError("Cannot update n_pca. Please create a new graph")
+        if "random_state" in params:
+            self.random_state = params["random_state"]
+        super().set_params(**params)
+        return self
+
+    def transform(self, Y):
+        """Map ``Y`` from the ambient space into the (PCA-)reduced space of ``data_nu``."""
+        try:
+            return self.data_pca.transform(Y)
+        except ValueError:
+            raise ValueError("data of shape {0} cannot be transformed to graph built on data of shape {1}. "
+                             "Expected shape ({2}, {3})".format(Y.shape, self.data.shape, Y.shape[0],
+                                                                self.data.shape[1]))
+        except AttributeError:  # no PCA
+            try:
+                if Y.shape[1] != self.data.shape[1]:
+                    raise ValueError
+                return Y
+            except IndexError:
+                raise ValueError("data of shape {0} cannot be transformed to graph built on data of shape {1}. "
+                                 "Expected shape ({2}, {3})".format(Y.shape, self.data.shape, Y.shape[0],
+                                                                    self.data.shape[1]))
+            except ValueError:
+                raise ValueError("data of shape {0} cannot be transformed to graph built on data of shape {1}. "
+                                 "Expected shape ({2}, {3})".format(Y.shape, self.data.shape, Y.shape[0],
+                                                                    self.data.shape[1]))
+
+    def inverse_transform(self, Y, columns=None):
+        """Map ``Y`` from the reduced space back to the ambient space."""
+        try:
+            if not hasattr(self, "data_pca"):
+                if Y.shape[1] != self.data_nu.shape[1]:
+                    raise ValueError
+                return Y if columns is None else Y[:, columns]
+            if columns is None:
+                return self.data_pca.inverse_transform(Y)
+            columns = np.array([columns]).flatten()
+            Y_inv = np.dot(Y, self.data_pca.components_[:, columns])
+            if hasattr(self.data_pca, "mean_"):
+                Y_inv += self.data_pca.mean_[columns]
+            return Y_inv
+        except ValueError:
+            raise ValueError("data of shape {0} cannot be inverse transformed from graph built on reduced data of "
+                             "shape ({1}, {2}). Expected shape ({3}, {2})".format(
+                                 Y.shape, self.data_nu.shape[0], self.data_nu.shape[1], Y.shape[0]))
+
+
+class BaseGraph(Base, metaclass=abc.ABCMeta):
+    """Kernel -> symmetrise -> anisotropy -> diffusion operator (reference base.py:427-724).
+
+    Subclasses implement ``build_kernel()`` returning either a ``pipeline.DeviceCSR`` (sparse graphs)
+    or a float64 CUDA tensor [N, N] (dense graphs); this class finishes it on the device.
+    """
+
+    def __init__(self, kernel_symm="+", theta=None, anisotropy=0, gamma=None, initialize=True, **kwargs):
+        if gamma is not None:
+            warnings.warn("gamma is deprecated. Setting theta={}".format(gamma), FutureWarning)
+            theta = gamma
+        for old in ("gamma", "theta"):
+            if kernel_symm == old:
+                warnings.warn("kernel_symm='{}' is deprecated. Setting kernel_symm='mnn'".format(old), FutureWarning)
+                kernel_symm = "mnn"
+        self.kernel_symm = kernel_symm
+        self.theta = theta
+        self._check_symmetrization(kernel_symm, theta)
+        if not (isinstance(anisotropy, numbers.Real) and 0 <= anisotropy <= 1):
+            raise ValueError("Expected 0 <= anisotropy <= 1. Got {}".format(anisotropy))
+        self.anisotropy = anisotropy
+        if initialize:
+            _logger.log_debug("Initializing kernel...")
+            self.K
+        else:
+            _logger.log_debug("Not initializing kernel.")
+        super().__init__(**kwargs)
+
+    def _check_symmetrization(self, kernel_symm, theta):
+        if kernel_symm not in ["+", "*", "mnn", None]:
+            raise ValueError("kernel_symm '{}' not recognized. Choose from '+', '*', 'mnn', or 'none'."
+                             .format(kernel_symm))
+        elif kernel_symm != "mnn" and theta is not None:
+            warnings.warn("kernel_symm='{}' but theta is not None. Setting kernel_symm='mnn'.".format(kernel_symm))
+            self.kernel_symm = kernel_symm = "mnn"
+        if kernel_symm == "mnn":
+            if theta is None:
+                self.theta = theta = 1
+                warnings.warn("kernel_symm='mnn' but theta not given. Defaulting to theta={}.".format(self.theta))
+            elif not isinstance(theta, numbers.Number) or theta < 0 or theta > 1:
+                raise ValueError("theta {} not recognized. Expected a float between 0 and 1".format(theta))
+
+    # ---------------------------------------------------------------- device-side build
+    def _build_kernel(self):
+        """build -> symmetrise -> anisotropy -> sanity checks, all on the GPU (base.py:534-555)."""
+        raw = self.build_kernel()
+        if isinstance(raw, pipeline.DeviceCSR):
+            K, P, degree, flags = pipeline.symmetrize_normalize(
+                raw, self.kernel_symm, self.theta, float(self.anisotropy))
+            self._dev_kernel, self._dev_P, self._dev_degree = K, P, degree
+            if flags & 1:
+                warnings.warn("K should be symmetric", RuntimeWarning)
+            if flags & 2:
+                warnings.warn("K should have a non-zero diagonal", RuntimeWarning)
+            return K
+        return self._finish_dense_kernel(raw)
+
+    def _finish_dense_kernel(self, raw):
+        raise NotImplementedError
+
+    def _ensure_built(self):
+        if not hasattr(self, "_dev_kernel") and not hasattr(self, "_kernel"):
+            self._dev_kernel = self._build_kernel()
+
+    def symmetrize_kernel(self, K):
+        """Host-callable symmetrisation of an arbitrary scipy / numpy kernel on the GPU."""
+        from .hostops import symmetrize_host_matrix
+        return symmetrize_host_matrix(K, self.kernel_symm, self.theta)
+
+    def apply_anisotropy(self, K):
+        if self.anisotropy == 0:
+            return K
+        from .hostops import anisotropy_host_matrix
+        return anisotropy_host_matrix(K, self.anisotropy)
+
+    def get_params(self):
+        return {"kernel_symm": self.kernel_symm, "theta": self.theta, "anisotropy": self.anisotropy}
+
+    def set_params(self, **params):
+        for name in ("theta", "anisotropy", "kernel_symm"):
+            if name in params and params[name] != getattr(self, name):
+                raise ValueError("Cannot update {}. Please create a new graph".format(name))
+        super().set_params(**params)
+        return self
+
+    # ---------------------------------------------------------------- cached host views
+    @property
+    def K(self):
+        """Kernel matrix (scipy CSR or ndarray), materialised from HBM on first access."""
+        try:
+            return self._kernel
+        except AttributeError:
+            self._ensure_built()
+            self._kernel = self._materialize(self._dev_kernel)
+            return self._kernel
+
+    @property
+    def kernel(self):
+        return self.K
+
+    @property
+    def P(self):
+        """Diffusion operator = row-L1-normalised kernel (base.py:629-646)."""
+        try:
+            return self._diff_op
+        except AttributeError:
+            self._ensure_built()
+            K = self._dev_kernel
+            if isinstance(K, pipeline.DeviceCSR):
+                if getattr(self, "_dev_P", None) is None:
+                    self._dev_P = pipeline.row_normalize(K)
+                self._diff_op = K.to_scipy(self._dev_P)
+            else:
+                self._diff_op = self._dev_P.cpu().numpy()
+            return self._diff_op
+
+    @property
+    def diff_op(self):
+        return self.P
+
+    @property
+    def kernel_degree(self):
+        """Row sums of the kernel, shape [N, 1] (base.py:648-666)."""
+        try:
+            return self._kernel_degree
+        except AttributeError:
+            self._ensure_built()
+            self._kernel_degree = self._dev_degree.cpu().numpy().reshape(-1, 1)
+            return self._kernel_degree
+
+    @property
+    def diff_aff(self):
+        """Symmetric diffusion affinity D^-1/2 K D^-1/2 (base.py:668-698)."""
+        deg = self.kernel_degree
+        K = self.kernel
+        if sparse.issparse(K):
+            n = len(deg)
+            D = sparse.csr_matrix((1 / np.sqrt(deg.flatten()), np.arange(n), np.arange(n + 1)))
+            return D @ K @ D
+        return (K / np.sqrt(deg)) / np.sqrt(deg.T)
+
+    @staticmethod
+    def _materialize(dev):
+        if isinstance(dev, pipeline.DeviceCSR):
+            return dev.to_scipy()
+        return dev.cpu().numpy()
+
+    @abc.abstractmethod
+    def build_kernel(self):
+        """Build the raw (unsymmetrised) kernel on the device."""
+        raise NotImplementedError
+
+    def __getstate__(self):
+        # device handles do not pickle: materialise the host views first (base.py:887-902 contract)
+        state = dict(self.__dict__)
+        if any(k.startswith("_dev_") for k in state):
+            self.K, self.P, self.kernel_degree
+            state = dict(self.__dict__)
+        for k in [k for k in state if k.startswith("_dev_") or k in ("_ref_operand", "_knn_tree")]:
+            del state[k]
+        return state
+
+    def to_pickle(self, path):
+        import pickle
+        with open(path, "wb") as f:
+            pickle.dump(self, f, protocol=pickle.HIGHEST_PROTOCOL)
+
+
+class DataGraph(Data, BaseGraph, metaclass=abc.ABCMeta):
+    """Graph built from a data matrix (reference base.py:1046-1254)."""
+
+    def __init__(self, data, verbose=True, n_jobs=1, **kwargs):
+        self.n_jobs = n_jobs
+        self.verbose = verbose
+        _logger.set_level(verbose)
+        super().__init__(data, **kwargs)
+
+    def get_params(self):
+        params = Data.get_params(self)
+        params.update(BaseGraph.get_params(self))
+        return params
+
+    @abc.abstractmethod
+    def build_kernel_to_data(self, Y):
+        raise NotImplementedError
+
+    def _check_extension_shape(self, Y):
+        if len(Y.shape) != 2:
+            raise ValueError("Expected a 2D matrix. Y has shape {}".format(Y.shape))
+        if not Y.shape[1] == self.data_nu.shape[1]:
+            if Y.shape[1] == self.data.shape[1]:
+                Y = self.transform(Y)
+            else:
+                if self.data.shape[1] != self.data_nu.shape[1]:
+                    msg = "Y must be of shape either (n, {}) or (n, {})".format(self.data.shape[1],
+                                                                                 self.data_nu.shape[1])
+                else:
+                    msg = "Y must be of shape (n, {})".format(self.data.shape[1])
+                raise ValueError(msg)
+        return Y
+
+    def extend_to_data(self, Y):
+        """Transition matrix from new points ``Y`` to the graph's samples (base.py:1166-1193):
+        out-of-sample kernel, L1-row-normalised on the device."""
+        Y = self._check_extension_shape(Y)
+        dev = self._kernel_to_data_device(Y)
+        if isinstance(dev, pipeline.DeviceCSR):
+            return dev.to_scipy(pipeline.row_normalize(dev))
+        from .dense import row_normalize_dense
+        return row_normalize_dense(dev).cpu().numpy()
+
+    def interpolate(self, transform, transitions=None, Y=None):
+        """``transitions.dot(transform)`` (base.py:1195-1229)."""
+        if transitions is None:
+            if Y is None:
+                raise ValueError("Either `transitions` or `Y` must be provided.")
+            transitions = self.extend_to_data(Y)
+        return transitions.dot(transform)
+
+    def set_params(self, **params):
+        if "n_jobs" in params:
+            self.n_jobs = params["n_jobs"]
+        if "verbose" in params:
+            self.verbose = params["verbose"]
+            _logger.set_level(self.verbose)
+        super().set_params(**params)
+        return self
+
+    # helper shared by the sparse graph types -------------------------------------------------
+    def _dense_f32(self, A):
+        """Densify (scipy sparse -> ndarray) and hand to the device as float32."""
+        if sparse.issparse(A):
+            A = A.toarray()
+        return pipeline.to_device_f32(np.asarray(A))

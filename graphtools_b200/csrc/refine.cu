@@ -1,0 +1,405 @@
+// K3: float64 re-evaluation of the selected candidates, bandwidth, certification of the
+// candidate set, alpha-decay affinities and per-row column-sorted staging for CSR emission.
+//
+// Replaces (reference graphtools/graphs.py): bandwidth / radius / update-set logic :886-911, the
+// per-row Python loop of _build_csr_from_neighbors :450-559, and the "is the row finished?" test
+// that drives the x6 escalation loop :917-976.  Instead of escalating the neighbour count, each
+// row is *certified*: every reference point NOT among the S candidates has approximate squared
+// distance >= tau (top-k epilogue invariant) and therefore exact squared distance >= tau - E,
+// E = eps_rel * (|x~|^2 + max|y~|^2) bounding the error of the fast pass.  A row is complete when
+// its kernel support radius r = bw * (-ln thresh)^(1/decay) (or its knn_max-th neighbour) lies
+// inside that certified radius; otherwise it is sent to the radius pass with an inflated limit.
+//
+// All distances that reach the output are float64 direct differences sum((x-y)^2) of the
+// ORIGINAL float32 rows.
+#include "common.cuh"
+#include "gtb200.h"
+#include <float.h>
+
+namespace {
+
+struct RowParams {
+  const float* Xq; const float* Xr; int d;
+  int knn; int64_t kmax;       // kmax = INT64_MAX when knn_max is None
+  double decay;                // < 0: binary kNN (decay=None)
+  double thresh; double rfac;  // rfac = (-ln thresh)^(1/decay)
+  const double* bw_fixed; int bw_mode;  // 0 adaptive (k-th neighbour), 1 scalar, 2 per-row
+  double bw_scale; double bw_floor;     // bw_floor = eps (np.finfo(float).eps)
+};
+
+// exact squared distance between query row xq and reference row xr, cooperatively by one warp
+__device__ __forceinline__ double warp_dist2(const float* __restrict__ xq, const float* __restrict__ xr,
+                                             int d, int lane) {
+  double s = 0.0;
+  for (int k = lane; k < d; k += 32) {
+    double df = (double)xq[k] - (double)xr[k];
+    s = fma(df, df, s);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  return s;
+}
+
+__device__ __forceinline__ int next_pow2(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+// Shared tail of both refine kernels.  On entry key[0..npow2) holds exact squared distances sorted
+// ascending by (d2, idx) with +inf padding, idx[] the reference indices, n_cand the valid count and
+// bw the row's bandwidth (already final).  Keeps the leading entries with affinity >= thresh among
+// the first min(n_cand, kmax), converts them to (column, weight) sorted by column in key[]/idx[].
+// Returns n_keep (uniform across the group).  scratch = one int in shared memory.
+template <int NT, typename SyncT>
+__device__ int finalize_sorted_row(double* key, int32_t* idx, int n_cand, double bw, const RowParams& rp,
+                                   int tid, int* scratch, SyncT sync) {
+  int64_t m64 = rp.kmax < (int64_t)n_cand ? rp.kmax : (int64_t)n_cand;
+  int m = (int)m64;
+  if (rp.decay < 0) {
+    // binary kNN: the knn nearest, weight 1 (graphs.py:872-877)
+    int keep = rp.knn < m ? rp.knn : m;
+    for (int t = tid; t < keep; t += NT) key[t] = 1.0;
+    if (tid == 0) *scratch = keep;
+  } else {
+    if (tid == 0) *scratch = m;
+    sync();
+    // first position whose affinity drops below thresh
+    for (int t = tid; t < m; t += NT) {
+      double w = gtb_affinity(sqrt(key[t]), bw, rp.decay);
+      if (w >= rp.thresh) key[t] = w;
+      else atomicMin(scratch, t);
+    }
+  }
+  sync();
+  int n_keep = *scratch;
+  sync();
+  int np2 = next_pow2(n_keep < 2 ? 2 : n_keep);
+  for (int t = n_keep + tid; t < np2; t += NT) { idx[t] = 0x7fffffff; key[t] = 0.0; }
+  sync();
+  GTB_BITONIC_SORT(idx, key, np2, tid, NT, sync, int32_t, double);
+  return n_keep;
+}
+
+// ------------------------------------------------------------------ stage 1: warp per row
+constexpr int R1_WARPS = 4;
+constexpr int R1_CAP = 128;  // max candidates per row handled by the warp kernel
+
+struct Refine1Params {
+  RowParams rp;
+  int64_t nq; int S;
+  const int32_t* cand_idx; const float* tau; const float* qn2; float maxrn2; double eps_rel;
+  int32_t* st_idx; double* st_val; int32_t* n_keep; double* bw_out; float* lim2_out;
+  int32_t* status; int32_t* nzero;
+};
+
+__global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Params p) {
+  __shared__ double key_s[R1_WARPS][R1_CAP];
+  __shared__ int32_t idx_s[R1_WARPS][R1_CAP];
+  __shared__ int scratch_s[R1_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * R1_WARPS + warp;
+  if (row >= p.nq) return;  // whole warp exits together
+  double* key = key_s[warp];
+  int32_t* idx = idx_s[warp];
+  const RowParams& rp = p.rp;
+  const int S = p.S;
+  const int np2 = next_pow2(S);
+  auto sync = [] { __syncwarp(); };
+
+  // 1. exact distances
+  const float* xq = rp.Xq + row * rp.d;
+  int n_cand = 0;
+  for (int c = 0; c < S; ++c) {
+    int j = p.cand_idx[row * S + c];  // uniform load
+    if (j >= 0) {
+      double d2 = warp_dist2(xq, rp.Xr + (int64_t)j * rp.d, rp.d, lane);
+      if (lane == 0) { key[c] = d2; idx[c] = j; }
+      ++n_cand;
+    } else if (lane == 0) {
+      key[c] = DBL_MAX * 2.0;  // +inf
+      idx[c] = 0x7fffffff;
+    }
+  }
+  for (int t = S + lane; t < np2; t += 32) { key[t] = DBL_MAX * 2.0; idx[t] = 0x7fffffff; }
+  __syncwarp();
+  // 2. sort by (d2, idx)
+  GTB_BITONIC_SORT(key, idx, np2, lane, 32, sync, double, int32_t);
+
+  // 3. zero-distance count (duplicate detection, graphs.py:787-817)
+  int nz = 0;
+  for (int t = lane; t < n_cand; t += 32) nz += (key[t] == 0.0);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, off);
+
+  // 4. bandwidth + certification
+  const float tau = p.tau[row];
+  const bool all_found = isinf(tau);  // list never filled: every reference is a candidate
+  const double E = p.eps_rel * ((double)p.qn2[row] + (double)p.maxrn2);
+  const double rho2 = (double)tau - E;  // exact d2 of every non-candidate is >= rho2
+  double bw = 0.0, r_search = 0.0, dk = 0.0;
+  bool done, bw_cert = true;
+  if (rp.decay < 0) {
+    double dk2 = key[rp.knn - 1];
+    done = all_found || dk2 < rho2;
+    r_search = sqrt(dk2);
+  } else {
+    if (rp.bw_mode == 0) {
+      double dk2 = key[rp.knn - 1];
+      dk = sqrt(dk2);
+      bw = fmax(dk * rp.bw_scale, rp.bw_floor);
+      bw_cert = all_found || dk2 < rho2;
+    } else {
+      bw = fmax((rp.bw_mode == 1 ? rp.bw_fixed[0] : rp.bw_fixed[row]) * rp.bw_scale, rp.bw_floor);
+    }
+    double r = bw * rp.rfac;
+    bool ball_cert = all_found || r * r < rho2;
+    bool kmax_cert = (rp.kmax <= (int64_t)n_cand) && key[rp.kmax - 1] < rho2;
+    done = bw_cert && (ball_cert || kmax_cert);
+    // an uncertified bandwidth is only an upper bound: the search ball must then also hold the
+    // true knn nearest (radius >= bw) so stage 2 can recompute it
+    r_search = bw_cert ? r : fmax(r, dk);
+    if (rp.kmax <= (int64_t)n_cand) r_search = fmin(r_search, sqrt(key[rp.kmax - 1]));
+  }
+  if (lane == 0) {
+    p.bw_out[row] = bw;
+    p.status[row] = done ? 1 : (bw_cert ? 0 : 2);
+    p.nzero[row] = nz;
+    if (!done) {
+      double l2 = r_search * r_search * (1.0 + 1e-6) + E;
+      p.lim2_out[row] = __double2float_ru(l2);
+      p.n_keep[row] = 0;
+    } else {
+      p.lim2_out[row] = 0.f;
+    }
+  }
+  if (!done) return;
+  __syncwarp();
+  // 5. affinities, threshold, column sort, staging
+  int n_keep = finalize_sorted_row<32>(key, idx, n_cand, bw, rp, lane, &scratch_s[warp], sync);
+  for (int t = lane; t < n_keep; t += 32) {
+    p.st_idx[row * S + t] = idx[t];
+    p.st_val[row * S + t] = key[t];
+  }
+  if (lane == 0) p.n_keep[row] = n_keep;
+}
+
+// ------------------------------------------------------------------ stage 2: block per row
+constexpr int R2_THREADS = 256;
+
+struct Refine2Params {
+  RowParams rp;
+  const int32_t* todo_rows; const int32_t* status; int64_t nt;
+  const int64_t* seg_ptr; int32_t* seg_idx; double* seg_val;
+  int32_t* n_keep_t; double* bw_out; int32_t* nzero; int32_t* overflow; int cap;
+};
+
+__global__ void __launch_bounds__(R2_THREADS) refine_ball_kernel(Refine2Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* key = reinterpret_cast<double*>(smem_raw);               // [cap]
+  int32_t* idx = reinterpret_cast<int32_t*>(key + p.cap);          // [cap]
+  __shared__ int scratch;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t t_row = blockIdx.x;
+  const int64_t row = p.todo_rows[t_row];
+  const int64_t p0 = p.seg_ptr[t_row], p1 = p.seg_ptr[t_row + 1];
+  const int64_t L64 = p1 - p0;
+  const RowParams& rp = p.rp;
+  auto sync = [] { __syncthreads(); };
+  if (L64 > p.cap) {
+    if (tid == 0) { atomicMax(p.overflow, (int)(L64 > 0x7fffffff ? 0x7fffffff : L64)); p.n_keep_t[t_row] = 0; }
+    return;
+  }
+  const int L = (int)L64;
+  const int np2 = next_pow2(L < 2 ? 2 : L);
+  const float* xq = rp.Xq + row * rp.d;
+  for (int c = warp; c < L; c += R2_THREADS / 32) {
+    int j = p.seg_idx[p0 + c];
+    double d2 = warp_dist2(xq, rp.Xr + (int64_t)j * rp.d, rp.d, lane);
+    if (lane == 0) { key[c] = d2; idx[c] = j; }
+  }
+  for (int t = L + tid; t < np2; t += R2_THREADS) { key[t] = DBL_MAX * 2.0; idx[t] = 0x7fffffff; }
+  __syncthreads();
+  GTB_BITONIC_SORT(key, idx, np2, tid, R2_THREADS, sync, double, int32_t);
+
+  if (warp == 0) {
+    int nz = 0;
+    for (int t = lane; t < L; t += 32) nz += (key[t] == 0.0);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, off);
+    if (lane == 0) p.nzero[row] = nz;
+  }
+  double bw = 0.0;
+  if (rp.decay >= 0) {
+    if (rp.bw_mode == 0) {
+      if (p.status[row] == 2) {
+        // the search ball (radius >= k-th candidate distance) holds the true k nearest
+        int kk = rp.knn - 1 < L ? rp.knn - 1 : L - 1;
+        bw = fmax(sqrt(key[kk < 0 ? 0 : kk]) * rp.bw_scale, rp.bw_floor);
+      } else {
+        bw = p.bw_out[row];  // certified in stage 1
+      }
+    } else {
+      bw = fmax((rp.bw_mode == 1 ? rp.bw_fixed[0] : rp.bw_fixed[row]) * rp.bw_scale, rp.bw_floor);
+    }
+  }
+  __syncthreads();
+  int n_keep = finalize_sorted_row<R2_THREADS>(key, idx, L, bw, rp, tid, &scratch, sync);
+  for (int t = tid; t < n_keep; t += R2_THREADS) {
+    p.seg_idx[p0 + t] = idx[t];
+    p.seg_val[p0 + t] = key[t];
+  }
+  if (tid == 0) { p.n_keep_t[t_row] = n_keep; p.bw_out[row] = bw; }
+}
+
+// segment scatter: pairs (slot, col) -> seg_idx[seg_ptr[slot] + cursor[slot]++]
+__global__ void scatter_pairs_kernel(const int2* __restrict__ pairs, int64_t npairs,
+                                     const int64_t* __restrict__ seg_ptr, int32_t* __restrict__ cursor,
+                                     int32_t* __restrict__ seg_idx) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npairs) return;
+  int2 pr = pairs[i];
+  int pos = atomicAdd(cursor + pr.x, 1);
+  seg_idx[seg_ptr[pr.x] + pos] = pr.y;
+}
+
+__global__ void scatter_counts_kernel(const int32_t* __restrict__ todo_rows, const int32_t* __restrict__ n_keep_t,
+                                      int64_t nt, int32_t* __restrict__ n_keep) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nt) n_keep[todo_rows[t]] = n_keep_t[t];
+}
+
+// CSR gather from the stage-1 staging area [nq][S]
+__global__ void csr_gather1_kernel(const int32_t* __restrict__ st_idx, const double* __restrict__ st_val,
+                                   const int32_t* __restrict__ n_keep, const int32_t* __restrict__ status,
+                                   const int64_t* __restrict__ indptr, int64_t nq, int S,
+                                   int32_t* __restrict__ out_idx, double* __restrict__ out_val) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq * S) return;
+  int64_t row = i / S;
+  int t = (int)(i - row * S);
+  if (status[row] == 1 && t < n_keep[row]) {
+    int64_t o = indptr[row] + t;
+    out_idx[o] = st_idx[i];
+    out_val[o] = st_val[i];
+  }
+}
+
+__global__ void csr_gather2_kernel(const int32_t* __restrict__ todo_rows, const int64_t* __restrict__ seg_ptr,
+                                   const int32_t* __restrict__ seg_idx, const double* __restrict__ seg_val,
+                                   const int32_t* __restrict__ n_keep_t, const int64_t* __restrict__ indptr,
+                                   int32_t* __restrict__ out_idx, double* __restrict__ out_val) {
+  int64_t t_row = blockIdx.x;
+  int64_t row = todo_rows[t_row];
+  int64_t src = seg_ptr[t_row], dst = indptr[row];
+  int n = n_keep_t[t_row];
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    out_idx[dst + t] = seg_idx[src + t];
+    out_val[dst + t] = seg_val[src + t];
+  }
+}
+
+// stream compaction of rows with status == 0 (order is irrelevant to the result)
+__global__ void compact_todo_kernel(const int32_t* __restrict__ status, int64_t nq, int32_t* __restrict__ todo_rows,
+                                    int32_t* __restrict__ count) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool todo = (i < nq) && status[i] != 1;
+  unsigned m = __ballot_sync(0xffffffffu, todo);
+  if (!m) return;
+  int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (todo) todo_rows[base + __popc(m & ((1u << lane) - 1))] = (int32_t)i;
+}
+
+RowParams make_row_params(const float* Xq, const float* Xr, int d, int knn, int64_t kmax, double decay,
+                          double thresh, const double* bw_fixed, int bw_mode, double bw_scale) {
+  RowParams rp;
+  rp.Xq = Xq; rp.Xr = Xr; rp.d = d; rp.knn = knn; rp.kmax = kmax <= 0 ? INT64_MAX : kmax;
+  rp.decay = decay; rp.thresh = thresh;
+  rp.rfac = decay >= 0 ? pow(-log(thresh), 1.0 / decay) : 0.0;
+  rp.bw_fixed = bw_fixed; rp.bw_mode = bw_mode; rp.bw_scale = bw_scale; rp.bw_floor = DBL_EPSILON;
+  return rp;
+}
+
+}  // namespace
+
+extern "C" int gtb_refine_topk(const float* Xq, int64_t nq, const float* Xr, int d, const int32_t* cand_idx,
+                               int S, const float* tau, const float* qn2, float maxrn2, double eps_rel,
+                               int knn, int64_t kmax, double decay, double thresh, const double* bw_fixed,
+                               int bw_mode, double bw_scale, int32_t* st_idx, double* st_val, int32_t* n_keep,
+                               double* bw_out, float* lim2_out, int32_t* status, int32_t* nzero, void* stream) {
+  GTB_CHECK_ARG(nq > 0 && S > 0 && S <= R1_CAP, "S out of range");
+  GTB_CHECK_ARG(knn >= 1 && knn <= S, "knn must be in [1, S]");
+  GTB_CHECK_ARG(decay < 0 || (thresh > 0 && thresh <= 1), "thresh must be in (0, 1]");
+  Refine1Params p;
+  p.rp = make_row_params(Xq, Xr, d, knn, kmax, decay, thresh, bw_fixed, bw_mode, bw_scale);
+  p.nq = nq; p.S = S; p.cand_idx = cand_idx; p.tau = tau; p.qn2 = qn2; p.maxrn2 = maxrn2; p.eps_rel = eps_rel;
+  p.st_idx = st_idx; p.st_val = st_val; p.n_keep = n_keep; p.bw_out = bw_out; p.lim2_out = lim2_out;
+  p.status = status; p.nzero = nzero;
+  refine_topk_kernel<<<(unsigned)gtb_cdiv(nq, R1_WARPS), R1_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_compact_todo(const int32_t* status, int64_t nq, int32_t* todo_rows, int32_t* count, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  GTB_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
+  compact_todo_kernel<<<(unsigned)gtb_cdiv(nq, 256), 256, 0, st>>>(status, nq, todo_rows, count);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_scatter_pairs(const int32_t* pairs, int64_t npairs, const int64_t* seg_ptr, int32_t* cursor,
+                                 int64_t nt, int32_t* seg_idx, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  GTB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * nt, st));
+  if (npairs > 0) {
+    scatter_pairs_kernel<<<(unsigned)gtb_cdiv(npairs, 256), 256, 0, st>>>(
+        reinterpret_cast<const int2*>(pairs), npairs, seg_ptr, cursor, seg_idx);
+    GTB_CHECK_LAUNCH();
+  }
+  return GTB_OK;
+}
+
+extern "C" int gtb_refine_ball(const float* Xq, const int32_t* todo_rows, const int32_t* status, int64_t nt, const float* Xr, int d,
+                               const int64_t* seg_ptr, int32_t* seg_idx, double* seg_val, int knn, int64_t kmax,
+                               double decay, double thresh, const double* bw_fixed, int bw_mode, double bw_scale,
+                               int32_t* n_keep_t, int32_t* n_keep, double* bw_out, int32_t* nzero,
+                               int32_t* overflow, int cap, void* stream) {
+  GTB_CHECK_ARG(nt > 0, "no rows");
+  GTB_CHECK_ARG(cap >= 2 && (cap & (cap - 1)) == 0 && cap <= 8192, "cap must be a power of two <= 8192");
+  cudaStream_t st = (cudaStream_t)stream;
+  Refine2Params p;
+  p.rp = make_row_params(Xq, Xr, d, knn, kmax, decay, thresh, bw_fixed, bw_mode, bw_scale);
+  p.todo_rows = todo_rows; p.status = status; p.nt = nt; p.seg_ptr = seg_ptr; p.seg_idx = seg_idx; p.seg_val = seg_val;
+  p.n_keep_t = n_keep_t; p.bw_out = bw_out; p.nzero = nzero; p.overflow = overflow; p.cap = cap;
+  size_t smem = (size_t)cap * 12;
+  GTB_CUDA(cudaFuncSetAttribute(refine_ball_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GTB_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int32_t), st));
+  refine_ball_kernel<<<(unsigned)nt, R2_THREADS, smem, st>>>(p);
+  GTB_CHECK_LAUNCH();
+  scatter_counts_kernel<<<(unsigned)gtb_cdiv(nt, 256), 256, 0, st>>>(todo_rows, n_keep_t, nt, n_keep);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_csr_gather(const int32_t* st_idx, const double* st_val, const int32_t* n_keep,
+                              const int32_t* status, const int64_t* indptr, int64_t nq, int S,
+                              const int32_t* todo_rows, int64_t nt, const int64_t* seg_ptr,
+                              const int32_t* seg_idx, const double* seg_val, const int32_t* n_keep_t,
+                              int32_t* out_idx, double* out_val, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (st_idx) {
+    csr_gather1_kernel<<<(unsigned)gtb_cdiv(nq * S, 256), 256, 0, st>>>(st_idx, st_val, n_keep, status, indptr, nq, S,
+                                                                      out_idx, out_val);
+    GTB_CHECK_LAUNCH();
+  }
+  if (nt > 0) {
+    csr_gather2_kernel<<<(unsigned)nt, 128, 0, st>>>(todo_rows, seg_ptr, seg_idx, seg_val, n_keep_t, indptr,
+                                                     out_idx, out_val);
+    GTB_CHECK_LAUNCH();
+  }
+  return GTB_OK;
+}

@@ -1,0 +1,284 @@
+"""Device pipeline: the order in which the C-ABI kernels are chained for one graph build.
+
+search operand -> fused distance/top-S -> float64 refine + certification -> (radius pass for
+uncertified rows) -> CSR emission -> symmetrise -> row-normalise.
+
+Everything stays in HBM as torch tensors; the two host synchronisations per kernel build are the
+reads of `number of uncertified rows` and `nnz` (sizes of the next allocations).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _engine as E
+
+SYM_MODES = {"+": 0, "*": 1, "mnn": 2, None: 3}
+BALL_CAP = 8192          # longest radius-pass row handled by refine_ball (shared-memory sort)
+_STATS = {}
+
+
+def stats():
+    """Counters of the last kernel build (rows sent to the radius pass, passes, nnz)."""
+    return dict(_STATS)
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _empty(shape, dtype):
+    return torch.empty(shape, dtype=dtype, device=_dev())
+
+
+def _zeros(shape, dtype):
+    return torch.zeros(shape, dtype=dtype, device=_dev())
+
+
+def to_device_f32(X):
+    """Host array / tensor -> contiguous float32 CUDA tensor."""
+    E.require_cuda()
+    if isinstance(X, torch.Tensor):
+        return X.to(device=_dev(), dtype=torch.float32).contiguous()
+    X = np.ascontiguousarray(np.asarray(X), dtype=np.float32)
+    t = torch.from_numpy(X)
+    return t.to(_dev(), non_blocking=False)
+
+
+class SearchOperand:
+    """k-major centred copy of a point set + squared norms (csrc/prep.cu)."""
+
+    def __init__(self, X, mean=None):
+        n, d = X.shape
+        self.X, self.n, self.d = X, n, d
+        self.n_pad = (n + 127) // 128 * 128
+        self.d_pad = (d + 7) // 8 * 8
+        if mean is None:
+            ws = _empty((E.lib().gtb_col_mean_ws_doubles(d),), torch.float64)
+            mean = _empty((d,), torch.float32)
+            E.call("gtb_col_mean", X, n, d, ws, mean)
+        self.mean = mean
+        self.XT = _empty((self.d_pad, self.n_pad), torch.float32)
+        self.n2 = _empty((self.n_pad,), torch.float32)
+        self._maxnorm = _empty((1,), torch.float32)
+        E.call("gtb_prepare_operand", X, n, d, mean, self.XT, self.n_pad, self.d_pad, self.n2, self._maxnorm)
+        self._maxnorm_host = None
+
+    @property
+    def maxnorm(self):
+        if self._maxnorm_host is None:
+            self._maxnorm_host = float(self._maxnorm.item())
+        return self._maxnorm_host
+
+
+class DeviceCSR:
+    """CSR in HBM: int64 indptr [n+1], int32 indices, float64 data."""
+
+    def __init__(self, indptr, indices, data, shape):
+        self.indptr, self.indices, self.data, self.shape = indptr, indices, data, tuple(shape)
+
+    @property
+    def nnz(self):
+        return int(self.indices.shape[0])
+
+    def to_scipy(self, data=None):
+        from scipy import sparse
+        n1 = self.indptr.shape[0]
+        ip32 = _empty((n1,), torch.int32)
+        E.call("gtb_cast_indptr", self.indptr, n1, ip32)
+        vals = self.data if data is None else data
+        M = sparse.csr_matrix((vals.cpu().numpy(), self.indices.cpu().numpy(), ip32.cpu().numpy()),
+                              shape=self.shape)
+        M.has_sorted_indices = True
+        M.has_canonical_format = True
+        return M
+
+
+def exclusive_scan(counts):
+    n = counts.shape[0]
+    out = _empty((n + 1,), torch.int64)
+    ws = _empty((E.lib().gtb_scan_ws_elems(n),), torch.int64)
+    E.call("gtb_exclusive_scan", counts, n, out, ws)
+    return out
+
+
+def choose_S(knn_eff, binary):
+    """Candidate-list length of the fused top-k: the reference's first search is
+    knn * search_multiplier = 36 wide (graphs.py:882); we keep a little more so that the
+    certification margin rarely sends a row to the radius pass."""
+    need = knn_eff + (4 if binary else 8)
+    for S in ((16, 32, 48, 64, 128) if binary else (48, 64, 128)):
+        if need <= S:
+            return S
+    raise NotImplementedError(
+        "knn={} needs a candidate list longer than 128; not supported by the fused top-k yet".format(knn_eff))
+
+
+def eps_rel_simt(d):
+    """Relative bound on |approx d^2 - exact d^2| / (|x~|^2 + |y~|^2) for the fp32 CUDA-core pass:
+    (d + 11) * 2^-24 from a standard rounding analysis (dot product, norms, centring), doubled."""
+    return 2.0 * (d + 16) * 2.0 ** -24
+
+
+def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, bandwidth=None,
+               bandwidth_scale=1.0, S=None, impl="simt"):
+    """Raw (unsymmetrised) kNN / alpha-decay kernel from the rows of ``Xq`` to ``ref`` as DeviceCSR.
+
+    Semantics = reference ``kNNGraph.build_kernel_to_data`` (graphs.py:819-982) with the float64
+    path: ``knn`` is the effective neighbour count (callers pass knn+1 for the self-including
+    in-sample build), ``knn_max`` likewise.  Returns (csr, info) with info['bandwidth'] (device),
+    info['nzero'] (zero-distance candidates per row, for duplicate warnings).
+    """
+    E.require_cuda()
+    if qry is None:
+        qry = ref
+    nq, nr, d = qry.n, ref.n, ref.d
+    binary = decay is None
+    knn = int(min(knn, nr))
+    kmax = 0 if knn_max is None else int(knn_max)
+    if kmax >= nr:
+        kmax = 0
+    if S is None:
+        S = choose_S(knn, binary)
+    eps_rel = eps_rel_simt(d)
+    dev = _dev()
+
+    cand = _empty((nq, S), torch.int32)
+    tau = _empty((nq,), torch.float32)
+    if impl == "simt":
+        E.call("gtb_knn_topk_simt", qry.XT, qry.n2, nq, qry.n_pad, ref.XT, ref.n2, nr, ref.n_pad, ref.d_pad, S,
+               cand, tau)
+    else:
+        raise ValueError("unknown impl %r" % (impl,))
+
+    # bandwidth argument
+    bw_mode, bw_fixed = 0, None
+    if not binary and bandwidth is not None:
+        if np.ndim(bandwidth) == 0:
+            bw_mode, bw_fixed = 1, torch.tensor([float(bandwidth)], dtype=torch.float64, device=dev)
+        else:
+            bw_arr = np.asarray(bandwidth, dtype=np.float64).reshape(-1)
+            if bw_arr.shape[0] != nq:
+                raise ValueError("bandwidth must be a scalar or have one entry per row ({}), got {}".format(
+                    nq, bw_arr.shape[0]))
+            bw_mode, bw_fixed = 2, torch.from_numpy(bw_arr).to(dev)
+    decay_f = -1.0 if binary else float(decay)
+    thresh_f = 1.0 if binary else float(thresh)
+
+    st_idx = _empty((nq, S), torch.int32)
+    st_val = _empty((nq, S), torch.float64)
+    n_keep = _empty((nq,), torch.int32)
+    bw_out = _empty((nq,), torch.float64)
+    lim2 = _empty((nq,), torch.float32)
+    status = _empty((nq,), torch.int32)
+    nzero = _empty((nq,), torch.int32)
+    E.call("gtb_refine_topk", qry.X, nq, ref.X, d, cand, S, tau, qry.n2, ref.maxnorm, eps_rel, knn, kmax, decay_f,
+           thresh_f, bw_fixed, bw_mode, float(bandwidth_scale), st_idx, st_val, n_keep, bw_out, lim2, status, nzero)
+
+    todo_rows = _empty((nq,), torch.int32)
+    count = _empty((1,), torch.int32)
+    E.call("gtb_compact_todo", status, nq, todo_rows, count)
+    nt = int(count.item())                       # host sync #1
+    _STATS.update(rows=nq, radius_rows=nt, S=S, radius_pairs=0)
+
+    seg_ptr = seg_idx = seg_val = n_keep_t = None
+    if nt > 0:
+        todo_rows = todo_rows[:nt].contiguous()
+        nt_pad = (nt + 127) // 128 * 128
+        QT = _empty((ref.d_pad, nt_pad), torch.float32)
+        qn2 = _empty((nt_pad,), torch.float32)
+        E.call("gtb_gather_operand", qry.XT, qry.n_pad, qry.n2, todo_rows, nt, QT, nt_pad, ref.d_pad, qn2)
+        lim_t = torch.zeros((nt_pad,), dtype=torch.float32, device=dev)
+        lim_t[:nt] = lim2[todo_rows.long()]
+        capacity = max(1 << 20, nt * 4 * S)
+        while True:
+            pairs = _empty((capacity, 2), torch.int32)
+            counter = _zeros((1,), torch.int64)
+            rowcnt = _zeros((nt_pad,), torch.int32)
+            E.call("gtb_knn_radius_simt", QT, qn2, lim_t, nt, nt_pad, ref.XT, ref.n2, nr, ref.n_pad, ref.d_pad,
+                   pairs, capacity, counter, rowcnt)
+            npairs = int(counter.item())
+            if npairs <= capacity:
+                break
+            capacity = npairs
+        _STATS.update(radius_pairs=npairs)
+        seg_ptr = exclusive_scan(rowcnt[:nt].contiguous())
+        seg_idx = _empty((max(npairs, 1),), torch.int32)
+        seg_val = _empty((max(npairs, 1),), torch.float64)
+        cursor = _empty((nt,), torch.int32)
+        E.call("gtb_scatter_pairs", pairs, npairs, seg_ptr, cursor, nt, seg_idx)
+        n_keep_t = _empty((nt,), torch.int32)
+        overflow = _empty((1,), torch.int32)
+        longest = int(rowcnt.max().item())
+        cap = 64
+        while cap < longest:
+            cap *= 2
+        if cap > BALL_CAP:
+            raise NotImplementedError(
+                "a row has {} neighbours inside the kernel radius; rows longer than {} are not supported "
+                "(use graphtype='exact' for such dense kernels)".format(longest, BALL_CAP))
+        E.call("gtb_refine_ball", qry.X, todo_rows, status, nt, ref.X, d, seg_ptr, seg_idx, seg_val, knn, kmax,
+               decay_f, thresh_f, bw_fixed, bw_mode, float(bandwidth_scale), n_keep_t, n_keep, bw_out, nzero,
+               overflow, cap)
+
+    indptr = exclusive_scan(n_keep)
+    nnz = int(indptr[-1].item())                 # host sync #2
+    out_idx = _empty((nnz,), torch.int32)
+    out_val = _empty((nnz,), torch.float64)
+    E.call("gtb_csr_gather", st_idx, st_val, n_keep, status, indptr, nq, S, todo_rows if nt else None, nt,
+           seg_ptr, seg_idx, seg_val, n_keep_t, out_idx, out_val)
+    _STATS.update(nnz_raw=nnz)
+    csr = DeviceCSR(indptr, out_idx, out_val, (nq, nr))
+    return csr, {"bandwidth": bw_out, "nzero": nzero}
+
+
+def symmetrize_normalize(R, kernel_symm="+", theta=None, anisotropy=0.0, want_p=True):
+    """``BaseGraph._build_kernel`` post-processing (base.py:534-592) + ``P`` (base.py:645).
+
+    Returns (K DeviceCSR, P values tensor | None, degree tensor, flags int) where flags bit 0 =
+    asymmetric beyond 1e-5 (only evaluated for kernel_symm=None), bit 1 = a row has no diagonal.
+    """
+    n = R.shape[0]
+    square = R.shape[0] == R.shape[1]
+    mode = SYM_MODES[kernel_symm]
+    flags = _zeros((1,), torch.int32)
+    if mode != 3 and not square:
+        raise ValueError("symmetrisation needs a square kernel")
+    if mode == 3:
+        if square:
+            dummy = _empty((n,), torch.int32)
+            E.call("gtb_sym_count", R.indptr, R.indices, R.data, n, 3, 0.0, dummy, flags)
+        K = R
+        P = _empty((R.nnz,), torch.float64) if want_p else None
+        degree = _empty((n,), torch.float64)
+        E.call("gtb_row_finalize", K.indptr, K.indices, K.data, n, 0, None, None, P, degree, flags, int(square))
+    else:
+        newlen = _empty((n,), torch.int32)
+        th = 0.0 if theta is None else float(theta)
+        E.call("gtb_sym_count", R.indptr, R.indices, R.data, n, mode, th, newlen, flags)
+        outptr = exclusive_scan(newlen)
+        nnz = int(outptr[-1].item())
+        tmp_idx = _empty((nnz,), torch.int32)
+        tmp_val = _empty((nnz,), torch.float64)
+        cursor = newlen  # reuse as the per-row cursor (zeroed by sym_fill)
+        E.call("gtb_sym_fill", R.indptr, R.indices, R.data, n, mode, th, outptr, cursor, tmp_idx, tmp_val)
+        k_idx = _empty((nnz,), torch.int32)
+        k_val = _empty((nnz,), torch.float64)
+        P = _empty((nnz,), torch.float64) if (want_p and anisotropy == 0) else None
+        degree = _empty((n,), torch.float64)
+        E.call("gtb_row_finalize", outptr, tmp_idx, tmp_val, n, 1, k_idx, k_val, P, degree, flags, 1)
+        K = DeviceCSR(outptr, k_idx, k_val, R.shape)
+    if anisotropy != 0:
+        E.call("gtb_anisotropy", K.indptr, K.indices, K.data, degree, float(anisotropy), n)
+        P = _empty((K.nnz,), torch.float64) if want_p else None
+        E.call("gtb_row_finalize", K.indptr, K.indices, K.data, n, 0, None, None, P, degree, flags, 0)
+    _STATS.update(nnz_sym=K.nnz)
+    return K, P, degree, int(flags.item())
+
+
+def row_normalize(K):
+    """sklearn ``normalize(K, 'l1', axis=1)`` on a DeviceCSR -> values tensor."""
+    P = _empty((K.nnz,), torch.float64)
+    flags = _zeros((1,), torch.int32)
+    E.call("gtb_row_finalize", K.indptr, K.indices, K.data, K.shape[0], 0, None, None, P, None, flags, 0)
+    return P

@@ -1,0 +1,106 @@
+/* gtb200 -- C ABI of the B200-native graph-construction engine (libgtb200.so).
+ *
+ * The reference (KrishnaswamyLab/graphtools v2.1.0) is pure Python and has no FFI: its seam is
+ * the pair of abstract methods BaseGraph.build_kernel() (graphtools/base.py:805-818) and
+ * DataGraph.build_kernel_to_data(Y) (base.py:1102-1127) plus the BaseGraph post-processing
+ * (base.py:534-592, :629-698).  Every entry point below replaces the third-party call the
+ * reference makes at the cited site.  INTEGRATION.md shows the ctypes stub a graphtools
+ * maintainer would add to call them.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless stated otherwise; the caller owns every buffer
+ *     (the Python host allocates them as torch tensors and passes tensor.data_ptr());
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream and
+ *     never synchronise;
+ *   - return value: 0 on success, negative on error (GTB_ERR_*); gtb_last_error() returns a
+ *     thread-local description;
+ *   - matrices are row-major; CSR uses int64 row pointers on the device (cast with
+ *     gtb_cast_indptr for the scipy int32 contract), int32 column indices, float64 values.
+ */
+#ifndef GTB200_H
+#define GTB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* gtb_last_error(void);
+int gtb_version(void);
+
+/* ---- operand preparation (no reference counterpart: sklearn NearestNeighbors.fit keeps a
+ * pointer for brute force, graphs.py:763-768) ------------------------------------------------ */
+/* column means of X[n,d] (float32); ws holds gtb_col_mean_ws_doubles(d) doubles */
+int64_t gtb_col_mean_ws_doubles(int d);
+int gtb_col_mean(const float* X, int64_t n, int d, double* ws, float* mean, void* stream);
+/* XT[d_pad][n_pad] = transpose(X - mean) zero padded (n_pad % 128 == 0, d_pad % 8 == 0);
+ * norm2[n_pad] = |row|^2 of the centred rows, +inf on padding; *maxnorm = max norm2 (optional) */
+int gtb_prepare_operand(const float* X, int64_t n, int d, const float* mean, float* XT, int64_t n_pad,
+                        int d_pad, float* norm2, float* maxnorm, void* stream);
+/* dstT[:, t] = srcT[:, rows[t]] for t < nt (query sub-set for the radius pass) */
+int gtb_gather_operand(const float* srcT, int64_t src_pad, const float* src_n2, const int32_t* rows,
+                       int64_t nt, float* dstT, int64_t dst_pad, int d_pad, float* dst_n2, void* stream);
+
+/* ---- K1/K2 distance + selection: replaces knn_tree.kneighbors (graphs.py:883, :922, :957),
+ * kneighbors_graph (:875-877) and radius_neighbors (:966-973) ------------------------------- */
+/* top-S candidates per query by approximate squared distance; cand_idx[nq][S] (-1 = empty),
+ * tau[nq] = S-th smallest approximate d^2 (+inf when fewer than S references). S in {16,32,48,64,128} */
+int gtb_knn_topk_simt(const float* QT, const float* qn2, int64_t nq, int64_t nq_pad, const float* RT,
+                      const float* rn2, int64_t nr, int64_t nr_pad, int d_pad, int S, int32_t* cand_idx,
+                      float* tau, void* stream);
+/* every (query slot, ref) pair with approximate d^2 <= lim2[slot] appended to pairs[capacity][2];
+ * *counter (zeroed by the caller) receives the number of qualifying pairs even past capacity;
+ * rowcnt[nq] (zeroed by the caller) receives the per-slot counts */
+int gtb_knn_radius_simt(const float* QT, const float* qn2, const float* lim2, int64_t nq, int64_t nq_pad,
+                        const float* RT, const float* rn2, int64_t nr, int64_t nr_pad, int d_pad,
+                        int32_t* pairs, int64_t capacity, unsigned long long* counter, int32_t* rowcnt,
+                        void* stream);
+
+/* ---- K3 float64 re-evaluation, bandwidth, affinities, CSR emission: replaces graphs.py:886-911
+ * and _build_csr_from_neighbors (graphs.py:450-559) ------------------------------------------ */
+/* decay < 0 means binary kNN (decay=None); kmax <= 0 means knn_max=None;
+ * bw_mode 0: bandwidth = distance to the knn-th candidate (graphs.py:892), 1: scalar bw_fixed[0],
+ * 2: per-row bw_fixed[nq].  status: 1 done, 0 needs radius pass, 2 needs radius pass and its
+ * bandwidth is not yet certified.  st_idx/st_val[nq][S]: kept entries sorted by column. */
+int gtb_refine_topk(const float* Xq, int64_t nq, const float* Xr, int d, const int32_t* cand_idx, int S,
+                    const float* tau, const float* qn2, float maxrn2, double eps_rel, int knn, int64_t kmax,
+                    double decay, double thresh, const double* bw_fixed, int bw_mode, double bw_scale,
+                    int32_t* st_idx, double* st_val, int32_t* n_keep, double* bw_out, float* lim2_out,
+                    int32_t* status, int32_t* nzero, void* stream);
+int gtb_compact_todo(const int32_t* status, int64_t nq, int32_t* todo_rows, int32_t* count, void* stream);
+int gtb_scatter_pairs(const int32_t* pairs, int64_t npairs, const int64_t* seg_ptr, int32_t* cursor,
+                      int64_t nt, int32_t* seg_idx, void* stream);
+/* block per radius-pass row; *overflow receives the longest row length that exceeded `cap` */
+int gtb_refine_ball(const float* Xq, const int32_t* todo_rows, const int32_t* status, int64_t nt,
+                    const float* Xr, int d, const int64_t* seg_ptr, int32_t* seg_idx, double* seg_val, int knn,
+                    int64_t kmax, double decay, double thresh, const double* bw_fixed, int bw_mode,
+                    double bw_scale, int32_t* n_keep_t, int32_t* n_keep, double* bw_out, int32_t* nzero,
+                    int32_t* overflow, int cap, void* stream);
+int gtb_csr_gather(const int32_t* st_idx, const double* st_val, const int32_t* n_keep, const int32_t* status,
+                   const int64_t* indptr, int64_t nq, int S, const int32_t* todo_rows, int64_t nt,
+                   const int64_t* seg_ptr, const int32_t* seg_idx, const double* seg_val,
+                   const int32_t* n_keep_t, int32_t* out_idx, double* out_val, void* stream);
+
+/* ---- K4 sparse symmetrise / normalise: replaces base.py:557-577, :579-592, :645, :648-666 --- */
+int64_t gtb_scan_ws_elems(int64_t n);
+/* out[n+1] = exclusive prefix sums of in[n] (int32 -> int64); ws: gtb_scan_ws_elems(n) int64 */
+int gtb_exclusive_scan(const int32_t* in, int64_t n, int64_t* out, int64_t* ws, void* stream);
+int gtb_cast_indptr(const int64_t* in, int64_t n1, int32_t* out, void* stream);
+/* mode 0 '+', 1 '*', 2 'mnn' (theta), 3 none (only sets flags bit 0 when max(K - K^T) > 1e-5) */
+int gtb_sym_count(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n, int mode,
+                  double theta, int32_t* newlen, int32_t* flags, void* stream);
+int gtb_sym_fill(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n, int mode,
+                 double theta, const int64_t* outptr, int32_t* cursor, int32_t* tmp_idx, double* tmp_val,
+                 void* stream);
+/* sort != 0: rows of tmp are unsorted -> write column-sorted K (out_idx/out_val); always (when
+ * non-NULL) p_val = val / sum|val| and degree = sum|val|; flags bit 1: a row lacks its diagonal */
+int gtb_row_finalize(const int64_t* ptr, const int32_t* tmp_idx, const double* tmp_val, int64_t n, int sort,
+                     int32_t* out_idx, double* out_val, double* p_val, double* degree, int32_t* flags,
+                     int check_diag, void* stream);
+int gtb_anisotropy(const int64_t* indptr, const int32_t* idx, double* val, const double* deg, double alpha,
+                   int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTB200_H */

@@ -1,0 +1,95 @@
+"""Unit tests of individual C-ABI kernels against numpy (run on the B200 box)."""
+import numpy as np
+import pytest
+import torch
+
+from graphtools_b200 import _engine as E
+from graphtools_b200 import pipeline, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("n", [1, 7, 2048, 2049, 100003, 3000017])
+def test_exclusive_scan(n):
+    rng = np.random.default_rng(n)
+    x = rng.integers(0, 50, size=n).astype(np.int32)
+    out = pipeline.exclusive_scan(_dev(x)).cpu().numpy()
+    ref = np.concatenate([[0], np.cumsum(x.astype(np.int64))])
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("n,d", [(1797, 64), (1000, 100), (130, 3), (5000, 37)])
+def test_prepare_operand(n, d):
+    X, _ = synth.gaussian_mixture(n, d, n_clusters=4, intrinsic_dim=min(5, d), seed=1)
+    op = pipeline.SearchOperand(_dev(X))
+    mean = X.astype(np.float64).mean(0)
+    assert np.allclose(op.mean.cpu().numpy(), mean, rtol=1e-6, atol=1e-6)
+    Xc = (X - op.mean.cpu().numpy()[None, :]).astype(np.float32)
+    XT = op.XT.cpu().numpy()
+    assert XT.shape == (op.d_pad, op.n_pad)
+    assert np.array_equal(XT[:d, :n], Xc.T)
+    assert (XT[d:, :] == 0).all() and (XT[:, n:] == 0).all()
+    n2 = op.n2.cpu().numpy()
+    ref_n2 = (Xc.astype(np.float64) ** 2).sum(1)
+    assert np.allclose(n2[:n], ref_n2, rtol=1e-6)
+    assert (n2[:n] >= ref_n2 * (1 - 1e-7)).all()
+    assert np.isinf(n2[n:]).all()
+    assert np.isclose(op.maxnorm, n2[:n].max())
+
+
+@pytest.mark.parametrize("n,d,S", [(1797, 64, 48), (3000, 100, 48), (700, 20, 16), (2500, 10, 64), (300, 5, 128),
+                                   (40, 3, 48)])
+def test_topk_candidates_contain_true_neighbours(n, d, S):
+    X, _ = synth.gaussian_mixture(n, d, n_clusters=5, intrinsic_dim=min(8, d), seed=3)
+    op = pipeline.SearchOperand(_dev(X))
+    cand = torch.empty((n, S), dtype=torch.int32, device="cuda")
+    tau = torch.empty((n,), dtype=torch.float32, device="cuda")
+    E.call("gtb_knn_topk_simt", op.XT, op.n2, n, op.n_pad, op.XT, op.n2, n, op.n_pad, op.d_pad, S, cand, tau)
+    cand = cand.cpu().numpy(); tau = tau.cpu().numpy()
+    X64 = X.astype(np.float64)
+    D2 = ((X64[:, None, :] - X64[None, :, :]) ** 2).sum(-1) if n <= 3000 else None
+    k_true = min(S - 8, n)
+    order = np.argsort(D2, axis=1, kind="stable")
+    for i in range(0, n, max(1, n // 200)):
+        c = cand[i][cand[i] >= 0]
+        assert len(np.unique(c)) == len(c), "duplicate candidate"
+        assert len(c) == min(S, n)
+        assert set(order[i, :k_true]).issubset(set(c)), "row %d misses a true neighbour" % i
+        if n > S:
+            # tau = S-th smallest approximate d2: every non-candidate is at least that far (up to fp32 error)
+            non = np.setdiff1d(np.arange(n), c)
+            Xc = X64 - X64.mean(0)
+            bound = pipeline.eps_rel_simt(d) * ((Xc[i] ** 2).sum() + (Xc ** 2).sum(1).max())
+            assert D2[i, non].min() >= tau[i] - bound
+        else:
+            assert np.isinf(tau[i])
+
+
+def test_radius_pairs_complete():
+    n, d = 2000, 30
+    X, _ = synth.gaussian_mixture(n, d, n_clusters=3, intrinsic_dim=6, seed=4)
+    op = pipeline.SearchOperand(_dev(X))
+    X64 = X.astype(np.float64)
+    D2 = ((X64[:, None, :] - X64[None, :, :]) ** 2).sum(-1)
+    r2 = np.partition(D2, 40, axis=1)[:, 40]
+    lim = _dev((r2 * 1.0001 + 1e-3).astype(np.float32))
+    limp = torch.zeros(op.n_pad, dtype=torch.float32, device="cuda"); limp[:n] = lim
+    cap = 1 << 20
+    pairs = torch.empty((cap, 2), dtype=torch.int32, device="cuda")
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    rowcnt = torch.zeros(op.n_pad, dtype=torch.int32, device="cuda")
+    E.call("gtb_knn_radius_simt", op.XT, op.n2, limp, n, op.n_pad, op.XT, op.n2, n, op.n_pad, op.d_pad, pairs, cap,
+           counter, rowcnt)
+    m = int(counter.item())
+    pr = pairs[:m].cpu().numpy()
+    got = set(map(tuple, pr))
+    assert len(got) == m
+    want = set(zip(*np.nonzero(D2 <= r2[:, None])))
+    assert want.issubset(got)
+    extra = got - want
+    assert len(extra) < 0.05 * len(want) + 50
+    assert np.array_equal(np.bincount(pr[:, 0], minlength=n), rowcnt[:n].cpu().numpy())
