@@ -52,10 +52,10 @@ class Base(object):
         names = set()
         for klass in cls.__mro__:
             init = klass.__dict__.get("__init__")
-            if init is None:
+            if init is None or klass is object:
                 continue
             for p in inspect.signature(init).parameters.values():
-                if p.name != "self" and p.kind is not p.VAR_KEYWORD:
+                if p.name != "self" and p.kind not in (p.VAR_KEYWORD, p.VAR_POSITIONAL):
                     names.add(p.name)
         return names
 
@@ -453,6 +453,9 @@ class DataGraph(Data, BaseGraph, metaclass=abc.ABCMeta):
     # helper shared by the sparse graph types -------------------------------------------------
     def _dense_f32(self, A):
         """Densify (scipy sparse -> ndarray) and hand to the device as float32."""
+        import torch
+        if isinstance(A, torch.Tensor):
+            return pipeline.to_device_f32(A)
         if sparse.issparse(A):
             A = A.toarray()
         return pipeline.to_device_f32(np.asarray(A))

@@ -246,6 +246,37 @@ __global__ void anisotropy_kernel(const int64_t* __restrict__ indptr, const int3
     val[e] = val[e] / pow(di * deg[idx[e]], alpha);
 }
 
+// ------------------------------------------------------------------ MNN block assembly
+__global__ void block_count_kernel(const int64_t* __restrict__ indptr, int64_t nb, const int32_t* __restrict__ row_map,
+                                   int32_t* __restrict__ rowlen) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nb) rowlen[row_map[i]] += (int32_t)(indptr[i + 1] - indptr[i]);
+}
+
+__global__ void __launch_bounds__(256) block_fill_kernel(
+    const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val, int64_t nb,
+    const int32_t* __restrict__ row_map, const int32_t* __restrict__ col_map, const double* __restrict__ within,
+    const double* __restrict__ between, double beta, const int64_t* __restrict__ outptr,
+    int32_t* __restrict__ cursor, int32_t* __restrict__ out_idx, double* __restrict__ out_val) {
+  const int sub = threadIdx.x % SYM_GROUP;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / SYM_GROUP;
+  if (i >= nb) return;  // whole 8-lane group leaves together
+  const int64_t e0 = indptr[i], e1 = indptr[i + 1];
+  const int32_t grow = row_map[i];
+  // every lane reads the cursor before the group leader advances it
+  const unsigned gmask = 0xffu << ((threadIdx.x & 31) / SYM_GROUP * SYM_GROUP);
+  int32_t cur = cursor[grow];
+  __syncwarp(gmask);
+  double scale = 1.0;
+  if (within) scale = fmin(1.0, within[i] / between[i]) * beta;  // graphs.py:1921-1925
+  const int64_t o0 = outptr[grow] + cur;
+  for (int64_t e = e0 + sub; e < e1; e += SYM_GROUP) {
+    out_idx[o0 + (e - e0)] = col_map[idx[e]];
+    out_val[o0 + (e - e0)] = val[e] * scale;
+  }
+  if (sub == 0) cursor[grow] = cur + (int32_t)(e1 - e0);
+}
+
 __global__ void cast_indptr_kernel(const int64_t* __restrict__ in, int64_t n1, int32_t* __restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n1) out[i] = (int32_t)in[i];
@@ -309,6 +340,25 @@ extern "C" int gtb_row_finalize(const int64_t* ptr, const int32_t* tmp_idx, cons
   else
     row_finalize_kernel<false><<<grid, FIN_WARPS * 32, 0, st>>>(ptr, tmp_idx, tmp_val, n, out_idx, out_val, p_val,
                                                                 degree, flags, check_diag);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_block_count(const int64_t* indptr, int64_t nb, const int32_t* row_map, int32_t* rowlen,
+                               void* stream) {
+  GTB_CHECK_ARG(nb > 0, "empty block");
+  block_count_kernel<<<(unsigned)gtb_cdiv(nb, 256), 256, 0, (cudaStream_t)stream>>>(indptr, nb, row_map, rowlen);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_block_fill(const int64_t* indptr, const int32_t* idx, const double* val, int64_t nb,
+                              const int32_t* row_map, const int32_t* col_map, const double* within,
+                              const double* between, double beta, const int64_t* outptr, int32_t* cursor,
+                              int32_t* out_idx, double* out_val, void* stream) {
+  GTB_CHECK_ARG(nb > 0, "empty block");
+  block_fill_kernel<<<(unsigned)gtb_cdiv(nb * SYM_GROUP, 256), 256, 0, (cudaStream_t)stream>>>(
+      indptr, idx, val, nb, row_map, col_map, within, between, beta, outptr, cursor, out_idx, out_val);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }

@@ -1,0 +1,87 @@
+"""Dense (exact-graph) device operations: thin wrappers over csrc/dense.cu."""
+import numpy as np
+import torch
+
+from . import _engine as E
+from . import pipeline
+
+SYM = {"+": 0, "*": 1, "mnn": 2, None: 3}
+
+
+def dense_affinity(Xq, Xr, bw_q, bw_r, decay, thresh, symm=None, theta=None, want_rowsum=True):
+    """[nq, nr] float64 thresholded alpha-decay affinities; symmetrised in the same sweep when
+    ``bw_r`` is given (square problems)."""
+    nq, d = Xq.shape
+    nr = Xr.shape[0]
+    out = pipeline._empty((nq, nr), torch.float64)
+    rowsum = pipeline._empty((nq,), torch.float64) if want_rowsum else None
+    what = 2 if bw_r is not None else 1
+    E.call("gtb_dense_kernel", Xq, nq, Xr, nr, d, what, bw_q, bw_r, float(decay), float(thresh),
+           SYM[symm], 0.0 if theta is None else float(theta), out, rowsum)
+    return out, rowsum
+
+
+def dense_distances(Xq, Xr):
+    nq, d = Xq.shape
+    nr = Xr.shape[0]
+    out = pipeline._empty((nq, nr), torch.float64)
+    E.call("gtb_dense_kernel", Xq, nq, Xr, nr, d, 0, None, None, 0.0, 0.0, 3, 0.0, out, None)
+    return out
+
+
+def rowsum_dense(K):
+    s = pipeline._empty((K.shape[0],), torch.float64)
+    E.call("gtb_dense_rowsum", K, K.shape[0], K.shape[1], s)
+    return s
+
+
+def row_normalize_dense(K, rowsum=None):
+    if rowsum is None:
+        rowsum = rowsum_dense(K)
+    out = pipeline._empty(tuple(K.shape), torch.float64)
+    E.call("gtb_dense_row_scale", K, rowsum, K.shape[0], K.shape[1], out)
+    return out
+
+
+def anisotropy_dense(K, alpha, deg=None):
+    if deg is None:
+        deg = rowsum_dense(K)
+    newsum = pipeline._empty((K.shape[0],), torch.float64)
+    E.call("gtb_dense_anisotropy", K, deg, float(alpha), K.shape[0], newsum)
+    return K
+
+
+def symmetrize_dense(K, kernel_symm, theta):
+    """Dense symmetrisation of an arbitrary square matrix already in HBM (host-callable helper).
+    The exact-graph build does not use this: it fuses the rule into the distance tile."""
+    if kernel_symm == "+":
+        return (K + K.T) / 2
+    if kernel_symm == "*":
+        return K * K.T
+    if kernel_symm == "mnn":
+        return theta * torch.minimum(K, K.T) + (1 - theta) * torch.maximum(K, K.T)
+    return K
+
+
+def _dense_to_csr(K):
+    """Dense [n, m] device matrix -> DeviceCSR of its non-zeros (used to feed the landmark kernels)."""
+    nz = K != 0
+    counts = nz.sum(dim=1, dtype=torch.int32)
+    indptr = pipeline.exclusive_scan(counts.contiguous())
+    cols = nz.nonzero()[:, 1].to(torch.int32).contiguous()
+    return pipeline.DeviceCSR(indptr, cols, K[nz].contiguous(), tuple(K.shape))
+
+
+def dense_landmark(K, labels, L):
+    from .landmark import aggregate_by_cluster
+    csr = _dense_to_csr(K)
+    pnm, pnm_norm, colsum = aggregate_by_cluster(csr, labels, L, want_colsum=True)
+    op = pipeline._empty((L, L), torch.float64)
+    E.call("gtb_landmark_op", pnm.indptr, pnm.indices, pnm.data, pnm_norm, colsum, K.shape[0], L, op)
+    return op.cpu().numpy(), pnm.to_scipy(pnm_norm).toarray()
+
+
+def dense_landmark_extend(Kyx, labels, L):
+    from .landmark import aggregate_by_cluster
+    agg, agg_norm, _ = aggregate_by_cluster(_dense_to_csr(Kyx), labels, L, want_colsum=False)
+    return agg.to_scipy(agg_norm).toarray()

@@ -1,0 +1,48 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch).
+
+Partitioning: query rows are block-partitioned over the ranks, the reference set is
+replicated (1M x 100 float32 = 400 MB << 180 GB).  Distance/top-k, float64 refine and CSR emission are
+independent per row, so each rank builds the raw kernel rows of its shard with no communication.
+The one exchange step is ahead of symmetrisation: the raw CSR row shards are all-gathered (variable
+length -> padded to the longest shard), after which symmetrise / normalise are local.  Because every row
+sees the whole reference set, the result is bit-identical for any number of ranks.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous row range [lo, hi) owned by ``rank``; multiples of 128 rows so query tiles stay full."""
+    tiles = (n + 127) // 128
+    per = (tiles + world - 1) // world
+    lo = min(n, rank * per * 128)
+    hi = min(n, (rank + 1) * per * 128)
+    return lo, hi
+
+
+def _allgather_padded(t, length, group=None):
+    """All-gather 1-D tensors of different lengths (``length`` = list of per-rank lengths)."""
+    world = dist.get_world_size(group)
+    m = max(max(length), 1)
+    buf = torch.zeros((m,), dtype=t.dtype, device=t.device)
+    buf[: t.shape[0]] = t
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, length)])
+
+
+def allgather_csr_rows(row_len, indices, data, n_rows_per_rank, scan_fn, group=None):
+    """Row-sharded CSR pieces -> the full CSR on every rank.
+
+    row_len [m_r] int32 (entries per local row), indices / data [nnz_r]; ``n_rows_per_rank`` = list of
+    shard heights; ``scan_fn(int32 tensor) -> int64 tensor [n+1]`` builds the row pointers (the CUDA
+    scan in production).  Returns (indptr [N+1] int64, indices [nnz], data [nnz])."""
+    world = dist.get_world_size(group)
+    nnz_local = torch.tensor([indices.shape[0]], dtype=torch.int64, device=indices.device)
+    nnz_all = [torch.empty_like(nnz_local) for _ in range(world)]
+    dist.all_gather(nnz_all, nnz_local, group=group)
+    nnz_all = [int(x.item()) for x in nnz_all]
+    full_len = _allgather_padded(row_len, list(n_rows_per_rank), group)
+    full_idx = _allgather_padded(indices, nnz_all, group)
+    full_val = _allgather_padded(data, nnz_all, group)
+    return scan_fn(full_len.contiguous()), full_idx, full_val

@@ -1,7 +1,171 @@
-"""LandmarkGraph stub (filled in next)."""
+"""LandmarkGraph on the CUDA engine (reference graphtools/graphs.py:985-1317).
+
+Cluster *selection* follows the reference: spectral = scikit-learn ``randomized_svd`` of ``diff_aff`` +
+``MiniBatchKMeans`` on the host with the same seeds (SURVEY.md section 8f ranks a GPU version as "next"); random
+landmarking = nearest of ``n_landmark`` randomly chosen samples, computed with the fused distance/top-1
+kernel.  Everything after the clusters -- ``pnm = K C`` aggregation, both L1 normalisations, the dense
+``landmark_op = rownorm(C^T K) rownorm(K C)`` and ``extend_to_data`` -- runs on the GPU (csrc/landmark.cu).
+"""
+import warnings
+
+import numpy as np
+import torch
+from scipy import sparse
+
+from . import _engine as E
+from . import pipeline
 from .core import DataGraph
+from .logging_util import logger as _logger
+
+
+def aggregate_by_cluster(K, labels_dev, n_label, want_colsum):
+    """Row-wise aggregation of DeviceCSR ``K`` by ``labels[col]`` -> (DeviceCSR raw sums, normalised
+    values, column sums | None)."""
+    n = K.shape[0]
+    cnt = pipeline._empty((n,), torch.int32)
+    E.call("gtb_cluster_aggregate_count", K.indptr, K.indices, K.data, n, labels_dev, cnt)
+    outptr = pipeline.exclusive_scan(cnt)
+    nnz = int(outptr[-1].item())
+    out_idx = pipeline._empty((nnz,), torch.int32)
+    out_raw = pipeline._empty((nnz,), torch.float64)
+    out_norm = pipeline._empty((nnz,), torch.float64)
+    colsum = pipeline._empty((n_label,), torch.float64) if want_colsum else None
+    E.call("gtb_cluster_aggregate_fill", K.indptr, K.indices, K.data, n, labels_dev, outptr, out_idx, out_raw,
+           out_norm, colsum, n_label)
+    return pipeline.DeviceCSR(outptr, out_idx, out_raw, (n, n_label)), out_norm, colsum
 
 
 class LandmarkGraph(DataGraph):
+    """Adds landmarking to any data graph: cluster the samples, then collapse the kernel into a
+    landmark-to-landmark diffusion operator and a sample-to-landmark transition matrix."""
+
     def __init__(self, data, n_landmark=2000, n_svd=100, random_landmarking=False, **kwargs):
-        raise NotImplementedError("LandmarkGraph: device path under construction")
+        if n_landmark >= data.shape[0]:
+            raise ValueError("n_landmark ({}) >= n_samples ({}). Use kNNGraph instead".format(
+                n_landmark, data.shape[0]))
+        if (n_svd >= data.shape[0]) and (not random_landmarking):
+            warnings.warn("n_svd ({}) >= n_samples ({}) Consider using kNNGraph or lower n_svd".format(
+                n_svd, data.shape[0]), RuntimeWarning)
+        self.random_landmarking = random_landmarking
+        self.n_landmark = n_landmark
+        self.n_svd = n_svd
+        super().__init__(data, **kwargs)
+
+    def get_params(self):
+        params = super().get_params()
+        params.update({"n_landmark": self.n_landmark, "n_pca": self.n_pca,
+                       "random_landmarking": self.random_landmarking})
+        return params
+
+    def set_params(self, **params):
+        reset = False
+        if "n_landmark" in params and params["n_landmark"] != self.n_landmark:
+            self.n_landmark = params["n_landmark"]
+            reset = True
+        if "n_svd" in params and params["n_svd"] != self.n_svd:
+            self.n_svd = params["n_svd"]
+            reset = True
+        if "random_landmarking" in params and params["random_landmarking"] != self.random_landmarking:
+            self.random_landmarking = params["random_landmarking"]
+            reset = True
+        super().set_params(**params)
+        if reset:
+            self._reset_landmarks()
+        return self
+
+    def _reset_landmarks(self):
+        for name in ("_landmark_op", "_transitions", "_clusters", "_dev_labels", "_n_label"):
+            if hasattr(self, name):
+                delattr(self, name)
+
+    @property
+    def landmark_op(self):
+        """Landmark diffusion operator, dense float64 [L, L]."""
+        if not hasattr(self, "_landmark_op"):
+            self.build_landmark_op()
+        return self._landmark_op
+
+    @property
+    def clusters(self):
+        """Cluster assignment of every sample."""
+        if not hasattr(self, "_clusters"):
+            self.build_landmark_op()
+        return self._clusters
+
+    @clusters.setter
+    def clusters(self, value):
+        self._reset_landmarks()
+        self._clusters = np.asarray(value)
+
+    @property
+    def transitions(self):
+        """Sample-to-landmark transition matrix, CSR [N, L]."""
+        if not hasattr(self, "_transitions"):
+            self.build_landmark_op()
+        return self._transitions
+
+    # ------------------------------------------------------------------ cluster selection
+    def _random_landmark_clusters(self):
+        n = self.data.shape[0]
+        rng = np.random.default_rng(self.random_state)
+        landmark_indices = rng.choice(n, self.n_landmark, replace=False)
+        data = self.data if not hasattr(self, "data_nu") else self.data_nu
+        X = self._dense_f32(data)
+        ref = pipeline.SearchOperand(X[torch.from_numpy(landmark_indices).to(X.device)].contiguous())
+        qry = pipeline.SearchOperand(X, mean=ref.mean)
+        nearest, _ = pipeline.knn_kernel(None, ref, qry, knn=1, decay=None)
+        return nearest.indices.cpu().numpy().astype(np.int64)
+
+    def _spectral_clusters(self):
+        from sklearn.cluster import MiniBatchKMeans
+        from sklearn.utils.extmath import randomized_svd
+        with _logger.log_task("SVD"):
+            _, _, VT = randomized_svd(self.diff_aff, n_components=self.n_svd, random_state=self.random_state)
+        with _logger.log_task("KMeans"):
+            kmeans = MiniBatchKMeans(self.n_landmark, init_size=3 * self.n_landmark, n_init=1, batch_size=10000,
+                                     random_state=self.random_state)
+            return kmeans.fit_predict(self.diff_op.dot(VT.T))
+
+    # ------------------------------------------------------------------ operator
+    def build_landmark_op(self):
+        """clusters -> transitions, landmark_op (graphs.py:1187-1246)."""
+        with _logger.log_task("landmark operator"):
+            self._ensure_built()
+            if not hasattr(self, "_clusters"):
+                if self.random_landmarking:
+                    self._clusters = self._random_landmark_clusters()
+                else:
+                    self._clusters = self._spectral_clusters()
+            K = self._dev_kernel
+            uniq, inv = np.unique(self._clusters, return_inverse=True)
+            L = len(uniq)
+            labels = torch.from_numpy(inv.astype(np.int32)).to(pipeline._dev())
+            self._dev_labels, self._n_label = labels, L
+            if isinstance(K, pipeline.DeviceCSR):
+                if self.kernel_symm is None:
+                    raise NotImplementedError("landmark operator needs a symmetric kernel (kernel_symm=None given)")
+                pnm, pnm_norm, colsum = aggregate_by_cluster(K, labels, L, want_colsum=True)
+                op = pipeline._empty((L, L), torch.float64)
+                E.call("gtb_landmark_op", pnm.indptr, pnm.indices, pnm.data, pnm_norm, colsum, K.shape[0], L, op)
+                self._landmark_op = op.cpu().numpy()
+                self._transitions = pnm.to_scipy(pnm_norm)
+            else:
+                from .dense import dense_landmark
+                self._landmark_op, self._transitions = dense_landmark(K, labels, L)
+
+    def extend_to_data(self, data, **kwargs):
+        """Transition matrix from new points to the landmarks (graphs.py:1248-1288)."""
+        self.clusters  # make sure labels exist
+        if not hasattr(self, "_dev_labels"):
+            self.build_landmark_op()
+        Kyx = self._kernel_to_data_device(data, **kwargs)
+        if isinstance(Kyx, pipeline.DeviceCSR):
+            agg, agg_norm, _ = aggregate_by_cluster(Kyx, self._dev_labels, self._n_label, want_colsum=False)
+            return agg.to_scipy(agg_norm)
+        from .dense import dense_landmark_extend
+        return dense_landmark_extend(Kyx, self._dev_labels, self._n_label)
+
+    def interpolate(self, transform, transitions=None, Y=None):
+        if transitions is None and Y is None:
+            transitions = self.transitions
+        return super().interpolate(transform, transitions=transitions, Y=Y)

@@ -100,6 +100,43 @@ int gtb_row_finalize(const int64_t* ptr, const int32_t* tmp_idx, const double* t
 int gtb_anisotropy(const int64_t* indptr, const int32_t* idx, double* val, const double* deg, double alpha,
                    int64_t n, void* stream);
 
+/* MNN block assembly: scatter a CSR block (local indices) into the global staging CSR.  Row i of the
+ * block goes to global row row_map[i], column j to col_map[j], values scaled by
+ * min(1, within[i] / between[i]) * beta when `within` is non-NULL (reference graphs.py:1904-1935,
+ * matrix.py:49-51).  block_count adds the block's row lengths to rowlen[]; block_fill appends at
+ * outptr[row] + cursor[row] and advances cursor (calls on one stream are ordered). */
+int gtb_block_count(const int64_t* indptr, int64_t nb, const int32_t* row_map, int32_t* rowlen, void* stream);
+int gtb_block_fill(const int64_t* indptr, const int32_t* idx, const double* val, int64_t nb,
+                   const int32_t* row_map, const int32_t* col_map, const double* within, const double* between,
+                   double beta, const int64_t* outptr, int32_t* cursor, int32_t* out_idx, double* out_val,
+                   void* stream);
+
+/* ---- K6 landmark operator: replaces LandmarkGraph._landmarks_to_data, build_landmark_op and
+ * extend_to_data (graphs.py:1169-1182, :1232-1246, :1272-1288) ------------------------------- */
+/* per row: aggregate entries by label[col]; cnt[row] = number of distinct labels */
+int gtb_cluster_aggregate_count(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n,
+                                const int32_t* label, int32_t* cnt, void* stream);
+/* out rows sorted by label: out_raw = sums, out_norm = sums / row L1 norm (optional),
+ * colsum[n_label] = column L1 sums of out_raw (optional) */
+int gtb_cluster_aggregate_fill(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n,
+                               const int32_t* label, const int64_t* outptr, int32_t* out_idx, double* out_raw,
+                               double* out_norm, double* colsum, int n_label, void* stream);
+/* op[L][L] = rownorm(pnm^T) . rownorm(pnm) from the aggregated rows */
+int gtb_landmark_op(const int64_t* ptr, const int32_t* lab, const double* raw, const double* nrm,
+                    const double* colsum, int64_t n, int L, double* op, void* stream);
+
+/* ---- K5 dense exact graph: replaces TraditionalGraph.build_kernel / build_kernel_to_data
+ * (graphs.py:1546-1609, :1651-1677) and the dense branches of base.py:557-592, :645 ---------- */
+/* what 0: out = distances; 1: out = thresholded affinities exp(-(d/bw_q[i])^decay);
+ * 2: additionally symmetrised with the transposed entry (symm 0 '+', 1 '*', 2 'mnn', 3 none);
+ * rowsum (optional) receives the row L1 sums */
+int gtb_dense_kernel(const float* Xq, int64_t nq, const float* Xr, int64_t nr, int d, int what,
+                     const double* bw_q, const double* bw_r, double decay, double thresh, int symm, double theta,
+                     double* out, double* rowsum, void* stream);
+int gtb_dense_row_scale(const double* in, const double* rowsum, int64_t nq, int64_t nr, double* out, void* stream);
+int gtb_dense_anisotropy(double* K, const double* deg, double alpha, int64_t n, double* newsum, void* stream);
+int gtb_dense_rowsum(const double* K, int64_t nq, int64_t nr, double* sum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
