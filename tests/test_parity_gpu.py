@@ -42,11 +42,14 @@ def test_knn_golden(name):
         assert np.allclose(G.kernel_degree, case.z["degree"], rtol=1e-5)
     else:
         # a tie / threshold-boundary entry changes its row's normalisation: check P on the rows whose
-        # structure agrees
-        Pg, Pr = G.diff_op, case.mat("P")
-        same = np.flatnonzero(np.diff(Pg.indptr) == np.diff(Pr.indptr))
-        same = [i for i in same if np.array_equal(Pg.indices[Pg.indptr[i]:Pg.indptr[i + 1]],
-                                                  Pr.indices[Pr.indptr[i]:Pr.indptr[i + 1]])]
+        # kernel row agrees with the reference
+        Pg, Pr, Kr = G.diff_op, case.mat("P"), case.mat("K")
+
+        def row_same(i):
+            a, b = K[i], Kr[i]
+            return (a.nnz == b.nnz and np.array_equal(a.indices, b.indices)
+                    and np.allclose(a.data, b.data, rtol=1e-5, atol=0))
+        same = [i for i in range(K.shape[0]) if row_same(i)]
         assert len(same) > 0.9 * Pg.shape[0]
         compare_sparse(Pg[same], Pr[same], what=name + ".P[agreeing rows]")
     # raw kernel through the public build_kernel() of a fresh, uninitialised graph
