@@ -87,7 +87,7 @@ constexpr int R1_CAP = 128;  // max candidates per row handled by the warp kerne
 
 struct Refine1Params {
   RowParams rp;
-  int64_t nq; int S;
+  int64_t nq; int S; int cand_stride;
   const int32_t* cand_idx; const float* tau; const float* qn2; float maxrn2; double eps_rel;
   int32_t* st_idx; double* st_val; int32_t* n_keep; double* bw_out; float* lim2_out;
   int32_t* status; int32_t* nzero;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Param
   const float* xq = rp.Xq + row * rp.d;
   int n_cand = 0;
   for (int c = 0; c < S; ++c) {
-    int j = p.cand_idx[row * S + c];  // uniform load
+    int j = p.cand_idx[row * p.cand_stride + c];  // uniform load
     if (j >= 0) {
       double d2 = warp_dist2(xq, rp.Xr + (int64_t)j * rp.d, rp.d, lane);
       if (lane == 0) { key[c] = d2; idx[c] = j; }
@@ -326,7 +326,7 @@ RowParams make_row_params(const float* Xq, const float* Xr, int d, int knn, int6
 }  // namespace
 
 extern "C" int gtb_refine_topk(const float* Xq, int64_t nq, const float* Xr, int d, const int32_t* cand_idx,
-                               int S, const float* tau, const float* qn2, float maxrn2, double eps_rel,
+                               int S, int cand_stride, const float* tau, const float* qn2, float maxrn2, double eps_rel,
                                int knn, int64_t kmax, double decay, double thresh, const double* bw_fixed,
                                int bw_mode, double bw_scale, int32_t* st_idx, double* st_val, int32_t* n_keep,
                                double* bw_out, float* lim2_out, int32_t* status, int32_t* nzero, void* stream) {
@@ -335,7 +335,8 @@ extern "C" int gtb_refine_topk(const float* Xq, int64_t nq, const float* Xr, int
   GTB_CHECK_ARG(decay < 0 || (thresh > 0 && thresh <= 1), "thresh must be in (0, 1]");
   Refine1Params p;
   p.rp = make_row_params(Xq, Xr, d, knn, kmax, decay, thresh, bw_fixed, bw_mode, bw_scale);
-  p.nq = nq; p.S = S; p.cand_idx = cand_idx; p.tau = tau; p.qn2 = qn2; p.maxrn2 = maxrn2; p.eps_rel = eps_rel;
+  GTB_CHECK_ARG(cand_stride >= S, "cand_stride must be >= S");
+  p.nq = nq; p.S = S; p.cand_stride = cand_stride; p.cand_idx = cand_idx; p.tau = tau; p.qn2 = qn2; p.maxrn2 = maxrn2; p.eps_rel = eps_rel;
   p.st_idx = st_idx; p.st_val = st_val; p.n_keep = n_keep; p.bw_out = bw_out; p.lim2_out = lim2_out;
   p.status = status; p.nzero = nzero;
   refine_topk_kernel<<<(unsigned)gtb_cdiv(nq, R1_WARPS), R1_WARPS * 32, 0, (cudaStream_t)stream>>>(p);

@@ -1,0 +1,541 @@
+// K1/K2 (tensor-core variant): pairwise squared distances on the 5th-gen tensor cores with the
+// per-query selection fused into the TMEM epilogue -- the N x N matrix never leaves the SM.
+//
+//   d~2(i,j) - |x_i|^2  =  |y_j|^2 - 2 x_i.y_j  =  sum_k A[i,k] * B[j,k]
+//       A (query role) = [ x~_1 .. x~_d , 1 , 0.. ]        B (ref role) = [ -2y~_1 .. -2y~_d , |y~|^2 , 0.. ]
+//
+// Every float32 operand value v is split v = hi + lo with hi = tf32(v), lo = tf32(v - hi) and the tile
+// is accumulated as A_hi.B_hi + A_hi.B_lo + A_lo.B_hi with tcgen05.mma.kind::tf32 into a float32 TMEM
+// accumulator (3xTF32: ~2^-21 relative to |x||y|, enough to SELECT candidates; every value that
+// reaches the output is re-evaluated in float64 by refine.cu).
+//
+// CTA = 128 query rows (UMMA M=128, cta_group::1) resident in shared memory for the whole sweep
+// (A_hi, A_lo: 2 x 128 x Kp floats); reference tiles of 64 rows (B_hi, B_lo) stream through a 2-stage
+// TMA/mbarrier ring; two 64-column TMEM accumulators let the epilogue of tile t overlap the MMAs of
+// tile t+1.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 =
+// epilogue (tcgen05.ld 32x32b: thread == query row).  Shared-memory operand tiles are K-major:
+// floor(Kp/32) SWIZZLE_128B blocks (32 floats per row) followed by (Kp%32)/8 SWIZZLE_32B blocks.
+//
+// Epilogue, TOPK mode: each thread keeps a running threshold; values under it are appended to the
+// row's 128-slot candidate buffer in global memory (L2 resident); when a buffer nears capacity the
+// warp cooperatively bitonic-sorts it in registers, keeps the 64 smallest and tightens the
+// threshold.  RADIUS mode: values under the row's limit are appended to the global pair list.
+//
+// Replaces sklearn ArgKmin / RadiusNeighbors behind knn_tree.kneighbors / radius_neighbors
+// (reference graphtools/graphs.py:883, :922, :957, :966).
+#include "common.cuh"
+#include "gtb200.h"
+#include <cuda.h>
+
+namespace {
+
+constexpr int TC_M = 128, TC_N = 64, TC_STAGES = 2, TC_CAP = 128, TC_S = 64, TC_THREADS = 192;
+constexpr float TC_BIG = 1e29f;       // "no threshold yet"; padded reference rows carry |y|^2 = 1e30
+constexpr float TC_PAD_NORM = 1e30f;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, K-major, dense 8-row groups (SBO = 8 * row bytes)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                                   // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                                   // descriptor version (sm_100)
+  d |= (uint64_t)layout_type << 61;                         // 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
+  return d;
+}
+
+struct TcParams {
+  int64_t nq, nq_pad, nr, nr_pad;
+  int Kp;
+  const float* qn2;
+  int32_t* cand_idx; float* cand_val; float* tau;          // TOPK
+  const float* lim2; int2* pairs; unsigned long long capacity; unsigned long long* counter; int32_t* rowcnt;
+};
+
+// ---------------------------------------------------------------- warp-cooperative compaction
+// Sort the 128 (value, index) pairs held 4 per lane (element e = i*32 + lane) ascending.
+__device__ __forceinline__ void warp_bitonic128(float (&val)[4], int32_t (&idx)[4], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 128; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int jj = j >> 5;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int pnr = i ^ jj;
+          if (pnr > i) {
+            const bool up = (((i * 32 + lane) & k) == 0);
+            const bool gt = (val[i] > val[pnr]) || (val[i] == val[pnr] && idx[i] > idx[pnr]);
+            if (gt == up) {
+              float tv = val[i]; val[i] = val[pnr]; val[pnr] = tv;
+              int32_t ti = idx[i]; idx[i] = idx[pnr]; idx[pnr] = ti;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool up = (((i * 32 + lane) & k) == 0);
+          const float ov = __shfl_xor_sync(0xffffffffu, val[i], j);
+          const int32_t oi = __shfl_xor_sync(0xffffffffu, idx[i], j);
+          const bool lower = ((lane & j) == 0);
+          const bool keep_min = (lower == up);
+          const bool mine_gt = (val[i] > ov) || (val[i] == ov && idx[i] > oi);
+          if (keep_min ? mine_gt : !mine_gt) { val[i] = ov; idx[i] = oi; }
+        }
+      }
+    }
+  }
+}
+
+// Compact the candidate buffer of row `grow` (owned by lane `owner`): keep the TC_S smallest.
+// Returns the TC_S-th smallest value (new threshold), uniform across the warp.
+__device__ __forceinline__ float compact_row(int32_t* cand_idx, float* cand_val, int64_t grow, int cnt, int lane) {
+  float val[4];
+  int32_t idx[4];
+  float* rv = cand_val + grow * TC_CAP;
+  int32_t* ri = cand_idx + grow * TC_CAP;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = i * 32 + lane;
+    if (e < cnt) { val[i] = rv[e]; idx[i] = ri[e]; }
+    else { val[i] = gtb_inf_f(); idx[i] = 0x7fffffff; }
+  }
+  warp_bitonic128(val, idx, lane);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int e = i * 32 + lane;
+    rv[e] = val[i];
+    ri[e] = idx[i];
+  }
+  return __shfl_sync(0xffffffffu, val[1], 31);  // element 63
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int MODE>  // 0 = TOPK, 1 = RADIUS
+__global__ void __launch_bounds__(TC_THREADS, 1)
+search_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAht,
+                 const __grid_constant__ CUtensorMap mAl, const __grid_constant__ CUtensorMap mAlt,
+                 const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBht,
+                 const __grid_constant__ CUtensorMap mBl, const __grid_constant__ CUtensorMap mBlt, TcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* gbase = smem_raw + (base - raw);
+
+  const int Kp = p.Kp;
+  const int nfull = Kp / 32, ntail = (Kp % 32) / 8, nks = Kp / 8;
+  const uint32_t sizeA = (uint32_t)TC_M * Kp * 4, sizeB = (uint32_t)TC_N * Kp * 4;
+  const uint32_t A_hi = base, A_lo = base + sizeA;
+  const uint32_t B0 = base + 2 * sizeA;                    // stage s, part q at B0 + (2*s+q)*sizeB
+  const uint32_t bar0 = B0 + 2 * TC_STAGES * sizeB;
+  const uint32_t bar_a = bar0, full_b = bar0 + 8, empty_b = bar0 + 24, tm_full = bar0 + 40, tm_empty = bar0 + 56;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (bar0 - base) + 72);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q0 = (int64_t)blockIdx.x * TC_M;
+  const int64_t ntiles = p.nr_pad / TC_N;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a, 1);
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(full_b + 8 * s, 1);
+      mbar_init(empty_b + 8 * s, 1);
+      mbar_init(tm_full + 8 * s, 1);
+      mbar_init(tm_empty + 8 * s, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_a, 2 * sizeA);
+      for (int part = 0; part < 2; ++part) {
+        const CUtensorMap* mm = part ? &mAl : &mAh;
+        const CUtensorMap* mt = part ? &mAlt : &mAht;
+        const uint32_t dst = part ? A_lo : A_hi;
+        for (int b = 0; b < nfull; ++b) tma_load_2d(dst + b * (TC_M * 128), mm, bar_a, b * 32, (int)q0);
+        for (int t = 0; t < ntail; ++t)
+          tma_load_2d(dst + nfull * (TC_M * 128) + t * (TC_M * 32), mt, bar_a, nfull * 32 + t * 8, (int)q0);
+      }
+      for (int64_t tile = 0; tile < ntiles; ++tile) {
+        const int s = (int)(tile % TC_STAGES);
+        const uint32_t ph = (uint32_t)((tile / TC_STAGES) & 1);
+        mbar_wait(empty_b + 8 * s, ph ^ 1);
+        mbar_arrive_expect_tx(full_b + 8 * s, 2 * sizeB);
+        for (int part = 0; part < 2; ++part) {
+          const CUtensorMap* mm = part ? &mBl : &mBh;
+          const CUtensorMap* mt = part ? &mBlt : &mBht;
+          const uint32_t dst = B0 + (2 * s + part) * sizeB;
+          for (int b = 0; b < nfull; ++b)
+            tma_load_2d(dst + b * (TC_N * 128), mm, full_b + 8 * s, b * 32, (int)(tile * TC_N));
+          for (int t = 0; t < ntail; ++t)
+            tma_load_2d(dst + nfull * (TC_N * 128) + t * (TC_N * 32), mt, full_b + 8 * s, nfull * 32 + t * 8,
+                        (int)(tile * TC_N));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, K-major both, N=64, M=128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
+                             ((uint32_t)(TC_M >> 4) << 24);
+      mbar_wait(bar_a, 0);
+      tc_fence_after();
+      for (int64_t tile = 0; tile < ntiles; ++tile) {
+        const int s = (int)(tile % TC_STAGES);
+        const uint32_t ph = (uint32_t)((tile / TC_STAGES) & 1);
+        mbar_wait(tm_empty + 8 * s, ph ^ 1);   // accumulator index == stage index (both 2-deep)
+        mbar_wait(full_b + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(s * TC_N);
+        const uint32_t Bh = B0 + (2 * s) * sizeB, Bl = Bh + sizeB;
+        uint32_t acc = 0;
+#pragma unroll 1
+        for (int prod = 0; prod < 3; ++prod) {
+          const uint32_t Ap = (prod == 2) ? A_lo : A_hi;
+          const uint32_t Bp = (prod == 1) ? Bl : Bh;
+#pragma unroll 1
+          for (int ks = 0; ks < nks; ++ks) {
+            uint64_t ad, bd;
+            if (ks < 4 * nfull) {
+              const int blk = ks >> 2, sub = ks & 3;
+              ad = make_desc(Ap + blk * (TC_M * 128) + sub * 32, 1024, 2);
+              bd = make_desc(Bp + blk * (TC_N * 128) + sub * 32, 1024, 2);
+            } else {
+              const int t = ks - 4 * nfull;
+              ad = make_desc(Ap + nfull * (TC_M * 128) + t * (TC_M * 32), 256, 6);
+              bd = make_desc(Bp + nfull * (TC_N * 128) + t * (TC_N * 32), 256, 6);
+            }
+            tc_mma_tf32(d_tmem, ad, bd, idesc, acc);
+            acc = 1;
+          }
+        }
+        tc_commit(empty_b + 8 * s);   // smem stage free once these MMAs retire
+        tc_commit(tm_full + 8 * s);   // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;
+    const int64_t gq = q0 + row;
+    const bool valid = gq < p.nq;
+    const float nx = valid ? p.qn2[gq] : 0.f;
+    float thr;
+    if (MODE == 0) thr = valid ? TC_BIG : -gtb_inf_f();
+    else thr = valid ? (p.lim2[gq] - nx) : -gtb_inf_f();
+    int cnt = 0;
+    float* my_val = (MODE == 0) ? p.cand_val + gq * TC_CAP : nullptr;
+    int32_t* my_idx = (MODE == 0) ? p.cand_idx + gq * TC_CAP : nullptr;
+
+    for (int64_t tile = 0; tile < ntiles; ++tile) {
+      const int s = (int)(tile % TC_STAGES);
+      const uint32_t ph = (uint32_t)((tile / TC_STAGES) & 1);
+      mbar_wait(tm_full + 8 * s, ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * TC_N + half * 32), v);
+        if (half == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tm_empty + 8 * s);
+        }
+        const int32_t col0 = (int32_t)(tile * TC_N) + half * 32;
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) any |= (MODE == 0) ? (v[j] < thr) : (v[j] <= thr);
+        if (MODE == 0) {
+          if (any) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (v[j] < thr) {
+                my_val[cnt] = v[j];
+                my_idx[cnt] = col0 + j;
+                ++cnt;
+              }
+            }
+          }
+          // keep >= 32 free slots for the next batch
+          unsigned need = __ballot_sync(0xffffffffu, cnt > TC_CAP - 32);
+          while (need) {
+            const int owner = __ffs(need) - 1;
+            need &= need - 1;
+            const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
+            const int64_t orow = q0 + quad * 32 + owner;
+            __syncwarp();
+            const float nt = compact_row(p.cand_idx, p.cand_val, orow, ocnt, lane);
+            __syncwarp();
+            if (lane == owner) { thr = nt; cnt = TC_S; }
+          }
+        } else {
+          if (any) {
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) c += (v[j] <= thr);
+            unsigned long long pos = atomicAdd(p.counter, (unsigned long long)c);
+            atomicAdd(p.rowcnt + gq, c);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (v[j] <= thr) {
+                if (pos < p.capacity) p.pairs[pos] = make_int2((int)gq, col0 + j);
+                ++pos;
+              }
+            }
+          }
+        }
+      }
+    }
+
+    if (MODE == 0) {
+      // final compaction of every row still holding more than TC_S candidates
+      unsigned need = __ballot_sync(0xffffffffu, cnt > TC_S);
+      while (need) {
+        const int owner = __ffs(need) - 1;
+        need &= need - 1;
+        const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
+        const int64_t orow = q0 + quad * 32 + owner;
+        __syncwarp();
+        const float nt = compact_row(p.cand_idx, p.cand_val, orow, ocnt, lane);
+        __syncwarp();
+        if (lane == owner) { thr = nt; cnt = TC_S; }
+      }
+      if (valid) {
+        for (int e = cnt; e < TC_S; ++e) my_idx[e] = -1;
+        p.tau[gq] = (cnt < TC_S || thr >= TC_BIG) ? gtb_inf_f() : thr + nx;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+  }
+}
+
+// ---------------------------------------------------------------- operand preparation (row-major hi/lo)
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__global__ void tc_norms_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ mean,
+                                int64_t n_pad, float* __restrict__ norm2, float* __restrict__ maxnorm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_pad) return;
+  float out = 0.f;
+  if (r < n) {
+    double s = 0.0;
+    for (int k = lane; k < d; k += 32) {
+      double v = (double)(X[r * d + k] - (mean ? mean[k] : 0.f));
+      s += v * v;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    out = __double2float_ru(s);
+  }
+  if (lane == 0) {
+    norm2[r] = (r < n) ? out : TC_PAD_NORM;
+    if (maxnorm && r < n) atomicMax((int*)maxnorm, __float_as_int(out));
+  }
+}
+
+__global__ void tc_split_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ mean,
+                                int role, const float* __restrict__ norm2, int64_t n_pad, int Kp,
+                                float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_pad * Kp) return;
+  const int64_t r = e / Kp;
+  const int k = (int)(e - r * Kp);
+  float v = 0.f;
+  if (r < n) {
+    if (k < d) {
+      v = X[r * d + k] - (mean ? mean[k] : 0.f);
+      if (role == 1) v *= -2.f;
+    } else if (k == d) {
+      v = (role == 1) ? norm2[r] : 1.f;
+    }
+  } else if (role == 1 && k == d) {
+    v = TC_PAD_NORM;
+  }
+  const float h = to_tf32(v);
+  hi[e] = h;
+  lo[e] = to_tf32(v - h);
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// 2-D map over a row-major [rows][Kp] float32 array; box = {box_k, box_rows}
+int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int Kp, int box_k, int box_rows, bool sw128) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { gtb_set_error("cuTensorMapEncodeTiled entry point not available"); return GTB_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kp * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { gtb_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return GTB_ERR_CUDA; }
+  return GTB_OK;
+}
+
+template <int MODE>
+int launch_tc(const float* q_hi, const float* q_lo, const float* r_hi, const float* r_lo, TcParams& p,
+              cudaStream_t st) {
+  CUtensorMap mAh, mAht, mAl, mAlt, mBh, mBht, mBl, mBlt;
+  int rc;
+  const int Kp = p.Kp;
+  if ((rc = make_map(&mAh, q_hi, p.nq_pad, Kp, 32, TC_M, true))) return rc;
+  if ((rc = make_map(&mAht, q_hi, p.nq_pad, Kp, 8, TC_M, false))) return rc;
+  if ((rc = make_map(&mAl, q_lo, p.nq_pad, Kp, 32, TC_M, true))) return rc;
+  if ((rc = make_map(&mAlt, q_lo, p.nq_pad, Kp, 8, TC_M, false))) return rc;
+  if ((rc = make_map(&mBh, r_hi, p.nr_pad, Kp, 32, TC_N, true))) return rc;
+  if ((rc = make_map(&mBht, r_hi, p.nr_pad, Kp, 8, TC_N, false))) return rc;
+  if ((rc = make_map(&mBl, r_lo, p.nr_pad, Kp, 32, TC_N, true))) return rc;
+  if ((rc = make_map(&mBlt, r_lo, p.nr_pad, Kp, 8, TC_N, false))) return rc;
+  size_t smem = 1024 + (size_t)2 * TC_M * Kp * 4 + (size_t)2 * TC_STAGES * TC_N * Kp * 4 + 128;
+  auto kern = search_tc_kernel<MODE>;
+  GTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)(p.nq_pad / TC_M), TC_THREADS, smem, st>>>(mAh, mAht, mAl, mAlt, mBh, mBht, mBl, mBlt, p);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+}  // namespace
+
+extern "C" int gtb_tc_max_kp(void) { return 104; }
+
+extern "C" int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const float* mean, int role, float* hi,
+                                      float* lo, int64_t n_pad, int Kp, float* norm2, float* maxnorm,
+                                      void* stream) {
+  GTB_CHECK_ARG(n > 0 && d > 0 && n_pad >= n && n_pad % 128 == 0, "bad shape");
+  GTB_CHECK_ARG(Kp % 8 == 0 && Kp >= d + 1 && Kp <= 104, "Kp must be a multiple of 8 with d+1 <= Kp <= 104");
+  GTB_CHECK_ARG(role == 0 || role == 1, "role must be 0 (query) or 1 (reference)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (maxnorm) GTB_CUDA(cudaMemsetAsync(maxnorm, 0, sizeof(float), st));
+  tc_norms_kernel<<<(unsigned)gtb_cdiv(n_pad * 32, 256), 256, 0, st>>>(X, n, d, mean, n_pad, norm2, maxnorm);
+  GTB_CHECK_LAUNCH();
+  tc_split_kernel<<<(unsigned)gtb_cdiv(n_pad * Kp, 256), 256, 0, st>>>(X, n, d, mean, role, norm2, n_pad, Kp, hi, lo);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_knn_topk_tc(const float* q_hi, const float* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
+                               const float* r_hi, const float* r_lo, int64_t nr, int64_t nr_pad, int Kp,
+                               int32_t* cand_idx, float* cand_val, float* tau, void* stream) {
+  GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TC_M == 0 && nr_pad % TC_N == 0, "bad shape");
+  GTB_CHECK_ARG(Kp % 8 == 0 && Kp >= 8 && Kp <= 104, "Kp must be a multiple of 8, <= 104");
+  GTB_CHECK_ARG(nr_pad < (1ll << 31) && nq_pad < (1ll << 31), "too many rows for 32-bit TMA coordinates");
+  TcParams p{};
+  p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.Kp = Kp; p.qn2 = qn2;
+  p.cand_idx = cand_idx; p.cand_val = cand_val; p.tau = tau;
+  return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, p, (cudaStream_t)stream);
+}
+
+extern "C" int gtb_knn_radius_tc(const float* q_hi, const float* q_lo, const float* qn2, const float* lim2,
+                                 int64_t nq, int64_t nq_pad, const float* r_hi, const float* r_lo, int64_t nr,
+                                 int64_t nr_pad, int Kp, int32_t* pairs, int64_t capacity,
+                                 unsigned long long* counter, int32_t* rowcnt, void* stream) {
+  GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TC_M == 0 && nr_pad % TC_N == 0, "bad shape");
+  GTB_CHECK_ARG(Kp % 8 == 0 && Kp >= 8 && Kp <= 104, "Kp must be a multiple of 8, <= 104");
+  TcParams p{};
+  p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.Kp = Kp; p.qn2 = qn2; p.lim2 = lim2;
+  p.pairs = reinterpret_cast<int2*>(pairs); p.capacity = (unsigned long long)capacity; p.counter = counter;
+  p.rowcnt = rowcnt;
+  return launch_tc<1>(q_hi, q_lo, r_hi, r_lo, p, (cudaStream_t)stream);
+}

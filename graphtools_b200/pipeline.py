@@ -58,15 +58,60 @@ class SearchOperand:
             mean = _empty((d,), torch.float32)
             E.call("gtb_col_mean", X, n, d, ws, mean)
         self.mean = mean
-        self.XT = _empty((self.d_pad, self.n_pad), torch.float32)
-        self.n2 = _empty((self.n_pad,), torch.float32)
-        self._maxnorm = _empty((1,), torch.float32)
-        E.call("gtb_prepare_operand", X, n, d, mean, self.XT, self.n_pad, self.d_pad, self.n2, self._maxnorm)
+        self._simt = None
+        self._tc = {}
+        self._maxnorm = None
         self._maxnorm_host = None
+
+    # -- CUDA-core operand: k-major [d_pad][n_pad] + norms
+    def simt(self):
+        if self._simt is None:
+            XT = _empty((self.d_pad, self.n_pad), torch.float32)
+            n2 = _empty((self.n_pad,), torch.float32)
+            mx = _empty((1,), torch.float32)
+            E.call("gtb_prepare_operand", self.X, self.n, self.d, self.mean, XT, self.n_pad, self.d_pad, n2, mx)
+            self._simt = (XT, n2)
+            if self._maxnorm is None:
+                self._maxnorm = mx
+        return self._simt
+
+    @property
+    def XT(self):
+        return self.simt()[0]
+
+    @property
+    def n2(self):
+        return self.simt()[1]
+
+    # -- tensor-core operand: row-major [n_pad][Kp] tf32 hi/lo pair for one role (0 query, 1 reference)
+    @property
+    def Kp(self):
+        return (self.d + 1 + 7) // 8 * 8
+
+    def tc_ok(self):
+        return self.Kp <= E.lib().gtb_tc_max_kp()
+
+    def tc(self, role):
+        if role not in self._tc:
+            hi = _empty((self.n_pad, self.Kp), torch.float32)
+            lo = _empty((self.n_pad, self.Kp), torch.float32)
+            n2 = _empty((self.n_pad,), torch.float32)
+            mx = _empty((1,), torch.float32)
+            E.call("gtb_prepare_operand_tc", self.X, self.n, self.d, self.mean, role, hi, lo, self.n_pad, self.Kp,
+                   n2, mx)
+            self._tc[role] = (hi, lo, n2)
+            if self._maxnorm is None:
+                self._maxnorm = mx
+        return self._tc[role]
+
+    def norms(self, impl):
+        return self.tc(0)[2] if impl == "tc" else self.n2
 
     @property
     def maxnorm(self):
         if self._maxnorm_host is None:
+            if self._maxnorm is None:
+                self.simt()
             self._maxnorm_host = float(self._maxnorm.item())
         return self._maxnorm_host
 
@@ -114,6 +159,19 @@ def choose_S(knn_eff, binary):
         "knn={} needs a candidate list longer than 128; not supported by the fused top-k yet".format(knn_eff))
 
 
+def default_impl():
+    """GTB_SEARCH_IMPL = tc | simt | auto (default auto: tensor cores whenever the operand fits)."""
+    import os
+    return os.environ.get("GTB_SEARCH_IMPL", "auto")
+
+
+def eps_rel_tc(d):
+    """Same bound for the 3xTF32 tensor-core pass: dropped lo*lo terms and the tf32 rounding of the lo
+    parts contribute 3 * 2^-22, float32 accumulation in the tensor core at most Kp * 2^-23 (truncation);
+    doubled."""
+    return 4.0 * (d + 16) * 2.0 ** -24
+
+
 def eps_rel_simt(d):
     """Relative bound on |approx d^2 - exact d^2| / (|x~|^2 + |y~|^2) for the fp32 CUDA-core pass:
     (d + 11) * 2^-24 from a standard rounding analysis (dot product, norms, centring), doubled."""
@@ -121,7 +179,7 @@ def eps_rel_simt(d):
 
 
 def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, bandwidth=None,
-               bandwidth_scale=1.0, S=None, impl="simt"):
+               bandwidth_scale=1.0, S=None, impl=None):
     """Raw (unsymmetrised) kNN / alpha-decay kernel from the rows of ``Xq`` to ``ref`` as DeviceCSR.
 
     Semantics = reference ``kNNGraph.build_kernel_to_data`` (graphs.py:819-982) with the float64
@@ -138,14 +196,32 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
     kmax = 0 if knn_max is None else int(knn_max)
     if kmax >= nr:
         kmax = 0
-    if S is None:
-        S = choose_S(knn, binary)
-    eps_rel = eps_rel_simt(d)
+    if impl is None:
+        impl = default_impl()
+    if impl == "auto":
+        impl = "tc" if (ref.tc_ok() and knn + 8 <= 64 and S in (None, 64)) else "simt"
     dev = _dev()
-
-    cand = _empty((nq, S), torch.int32)
     tau = _empty((nq,), torch.float32)
-    if impl == "simt":
+    if impl == "tc":
+        if not ref.tc_ok():
+            raise ValueError("tensor-core search needs d + 1 <= {}".format(E.lib().gtb_tc_max_kp()))
+        S, stride = 64, 128
+        if knn > S:
+            raise NotImplementedError("knn={} exceeds the tensor-core candidate list (64)".format(knn))
+        eps_rel = eps_rel_tc(d)
+        q_hi, q_lo, q_n2 = qry.tc(0)
+        r_hi, r_lo, _ = ref.tc(1)
+        cand = _empty((qry.n_pad, stride), torch.int32)
+        cand_val = _empty((qry.n_pad, stride), torch.float32)
+        E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, nq, qry.n_pad, r_hi, r_lo, nr, ref.n_pad, ref.Kp, cand,
+               cand_val, tau)
+    elif impl == "simt":
+        if S is None:
+            S = choose_S(knn, binary)
+        stride = S
+        eps_rel = eps_rel_simt(d)
+        q_n2 = qry.n2
+        cand = _empty((nq, S), torch.int32)
         E.call("gtb_knn_topk_simt", qry.XT, qry.n2, nq, qry.n_pad, ref.XT, ref.n2, nr, ref.n_pad, ref.d_pad, S,
                cand, tau)
     else:
@@ -172,31 +248,41 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
     lim2 = _empty((nq,), torch.float32)
     status = _empty((nq,), torch.int32)
     nzero = _empty((nq,), torch.int32)
-    E.call("gtb_refine_topk", qry.X, nq, ref.X, d, cand, S, tau, qry.n2, ref.maxnorm, eps_rel, knn, kmax, decay_f,
+    E.call("gtb_refine_topk", qry.X, nq, ref.X, d, cand, S, stride, tau, q_n2, ref.maxnorm, eps_rel, knn, kmax, decay_f,
            thresh_f, bw_fixed, bw_mode, float(bandwidth_scale), st_idx, st_val, n_keep, bw_out, lim2, status, nzero)
 
     todo_rows = _empty((nq,), torch.int32)
     count = _empty((1,), torch.int32)
     E.call("gtb_compact_todo", status, nq, todo_rows, count)
     nt = int(count.item())                       # host sync #1
-    _STATS.update(rows=nq, radius_rows=nt, S=S, radius_pairs=0)
+    _STATS.update(rows=nq, radius_rows=nt, S=S, radius_pairs=0, impl=impl)
 
     seg_ptr = seg_idx = seg_val = n_keep_t = None
     if nt > 0:
         todo_rows = todo_rows[:nt].contiguous()
         nt_pad = (nt + 127) // 128 * 128
-        QT = _empty((ref.d_pad, nt_pad), torch.float32)
-        qn2 = _empty((nt_pad,), torch.float32)
-        E.call("gtb_gather_operand", qry.XT, qry.n_pad, qry.n2, todo_rows, nt, QT, nt_pad, ref.d_pad, qn2)
         lim_t = torch.zeros((nt_pad,), dtype=torch.float32, device=dev)
         lim_t[:nt] = lim2[todo_rows.long()]
+        if impl == "tc":
+            # the radius rows form their own (small) query operand; build it from the gathered rows
+            sub = SearchOperand(qry.X[todo_rows.long()].contiguous(), mean=ref.mean)
+            s_hi, s_lo, s_n2 = sub.tc(0)
+            r_hi, r_lo, _ = ref.tc(1)
+        else:
+            QT = _empty((ref.d_pad, nt_pad), torch.float32)
+            qn2 = _empty((nt_pad,), torch.float32)
+            E.call("gtb_gather_operand", qry.XT, qry.n_pad, qry.n2, todo_rows, nt, QT, nt_pad, ref.d_pad, qn2)
         capacity = max(1 << 20, nt * 4 * S)
         while True:
             pairs = _empty((capacity, 2), torch.int32)
             counter = _zeros((1,), torch.int64)
             rowcnt = _zeros((nt_pad,), torch.int32)
-            E.call("gtb_knn_radius_simt", QT, qn2, lim_t, nt, nt_pad, ref.XT, ref.n2, nr, ref.n_pad, ref.d_pad,
-                   pairs, capacity, counter, rowcnt)
+            if impl == "tc":
+                E.call("gtb_knn_radius_tc", s_hi, s_lo, s_n2, lim_t, nt, nt_pad, r_hi, r_lo, nr, ref.n_pad, ref.Kp,
+                       pairs, capacity, counter, rowcnt)
+            else:
+                E.call("gtb_knn_radius_simt", QT, qn2, lim_t, nt, nt_pad, ref.XT, ref.n2, nr, ref.n_pad, ref.d_pad,
+                       pairs, capacity, counter, rowcnt)
             npairs = int(counter.item())
             if npairs <= capacity:
                 break

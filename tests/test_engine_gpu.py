@@ -93,3 +93,101 @@ def test_radius_pairs_complete():
     extra = got - want
     assert len(extra) < 0.05 * len(want) + 50
     assert np.array_equal(np.bincount(pr[:, 0], minlength=n), rowcnt[:n].cpu().numpy())
+
+
+# ------------------------------------------------------------------ tensor-core (tcgen05) search
+def _tc_topk(X, Y=None):
+    ref = pipeline.SearchOperand(_dev(X))
+    qry = ref if Y is None else pipeline.SearchOperand(_dev(Y), mean=ref.mean)
+    q_hi, q_lo, q_n2 = qry.tc(0)
+    r_hi, r_lo, _ = ref.tc(1)
+    cand = torch.full((qry.n_pad, 128), -7, dtype=torch.int32, device="cuda")
+    val = torch.zeros((qry.n_pad, 128), dtype=torch.float32, device="cuda")
+    tau = torch.empty((qry.n,), dtype=torch.float32, device="cuda")
+    E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, qry.n, qry.n_pad, r_hi, r_lo, ref.n, ref.n_pad, ref.Kp, cand, val, tau)
+    torch.cuda.synchronize()
+    return cand.cpu().numpy()[:qry.n, :64], val.cpu().numpy()[:qry.n, :64], tau.cpu().numpy(), qry, ref
+
+
+def test_tc_operand_split():
+    X, _ = synth.gaussian_mixture(300, 100, n_clusters=3, intrinsic_dim=10, seed=2)
+    op = pipeline.SearchOperand(_dev(X))
+    hi, lo, n2 = [t.cpu().numpy() for t in op.tc(1)]
+    assert hi.shape == (384, 104)
+    Xc = (X - op.mean.cpu().numpy()[None, :]).astype(np.float32)
+    full = hi.astype(np.float64) + lo.astype(np.float64)
+    assert np.allclose(full[:300, :100], -2.0 * Xc, rtol=2e-6, atol=1e-9)
+    assert (hi.view(np.uint32) & 0x1FFF == 0).all() and (lo.view(np.uint32) & 0x1FFF == 0).all()
+    assert np.allclose(full[:300, 100], (Xc.astype(np.float64) ** 2).sum(1), rtol=2e-6)
+    assert (full[:300, 101:] == 0).all()
+    assert np.allclose(full[300:, 100], 1e30, rtol=1e-3) and (full[300:, :100] == 0).all()
+    qhi, qlo, _ = [t.cpu().numpy() for t in op.tc(0)]
+    qfull = qhi.astype(np.float64) + qlo.astype(np.float64)
+    assert np.allclose(qfull[:300, :100], Xc, rtol=2e-6, atol=1e-9) and (qfull[:300, 100] == 1).all()
+
+
+@pytest.mark.parametrize("n,d", [(1797, 64), (3000, 100), (700, 20), (2500, 10), (300, 5), (40, 3), (1000, 31),
+                                 (1000, 55), (777, 103)])
+def test_tc_topk_candidates(n, d):
+    X, _ = synth.gaussian_mixture(n, d, n_clusters=5, intrinsic_dim=min(8, d), seed=3)
+    cand, val, tau, qry, ref = _tc_topk(X)
+    X64 = X.astype(np.float64)
+    D2 = ((X64[:, None, :] - X64[None, :, :]) ** 2).sum(-1)
+    order = np.argsort(D2, axis=1, kind="stable")
+    Xc = X64 - X64.mean(0)
+    nrm = (Xc ** 2).sum(1)
+    eps = pipeline.eps_rel_tc(d)
+    S = 64
+    for i in range(0, n, max(1, n // 300)):
+        c = cand[i][cand[i] >= 0]
+        assert (c < n).all(), "padded reference leaked into the candidates"
+        assert len(np.unique(c)) == len(c), "duplicate candidate"
+        assert len(c) == min(S, n), (i, len(c))
+        assert set(order[i, :min(S - 8, n)]).issubset(set(c)), "row %d misses a true neighbour" % i
+        bound = eps * (nrm[i] + nrm.max())
+        if n > S:
+            non = np.setdiff1d(np.arange(n), c)
+            assert D2[i, non].min() >= tau[i] - bound
+            # stored approximate values: v' + |x|^2 ~ exact d2
+            approx = val[i][: len(c)] + nrm[i]
+            assert np.abs(approx - D2[i, cand[i][: len(c)]]).max() <= bound
+        else:
+            assert np.isinf(tau[i])
+
+
+def test_tc_topk_out_of_sample():
+    X, _ = synth.gaussian_mixture(5000, 100, n_clusters=6, intrinsic_dim=10, seed=5)
+    Y, _ = synth.gaussian_mixture(333, 100, n_clusters=6, intrinsic_dim=10, seed=5)
+    Y = Y + np.float32(0.01)
+    cand, val, tau, qry, ref = _tc_topk(X, Y)
+    D2 = ((Y.astype(np.float64)[:, None, :] - X.astype(np.float64)[None, :, :]) ** 2).sum(-1)
+    order = np.argsort(D2, axis=1, kind="stable")
+    for i in range(333):
+        assert set(order[i, :56]).issubset(set(cand[i]))
+
+
+def test_tc_radius_pairs_complete():
+    n, d = 2000, 30
+    X, _ = synth.gaussian_mixture(n, d, n_clusters=3, intrinsic_dim=6, seed=4)
+    op = pipeline.SearchOperand(_dev(X))
+    X64 = X.astype(np.float64)
+    D2 = ((X64[:, None, :] - X64[None, :, :]) ** 2).sum(-1)
+    r2 = np.partition(D2, 40, axis=1)[:, 40]
+    limp = torch.zeros(op.n_pad, dtype=torch.float32, device="cuda")
+    limp[:n] = _dev((r2 * 1.0001 + 1e-3).astype(np.float32))
+    cap = 1 << 20
+    pairs = torch.empty((cap, 2), dtype=torch.int32, device="cuda")
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    rowcnt = torch.zeros(op.n_pad, dtype=torch.int32, device="cuda")
+    q_hi, q_lo, q_n2 = op.tc(0)
+    r_hi, r_lo, _ = op.tc(1)
+    E.call("gtb_knn_radius_tc", q_hi, q_lo, q_n2, limp, n, op.n_pad, r_hi, r_lo, n, op.n_pad, op.Kp, pairs, cap,
+           counter, rowcnt)
+    m = int(counter.item())
+    pr = pairs[:m].cpu().numpy()
+    got = set(map(tuple, pr))
+    assert len(got) == m
+    want = set(zip(*np.nonzero(D2 <= r2[:, None])))
+    assert want.issubset(got)
+    assert len(got - want) < 0.05 * len(want) + 50
+    assert np.array_equal(np.bincount(pr[:, 0], minlength=n), rowcnt[:n].cpu().numpy())

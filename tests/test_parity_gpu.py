@@ -22,8 +22,14 @@ def _build(case, **extra):
         return gt.Graph(case.X, n_jobs=-1, verbose=0, **dict(case.params, **extra))
 
 
+@pytest.fixture(params=["tc", "simt"])
+def impl(request, monkeypatch):
+    monkeypatch.setenv("GTB_SEARCH_IMPL", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("name", KNN_CASES)
-def test_knn_golden(name):
+def test_knn_golden(name, impl):
     case = Case(name)
     G = _build(case)
     assert type(G).__name__ == case.cls
@@ -64,7 +70,7 @@ def test_knn_golden(name):
         compare_sparse(G.extend_to_data(case.z["Y"]), case.mat("ext"), thresh=thresh, what=name + ".ext")
 
 
-def test_row_sums_and_symmetry_100k():
+def test_row_sums_and_symmetry_100k(impl):
     """Size-independent properties at the BASELINE config-2 size (100k x 100)."""
     X, _ = synth.gaussian_mixture(100_000, 100, n_clusters=20, intrinsic_dim=10, seed=0)
     G = gt.Graph(X, knn=5, decay=40, thresh=1e-4, verbose=0)
@@ -75,10 +81,10 @@ def test_row_sums_and_symmetry_100k():
     assert K.data.min() >= 1e-4 / 2 - 1e-12 and K.data.max() <= 1.0
     assert np.array_equal(K.indptr, P.indptr) and np.array_equal(K.indices, P.indices)
     st = pipeline.stats()
-    assert st["rows"] == 100_000
+    assert st["rows"] == 100_000 and st["impl"] == impl
 
 
-def test_oracle_parity_20k():
+def test_oracle_parity_20k(impl):
     """Full-pipeline parity against the CPU oracle on a seeded 20k x 100 mixture."""
     from oracle import graph_oracle as go
     X, _ = synth.gaussian_mixture(20_000, 100, n_clusters=20, intrinsic_dim=10, seed=7)
@@ -89,7 +95,7 @@ def test_oracle_parity_20k():
                    rtol=1e-5 if r["n_exempt"] == 0 else 1e-3)
 
 
-def test_oracle_parity_isotropic():
+def test_oracle_parity_isotropic(impl):
     """High intrinsic dimension: most rows go through the radius pass."""
     from oracle import graph_oracle as go
     X, _ = synth.gaussian_mixture(6000, 40, n_clusters=4, intrinsic_dim=None, seed=11)
