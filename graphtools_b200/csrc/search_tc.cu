@@ -9,12 +9,13 @@
 // accumulator (3xTF32: ~2^-21 relative to |x||y|, enough to SELECT candidates; every value that
 // reaches the output is re-evaluated in float64 by refine.cu).
 //
-// CTA = 128 query rows (UMMA M=128, cta_group::1) resident in shared memory for the whole sweep
-// (A_hi, A_lo: 2 x 128 x Kp floats); reference tiles of 64 rows (B_hi, B_lo) stream through a 2-stage
-// TMA/mbarrier ring; two 64-column TMEM accumulators let the epilogue of tile t overlap the MMAs of
-// tile t+1.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 =
-// epilogue (tcgen05.ld 32x32b: thread == query row).  Shared-memory operand tiles are K-major:
-// floor(Kp/32) SWIZZLE_128B blocks (32 floats per row) followed by (Kp%32)/8 SWIZZLE_32B blocks.
+// CTA = 128 query rows (UMMA M=128, cta_group::1).  The query tile (A_hi, A_lo) lives in TENSOR MEMORY for
+// the whole sweep (tcgen05.st by the epilogue warps, 2 x Kp columns; the MMA reads A from TMEM, so
+// shared-memory bandwidth is spent on B only); reference tiles of 128 rows (B_hi, B_lo) stream through
+// a 2-stage TMA/mbarrier ring that owns all of shared memory; two 128-column TMEM accumulators let the
+// epilogue of tile t overlap the MMAs of tile t+1.  Warp roles: warp 0 = TMA producer, warp 1 = MMA
+// issuer (+TMEM alloc), warps 2-5 = epilogue (tcgen05.ld 32x32b: thread == query row).  Shared-memory B
+// tiles are K-major: floor(Kp/32) SWIZZLE_128B blocks (32 floats per row) then (Kp%32)/8 SWIZZLE_32B blocks.
 //
 // Epilogue, TOPK mode: each thread keeps a running threshold; values under it are appended to the
 // row's 128-slot candidate buffer in global memory (L2 resident); when a buffer nears capacity the
@@ -29,7 +30,7 @@
 
 namespace {
 
-constexpr int TC_M = 128, TC_N = 64, TC_STAGES = 2, TC_CAP = 128, TC_S = 64, TC_THREADS = 192;
+constexpr int TC_M = 128, TC_N = 128, TC_STAGES = 2, TC_CAP = 128, TC_S = 64, TC_THREADS = 192;
 constexpr float TC_BIG = 1e29f;       // "no threshold yet"; padded reference rows carry |y|^2 = 1e30
 constexpr float TC_PAD_NORM = 1e30f;
 
@@ -172,12 +173,32 @@ __device__ __forceinline__ float compact_row(int32_t* cand_idx, float* cand_val,
 }
 
 // ---------------------------------------------------------------- the kernel
+// TMEM column map (512 columns allocated): [0, Kp) A_hi, [TC_ALO, TC_ALO+Kp) A_lo,
+// [TC_ACC0 + s*TC_N, +TC_N) accumulator s.
+constexpr int TC_ALO = 104, TC_ACC0 = 256;
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float4& a, const float4& b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)),
+               "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)),
+               "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w))
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]   (A: lane = row, one 32-bit column per K element)
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 template <int MODE>  // 0 = TOPK, 1 = RADIUS
 __global__ void __launch_bounds__(TC_THREADS, 1)
-search_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAht,
-                 const __grid_constant__ CUtensorMap mAl, const __grid_constant__ CUtensorMap mAlt,
-                 const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBht,
-                 const __grid_constant__ CUtensorMap mBl, const __grid_constant__ CUtensorMap mBlt, TcParams p) {
+search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBht,
+                 const __grid_constant__ CUtensorMap mBl, const __grid_constant__ CUtensorMap mBlt,
+                 const float* __restrict__ q_hi, const float* __restrict__ q_lo, TcParams p) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -185,19 +206,21 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
 
   const int Kp = p.Kp;
   const int nfull = Kp / 32, ntail = (Kp % 32) / 8, nks = Kp / 8;
-  const uint32_t sizeA = (uint32_t)TC_M * Kp * 4, sizeB = (uint32_t)TC_N * Kp * 4;
-  const uint32_t A_hi = base, A_lo = base + sizeA;
-  const uint32_t B0 = base + 2 * sizeA;                    // stage s, part q at B0 + (2*s+q)*sizeB
+  const uint32_t sizeB = (uint32_t)TC_N * Kp * 4;            // one part (hi or lo) of one stage
+  const uint32_t B0 = base;                                  // stage s, part q at B0 + (2*s+q)*sizeB
   const uint32_t bar0 = B0 + 2 * TC_STAGES * sizeB;
   const uint32_t bar_a = bar0, full_b = bar0 + 8, empty_b = bar0 + 24, tm_full = bar0 + 40, tm_empty = bar0 + 56;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (bar0 - base) + 72);
+  // tile-invariant MMA operands in issue order: stage-0 B descriptors and A TMEM column offsets
+  uint64_t* dtab = reinterpret_cast<uint64_t*>(gbase + (bar0 - base) + 128);
+  uint32_t* atab = reinterpret_cast<uint32_t*>(gbase + (bar0 - base) + 128 + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q0 = (int64_t)blockIdx.x * TC_M;
   const int64_t ntiles = p.nr_pad / TC_N;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_a, 1);
+    mbar_init(bar_a, 4);
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(full_b + 8 * s, 1);
       mbar_init(empty_b + 8 * s, 1);
@@ -209,7 +232,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(128));
+                 "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -220,15 +243,6 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_a, 2 * sizeA);
-      for (int part = 0; part < 2; ++part) {
-        const CUtensorMap* mm = part ? &mAl : &mAh;
-        const CUtensorMap* mt = part ? &mAlt : &mAht;
-        const uint32_t dst = part ? A_lo : A_hi;
-        for (int b = 0; b < nfull; ++b) tma_load_2d(dst + b * (TC_M * 128), mm, bar_a, b * 32, (int)q0);
-        for (int t = 0; t < ntail; ++t)
-          tma_load_2d(dst + nfull * (TC_M * 128) + t * (TC_M * 32), mt, bar_a, nfull * 32 + t * 8, (int)q0);
-      }
       for (int64_t tile = 0; tile < ntiles; ++tile) {
         const int s = (int)(tile % TC_STAGES);
         const uint32_t ph = (uint32_t)((tile / TC_STAGES) & 1);
@@ -248,11 +262,22 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    const int nmma = 3 * nks;
+    for (int e = lane; e < nmma; e += 32) {
+      const int prod = e / nks, ks = e - prod * nks;     // (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi)
+      const uint32_t Bp = B0 + ((prod == 1) ? sizeB : 0u);
+      uint64_t bd;
+      if (ks < 4 * nfull) bd = make_desc(Bp + (ks >> 2) * (TC_N * 128) + (ks & 3) * 32, 1024, 2);
+      else bd = make_desc(Bp + nfull * (TC_N * 128) + (ks - 4 * nfull) * (TC_N * 32), 256, 6);
+      dtab[e] = bd;
+      atab[e] = (uint32_t)(((prod == 2) ? TC_ALO : 0) + ks * 8);
+    }
+    __syncwarp();
     if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=tf32, K-major both, N=64, M=128
+      // instruction descriptor: D=f32, A=B=tf32, K-major, N=TC_N, M=128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                              ((uint32_t)(TC_M >> 4) << 24);
-      mbar_wait(bar_a, 0);
+      mbar_wait(bar_a, 0);                     // A rows stored to TMEM by the epilogue warps
       tc_fence_after();
       for (int64_t tile = 0; tile < ntiles; ++tile) {
         const int s = (int)(tile % TC_STAGES);
@@ -260,39 +285,38 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
         mbar_wait(tm_empty + 8 * s, ph ^ 1);   // accumulator index == stage index (both 2-deep)
         mbar_wait(full_b + 8 * s, ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(s * TC_N);
-        const uint32_t Bh = B0 + (2 * s) * sizeB, Bl = Bh + sizeB;
-        uint32_t acc = 0;
-#pragma unroll 1
-        for (int prod = 0; prod < 3; ++prod) {
-          const uint32_t Ap = (prod == 2) ? A_lo : A_hi;
-          const uint32_t Bp = (prod == 1) ? Bl : Bh;
-#pragma unroll 1
-          for (int ks = 0; ks < nks; ++ks) {
-            uint64_t ad, bd;
-            if (ks < 4 * nfull) {
-              const int blk = ks >> 2, sub = ks & 3;
-              ad = make_desc(Ap + blk * (TC_M * 128) + sub * 32, 1024, 2);
-              bd = make_desc(Bp + blk * (TC_N * 128) + sub * 32, 1024, 2);
-            } else {
-              const int t = ks - 4 * nfull;
-              ad = make_desc(Ap + nfull * (TC_M * 128) + t * (TC_M * 32), 256, 6);
-              bd = make_desc(Bp + nfull * (TC_N * 128) + t * (TC_N * 32), 256, 6);
-            }
-            tc_mma_tf32(d_tmem, ad, bd, idesc, acc);
-            acc = 1;
-          }
-        }
+        const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC0 + s * TC_N);
+        // stage offset added to the 14-bit start-address field (smem < 256 KB: no carry out of the field)
+        const uint64_t boff = (uint64_t)((s * 2 * sizeB) >> 4);
+        tc_mma_tf32_ts(d_tmem, tmem_base + atab[0], dtab[0] + boff, idesc, 0u);
+#pragma unroll 4
+        for (int e = 1; e < nmma; ++e) tc_mma_tf32_ts(d_tmem, tmem_base + atab[e], dtab[e] + boff, idesc, 1u);
         tc_commit(empty_b + 8 * s);   // smem stage free once these MMAs retire
         tc_commit(tm_full + 8 * s);   // accumulator ready for the epilogue
       }
     }
   } else {
     // ===================== epilogue warps =====================
-    const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
     const int64_t gq = q0 + row;
     const bool valid = gq < p.nq;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+
+    // ---- stage the query tile into TMEM: thread == row, one column per K element
+    {
+      const float4* rh = reinterpret_cast<const float4*>(q_hi + gq * Kp);
+      const float4* rl = reinterpret_cast<const float4*>(q_lo + gq * Kp);
+      for (int ks = 0; ks < nks; ++ks) {
+        tmem_st8(lane_addr + (uint32_t)(ks * 8), rh[2 * ks], rh[2 * ks + 1]);
+        tmem_st8(lane_addr + (uint32_t)(TC_ALO + ks * 8), rl[2 * ks], rl[2 * ks + 1]);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a);
+    }
+
     const float nx = valid ? p.qn2[gq] : 0.f;
     float thr;
     if (MODE == 0) thr = valid ? TC_BIG : -gtb_inf_f();
@@ -307,16 +331,16 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
       mbar_wait(tm_full + 8 * s, ph);
       tc_fence_after();
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
+      for (int part = 0; part < TC_N / 32; ++part) {
         float v[32];
         __syncwarp();
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * TC_N + half * 32), v);
-        if (half == 1) {
+        tmem_ld32(lane_addr + (uint32_t)(TC_ACC0 + s * TC_N + part * 32), v);
+        if (part == TC_N / 32 - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tm_empty + 8 * s);
         }
-        const int32_t col0 = (int32_t)(tile * TC_N) + half * 32;
+        const int32_t col0 = (int32_t)(tile * TC_N) + part * 32;
         bool any = false;
 #pragma unroll
         for (int j = 0; j < 32; ++j) any |= (MODE == 0) ? (v[j] < thr) : (v[j] <= thr);
@@ -386,7 +410,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -477,21 +501,17 @@ int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int Kp, int box_k, 
 template <int MODE>
 int launch_tc(const float* q_hi, const float* q_lo, const float* r_hi, const float* r_lo, TcParams& p,
               cudaStream_t st) {
-  CUtensorMap mAh, mAht, mAl, mAlt, mBh, mBht, mBl, mBlt;
+  CUtensorMap mBh, mBht, mBl, mBlt;
   int rc;
   const int Kp = p.Kp;
-  if ((rc = make_map(&mAh, q_hi, p.nq_pad, Kp, 32, TC_M, true))) return rc;
-  if ((rc = make_map(&mAht, q_hi, p.nq_pad, Kp, 8, TC_M, false))) return rc;
-  if ((rc = make_map(&mAl, q_lo, p.nq_pad, Kp, 32, TC_M, true))) return rc;
-  if ((rc = make_map(&mAlt, q_lo, p.nq_pad, Kp, 8, TC_M, false))) return rc;
   if ((rc = make_map(&mBh, r_hi, p.nr_pad, Kp, 32, TC_N, true))) return rc;
   if ((rc = make_map(&mBht, r_hi, p.nr_pad, Kp, 8, TC_N, false))) return rc;
   if ((rc = make_map(&mBl, r_lo, p.nr_pad, Kp, 32, TC_N, true))) return rc;
   if ((rc = make_map(&mBlt, r_lo, p.nr_pad, Kp, 8, TC_N, false))) return rc;
-  size_t smem = 1024 + (size_t)2 * TC_M * Kp * 4 + (size_t)2 * TC_STAGES * TC_N * Kp * 4 + 128;
+  size_t smem = 1024 + (size_t)2 * TC_STAGES * TC_N * Kp * 4 + 128 + 1024;
   auto kern = search_tc_kernel<MODE>;
   GTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)(p.nq_pad / TC_M), TC_THREADS, smem, st>>>(mAh, mAht, mAl, mAlt, mBh, mBht, mBl, mBlt, p);
+  kern<<<(unsigned)(p.nq_pad / TC_M), TC_THREADS, smem, st>>>(mBh, mBht, mBl, mBlt, q_hi, q_lo, p);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }
@@ -518,7 +538,7 @@ extern "C" int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const fl
 extern "C" int gtb_knn_topk_tc(const float* q_hi, const float* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
                                const float* r_hi, const float* r_lo, int64_t nr, int64_t nr_pad, int Kp,
                                int32_t* cand_idx, float* cand_val, float* tau, void* stream) {
-  GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TC_M == 0 && nr_pad % TC_N == 0, "bad shape");
+  GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TC_M == 0 && nr_pad % TC_N == 0, "bad shape (pads must be x128)");
   GTB_CHECK_ARG(Kp % 8 == 0 && Kp >= 8 && Kp <= 104, "Kp must be a multiple of 8, <= 104");
   GTB_CHECK_ARG(nr_pad < (1ll << 31) && nq_pad < (1ll << 31), "too many rows for 32-bit TMA coordinates");
   TcParams p{};
@@ -531,7 +551,7 @@ extern "C" int gtb_knn_radius_tc(const float* q_hi, const float* q_lo, const flo
                                  int64_t nq, int64_t nq_pad, const float* r_hi, const float* r_lo, int64_t nr,
                                  int64_t nr_pad, int Kp, int32_t* pairs, int64_t capacity,
                                  unsigned long long* counter, int32_t* rowcnt, void* stream) {
-  GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TC_M == 0 && nr_pad % TC_N == 0, "bad shape");
+  GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TC_M == 0 && nr_pad % TC_N == 0, "bad shape (pads must be x128)");
   GTB_CHECK_ARG(Kp % 8 == 0 && Kp >= 8 && Kp <= 104, "Kp must be a multiple of 8, <= 104");
   TcParams p{};
   p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.Kp = Kp; p.qn2 = qn2; p.lim2 = lim2;

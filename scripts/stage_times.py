@@ -33,5 +33,6 @@ for rep in range(a.reps):
     for k, (c, ms) in sorted(tm.items(), key=lambda kv: -kv[1][1]):
         print("   %-24s calls=%d %.3f ms" % (k, c, ms))
     flop = 2.0 * a.n * a.n * a.d
-    ms = tm["gtb_knn_topk_simt"][1]
-    print("   topk: %.2f TFLOP/s algorithmic (2*N*N*d)" % (flop / ms / 1e9))
+    key = "gtb_knn_topk_tc" if "gtb_knn_topk_tc" in tm else "gtb_knn_topk_simt"
+    ms = tm[key][1]
+    print("   %s: %.2f TFLOP/s algorithmic (2*N*N*d)" % (key, flop / ms / 1e9))

@@ -98,11 +98,13 @@ def test_oracle_parity_20k(impl):
 def test_oracle_parity_isotropic(impl):
     """High intrinsic dimension: most rows go through the radius pass."""
     from oracle import graph_oracle as go
-    X, _ = synth.gaussian_mixture(6000, 40, n_clusters=4, intrinsic_dim=None, seed=11)
+    X, _ = synth.gaussian_mixture(6000, 100, n_clusters=2, intrinsic_dim=None, seed=11)
     K_ref, P_ref = go.knn_graph(X.astype(np.float64), knn=5, decay=40, thresh=1e-4)
     G = gt.Graph(X, knn=5, decay=40, thresh=1e-4, verbose=0)
-    assert pipeline.stats()["radius_rows"] > 0
+    st = pipeline.stats()
     compare_sparse(G.kernel, K_ref, thresh=1e-4, what="K")
+    compare_sparse(G.diff_op, P_ref, what="P")
+    assert st["radius_rows"] > 0, "stress case did not exercise the radius pass"
 
 
 EXACT_CASES = [n for n in names() if Case(n).cls == "TraditionalGraph"]
