@@ -62,6 +62,7 @@ _PLAIN = {
     "gtb_col_mean_ws_doubles": ([c_int], c_int64),
     "gtb_scan_ws_elems": ([c_int64], c_int64),
     "gtb_tc_max_kp": ([], c_int),
+    "gtb_tc_set_cluster": ([c_int], c_int),
 }
 
 

@@ -63,6 +63,34 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -194,7 +222,11 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
       : "memory");
 }
 
-template <int MODE>  // 0 = TOPK, 1 = RADIUS
+// CL = thread-block cluster size: the CL CTAs of a cluster sweep the same reference tiles for CL different
+// query tiles; each loads 1/CL of every B stage and TMA-multicasts it to all of them, so the L2 -> SM
+// traffic per output drops by CL.  A stage is recycled once every CTA's MMAs have retired (commit
+// multicast to all empty barriers).
+template <int MODE, int CL>  // MODE 0 = TOPK, 1 = RADIUS
 __global__ void __launch_bounds__(TC_THREADS, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBht,
                  const __grid_constant__ CUtensorMap mBl, const __grid_constant__ CUtensorMap mBlt,
@@ -211,19 +243,19 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   const uint32_t bar0 = B0 + 2 * TC_STAGES * sizeB;
   const uint32_t bar_a = bar0, full_b = bar0 + 8, empty_b = bar0 + 24, tm_full = bar0 + 40, tm_empty = bar0 + 56;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (bar0 - base) + 72);
-  // tile-invariant MMA operands in issue order: stage-0 B descriptors and A TMEM column offsets
-  uint64_t* dtab = reinterpret_cast<uint64_t*>(gbase + (bar0 - base) + 128);
-  uint32_t* atab = reinterpret_cast<uint32_t*>(gbase + (bar0 - base) + 128 + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q0 = (int64_t)blockIdx.x * TC_M;
   const int64_t ntiles = p.nr_pad / TC_N;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+  constexpr int ROWS = TC_N / CL;                            // rows of each B block this CTA loads
 
   if (threadIdx.x == 0) {
     mbar_init(bar_a, 4);
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(full_b + 8 * s, 1);
-      mbar_init(empty_b + 8 * s, 1);
+      mbar_init(empty_b + 8 * s, CL);
       mbar_init(tm_full + 8 * s, 1);
       mbar_init(tm_empty + 8 * s, 4);
     }
@@ -237,6 +269,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();               // peers' barriers are initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -246,54 +279,80 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
       for (int64_t tile = 0; tile < ntiles; ++tile) {
         const int s = (int)(tile % TC_STAGES);
         const uint32_t ph = (uint32_t)((tile / TC_STAGES) & 1);
-        mbar_wait(empty_b + 8 * s, ph ^ 1);
+        mbar_wait(empty_b + 8 * s, ph ^ 1);      // every CTA of the cluster has consumed this stage
         mbar_arrive_expect_tx(full_b + 8 * s, 2 * sizeB);
+        const int row0 = (int)(tile * TC_N) + (int)crank * ROWS;
         for (int part = 0; part < 2; ++part) {
           const CUtensorMap* mm = part ? &mBl : &mBh;
           const CUtensorMap* mt = part ? &mBlt : &mBht;
           const uint32_t dst = B0 + (2 * s + part) * sizeB;
-          for (int b = 0; b < nfull; ++b)
-            tma_load_2d(dst + b * (TC_N * 128), mm, full_b + 8 * s, b * 32, (int)(tile * TC_N));
-          for (int t = 0; t < ntail; ++t)
-            tma_load_2d(dst + nfull * (TC_N * 128) + t * (TC_N * 32), mt, full_b + 8 * s, nfull * 32 + t * 8,
-                        (int)(tile * TC_N));
+          for (int b = 0; b < nfull; ++b) {
+            const uint32_t d = dst + b * (TC_N * 128) + crank * (ROWS * 128);
+            if (CL > 1) tma_load_2d_mc(d, mm, full_b + 8 * s, b * 32, row0, cmask);
+            else tma_load_2d(d, mm, full_b + 8 * s, b * 32, row0);
+          }
+          for (int t = 0; t < ntail; ++t) {
+            const uint32_t d = dst + nfull * (TC_N * 128) + t * (TC_N * 32) + crank * (ROWS * 32);
+            if (CL > 1) tma_load_2d_mc(d, mt, full_b + 8 * s, nfull * 32 + t * 8, row0, cmask);
+            else tma_load_2d(d, mt, full_b + 8 * s, nfull * 32 + t * 8, row0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const int nmma = 3 * nks;
-    for (int e = lane; e < nmma; e += 32) {
-      const int prod = e / nks, ks = e - prod * nks;     // (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi)
-      const uint32_t Bp = B0 + ((prod == 1) ? sizeB : 0u);
-      uint64_t bd;
-      if (ks < 4 * nfull) bd = make_desc(Bp + (ks >> 2) * (TC_N * 128) + (ks & 3) * 32, 1024, 2);
-      else bd = make_desc(Bp + nfull * (TC_N * 128) + (ks - 4 * nfull) * (TC_N * 32), 256, 6);
-      dtab[e] = bd;
-      atab[e] = (uint32_t)(((prod == 2) ? TC_ALO : 0) + ks * 8);
-    }
-    __syncwarp();
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=tf32, K-major, N=TC_N, M=128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
-                             ((uint32_t)(TC_M >> 4) << 24);
-      mbar_wait(bar_a, 0);                     // A rows stored to TMEM by the epilogue warps
+    // The whole warp runs this loop in uniform control flow so that every MMA operand (descriptors,
+    // TMEM addresses) is computed on the uniform datapath; only the tcgen05 instructions themselves
+    // are predicated on the elected lane.  (Issuing from inside an `if (lane == 0)` region costs ~18
+    // SASS instructions per MMA -- R2UR + an ELECT loop -- and left the tensor pipe 3/4 idle.)
+    const bool leader = elect_one();
+    // instruction descriptor: D=f32, A=B=tf32, K-major, N=TC_N, M=128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
+                           ((uint32_t)(TC_M >> 4) << 24);
+    const uint64_t bd_main0 = make_desc(B0, 1024, 2);                          // stage 0, hi part, block 0
+    const uint64_t bd_tail0 = make_desc(B0 + nfull * (TC_N * 128), 256, 6);    // stage 0, hi part, first tail block
+    const uint32_t part_off = sizeB >> 4, stage_off = (2 * sizeB) >> 4;         // in descriptor address units (16 B)
+    mbar_wait(bar_a, 0);                     // A rows stored to TMEM by the epilogue warps
+    tc_fence_after();
+    for (int64_t tile = 0; tile < ntiles; ++tile) {
+      const int s = (int)(tile % TC_STAGES);
+      const uint32_t ph = (uint32_t)((tile / TC_STAGES) & 1);
+      mbar_wait(tm_empty + 8 * s, ph ^ 1);   // accumulator index == stage index (both 2-deep)
+      mbar_wait(full_b + 8 * s, ph);
       tc_fence_after();
-      for (int64_t tile = 0; tile < ntiles; ++tile) {
-        const int s = (int)(tile % TC_STAGES);
-        const uint32_t ph = (uint32_t)((tile / TC_STAGES) & 1);
-        mbar_wait(tm_empty + 8 * s, ph ^ 1);   // accumulator index == stage index (both 2-deep)
-        mbar_wait(full_b + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC0 + s * TC_N);
-        // stage offset added to the 14-bit start-address field (smem < 256 KB: no carry out of the field)
-        const uint64_t boff = (uint64_t)((s * 2 * sizeB) >> 4);
-        tc_mma_tf32_ts(d_tmem, tmem_base + atab[0], dtab[0] + boff, idesc, 0u);
-#pragma unroll 4
-        for (int e = 1; e < nmma; ++e) tc_mma_tf32_ts(d_tmem, tmem_base + atab[e], dtab[e] + boff, idesc, 1u);
-        tc_commit(empty_b + 8 * s);   // smem stage free once these MMAs retire
+      const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC0 + s * TC_N);
+      uint32_t accum = 0;
+#pragma unroll 1
+      for (int prod = 0; prod < 3; ++prod) {   // (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi)
+        uint32_t ac = tmem_base + (uint32_t)((prod == 2) ? TC_ALO : 0);
+        const uint64_t boff = (uint64_t)(s * stage_off + ((prod == 1) ? part_off : 0u));
+        uint64_t bd = bd_main0 + boff;
+#pragma unroll 1
+        for (int blk = 0; blk < nfull; ++blk) {
+#pragma unroll
+          for (int sub = 0; sub < 4; ++sub) {
+            if (leader) tc_mma_tf32_ts(d_tmem, ac + sub * 8, bd + sub * 2, idesc, accum);
+            accum = 1;
+          }
+          bd += (TC_N * 128) >> 4;
+          ac += 32;
+        }
+        bd = bd_tail0 + boff;
+#pragma unroll 1
+        for (int t = 0; t < ntail; ++t) {
+          if (leader) tc_mma_tf32_ts(d_tmem, ac, bd, idesc, accum);
+          accum = 1;
+          bd += (TC_N * 32) >> 4;
+          ac += 8;
+        }
+      }
+      if (leader) {
+        // smem stage free once these MMAs retire -- signalled to every CTA that multicasts into it
+        if (CL > 1) tc_commit_mc(empty_b + 8 * s, cmask);
+        else tc_commit(empty_b + 8 * s);
         tc_commit(tm_full + 8 * s);   // accumulator ready for the epilogue
       }
+      __syncwarp();
     }
   } else {
     // ===================== epilogue warps =====================
@@ -305,11 +364,13 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
 
     // ---- stage the query tile into TMEM: thread == row, one column per K element
     {
-      const float4* rh = reinterpret_cast<const float4*>(q_hi + gq * Kp);
-      const float4* rl = reinterpret_cast<const float4*>(q_lo + gq * Kp);
+      const bool in_pad = gq < p.nq_pad;             // cluster padding CTAs carry all-zero query rows
+      const float4* rh = reinterpret_cast<const float4*>(q_hi + (in_pad ? gq : 0) * Kp);
+      const float4* rl = reinterpret_cast<const float4*>(q_lo + (in_pad ? gq : 0) * Kp);
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int ks = 0; ks < nks; ++ks) {
-        tmem_st8(lane_addr + (uint32_t)(ks * 8), rh[2 * ks], rh[2 * ks + 1]);
-        tmem_st8(lane_addr + (uint32_t)(TC_ALO + ks * 8), rl[2 * ks], rl[2 * ks + 1]);
+        tmem_st8(lane_addr + (uint32_t)(ks * 8), in_pad ? rh[2 * ks] : z4, in_pad ? rh[2 * ks + 1] : z4);
+        tmem_st8(lane_addr + (uint32_t)(TC_ALO + ks * 8), in_pad ? rl[2 * ks] : z4, in_pad ? rl[2 * ks + 1] : z4);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
@@ -322,8 +383,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     if (MODE == 0) thr = valid ? TC_BIG : -gtb_inf_f();
     else thr = valid ? (p.lim2[gq] - nx) : -gtb_inf_f();
     int cnt = 0;
-    float* my_val = (MODE == 0) ? p.cand_val + gq * TC_CAP : nullptr;
-    int32_t* my_idx = (MODE == 0) ? p.cand_idx + gq * TC_CAP : nullptr;
+    float* my_val = (MODE == 0 && valid) ? p.cand_val + gq * TC_CAP : nullptr;
+    int32_t* my_idx = (MODE == 0 && valid) ? p.cand_idx + gq * TC_CAP : nullptr;
 
     for (int64_t tile = 0; tile < ntiles; ++tile) {
       const int s = (int)(tile % TC_STAGES);
@@ -412,6 +473,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
+  if (CL > 1) cluster_sync_all();               // no CTA exits while a peer may still signal its barriers
 }
 
 // ---------------------------------------------------------------- operand preparation (row-major hi/lo)
@@ -498,27 +560,60 @@ int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int Kp, int box_k, 
   return GTB_OK;
 }
 
-template <int MODE>
-int launch_tc(const float* q_hi, const float* q_lo, const float* r_hi, const float* r_lo, TcParams& p,
-              cudaStream_t st) {
+template <int MODE, int CL>
+int launch_tc_cl(const float* q_hi, const float* q_lo, const float* r_hi, const float* r_lo, TcParams& p,
+                 cudaStream_t st) {
   CUtensorMap mBh, mBht, mBl, mBlt;
   int rc;
   const int Kp = p.Kp;
-  if ((rc = make_map(&mBh, r_hi, p.nr_pad, Kp, 32, TC_N, true))) return rc;
-  if ((rc = make_map(&mBht, r_hi, p.nr_pad, Kp, 8, TC_N, false))) return rc;
-  if ((rc = make_map(&mBl, r_lo, p.nr_pad, Kp, 32, TC_N, true))) return rc;
-  if ((rc = make_map(&mBlt, r_lo, p.nr_pad, Kp, 8, TC_N, false))) return rc;
+  if ((rc = make_map(&mBh, r_hi, p.nr_pad, Kp, 32, TC_N / CL, true))) return rc;
+  if ((rc = make_map(&mBht, r_hi, p.nr_pad, Kp, 8, TC_N / CL, false))) return rc;
+  if ((rc = make_map(&mBl, r_lo, p.nr_pad, Kp, 32, TC_N / CL, true))) return rc;
+  if ((rc = make_map(&mBlt, r_lo, p.nr_pad, Kp, 8, TC_N / CL, false))) return rc;
   size_t smem = 1024 + (size_t)2 * TC_STAGES * TC_N * Kp * 4 + 128 + 1024;
-  auto kern = search_tc_kernel<MODE>;
+  auto kern = search_tc_kernel<MODE, CL>;
   GTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)(p.nq_pad / TC_M), TC_THREADS, smem, st>>>(mBh, mBht, mBl, mBlt, q_hi, q_lo, p);
+  const unsigned nblk = (unsigned)(gtb_cdiv(p.nq_pad / TC_M, CL) * CL);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nblk);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GTB_CUDA(cudaLaunchKernelEx(&cfg, kern, mBh, mBht, mBl, mBlt, q_hi, q_lo, p));
   GTB_CHECK_LAUNCH();
   return GTB_OK;
+}
+
+int g_tc_cluster = 2;
+
+template <int MODE>
+int launch_tc(const float* q_hi, const float* q_lo, const float* r_hi, const float* r_lo, TcParams& p,
+              cudaStream_t st) {
+  switch (g_tc_cluster) {
+    case 1: return launch_tc_cl<MODE, 1>(q_hi, q_lo, r_hi, r_lo, p, st);
+    case 2: return launch_tc_cl<MODE, 2>(q_hi, q_lo, r_hi, r_lo, p, st);
+    case 4: return launch_tc_cl<MODE, 4>(q_hi, q_lo, r_hi, r_lo, p, st);
+    default: gtb_set_error("cluster size must be 1, 2 or 4"); return GTB_ERR_ARG;
+  }
 }
 
 }  // namespace
 
 extern "C" int gtb_tc_max_kp(void) { return 104; }
+
+// cluster size used by the tensor-core search (1, 2 or 4 CTAs sharing each reference tile via TMA multicast)
+extern "C" int gtb_tc_set_cluster(int cl) {
+  GTB_CHECK_ARG(cl == 1 || cl == 2 || cl == 4, "cluster size must be 1, 2 or 4");
+  g_tc_cluster = cl;
+  return GTB_OK;
+}
 
 extern "C" int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const float* mean, int role, float* hi,
                                       float* lo, int64_t n_pad, int Kp, float* norm2, float* maxnorm,

@@ -159,6 +159,12 @@ def choose_S(knn_eff, binary):
         "knn={} needs a candidate list longer than 128; not supported by the fused top-k yet".format(knn_eff))
 
 
+def tc_cluster():
+    """GTB_TC_CLUSTER = 1 | 2 | 4: CTAs per cluster sharing each reference tile by TMA multicast."""
+    import os
+    return int(os.environ.get("GTB_TC_CLUSTER", "2"))
+
+
 def default_impl():
     """GTB_SEARCH_IMPL = tc | simt | auto (default auto: tensor cores whenever the operand fits)."""
     import os
@@ -206,6 +212,8 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         if not ref.tc_ok():
             raise ValueError("tensor-core search needs d + 1 <= {}".format(E.lib().gtb_tc_max_kp()))
         S, stride = 64, 128
+        if E.lib().gtb_tc_set_cluster(tc_cluster()) != 0:
+            raise ValueError("GTB_TC_CLUSTER must be 1, 2 or 4")
         if knn > S:
             raise NotImplementedError("knn={} exceeds the tensor-core candidate list (64)".format(knn))
         eps_rel = eps_rel_tc(d)

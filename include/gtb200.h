@@ -62,6 +62,9 @@ int gtb_knn_radius_simt(const float* QT, const float* qn2, const float* lim2, in
  * topk: cand_idx / cand_val are [nq_pad][128] scratch+output, the first 64 slots of each row hold the
  * result (-1 = empty); tau[nq] as for the SIMT variant.  radius: same contract as gtb_knn_radius_simt. */
 int gtb_tc_max_kp(void);
+/* thread-block cluster size of the search kernel: 1, 2 (default) or 4 CTAs share each reference tile
+ * through TMA multicast */
+int gtb_tc_set_cluster(int cl);
 int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const float* mean, int role, float* hi, float* lo,
                            int64_t n_pad, int Kp, float* norm2, float* maxnorm, void* stream);
 int gtb_knn_topk_tc(const float* q_hi, const float* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
