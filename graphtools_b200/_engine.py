@@ -32,7 +32,7 @@ _SIGS = {
     "gtb_knn_topk_tc": ([_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, _P, _P, _P, _P], 1),
     "gtb_knn_radius_tc": ([_P, _P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, _P, c_int64, _P, _P,
                            _P], 1),
-    "gtb_refine_topk": ([_P, c_int64, _P, c_int, _P, c_int, c_int, _P, _P, c_float, c_double, c_int, c_int64, c_double,
+    "gtb_refine_topk": ([_P, c_int64, _P, c_int, _P, c_int, c_int, _P, c_int, _P, c_float, c_double, c_int, c_int64, c_double,
                          c_double, _P, c_int, c_double, _P, _P, _P, _P, _P, _P, _P, _P], 1),
     "gtb_compact_todo": ([_P, c_int64, _P, _P, _P], 1),
     "gtb_scatter_pairs": ([_P, c_int64, _P, _P, c_int64, _P, _P], 1),
@@ -63,6 +63,7 @@ _PLAIN = {
     "gtb_scan_ws_elems": ([c_int64], c_int64),
     "gtb_tc_max_kp": ([], c_int),
     "gtb_tc_set_cluster": ([c_int], c_int),
+    "gtb_tc_scratch_bytes": ([c_int64], c_int64),
 }
 
 

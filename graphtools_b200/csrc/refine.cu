@@ -87,7 +87,7 @@ constexpr int R1_CAP = 128;  // max candidates per row handled by the warp kerne
 
 struct Refine1Params {
   RowParams rp;
-  int64_t nq; int S; int cand_stride;
+  int64_t nq; int S; int cand_stride; int ntau;
   const int32_t* cand_idx; const float* tau; const float* qn2; float maxrn2; double eps_rel;
   int32_t* st_idx; double* st_val; int32_t* n_keep; double* bw_out; float* lim2_out;
   int32_t* status; int32_t* nzero;
@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Param
   for (int off = 16; off > 0; off >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, off);
 
   // 4. bandwidth + certification
-  const float tau = p.tau[row];
+  float tau = p.tau[row * p.ntau];
+  for (int t = 1; t < p.ntau; ++t) tau = fminf(tau, p.tau[row * p.ntau + t]);  // lists of disjoint reference subsets
   const bool all_found = isinf(tau);  // list never filled: every reference is a candidate
   const double E = p.eps_rel * ((double)p.qn2[row] + (double)p.maxrn2);
   const double rho2 = (double)tau - E;  // exact d2 of every non-candidate is >= rho2
@@ -326,7 +327,7 @@ RowParams make_row_params(const float* Xq, const float* Xr, int d, int knn, int6
 }  // namespace
 
 extern "C" int gtb_refine_topk(const float* Xq, int64_t nq, const float* Xr, int d, const int32_t* cand_idx,
-                               int S, int cand_stride, const float* tau, const float* qn2, float maxrn2, double eps_rel,
+                               int S, int cand_stride, const float* tau, int ntau, const float* qn2, float maxrn2, double eps_rel,
                                int knn, int64_t kmax, double decay, double thresh, const double* bw_fixed,
                                int bw_mode, double bw_scale, int32_t* st_idx, double* st_val, int32_t* n_keep,
                                double* bw_out, float* lim2_out, int32_t* status, int32_t* nzero, void* stream) {
@@ -336,7 +337,7 @@ extern "C" int gtb_refine_topk(const float* Xq, int64_t nq, const float* Xr, int
   Refine1Params p;
   p.rp = make_row_params(Xq, Xr, d, knn, kmax, decay, thresh, bw_fixed, bw_mode, bw_scale);
   GTB_CHECK_ARG(cand_stride >= S, "cand_stride must be >= S");
-  p.nq = nq; p.S = S; p.cand_stride = cand_stride; p.cand_idx = cand_idx; p.tau = tau; p.qn2 = qn2; p.maxrn2 = maxrn2; p.eps_rel = eps_rel;
+  p.nq = nq; p.S = S; p.cand_stride = cand_stride; p.ntau = ntau < 1 ? 1 : ntau; p.cand_idx = cand_idx; p.tau = tau; p.qn2 = qn2; p.maxrn2 = maxrn2; p.eps_rel = eps_rel;
   p.st_idx = st_idx; p.st_val = st_val; p.n_keep = n_keep; p.bw_out = bw_out; p.lim2_out = lim2_out;
   p.status = status; p.nzero = nzero;
   refine_topk_kernel<<<(unsigned)gtb_cdiv(nq, R1_WARPS), R1_WARPS * 32, 0, (cudaStream_t)stream>>>(p);

@@ -30,7 +30,7 @@
 
 namespace {
 
-constexpr int TC_M = 128, TC_N = 128, TC_STAGES = 2, TC_CAP = 128, TC_S = 64, TC_THREADS = 192;
+constexpr int TC_M = 128, TC_N = 128, TC_STAGES = 2, TC_CAP = 96, TC_S = 32, TC_GROUPS = 2, TC_THREADS = 64 + 128 * TC_GROUPS;
 constexpr float TC_BIG = 1e29f;       // "no threshold yet"; padded reference rows carry |y|^2 = 1e30
 constexpr float TC_PAD_NORM = 1e30f;
 
@@ -104,6 +104,26 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// wait for all outstanding tcgen05.ld of this thread; the "+r" operands pin every loaded register behind it
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&a)[32], uint32_t (&b)[32], uint32_t (&c)[32], uint32_t (&d)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    asm volatile("" : "+r"(a[i]), "+r"(b[i]), "+r"(c[i]), "+r"(d[i]));
+  }
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -136,7 +156,7 @@ struct TcParams {
   int64_t nq, nq_pad, nr, nr_pad;
   int Kp;
   const float* qn2;
-  int32_t* cand_idx; float* cand_val; float* tau;          // TOPK
+  int32_t* cand_idx; uint2* cand_buf; float* tau;          // TOPK: out [nq][2*TC_S], scratch [nq_pad][2][TC_CAP], tau [nq][2]
   const float* lim2; int2* pairs; unsigned long long capacity; unsigned long long* counter; int32_t* rowcnt;
 };
 
@@ -177,27 +197,21 @@ __device__ __forceinline__ void warp_bitonic128(float (&val)[4], int32_t (&idx)[
   }
 }
 
-// Compact the candidate buffer of row `grow` (owned by lane `owner`): keep the TC_S smallest.
-// Returns the TC_S-th smallest value (new threshold), uniform across the warp.
-__device__ __forceinline__ float compact_row(int32_t* cand_idx, float* cand_val, int64_t grow, int cnt, int lane) {
+// Compact one candidate buffer (TC_CAP (value, index) pairs owned by one thread): keep the TC_S smallest.
+// Returns the TC_S-th smallest value (the new threshold), uniform across the warp.
+__device__ __noinline__ float compact_row(uint2* buf, int cnt, int lane) {
   float val[4];
   int32_t idx[4];
-  float* rv = cand_val + grow * TC_CAP;
-  int32_t* ri = cand_idx + grow * TC_CAP;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int e = i * 32 + lane;
-    if (e < cnt) { val[i] = rv[e]; idx[i] = ri[e]; }
+    if (e < cnt) { uint2 t = buf[e]; val[i] = __uint_as_float(t.x); idx[i] = (int32_t)t.y; }
     else { val[i] = gtb_inf_f(); idx[i] = 0x7fffffff; }
   }
   warp_bitonic128(val, idx, lane);
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int e = i * 32 + lane;
-    rv[e] = val[i];
-    ri[e] = idx[i];
-  }
-  return __shfl_sync(0xffffffffu, val[1], 31);  // element 63
+  static_assert(TC_S == 32, "compact_row writes exactly one element per lane");
+  buf[lane] = make_uint2(__float_as_uint(val[0]), (uint32_t)idx[0]);
+  return __shfl_sync(0xffffffffu, val[0], 31);  // element TC_S - 1
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -356,14 +370,19 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     }
   } else {
     // ===================== epilogue warps =====================
+    // Two groups of four warps: group g owns accumulator g, i.e. the reference tiles with tile % 2 == g,
+    // and keeps its own per-row threshold and candidate buffer (no state shared between groups; two
+    // epilogue warps per SM sub-partition hide each other's latencies).  The refine stage merges the two
+    // lists; every non-candidate of group g has approximate d2 >= tau[row][g].
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int grp = (warp - 2) >> 2;                 // 0 or 1
     const int row = quad * 32 + lane;
     const int64_t gq = q0 + row;
     const bool valid = gq < p.nq;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
 
-    // ---- stage the query tile into TMEM: thread == row, one column per K element
-    {
+    if (grp == 0) {
+      // ---- stage the query tile into TMEM: thread == row, one column per K element
       const bool in_pad = gq < p.nq_pad;             // cluster padding CTAs carry all-zero query rows
       const float4* rh = reinterpret_cast<const float4*>(q_hi + (in_pad ? gq : 0) * Kp);
       const float4* rl = reinterpret_cast<const float4*>(q_lo + (in_pad ? gq : 0) * Kp);
@@ -383,35 +402,44 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     if (MODE == 0) thr = valid ? TC_BIG : -gtb_inf_f();
     else thr = valid ? (p.lim2[gq] - nx) : -gtb_inf_f();
     int cnt = 0;
-    float* my_val = (MODE == 0 && valid) ? p.cand_val + gq * TC_CAP : nullptr;
-    int32_t* my_idx = (MODE == 0 && valid) ? p.cand_idx + gq * TC_CAP : nullptr;
+    // this thread's candidate buffer: uniform base + per-thread offset (rows past nq never append)
+    const int64_t boff = valid ? (gq * TC_GROUPS + grp) * TC_CAP : 0;
+    uint2* wbuf = p.cand_buf + (q0 + quad * 32) * TC_GROUPS * TC_CAP;   // warp-uniform: first row of this quadrant
 
-    for (int64_t tile = 0; tile < ntiles; ++tile) {
-      const int s = (int)(tile % TC_STAGES);
+    for (int64_t tile = grp; tile < ntiles; tile += TC_GROUPS) {
+      const int s = grp;                               // accumulator / smem stage of this tile
       const uint32_t ph = (uint32_t)((tile / TC_STAGES) & 1);
       mbar_wait(tm_full + 8 * s, ph);
       tc_fence_after();
-#pragma unroll 1
+      // drain the whole accumulator into registers, hand it back to the MMA warp, THEN select: the
+      // accumulator is held for four back-to-back tcgen05.ld only, never across the selection work
+      uint32_t r0[32], r1[32], r2[32], r3[32];
+      __syncwarp();
+      const uint32_t acc_addr = lane_addr + (uint32_t)(TC_ACC0 + s * TC_N);
+      tmem_ld32_nowait(acc_addr, r0);
+      tmem_ld32_nowait(acc_addr + 32, r1);
+      tmem_ld32_nowait(acc_addr + 64, r2);
+      tmem_ld32_nowait(acc_addr + 96, r3);
+      tmem_wait_ld(r0, r1, r2, r3);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tm_empty + 8 * s);
+#pragma unroll
       for (int part = 0; part < TC_N / 32; ++part) {
         float v[32];
-        __syncwarp();
-        tmem_ld32(lane_addr + (uint32_t)(TC_ACC0 + s * TC_N + part * 32), v);
-        if (part == TC_N / 32 - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tm_empty + 8 * s);
-        }
-        const int32_t col0 = (int32_t)(tile * TC_N) + part * 32;
-        bool any = false;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) any |= (MODE == 0) ? (v[j] < thr) : (v[j] <= thr);
+        for (int j = 0; j < 32; ++j)
+          v[j] = __uint_as_float(part == 0 ? r0[j] : part == 1 ? r1[j] : part == 2 ? r2[j] : r3[j]);
+        const int32_t col0 = (int32_t)(tile * TC_N) + part * 32;
+        float vmin = v[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) vmin = fminf(vmin, v[j]);
         if (MODE == 0) {
-          if (any) {
+          if (vmin < thr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (v[j] < thr) {
-                my_val[cnt] = v[j];
-                my_idx[cnt] = col0 + j;
+                p.cand_buf[boff + cnt] = make_uint2(__float_as_uint(v[j]), (uint32_t)(col0 + j));
                 ++cnt;
               }
             }
@@ -422,14 +450,13 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
             const int owner = __ffs(need) - 1;
             need &= need - 1;
             const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
-            const int64_t orow = q0 + quad * 32 + owner;
             __syncwarp();
-            const float nt = compact_row(p.cand_idx, p.cand_val, orow, ocnt, lane);
+            const float nt = compact_row(wbuf + (owner * TC_GROUPS + grp) * TC_CAP, ocnt, lane);
             __syncwarp();
             if (lane == owner) { thr = nt; cnt = TC_S; }
           }
         } else {
-          if (any) {
+          if (vmin <= thr) {
             int c = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) c += (v[j] <= thr);
@@ -448,21 +475,22 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     }
 
     if (MODE == 0) {
-      // final compaction of every row still holding more than TC_S candidates
+      // final compaction of every buffer still holding more than TC_S candidates
       unsigned need = __ballot_sync(0xffffffffu, cnt > TC_S);
       while (need) {
         const int owner = __ffs(need) - 1;
         need &= need - 1;
         const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
-        const int64_t orow = q0 + quad * 32 + owner;
         __syncwarp();
-        const float nt = compact_row(p.cand_idx, p.cand_val, orow, ocnt, lane);
+        const float nt = compact_row(wbuf + (owner * TC_GROUPS + grp) * TC_CAP, ocnt, lane);
         __syncwarp();
         if (lane == owner) { thr = nt; cnt = TC_S; }
       }
+      __syncwarp();
       if (valid) {
-        for (int e = cnt; e < TC_S; ++e) my_idx[e] = -1;
-        p.tau[gq] = (cnt < TC_S || thr >= TC_BIG) ? gtb_inf_f() : thr + nx;
+        int32_t* out = p.cand_idx + gq * (TC_GROUPS * TC_S) + grp * TC_S;
+        for (int e = 0; e < TC_S; ++e) out[e] = (e < cnt) ? (int32_t)p.cand_buf[boff + e].y : -1;
+        p.tau[gq * TC_GROUPS + grp] = (cnt < TC_S || thr >= TC_BIG) ? gtb_inf_f() : thr + nx;
       }
     }
   }
@@ -630,15 +658,17 @@ extern "C" int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const fl
   return GTB_OK;
 }
 
+extern "C" int64_t gtb_tc_scratch_bytes(int64_t nq_pad) { return nq_pad * TC_GROUPS * TC_CAP * (int64_t)sizeof(uint2); }
+
 extern "C" int gtb_knn_topk_tc(const float* q_hi, const float* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
                                const float* r_hi, const float* r_lo, int64_t nr, int64_t nr_pad, int Kp,
-                               int32_t* cand_idx, float* cand_val, float* tau, void* stream) {
+                               int32_t* cand_idx, void* scratch, float* tau, void* stream) {
   GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TC_M == 0 && nr_pad % TC_N == 0, "bad shape (pads must be x128)");
   GTB_CHECK_ARG(Kp % 8 == 0 && Kp >= 8 && Kp <= 104, "Kp must be a multiple of 8, <= 104");
   GTB_CHECK_ARG(nr_pad < (1ll << 31) && nq_pad < (1ll << 31), "too many rows for 32-bit TMA coordinates");
   TcParams p{};
   p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.Kp = Kp; p.qn2 = qn2;
-  p.cand_idx = cand_idx; p.cand_val = cand_val; p.tau = tau;
+  p.cand_idx = cand_idx; p.cand_buf = reinterpret_cast<uint2*>(scratch); p.tau = tau;
   return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, p, (cudaStream_t)stream);
 }
 

@@ -205,30 +205,33 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
     if impl is None:
         impl = default_impl()
     if impl == "auto":
-        impl = "tc" if (ref.tc_ok() and knn + 8 <= 64 and S in (None, 64)) else "simt"
+        impl = "tc" if (ref.tc_ok() and knn + 8 <= 32 and S in (None, 64)) else "simt"
     dev = _dev()
-    tau = _empty((nq,), torch.float32)
+    ntau = 1
     if impl == "tc":
         if not ref.tc_ok():
             raise ValueError("tensor-core search needs d + 1 <= {}".format(E.lib().gtb_tc_max_kp()))
-        S, stride = 64, 128
+        S, stride, ntau = 64, 64, 2
         if E.lib().gtb_tc_set_cluster(tc_cluster()) != 0:
             raise ValueError("GTB_TC_CLUSTER must be 1, 2 or 4")
-        if knn > S:
-            raise NotImplementedError("knn={} exceeds the tensor-core candidate list (64)".format(knn))
+        if knn > 32:
+            raise NotImplementedError("knn={} exceeds the tensor-core candidate lists (2 x 32)".format(knn))
         eps_rel = eps_rel_tc(d)
         q_hi, q_lo, q_n2 = qry.tc(0)
         r_hi, r_lo, _ = ref.tc(1)
-        cand = _empty((qry.n_pad, stride), torch.int32)
-        cand_val = _empty((qry.n_pad, stride), torch.float32)
+        cand = _empty((nq, stride), torch.int32)
+        tau = _empty((nq, ntau), torch.float32)
+        scratch = _empty((E.lib().gtb_tc_scratch_bytes(qry.n_pad),), torch.uint8)
         E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, nq, qry.n_pad, r_hi, r_lo, nr, ref.n_pad, ref.Kp, cand,
-               cand_val, tau)
+               scratch, tau)
+        del scratch
     elif impl == "simt":
         if S is None:
             S = choose_S(knn, binary)
         stride = S
         eps_rel = eps_rel_simt(d)
         q_n2 = qry.n2
+        tau = _empty((nq,), torch.float32)
         cand = _empty((nq, S), torch.int32)
         E.call("gtb_knn_topk_simt", qry.XT, qry.n2, nq, qry.n_pad, ref.XT, ref.n2, nr, ref.n_pad, ref.d_pad, S,
                cand, tau)
@@ -256,7 +259,7 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
     lim2 = _empty((nq,), torch.float32)
     status = _empty((nq,), torch.int32)
     nzero = _empty((nq,), torch.int32)
-    E.call("gtb_refine_topk", qry.X, nq, ref.X, d, cand, S, stride, tau, q_n2, ref.maxnorm, eps_rel, knn, kmax, decay_f,
+    E.call("gtb_refine_topk", qry.X, nq, ref.X, d, cand, S, stride, tau, ntau, q_n2, ref.maxnorm, eps_rel, knn, kmax, decay_f,
            thresh_f, bw_fixed, bw_mode, float(bandwidth_scale), st_idx, st_val, n_keep, bw_out, lim2, status, nzero)
 
     todo_rows = _empty((nq,), torch.int32)

@@ -59,8 +59,8 @@ int gtb_knn_radius_simt(const float* QT, const float* qn2, const float* lim2, in
 /* Tensor-core variant (tcgen05.mma kind::tf32, 3xTF32 split, TMA-fed, TMEM accumulators).  Operands are
  * row-major [n_pad][Kp] float32 hi/lo pairs built by gtb_prepare_operand_tc: role 0 (query)
  * = [x~, 1, 0..], role 1 (reference) = [-2y~, |y~|^2, 0..]; Kp = roundup(d+1, 8) <= gtb_tc_max_kp().
- * topk: cand_idx / cand_val are [nq_pad][128] scratch+output, the first 64 slots of each row hold the
- * result (-1 = empty); tau[nq] as for the SIMT variant.  radius: same contract as gtb_knn_radius_simt. */
+ * topk: cand_idx[nq][64] = two lists of 32 (even / odd reference tiles, -1 = empty) with their thresholds
+ * tau[nq][2]; scratch = gtb_tc_scratch_bytes(nq_pad) bytes.  radius: same contract as gtb_knn_radius_simt. */
 int gtb_tc_max_kp(void);
 /* thread-block cluster size of the search kernel: 1, 2 (default) or 4 CTAs share each reference tile
  * through TMA multicast */
@@ -69,7 +69,8 @@ int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const float* mean, 
                            int64_t n_pad, int Kp, float* norm2, float* maxnorm, void* stream);
 int gtb_knn_topk_tc(const float* q_hi, const float* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
                     const float* r_hi, const float* r_lo, int64_t nr, int64_t nr_pad, int Kp, int32_t* cand_idx,
-                    float* cand_val, float* tau, void* stream);
+                    void* scratch, float* tau, void* stream);
+int64_t gtb_tc_scratch_bytes(int64_t nq_pad);
 int gtb_knn_radius_tc(const float* q_hi, const float* q_lo, const float* qn2, const float* lim2, int64_t nq,
                       int64_t nq_pad, const float* r_hi, const float* r_lo, int64_t nr, int64_t nr_pad, int Kp,
                       int32_t* pairs, int64_t capacity, unsigned long long* counter, int32_t* rowcnt,
@@ -79,10 +80,11 @@ int gtb_knn_radius_tc(const float* q_hi, const float* q_lo, const float* qn2, co
  * and _build_csr_from_neighbors (graphs.py:450-559) ------------------------------------------ */
 /* decay < 0 means binary kNN (decay=None); kmax <= 0 means knn_max=None;
  * bw_mode 0: bandwidth = distance to the knn-th candidate (graphs.py:892), 1: scalar bw_fixed[0],
- * 2: per-row bw_fixed[nq].  cand_idx rows are cand_stride apart (first S entries used).  status: 1 done, 0 needs radius pass, 2 needs radius pass and its
+ * 2: per-row bw_fixed[nq].  cand_idx rows are cand_stride apart (first S entries used); tau holds ntau
+ * thresholds per row (lists built over disjoint reference subsets), the row's bound is their minimum.  status: 1 done, 0 needs radius pass, 2 needs radius pass and its
  * bandwidth is not yet certified.  st_idx/st_val[nq][S]: kept entries sorted by column. */
 int gtb_refine_topk(const float* Xq, int64_t nq, const float* Xr, int d, const int32_t* cand_idx, int S,
-                    int cand_stride, const float* tau, const float* qn2, float maxrn2, double eps_rel, int knn, int64_t kmax,
+                    int cand_stride, const float* tau, int ntau, const float* qn2, float maxrn2, double eps_rel, int knn, int64_t kmax,
                     double decay, double thresh, const double* bw_fixed, int bw_mode, double bw_scale,
                     int32_t* st_idx, double* st_val, int32_t* n_keep, double* bw_out, float* lim2_out,
                     int32_t* status, int32_t* nzero, void* stream);

@@ -101,12 +101,13 @@ def _tc_topk(X, Y=None):
     qry = ref if Y is None else pipeline.SearchOperand(_dev(Y), mean=ref.mean)
     q_hi, q_lo, q_n2 = qry.tc(0)
     r_hi, r_lo, _ = ref.tc(1)
-    cand = torch.full((qry.n_pad, 128), -7, dtype=torch.int32, device="cuda")
-    val = torch.zeros((qry.n_pad, 128), dtype=torch.float32, device="cuda")
-    tau = torch.empty((qry.n,), dtype=torch.float32, device="cuda")
-    E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, qry.n, qry.n_pad, r_hi, r_lo, ref.n, ref.n_pad, ref.Kp, cand, val, tau)
+    cand = torch.full((qry.n, 64), -7, dtype=torch.int32, device="cuda")
+    scratch = torch.zeros((E.lib().gtb_tc_scratch_bytes(qry.n_pad),), dtype=torch.uint8, device="cuda")
+    tau = torch.empty((qry.n, 2), dtype=torch.float32, device="cuda")
+    E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, qry.n, qry.n_pad, r_hi, r_lo, ref.n, ref.n_pad, ref.Kp, cand,
+           scratch, tau)
     torch.cuda.synchronize()
-    return cand.cpu().numpy()[:qry.n, :64], val.cpu().numpy()[:qry.n, :64], tau.cpu().numpy(), qry, ref
+    return cand.cpu().numpy(), tau.cpu().numpy().min(axis=1), qry, ref
 
 
 def test_tc_operand_split():
@@ -130,28 +131,31 @@ def test_tc_operand_split():
                                  (1000, 55), (777, 103)])
 def test_tc_topk_candidates(n, d):
     X, _ = synth.gaussian_mixture(n, d, n_clusters=5, intrinsic_dim=min(8, d), seed=3)
-    cand, val, tau, qry, ref = _tc_topk(X)
+    cand, tau, qry, ref = _tc_topk(X)
     X64 = X.astype(np.float64)
     D2 = ((X64[:, None, :] - X64[None, :, :]) ** 2).sum(-1)
     order = np.argsort(D2, axis=1, kind="stable")
     Xc = X64 - X64.mean(0)
     nrm = (Xc ** 2).sum(1)
     eps = pipeline.eps_rel_tc(d)
-    S = 64
+    # two lists of 32: references in even / odd 128-row tiles
+    tile_par = (np.arange(n) // 128) % 2
+    n_even, n_odd = int((tile_par == 0).sum()), int((tile_par == 1).sum())
     for i in range(0, n, max(1, n // 300)):
+        assert (cand[i] != -7).all(), "output slot never written"
         c = cand[i][cand[i] >= 0]
         assert (c < n).all(), "padded reference leaked into the candidates"
         assert len(np.unique(c)) == len(c), "duplicate candidate"
-        assert len(c) == min(S, n), (i, len(c))
-        assert set(order[i, :min(S - 8, n)]).issubset(set(c)), "row %d misses a true neighbour" % i
+        assert len(c) == min(32, n_even) + min(32, n_odd), (i, len(c))
+        assert (tile_par[cand[i][:32][cand[i][:32] >= 0]] == 0).all() and \
+            (tile_par[cand[i][32:][cand[i][32:] >= 0]] == 1).all()
+        assert set(order[i, :min(24, n)]).issubset(set(c)), "row %d misses a true neighbour" % i
         bound = eps * (nrm[i] + nrm.max())
-        if n > S:
-            non = np.setdiff1d(np.arange(n), c)
+        non = np.setdiff1d(np.arange(n), c)
+        if len(non):
+            assert np.isfinite(tau[i])
             assert D2[i, non].min() >= tau[i] - bound
-            # stored approximate values: v' + |x|^2 ~ exact d2
-            approx = val[i][: len(c)] + nrm[i]
-            assert np.abs(approx - D2[i, cand[i][: len(c)]]).max() <= bound
-        else:
+        if n_even <= 32 and n_odd <= 32:
             assert np.isinf(tau[i])
 
 
@@ -159,11 +163,11 @@ def test_tc_topk_out_of_sample():
     X, _ = synth.gaussian_mixture(5000, 100, n_clusters=6, intrinsic_dim=10, seed=5)
     Y, _ = synth.gaussian_mixture(333, 100, n_clusters=6, intrinsic_dim=10, seed=5)
     Y = Y + np.float32(0.01)
-    cand, val, tau, qry, ref = _tc_topk(X, Y)
+    cand, tau, qry, ref = _tc_topk(X, Y)
     D2 = ((Y.astype(np.float64)[:, None, :] - X.astype(np.float64)[None, :, :]) ** 2).sum(-1)
     order = np.argsort(D2, axis=1, kind="stable")
     for i in range(333):
-        assert set(order[i, :56]).issubset(set(cand[i]))
+        assert set(order[i, :24]).issubset(set(cand[i]))
 
 
 def test_tc_radius_pairs_complete():
