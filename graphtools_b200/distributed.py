@@ -11,6 +11,14 @@ import torch
 import torch.distributed as dist
 
 
+def active():
+    """True when the graph build should shard its query rows over the ranks of the default process
+    group (one process per GPU launched by torchrun; set GTB_DISTRIBUTED=0 to opt out)."""
+    import os
+    return (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            and os.environ.get("GTB_DISTRIBUTED", "1") != "0")
+
+
 def shard_bounds(n, world, rank):
     """Contiguous row range [lo, hi) owned by ``rank``; multiples of 128 rows so query tiles stay full."""
     tiles = (n + 127) // 128

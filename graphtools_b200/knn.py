@@ -102,13 +102,41 @@ class kNNGraph(DataGraph):
         """Raw in-sample kernel: every sample queried against all samples with knn+1 neighbours
         (self included), graphs.py:771-785."""
         knn_max = self.knn_max + 1 if self.knn_max else None
+        from . import distributed as gd
         with _logger.log_task("KNN search"):
             ref = self.knn_tree
+            if gd.active() and np.ndim(self.bandwidth) == 0:
+                return self._build_kernel_sharded(ref, knn_max)
             R, info = self._kernel_device(ref, ref, knn=self.knn + 1, knn_max=knn_max,
                                           bandwidth=self.bandwidth, bandwidth_scale=self.bandwidth_scale)
         self._check_duplicates(info, ref, ref)
         self._dev_bandwidth = info["bandwidth"]
         return R
+
+    def _build_kernel_sharded(self, ref, knn_max):
+        """One process per GPU: this rank builds the kernel rows of its contiguous query shard against the
+        replicated reference set, then the raw CSR shards are all-gathered (NCCL) so that symmetrisation
+        and normalisation are local.  Every rank ends up with the complete, identical kernel."""
+        import torch
+        import torch.distributed as dist
+        from . import distributed as gd
+        world, rank = dist.get_world_size(), dist.get_rank()
+        n = ref.n
+        bounds = [gd.shard_bounds(n, world, r) for r in range(world)]
+        lo, hi = bounds[rank]
+        if hi > lo:
+            qry = pipeline.SearchOperand(ref.X[lo:hi], mean=ref.mean)
+            Rl, _ = self._kernel_device(qry, ref, knn=self.knn + 1, knn_max=knn_max, bandwidth=self.bandwidth,
+                                        bandwidth_scale=self.bandwidth_scale)
+            row_len = (Rl.indptr[1:] - Rl.indptr[:-1]).to(torch.int32)
+            idx, val = Rl.indices, Rl.data
+        else:
+            row_len = torch.zeros((0,), dtype=torch.int32, device=ref.X.device)
+            idx = torch.zeros((0,), dtype=torch.int32, device=ref.X.device)
+            val = torch.zeros((0,), dtype=torch.float64, device=ref.X.device)
+        indptr, idx, val = gd.allgather_csr_rows(row_len, idx, val, [b[1] - b[0] for b in bounds],
+                                                 pipeline.exclusive_scan)
+        return pipeline.DeviceCSR(indptr, idx, val, (n, n))
 
     def _kernel_device(self, qry, ref, knn, knn_max, bandwidth, bandwidth_scale):
         if self.decay is None or self.thresh == 1:
