@@ -17,6 +17,11 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:
+    # the CPU arm uses every host thread (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -60,6 +65,11 @@ def cpu_sample_rate(X, seconds, fixed_rows=None):
     job's per-point cost, so points/s = m / t.  Symmetrise + normalise (<1% of CPU time) are
     not in the sample."""
     from oracle import graph_oracle as go
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     X64 = X.astype(np.float64)
     g = go.KnnOracle(X64, knn=KNN, decay=DECAY, thresh=THRESH, n_jobs=-1)
     g.tree  # fit (brute force: keeps a pointer)
