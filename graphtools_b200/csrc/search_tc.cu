@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "gtb200.h"
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -154,7 +155,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
 
 struct TcParams {
   int64_t nq, nq_pad, nr, nr_pad;
-  int Kp;
+  int nks;                                                 // 32-byte k-steps per operand row
+  int64_t nrounds;
   const float* qn2;
   int32_t* cand_idx; uint2* cand_buf; float* tau;          // TOPK: out [nq][2*TC_S], scratch [nq_pad][2][TC_CAP], tau [nq][2]
   const float* lim2; int2* pairs; unsigned long long capacity; unsigned long long* counter; int32_t* rowcnt;
@@ -215,9 +217,9 @@ __device__ __noinline__ float compact_row(uint2* buf, int cnt, int lane) {
 }
 
 // ---------------------------------------------------------------- the kernel
-// TMEM column map (512 columns allocated): [0, Kp) A_hi, [TC_ALO, TC_ALO+Kp) A_lo,
+// TMEM column map (512 columns allocated): [0, 8*nks) A_hi, [8*nks, 16*nks) A_lo (nks <= 13),
 // [TC_ACC0 + s*TC_N, +TC_N) accumulator s.
-constexpr int TC_ALO = 104, TC_ACC0 = 256;
+constexpr int TC_ACC0 = 256;
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float4& a, const float4& b) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -240,33 +242,59 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
 // query tiles; each loads 1/CL of every B stage and TMA-multicasts it to all of them, so the L2 -> SM
 // traffic per output drops by CL.  A stage is recycled once every CTA's MMAs have retired (commit
 // multicast to all empty barriers).
-template <int MODE, int CL>  // MODE 0 = TOPK, 1 = RADIUS
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// BF16 = false: operands are tf32 hi/lo float32 pairs (3xTF32, kind::tf32, 8 elements per 32-byte k-step);
+// BF16 = true : operands are bfloat16 hi/lo pairs (bf16x3, kind::f16, 16 elements per k-step, twice the MMA rate;
+//               the split keeps 16 mantissa bits -- still only used to SELECT candidates).
+template <int MODE, int CL, bool BF16>  // MODE 0 = TOPK, 1 = RADIUS
 __global__ void __launch_bounds__(TC_THREADS, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBht,
                  const __grid_constant__ CUtensorMap mBl, const __grid_constant__ CUtensorMap mBlt,
-                 const float* __restrict__ q_hi, const float* __restrict__ q_lo, TcParams p) {
+                 const void* __restrict__ q_hi_v, const void* __restrict__ q_lo_v, TcParams p) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* gbase = smem_raw + (base - raw);
 
-  const int Kp = p.Kp;
-  const int nfull = Kp / 32, ntail = (Kp % 32) / 8, nks = Kp / 8;
-  const uint32_t sizeB = (uint32_t)TC_N * Kp * 4;            // one part (hi or lo) of one stage
+  constexpr int EPK = BF16 ? 16 : 8;                         // elements per 32-byte k-step
+  const int nks = p.nks;                                     // 32-byte k-steps per operand row
+  const int nfull = nks / 4, ntail = nks % 4;                // SWIZZLE_128B blocks (4 k-steps) + SWIZZLE_32B tail blocks
+  const int a_lo_col = nks * 8;                              // TMEM column of A_lo (A_hi at 0)
+  const uint32_t sizeB = (uint32_t)TC_N * nks * 32;          // one part (hi or lo) of one stage
+  const char* q_hi = reinterpret_cast<const char*>(q_hi_v);
+  const char* q_lo = reinterpret_cast<const char*>(q_lo_v);
   const uint32_t B0 = base;                                  // stage s, part q at B0 + (2*s+q)*sizeB
   const uint32_t bar0 = B0 + 2 * TC_STAGES * sizeB;
   const uint32_t bar_a = bar0, full_b = bar0 + 8, empty_b = bar0 + 24, tm_full = bar0 + 40, tm_empty = bar0 + 56;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (bar0 - base) + 72);
+  const uint32_t round_done = bar0 + 72;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (bar0 - base) + 96);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t q0 = (int64_t)blockIdx.x * TC_M;
   const int64_t ntiles = p.nr_pad / TC_N;
+  // Persistent CTAs: cluster c sweeps the whole reference set once per ROUND for the query tiles
+  // (c + round * n_clusters) * CL + rank.  All resident CTAs therefore stream the same reference tiles
+  // at the same time (one DRAM read per round instead of one per CTA), and odd rounds sweep backwards so
+  // the tail of the previous sweep is still in L2.
+  const int64_t n_clusters = gridDim.x / CL;
+  const int64_t cluster_id = blockIdx.x / CL;
+  const int64_t nrounds = p.nrounds;
+  auto q0_of = [&](int64_t round) { return ((cluster_id + round * n_clusters) * CL + (blockIdx.x % CL)) * TC_M; };
+  auto btile = [&](int64_t round, int64_t t) { return (round & 1) ? (ntiles - 1 - t) : t; };
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
   constexpr int ROWS = TC_N / CL;                            // rows of each B block this CTA loads
 
   if (threadIdx.x == 0) {
     mbar_init(bar_a, 4);
+    mbar_init(round_done, 1);
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(full_b + 8 * s, 1);
       mbar_init(empty_b + 8 * s, CL);
@@ -290,25 +318,28 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int64_t tile = 0; tile < ntiles; ++tile) {
-        const int s = (int)(tile % TC_STAGES);
-        const uint32_t ph = (uint32_t)((tile / TC_STAGES) & 1);
-        mbar_wait(empty_b + 8 * s, ph ^ 1);      // every CTA of the cluster has consumed this stage
-        mbar_arrive_expect_tx(full_b + 8 * s, 2 * sizeB);
-        const int row0 = (int)(tile * TC_N) + (int)crank * ROWS;
-        for (int part = 0; part < 2; ++part) {
-          const CUtensorMap* mm = part ? &mBl : &mBh;
-          const CUtensorMap* mt = part ? &mBlt : &mBht;
-          const uint32_t dst = B0 + (2 * s + part) * sizeB;
-          for (int b = 0; b < nfull; ++b) {
-            const uint32_t d = dst + b * (TC_N * 128) + crank * (ROWS * 128);
-            if (CL > 1) tma_load_2d_mc(d, mm, full_b + 8 * s, b * 32, row0, cmask);
-            else tma_load_2d(d, mm, full_b + 8 * s, b * 32, row0);
-          }
-          for (int t = 0; t < ntail; ++t) {
-            const uint32_t d = dst + nfull * (TC_N * 128) + t * (TC_N * 32) + crank * (ROWS * 32);
-            if (CL > 1) tma_load_2d_mc(d, mt, full_b + 8 * s, nfull * 32 + t * 8, row0, cmask);
-            else tma_load_2d(d, mt, full_b + 8 * s, nfull * 32 + t * 8, row0);
+      int64_t it = 0;                              // running stage counter across rounds
+      for (int64_t round = 0; round < nrounds; ++round) {
+        for (int64_t t = 0; t < ntiles; ++t, ++it) {
+          const int s = (int)(it % TC_STAGES);
+          const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+          mbar_wait(empty_b + 8 * s, ph ^ 1);      // every CTA of the cluster has consumed this stage
+          mbar_arrive_expect_tx(full_b + 8 * s, 2 * sizeB);
+          const int row0 = (int)(btile(round, t) * TC_N) + (int)crank * ROWS;
+          for (int part = 0; part < 2; ++part) {
+            const CUtensorMap* mm = part ? &mBl : &mBh;
+            const CUtensorMap* mt = part ? &mBlt : &mBht;
+            const uint32_t dst = B0 + (2 * s + part) * sizeB;
+            for (int b = 0; b < nfull; ++b) {
+              const uint32_t d = dst + b * (TC_N * 128) + crank * (ROWS * 128);
+              if (CL > 1) tma_load_2d_mc(d, mm, full_b + 8 * s, b * 4 * EPK, row0, cmask);
+              else tma_load_2d(d, mm, full_b + 8 * s, b * 4 * EPK, row0);
+            }
+            for (int t2 = 0; t2 < ntail; ++t2) {
+              const uint32_t d = dst + nfull * (TC_N * 128) + t2 * (TC_N * 32) + crank * (ROWS * 32);
+              if (CL > 1) tma_load_2d_mc(d, mt, full_b + 8 * s, (nfull * 4 + t2) * EPK, row0, cmask);
+              else tma_load_2d(d, mt, full_b + 8 * s, (nfull * 4 + t2) * EPK, row0);
+            }
           }
         }
       }
@@ -320,17 +351,20 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     // are predicated on the elected lane.  (Issuing from inside an `if (lane == 0)` region costs ~18
     // SASS instructions per MMA -- R2UR + an ELECT loop -- and left the tensor pipe 3/4 idle.)
     const bool leader = elect_one();
-    // instruction descriptor: D=f32, A=B=tf32, K-major, N=TC_N, M=128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
+    // instruction descriptor: D=f32, A=B=tf32 (2) or bf16 (1), K-major, N=TC_N, M=128
+    constexpr uint32_t fmt = BF16 ? 1u : 2u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                            ((uint32_t)(TC_M >> 4) << 24);
     const uint64_t bd_main0 = make_desc(B0, 1024, 2);                          // stage 0, hi part, block 0
     const uint64_t bd_tail0 = make_desc(B0 + nfull * (TC_N * 128), 256, 6);    // stage 0, hi part, first tail block
     const uint32_t part_off = sizeB >> 4, stage_off = (2 * sizeB) >> 4;         // in descriptor address units (16 B)
-    mbar_wait(bar_a, 0);                     // A rows stored to TMEM by the epilogue warps
+    int64_t it = 0;
+    for (int64_t round = 0; round < nrounds; ++round) {
+    mbar_wait(bar_a, (uint32_t)(round & 1));   // this round's A rows stored to TMEM by the epilogue warps
     tc_fence_after();
-    for (int64_t tile = 0; tile < ntiles; ++tile) {
-      const int s = (int)(tile % TC_STAGES);
-      const uint32_t ph = (uint32_t)((tile / TC_STAGES) & 1);
+    for (int64_t tile = 0; tile < ntiles; ++tile, ++it) {
+      const int s = (int)(it % TC_STAGES);
+      const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
       mbar_wait(tm_empty + 8 * s, ph ^ 1);   // accumulator index == stage index (both 2-deep)
       mbar_wait(full_b + 8 * s, ph);
       tc_fence_after();
@@ -338,14 +372,17 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
       uint32_t accum = 0;
 #pragma unroll 1
       for (int prod = 0; prod < 3; ++prod) {   // (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi)
-        uint32_t ac = tmem_base + (uint32_t)((prod == 2) ? TC_ALO : 0);
+        uint32_t ac = tmem_base + (uint32_t)((prod == 2) ? a_lo_col : 0);
         const uint64_t boff = (uint64_t)(s * stage_off + ((prod == 1) ? part_off : 0u));
         uint64_t bd = bd_main0 + boff;
 #pragma unroll 1
         for (int blk = 0; blk < nfull; ++blk) {
 #pragma unroll
           for (int sub = 0; sub < 4; ++sub) {
-            if (leader) tc_mma_tf32_ts(d_tmem, ac + sub * 8, bd + sub * 2, idesc, accum);
+            if (leader) {
+              if (BF16) tc_mma_bf16_ts(d_tmem, ac + sub * 8, bd + sub * 2, idesc, accum);
+              else tc_mma_tf32_ts(d_tmem, ac + sub * 8, bd + sub * 2, idesc, accum);
+            }
             accum = 1;
           }
           bd += (TC_N * 128) >> 4;
@@ -354,7 +391,10 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         bd = bd_tail0 + boff;
 #pragma unroll 1
         for (int t = 0; t < ntail; ++t) {
-          if (leader) tc_mma_tf32_ts(d_tmem, ac, bd, idesc, accum);
+          if (leader) {
+            if (BF16) tc_mma_bf16_ts(d_tmem, ac, bd, idesc, accum);
+            else tc_mma_tf32_ts(d_tmem, ac, bd, idesc, accum);
+          }
           accum = 1;
           bd += (TC_N * 32) >> 4;
           ac += 8;
@@ -368,6 +408,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
       }
       __syncwarp();
     }
+    if (leader) tc_commit(round_done);       // every MMA that reads this round's A has retired
+    __syncwarp();
+    }
   } else {
     // ===================== epilogue warps =====================
     // Two groups of four warps: group g owns accumulator g, i.e. the reference tiles with tile % 2 == g,
@@ -377,19 +420,22 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     const int grp = (warp - 2) >> 2;                 // 0 or 1
     const int row = quad * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    for (int64_t round = 0; round < nrounds; ++round) {
+    const int64_t q0 = q0_of(round);
     const int64_t gq = q0 + row;
     const bool valid = gq < p.nq;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
 
     if (grp == 0) {
+      if (round > 0) { mbar_wait(round_done, (uint32_t)((round - 1) & 1)); tc_fence_after(); }
       // ---- stage the query tile into TMEM: thread == row, one column per K element
       const bool in_pad = gq < p.nq_pad;             // cluster padding CTAs carry all-zero query rows
-      const float4* rh = reinterpret_cast<const float4*>(q_hi + (in_pad ? gq : 0) * Kp);
-      const float4* rl = reinterpret_cast<const float4*>(q_lo + (in_pad ? gq : 0) * Kp);
+      const float4* rh = reinterpret_cast<const float4*>(q_hi + (in_pad ? gq : 0) * (int64_t)(nks * 32));
+      const float4* rl = reinterpret_cast<const float4*>(q_lo + (in_pad ? gq : 0) * (int64_t)(nks * 32));
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int ks = 0; ks < nks; ++ks) {
         tmem_st8(lane_addr + (uint32_t)(ks * 8), in_pad ? rh[2 * ks] : z4, in_pad ? rh[2 * ks + 1] : z4);
-        tmem_st8(lane_addr + (uint32_t)(TC_ALO + ks * 8), in_pad ? rl[2 * ks] : z4, in_pad ? rl[2 * ks + 1] : z4);
+        tmem_st8(lane_addr + (uint32_t)(a_lo_col + ks * 8), in_pad ? rl[2 * ks] : z4, in_pad ? rl[2 * ks + 1] : z4);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
@@ -406,9 +452,13 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     const int64_t boff = valid ? (gq * TC_GROUPS + grp) * TC_CAP : 0;
     uint2* wbuf = p.cand_buf + (q0 + quad * 32) * TC_GROUPS * TC_CAP;   // warp-uniform: first row of this quadrant
 
-    for (int64_t tile = grp; tile < ntiles; tile += TC_GROUPS) {
-      const int s = grp;                               // accumulator / smem stage of this tile
-      const uint32_t ph = (uint32_t)((tile / TC_STAGES) & 1);
+    // this group's tiles: running iteration index it = round * ntiles + t with it % 2 == grp
+    const int64_t it0 = round * ntiles;
+    for (int64_t t = (grp + (it0 & 1)) & 1; t < ntiles; t += TC_GROUPS) {
+      const int64_t it = it0 + t;
+      const int64_t tile = btile(round, t);
+      const int s = grp;                               // accumulator / smem stage of this iteration
+      const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
       mbar_wait(tm_full + 8 * s, ph);
       tc_fence_after();
       // drain the whole accumulator into registers, hand it back to the MMA warp, THEN select: the
@@ -493,6 +543,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         p.tau[gq * TC_GROUPS + grp] = (cnt < TC_S || thr >= TC_BIG) ? gtb_inf_f() : thr + nx;
       }
     }
+    }  // rounds
   }
 
   tc_fence_before();
@@ -556,6 +607,29 @@ __global__ void tc_split_kernel(const float* __restrict__ X, int64_t n, int d, c
   lo[e] = to_tf32(v - h);
 }
 
+__global__ void tc_split16_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ mean,
+                                  int role, const float* __restrict__ norm2, int64_t n_pad, int Kp,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_pad * Kp) return;
+  const int64_t r = e / Kp;
+  const int k = (int)(e - r * Kp);
+  float v = 0.f;
+  if (r < n) {
+    if (k < d) {
+      v = X[r * d + k] - (mean ? mean[k] : 0.f);
+      if (role == 1) v *= -2.f;
+    } else if (k == d) {
+      v = (role == 1) ? norm2[r] : 1.f;
+    }
+  } else if (role == 1 && k == d) {
+    v = TC_PAD_NORM;
+  }
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[e] = h;
+  lo[e] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -573,35 +647,42 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D map over a row-major [rows][Kp] float32 array; box = {box_k, box_rows}
-int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int Kp, int box_k, int box_rows, bool sw128) {
+// 2-D map over a row-major [rows][Kp] float32 / bfloat16 array; box = {box_k elements, box_rows}
+int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int Kp, int box_k, int box_rows, bool sw128, bool bf16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { gtb_set_error("cuTensorMapEncodeTiled entry point not available"); return GTB_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)Kp * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)Kp * (bf16 ? 2 : 4)};
   cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { gtb_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return GTB_ERR_CUDA; }
   return GTB_OK;
 }
 
-template <int MODE, int CL>
-int launch_tc_cl(const float* q_hi, const float* q_lo, const float* r_hi, const float* r_lo, TcParams& p,
+template <int MODE, int CL, bool BF16>
+int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, TcParams& p,
                  cudaStream_t st) {
   CUtensorMap mBh, mBht, mBl, mBlt;
   int rc;
-  const int Kp = p.Kp;
-  if ((rc = make_map(&mBh, r_hi, p.nr_pad, Kp, 32, TC_N / CL, true))) return rc;
-  if ((rc = make_map(&mBht, r_hi, p.nr_pad, Kp, 8, TC_N / CL, false))) return rc;
-  if ((rc = make_map(&mBl, r_lo, p.nr_pad, Kp, 32, TC_N / CL, true))) return rc;
-  if ((rc = make_map(&mBlt, r_lo, p.nr_pad, Kp, 8, TC_N / CL, false))) return rc;
-  size_t smem = 1024 + (size_t)2 * TC_STAGES * TC_N * Kp * 4 + 128 + 1024;
-  auto kern = search_tc_kernel<MODE, CL>;
+  constexpr int EPK = BF16 ? 16 : 8;
+  p.nks = Kp / EPK;
+  if ((rc = make_map(&mBh, r_hi, p.nr_pad, Kp, 4 * EPK, TC_N / CL, true, BF16))) return rc;
+  if ((rc = make_map(&mBht, r_hi, p.nr_pad, Kp, EPK, TC_N / CL, false, BF16))) return rc;
+  if ((rc = make_map(&mBl, r_lo, p.nr_pad, Kp, 4 * EPK, TC_N / CL, true, BF16))) return rc;
+  if ((rc = make_map(&mBlt, r_lo, p.nr_pad, Kp, EPK, TC_N / CL, false, BF16))) return rc;
+  size_t smem = 1024 + (size_t)2 * TC_STAGES * TC_N * p.nks * 32 + 128 + 1024;
+  auto kern = search_tc_kernel<MODE, CL, BF16>;
   GTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned nblk = (unsigned)(gtb_cdiv(p.nq_pad / TC_M, CL) * CL);
+  int dev = 0, nsm = 0;
+  GTB_CUDA(cudaGetDevice(&dev));
+  GTB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t n_cluster_tiles = gtb_cdiv(p.nq_pad / TC_M, CL);
+  const int64_t n_clusters = n_cluster_tiles < (nsm / CL) ? n_cluster_tiles : (nsm / CL);
+  p.nrounds = gtb_cdiv(n_cluster_tiles, n_clusters);
+  const unsigned nblk = (unsigned)(n_clusters * CL);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nblk);
   cfg.blockDim = dim3(TC_THREADS);
@@ -622,18 +703,26 @@ int launch_tc_cl(const float* q_hi, const float* q_lo, const float* r_hi, const 
 int g_tc_cluster = 2;
 
 template <int MODE>
-int launch_tc(const float* q_hi, const float* q_lo, const float* r_hi, const float* r_lo, TcParams& p,
+int launch_tc(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, bool bf16, TcParams& p,
               cudaStream_t st) {
+  if (bf16) {
+    switch (g_tc_cluster) {
+      case 1: return launch_tc_cl<MODE, 1, true>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+      case 2: return launch_tc_cl<MODE, 2, true>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+      default: gtb_set_error("cluster size must be 1 or 2 for the bf16 variant"); return GTB_ERR_ARG;
+    }
+  }
   switch (g_tc_cluster) {
-    case 1: return launch_tc_cl<MODE, 1>(q_hi, q_lo, r_hi, r_lo, p, st);
-    case 2: return launch_tc_cl<MODE, 2>(q_hi, q_lo, r_hi, r_lo, p, st);
-    case 4: return launch_tc_cl<MODE, 4>(q_hi, q_lo, r_hi, r_lo, p, st);
+    case 1: return launch_tc_cl<MODE, 1, false>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+    case 2: return launch_tc_cl<MODE, 2, false>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+    case 4: return launch_tc_cl<MODE, 4, false>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
     default: gtb_set_error("cluster size must be 1, 2 or 4"); return GTB_ERR_ARG;
   }
 }
 
 }  // namespace
 
+// largest operand row: 13 k-steps of 32 bytes = 104 tf32 or 208 bf16 elements (TMEM: 2 x 104 columns for A)
 extern "C" int gtb_tc_max_kp(void) { return 104; }
 
 // cluster size used by the tensor-core search (1, 2 or 4 CTAs sharing each reference tile via TMA multicast)
@@ -643,44 +732,59 @@ extern "C" int gtb_tc_set_cluster(int cl) {
   return GTB_OK;
 }
 
-extern "C" int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const float* mean, int role, float* hi,
-                                      float* lo, int64_t n_pad, int Kp, float* norm2, float* maxnorm,
+extern "C" int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const float* mean, int role, void* hi,
+                                      void* lo, int64_t n_pad, int Kp, int dtype, float* norm2, float* maxnorm,
                                       void* stream) {
   GTB_CHECK_ARG(n > 0 && d > 0 && n_pad >= n && n_pad % 128 == 0, "bad shape");
-  GTB_CHECK_ARG(Kp % 8 == 0 && Kp >= d + 1 && Kp <= 104, "Kp must be a multiple of 8 with d+1 <= Kp <= 104");
+  GTB_CHECK_ARG(dtype == 0 || dtype == 1, "dtype must be 0 (tf32 pairs in float32) or 1 (bfloat16 pairs)");
+  const int epk = dtype ? 16 : 8;
+  GTB_CHECK_ARG(Kp % epk == 0 && Kp >= d + 1 && Kp / epk <= 13, "Kp must be a multiple of 8 (tf32) / 16 (bf16), >= d+1, <= 13 k-steps");
   GTB_CHECK_ARG(role == 0 || role == 1, "role must be 0 (query) or 1 (reference)");
   cudaStream_t st = (cudaStream_t)stream;
   if (maxnorm) GTB_CUDA(cudaMemsetAsync(maxnorm, 0, sizeof(float), st));
   tc_norms_kernel<<<(unsigned)gtb_cdiv(n_pad * 32, 256), 256, 0, st>>>(X, n, d, mean, n_pad, norm2, maxnorm);
   GTB_CHECK_LAUNCH();
-  tc_split_kernel<<<(unsigned)gtb_cdiv(n_pad * Kp, 256), 256, 0, st>>>(X, n, d, mean, role, norm2, n_pad, Kp, hi, lo);
+  if (dtype == 0)
+    tc_split_kernel<<<(unsigned)gtb_cdiv(n_pad * Kp, 256), 256, 0, st>>>(X, n, d, mean, role, norm2, n_pad, Kp,
+                                                                        (float*)hi, (float*)lo);
+  else
+    tc_split16_kernel<<<(unsigned)gtb_cdiv(n_pad * Kp, 256), 256, 0, st>>>(X, n, d, mean, role, norm2, n_pad, Kp,
+                                                                          (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }
 
 extern "C" int64_t gtb_tc_scratch_bytes(int64_t nq_pad) { return nq_pad * TC_GROUPS * TC_CAP * (int64_t)sizeof(uint2); }
 
-extern "C" int gtb_knn_topk_tc(const float* q_hi, const float* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
-                               const float* r_hi, const float* r_lo, int64_t nr, int64_t nr_pad, int Kp,
-                               int32_t* cand_idx, void* scratch, float* tau, void* stream) {
+static int tc_check(int64_t nq, int64_t nr, int64_t nq_pad, int64_t nr_pad, int Kp, int dtype) {
   GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TC_M == 0 && nr_pad % TC_N == 0, "bad shape (pads must be x128)");
-  GTB_CHECK_ARG(Kp % 8 == 0 && Kp >= 8 && Kp <= 104, "Kp must be a multiple of 8, <= 104");
+  GTB_CHECK_ARG(dtype == 0 || dtype == 1, "dtype must be 0 (tf32) or 1 (bf16)");
+  const int epk = dtype ? 16 : 8;
+  GTB_CHECK_ARG(Kp % epk == 0 && Kp >= epk && Kp / epk <= 13, "Kp out of range");
   GTB_CHECK_ARG(nr_pad < (1ll << 31) && nq_pad < (1ll << 31), "too many rows for 32-bit TMA coordinates");
-  TcParams p{};
-  p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.Kp = Kp; p.qn2 = qn2;
-  p.cand_idx = cand_idx; p.cand_buf = reinterpret_cast<uint2*>(scratch); p.tau = tau;
-  return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, p, (cudaStream_t)stream);
+  return GTB_OK;
 }
 
-extern "C" int gtb_knn_radius_tc(const float* q_hi, const float* q_lo, const float* qn2, const float* lim2,
-                                 int64_t nq, int64_t nq_pad, const float* r_hi, const float* r_lo, int64_t nr,
-                                 int64_t nr_pad, int Kp, int32_t* pairs, int64_t capacity,
-                                 unsigned long long* counter, int32_t* rowcnt, void* stream) {
-  GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TC_M == 0 && nr_pad % TC_N == 0, "bad shape (pads must be x128)");
-  GTB_CHECK_ARG(Kp % 8 == 0 && Kp >= 8 && Kp <= 104, "Kp must be a multiple of 8, <= 104");
+extern "C" int gtb_knn_topk_tc(const void* q_hi, const void* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
+                               const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp, int dtype,
+                               int32_t* cand_idx, void* scratch, float* tau, void* stream) {
+  int rc = tc_check(nq, nr, nq_pad, nr_pad, Kp, dtype);
+  if (rc) return rc;
   TcParams p{};
-  p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.Kp = Kp; p.qn2 = qn2; p.lim2 = lim2;
+  p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.qn2 = qn2;
+  p.cand_idx = cand_idx; p.cand_buf = reinterpret_cast<uint2*>(scratch); p.tau = tau;
+  return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, Kp, dtype == 1, p, (cudaStream_t)stream);
+}
+
+extern "C" int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float* qn2, const float* lim2,
+                                 int64_t nq, int64_t nq_pad, const void* r_hi, const void* r_lo, int64_t nr,
+                                 int64_t nr_pad, int Kp, int dtype, int32_t* pairs, int64_t capacity,
+                                 unsigned long long* counter, int32_t* rowcnt, void* stream) {
+  int rc = tc_check(nq, nr, nq_pad, nr_pad, Kp, dtype);
+  if (rc) return rc;
+  TcParams p{};
+  p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.qn2 = qn2; p.lim2 = lim2;
   p.pairs = reinterpret_cast<int2*>(pairs); p.capacity = (unsigned long long)capacity; p.counter = counter;
   p.rowcnt = rowcnt;
-  return launch_tc<1>(q_hi, q_lo, r_hi, r_lo, p, (cudaStream_t)stream);
+  return launch_tc<1>(q_hi, q_lo, r_hi, r_lo, Kp, dtype == 1, p, (cudaStream_t)stream);
 }

@@ -14,6 +14,7 @@ import torch
 from . import _engine as E
 
 SYM_MODES = {"+": 0, "*": 1, "mnn": 2, None: 3}
+AUTO_TC = "tc"           # tensor-core flavour picked by impl="auto": "tc" (3xTF32) or "tc16" (bf16x3)
 BALL_CAP = 8192          # longest radius-pass row handled by refine_ball (shared-memory sort)
 _STATS = {}
 
@@ -83,29 +84,34 @@ class SearchOperand:
     def n2(self):
         return self.simt()[1]
 
-    # -- tensor-core operand: row-major [n_pad][Kp] tf32 hi/lo pair for one role (0 query, 1 reference)
+    # -- tensor-core operand: row-major [n_pad][Kp] hi/lo pair for one role (0 query, 1 reference);
+    #    dtype 0 = tf32 pairs stored as float32 (3xTF32), dtype 1 = bfloat16 pairs (bf16x3)
+    def kp(self, dtype=0):
+        step = 16 if dtype else 8
+        return (self.d + 1 + step - 1) // step * step
+
     @property
     def Kp(self):
-        return (self.d + 1 + 7) // 8 * 8
+        return self.kp(0)
 
-    def tc_ok(self):
-        return self.Kp <= E.lib().gtb_tc_max_kp()
+    def tc_ok(self, dtype=0):
+        return self.kp(dtype) // (16 if dtype else 8) <= 13
 
-    def tc(self, role):
-        if role not in self._tc:
-            hi = _empty((self.n_pad, self.Kp), torch.float32)
-            lo = _empty((self.n_pad, self.Kp), torch.float32)
+    def tc(self, role, dtype=0):
+        key = (role, dtype)
+        if key not in self._tc:
+            Kp = self.kp(dtype)
+            st = torch.bfloat16 if dtype else torch.float32
+            hi = _empty((self.n_pad, Kp), st)
+            lo = _empty((self.n_pad, Kp), st)
             n2 = _empty((self.n_pad,), torch.float32)
             mx = _empty((1,), torch.float32)
-            E.call("gtb_prepare_operand_tc", self.X, self.n, self.d, self.mean, role, hi, lo, self.n_pad, self.Kp,
-                   n2, mx)
-            self._tc[role] = (hi, lo, n2)
+            E.call("gtb_prepare_operand_tc", self.X, self.n, self.d, self.mean, role, hi, lo, self.n_pad, Kp,
+                   dtype, n2, mx)
+            self._tc[key] = (hi, lo, n2)
             if self._maxnorm is None:
                 self._maxnorm = mx
-        return self._tc[role]
-
-    def norms(self, impl):
-        return self.tc(0)[2] if impl == "tc" else self.n2
+        return self._tc[key]
 
     @property
     def maxnorm(self):
@@ -166,7 +172,8 @@ def tc_cluster():
 
 
 def default_impl():
-    """GTB_SEARCH_IMPL = tc | simt | auto (default auto: tensor cores whenever the operand fits)."""
+    """GTB_SEARCH_IMPL = tc (3xTF32 tensor cores) | tc16 (bf16x3 tensor cores) | simt (fp32 CUDA cores) |
+    auto (default: tensor cores whenever the operand fits)."""
     import os
     return os.environ.get("GTB_SEARCH_IMPL", "auto")
 
@@ -176,6 +183,12 @@ def eps_rel_tc(d):
     parts contribute 3 * 2^-22, float32 accumulation in the tensor core at most Kp * 2^-23 (truncation);
     doubled."""
     return 4.0 * (d + 16) * 2.0 ** -24
+
+
+def eps_rel_tc16(d):
+    """bf16x3 (hi*hi + hi*lo + lo*hi, 16 mantissa bits kept): dropped terms <= (2^-16 + 2^-18) |a||b| per
+    product, sum |a||b| <= 2 (|x~|^2 + max|y~|^2); float32 accumulation as for tf32."""
+    return 2.0 * (2.0 ** -16 + 2.0 ** -18) + 2.0 * (d + 32) * 2.0 ** -24
 
 
 def eps_rel_simt(d):
@@ -205,24 +218,26 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
     if impl is None:
         impl = default_impl()
     if impl == "auto":
-        impl = "tc" if (ref.tc_ok() and knn + 8 <= 32 and S in (None, 64)) else "simt"
+        impl = AUTO_TC if (ref.tc_ok(1 if AUTO_TC == "tc16" else 0) and knn + 8 <= 32 and S in (None, 64)) else "simt"
     dev = _dev()
     ntau = 1
-    if impl == "tc":
-        if not ref.tc_ok():
-            raise ValueError("tensor-core search needs d + 1 <= {}".format(E.lib().gtb_tc_max_kp()))
+    tcd = 1 if impl == "tc16" else 0
+    if impl in ("tc", "tc16"):
+        if not ref.tc_ok(tcd):
+            raise ValueError("tensor-core search: d = {} does not fit the resident query tile".format(d))
         S, stride, ntau = 64, 64, 2
-        if E.lib().gtb_tc_set_cluster(tc_cluster()) != 0:
+        if E.lib().gtb_tc_set_cluster(min(tc_cluster(), 2) if tcd else tc_cluster()) != 0:
             raise ValueError("GTB_TC_CLUSTER must be 1, 2 or 4")
         if knn > 32:
             raise NotImplementedError("knn={} exceeds the tensor-core candidate lists (2 x 32)".format(knn))
-        eps_rel = eps_rel_tc(d)
-        q_hi, q_lo, q_n2 = qry.tc(0)
-        r_hi, r_lo, _ = ref.tc(1)
+        eps_rel = eps_rel_tc16(d) if tcd else eps_rel_tc(d)
+        q_hi, q_lo, q_n2 = qry.tc(0, tcd)
+        r_hi, r_lo, _ = ref.tc(1, tcd)
+        Kp = ref.kp(tcd)
         cand = _empty((nq, stride), torch.int32)
         tau = _empty((nq, ntau), torch.float32)
         scratch = _empty((E.lib().gtb_tc_scratch_bytes(qry.n_pad),), torch.uint8)
-        E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, nq, qry.n_pad, r_hi, r_lo, nr, ref.n_pad, ref.Kp, cand,
+        E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, nq, qry.n_pad, r_hi, r_lo, nr, ref.n_pad, Kp, tcd, cand,
                scratch, tau)
         del scratch
     elif impl == "simt":
@@ -274,11 +289,11 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         nt_pad = (nt + 127) // 128 * 128
         lim_t = torch.zeros((nt_pad,), dtype=torch.float32, device=dev)
         lim_t[:nt] = lim2[todo_rows.long()]
-        if impl == "tc":
+        if impl in ("tc", "tc16"):
             # the radius rows form their own (small) query operand; build it from the gathered rows
             sub = SearchOperand(qry.X[todo_rows.long()].contiguous(), mean=ref.mean)
-            s_hi, s_lo, s_n2 = sub.tc(0)
-            r_hi, r_lo, _ = ref.tc(1)
+            s_hi, s_lo, s_n2 = sub.tc(0, tcd)
+            r_hi, r_lo, _ = ref.tc(1, tcd)
         else:
             QT = _empty((ref.d_pad, nt_pad), torch.float32)
             qn2 = _empty((nt_pad,), torch.float32)
@@ -288,8 +303,8 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
             pairs = _empty((capacity, 2), torch.int32)
             counter = _zeros((1,), torch.int64)
             rowcnt = _zeros((nt_pad,), torch.int32)
-            if impl == "tc":
-                E.call("gtb_knn_radius_tc", s_hi, s_lo, s_n2, lim_t, nt, nt_pad, r_hi, r_lo, nr, ref.n_pad, ref.Kp,
+            if impl in ("tc", "tc16"):
+                E.call("gtb_knn_radius_tc", s_hi, s_lo, s_n2, lim_t, nt, nt_pad, r_hi, r_lo, nr, ref.n_pad, Kp, tcd,
                        pairs, capacity, counter, rowcnt)
             else:
                 E.call("gtb_knn_radius_simt", QT, qn2, lim_t, nt, nt_pad, ref.XT, ref.n2, nr, ref.n_pad, ref.d_pad,

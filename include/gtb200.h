@@ -56,24 +56,26 @@ int gtb_knn_radius_simt(const float* QT, const float* qn2, const float* lim2, in
                         int32_t* pairs, int64_t capacity, unsigned long long* counter, int32_t* rowcnt,
                         void* stream);
 
-/* Tensor-core variant (tcgen05.mma kind::tf32, 3xTF32 split, TMA-fed, TMEM accumulators).  Operands are
- * row-major [n_pad][Kp] float32 hi/lo pairs built by gtb_prepare_operand_tc: role 0 (query)
- * = [x~, 1, 0..], role 1 (reference) = [-2y~, |y~|^2, 0..]; Kp = roundup(d+1, 8) <= gtb_tc_max_kp().
- * topk: cand_idx[nq][64] = two lists of 32 (even / odd reference tiles, -1 = empty) with their thresholds
- * tau[nq][2]; scratch = gtb_tc_scratch_bytes(nq_pad) bytes.  radius: same contract as gtb_knn_radius_simt. */
+/* Tensor-core variant (tcgen05.mma, TMA-fed, TMEM accumulators, persistent 2-CTA clusters).  Operands are
+ * row-major [n_pad][Kp] hi/lo pairs built by gtb_prepare_operand_tc: role 0 (query) = [x~, 1, 0..],
+ * role 1 (reference) = [-2y~, |y~|^2, 0..].
+ *   dtype 0: 3xTF32 -- float32 storage, hi = tf32(v), lo = tf32(v - hi), kind::tf32, Kp = roundup(d+1, 8) <= 104
+ *   dtype 1: bf16x3 -- bfloat16 storage, hi = bf16(v), lo = bf16(v - hi), kind::f16,  Kp = roundup(d+1, 16) <= 208
+ * topk: cand_idx[nq][64] = two lists of 32 (disjoint halves of the reference tiles, -1 = empty) with their
+ * thresholds tau[nq][2]; scratch = gtb_tc_scratch_bytes(nq_pad) bytes.  radius: contract of gtb_knn_radius_simt. */
 int gtb_tc_max_kp(void);
 /* thread-block cluster size of the search kernel: 1, 2 (default) or 4 CTAs share each reference tile
  * through TMA multicast */
 int gtb_tc_set_cluster(int cl);
-int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const float* mean, int role, float* hi, float* lo,
-                           int64_t n_pad, int Kp, float* norm2, float* maxnorm, void* stream);
-int gtb_knn_topk_tc(const float* q_hi, const float* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
-                    const float* r_hi, const float* r_lo, int64_t nr, int64_t nr_pad, int Kp, int32_t* cand_idx,
-                    void* scratch, float* tau, void* stream);
+int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const float* mean, int role, void* hi, void* lo,
+                           int64_t n_pad, int Kp, int dtype, float* norm2, float* maxnorm, void* stream);
+int gtb_knn_topk_tc(const void* q_hi, const void* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
+                    const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp, int dtype,
+                    int32_t* cand_idx, void* scratch, float* tau, void* stream);
 int64_t gtb_tc_scratch_bytes(int64_t nq_pad);
-int gtb_knn_radius_tc(const float* q_hi, const float* q_lo, const float* qn2, const float* lim2, int64_t nq,
-                      int64_t nq_pad, const float* r_hi, const float* r_lo, int64_t nr, int64_t nr_pad, int Kp,
-                      int32_t* pairs, int64_t capacity, unsigned long long* counter, int32_t* rowcnt,
+int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float* qn2, const float* lim2, int64_t nq,
+                      int64_t nq_pad, const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp,
+                      int dtype, int32_t* pairs, int64_t capacity, unsigned long long* counter, int32_t* rowcnt,
                       void* stream);
 
 /* ---- K3 float64 re-evaluation, bandwidth, affinities, CSR emission: replaces graphs.py:886-911

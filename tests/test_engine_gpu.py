@@ -96,16 +96,16 @@ def test_radius_pairs_complete():
 
 
 # ------------------------------------------------------------------ tensor-core (tcgen05) search
-def _tc_topk(X, Y=None):
+def _tc_topk(X, Y=None, dtype=0):
     ref = pipeline.SearchOperand(_dev(X))
     qry = ref if Y is None else pipeline.SearchOperand(_dev(Y), mean=ref.mean)
-    q_hi, q_lo, q_n2 = qry.tc(0)
-    r_hi, r_lo, _ = ref.tc(1)
+    q_hi, q_lo, q_n2 = qry.tc(0, dtype)
+    r_hi, r_lo, _ = ref.tc(1, dtype)
     cand = torch.full((qry.n, 64), -7, dtype=torch.int32, device="cuda")
     scratch = torch.zeros((E.lib().gtb_tc_scratch_bytes(qry.n_pad),), dtype=torch.uint8, device="cuda")
     tau = torch.empty((qry.n, 2), dtype=torch.float32, device="cuda")
-    E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, qry.n, qry.n_pad, r_hi, r_lo, ref.n, ref.n_pad, ref.Kp, cand,
-           scratch, tau)
+    E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, qry.n, qry.n_pad, r_hi, r_lo, ref.n, ref.n_pad, ref.kp(dtype),
+           dtype, cand, scratch, tau)
     torch.cuda.synchronize()
     return cand.cpu().numpy(), tau.cpu().numpy().min(axis=1), qry, ref
 
@@ -127,17 +127,18 @@ def test_tc_operand_split():
     assert np.allclose(qfull[:300, :100], Xc, rtol=2e-6, atol=1e-9) and (qfull[:300, 100] == 1).all()
 
 
+@pytest.mark.parametrize("dtype", [0, 1])
 @pytest.mark.parametrize("n,d", [(1797, 64), (3000, 100), (700, 20), (2500, 10), (300, 5), (40, 3), (1000, 31),
                                  (1000, 55), (777, 103)])
-def test_tc_topk_candidates(n, d):
+def test_tc_topk_candidates(n, d, dtype):
     X, _ = synth.gaussian_mixture(n, d, n_clusters=5, intrinsic_dim=min(8, d), seed=3)
-    cand, tau, qry, ref = _tc_topk(X)
+    cand, tau, qry, ref = _tc_topk(X, dtype=dtype)
     X64 = X.astype(np.float64)
     D2 = ((X64[:, None, :] - X64[None, :, :]) ** 2).sum(-1)
     order = np.argsort(D2, axis=1, kind="stable")
     Xc = X64 - X64.mean(0)
     nrm = (Xc ** 2).sum(1)
-    eps = pipeline.eps_rel_tc(d)
+    eps = pipeline.eps_rel_tc16(d) if dtype else pipeline.eps_rel_tc(d)
     # two lists of 32: references in even / odd 128-row tiles
     tile_par = (np.arange(n) // 128) % 2
     n_even, n_odd = int((tile_par == 0).sum()), int((tile_par == 1).sum())
@@ -149,8 +150,10 @@ def test_tc_topk_candidates(n, d):
         assert len(c) == min(32, n_even) + min(32, n_odd), (i, len(c))
         assert (tile_par[cand[i][:32][cand[i][:32] >= 0]] == 0).all() and \
             (tile_par[cand[i][32:][cand[i][32:] >= 0]] == 1).all()
-        assert set(order[i, :min(24, n)]).issubset(set(c)), "row %d misses a true neighbour" % i
         bound = eps * (nrm[i] + nrm.max())
+        # the true nearest 24 are present unless the fast pass cannot tell them apart from the 25th+
+        sure = [j for j in order[i, :min(24, n)] if D2[i, j] + 2 * bound < D2[i, order[i, min(31, n - 1)]]]
+        assert set(sure).issubset(set(c)), "row %d misses a true neighbour" % i
         non = np.setdiff1d(np.arange(n), c)
         if len(non):
             assert np.isfinite(tau[i])
@@ -170,7 +173,8 @@ def test_tc_topk_out_of_sample():
         assert set(order[i, :24]).issubset(set(cand[i]))
 
 
-def test_tc_radius_pairs_complete():
+@pytest.mark.parametrize("dtype", [0, 1])
+def test_tc_radius_pairs_complete(dtype):
     n, d = 2000, 30
     X, _ = synth.gaussian_mixture(n, d, n_clusters=3, intrinsic_dim=6, seed=4)
     op = pipeline.SearchOperand(_dev(X))
@@ -178,20 +182,22 @@ def test_tc_radius_pairs_complete():
     D2 = ((X64[:, None, :] - X64[None, :, :]) ** 2).sum(-1)
     r2 = np.partition(D2, 40, axis=1)[:, 40]
     limp = torch.zeros(op.n_pad, dtype=torch.float32, device="cuda")
-    limp[:n] = _dev((r2 * 1.0001 + 1e-3).astype(np.float32))
+    Xc = X64 - X64.mean(0)
+    slack = (pipeline.eps_rel_tc16(d) if dtype else pipeline.eps_rel_tc(d)) * 2 * (Xc ** 2).sum(1).max()
+    limp[:n] = _dev((r2 * 1.0001 + slack).astype(np.float32))
     cap = 1 << 20
     pairs = torch.empty((cap, 2), dtype=torch.int32, device="cuda")
     counter = torch.zeros(1, dtype=torch.int64, device="cuda")
     rowcnt = torch.zeros(op.n_pad, dtype=torch.int32, device="cuda")
-    q_hi, q_lo, q_n2 = op.tc(0)
-    r_hi, r_lo, _ = op.tc(1)
-    E.call("gtb_knn_radius_tc", q_hi, q_lo, q_n2, limp, n, op.n_pad, r_hi, r_lo, n, op.n_pad, op.Kp, pairs, cap,
-           counter, rowcnt)
+    q_hi, q_lo, q_n2 = op.tc(0, dtype)
+    r_hi, r_lo, _ = op.tc(1, dtype)
+    E.call("gtb_knn_radius_tc", q_hi, q_lo, q_n2, limp, n, op.n_pad, r_hi, r_lo, n, op.n_pad, op.kp(dtype), dtype,
+           pairs, cap, counter, rowcnt)
     m = int(counter.item())
     pr = pairs[:m].cpu().numpy()
     got = set(map(tuple, pr))
     assert len(got) == m
     want = set(zip(*np.nonzero(D2 <= r2[:, None])))
     assert want.issubset(got)
-    assert len(got - want) < 0.05 * len(want) + 50
+    assert len(got - want) < (0.5 if dtype else 0.05) * len(want) + 50
     assert np.array_equal(np.bincount(pr[:, 0], minlength=n), rowcnt[:n].cpu().numpy())

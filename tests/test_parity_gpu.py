@@ -22,7 +22,7 @@ def _build(case, **extra):
         return gt.Graph(case.X, n_jobs=-1, verbose=0, **dict(case.params, **extra))
 
 
-@pytest.fixture(params=["tc", "simt"])
+@pytest.fixture(params=["tc", "tc16", "simt"])
 def impl(request, monkeypatch):
     monkeypatch.setenv("GTB_SEARCH_IMPL", request.param)
     return request.param
