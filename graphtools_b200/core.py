@@ -244,8 +244,10 @@ class BaseGraph(Base, metaclass=abc.ABCMeta):
             raise ValueError("Expected 0 <= anisotropy <= 1. Got {}".format(anisotropy))
         self.anisotropy = anisotropy
         if initialize:
+            # build on the device now (as the reference builds K in the constructor, base.py:501-503);
+            # the host copy is only materialised when .K / .kernel is read
             _logger.log_debug("Initializing kernel...")
-            self.K
+            self._ensure_built()
         else:
             _logger.log_debug("Not initializing kernel.")
         super().__init__(**kwargs)

@@ -27,8 +27,9 @@ __device__ __forceinline__ double sym_dense(int mode, double theta, double a, do
 __global__ void __launch_bounds__(256) dense_kernel(const float* __restrict__ Xq, int64_t nq,
                                                     const float* __restrict__ Xr, int64_t nr, int d, int what,
                                                     const double* __restrict__ bw_q, const double* __restrict__ bw_r,
-                                                    double decay, double thresh, int symm, double theta,
-                                                    double* __restrict__ out, double* __restrict__ rowsum) {
+                                                    double decay, double thresh, double rfac, int symm,
+                                                    double theta, double* __restrict__ out,
+                                                    double* __restrict__ rowsum) {
   __shared__ double qs[DK][DT + 1];
   __shared__ double rs[DK][DT + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x 4 outputs each
@@ -79,11 +80,20 @@ __global__ void __launch_bounds__(256) dense_kernel(const float* __restrict__ Xq
         if (what == DENSE_DIST) {
           v = dist;
         } else {
-          v = gtb_affinity(dist, bwi, decay);
-          if (v < thresh) v = 0.0;
+          // pairs beyond the kernel support radius bw * (-ln thresh)^(1/decay) are zero: skip pow/exp
+          // (the 1e-9 guard keeps every value that could round to >= thresh on the exact path)
+          v = 0.0;
+          if (dist <= bwi * rfac) {
+            v = gtb_affinity(dist, bwi, decay);
+            if (v < thresh) v = 0.0;
+          }
           if (what == DENSE_KERNEL_SYM) {
-            double vr = gtb_affinity(dist, bw_r[j], decay);
-            if (vr < thresh) vr = 0.0;
+            double vr = 0.0;
+            const double bwj = bw_r[j];
+            if (dist <= bwj * rfac) {
+              vr = gtb_affinity(dist, bwj, decay);
+              if (vr < thresh) vr = 0.0;
+            }
             v = sym_dense(symm, theta, v, vr);
           }
         }
@@ -151,7 +161,11 @@ extern "C" int gtb_dense_kernel(const float* Xq, int64_t nq, const float* Xr, in
   cudaStream_t st = (cudaStream_t)stream;
   if (rowsum) GTB_CUDA(cudaMemsetAsync(rowsum, 0, sizeof(double) * nq, st));
   dim3 grid((unsigned)gtb_cdiv(nr, DT), (unsigned)gtb_cdiv(nq, DT));
-  dense_kernel<<<grid, 256, 0, st>>>(Xq, nq, Xr, nr, d, what, bw_q, bw_r, decay, thresh, symm, theta, out, rowsum);
+  // support radius factor; +inf when nothing is thresholded away (thresh <= 0) or in distance mode
+  double rfac = INFINITY;
+  if (what != DENSE_DIST && thresh > 0 && thresh < 1 && decay > 0) rfac = pow(-log(thresh), 1.0 / decay) * (1.0 + 1e-9);
+  dense_kernel<<<grid, 256, 0, st>>>(Xq, nq, Xr, nr, d, what, bw_q, bw_r, decay, thresh, rfac, symm, theta, out,
+                                     rowsum);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }

@@ -486,12 +486,20 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         for (int j = 1; j < 32; ++j) vmin = fminf(vmin, v[j]);
         if (MODE == 0) {
           if (vmin < thr) {
+            // branch-free append: predicated store + predicated counter bump per column (the compiler
+            // turns the plain C++ `if` into 32 BSSY/BRA/BSYNC regions, ~30 cycles each)
+            uint2* my = p.cand_buf + boff;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              if (v[j] < thr) {
-                p.cand_buf[boff + cnt] = make_uint2(__float_as_uint(v[j]), (uint32_t)(col0 + j));
-                ++cnt;
-              }
+              asm volatile(
+                  "{\n .reg .pred q;\n .reg .b64 a;\n"
+                  " setp.lt.f32 q, %1, %2;\n"
+                  " mad.wide.s32 a, %0, 8, %3;\n"
+                  " @q st.global.v2.b32 [a], {%4, %5};\n"
+                  " @q add.s32 %0, %0, 1;\n}"
+                  : "+r"(cnt)
+                  : "f"(v[j]), "f"(thr), "l"(my), "r"(__float_as_uint(v[j])), "r"(col0 + j)
+                  : "memory");
             }
           }
           // keep >= 32 free slots for the next batch
@@ -512,12 +520,22 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
             for (int j = 0; j < 32; ++j) c += (v[j] <= thr);
             unsigned long long pos = atomicAdd(p.counter, (unsigned long long)c);
             atomicAdd(p.rowcnt + gq, c);
+            // positions past the capacity are counted but not written (the host re-runs with a larger buffer)
+            const bool room = pos + (unsigned long long)c <= p.capacity;
+            int2* dst = p.pairs + (room ? pos : 0);
+            int k = 0;
+            const float lim = room ? thr : -gtb_inf_f();
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              if (v[j] <= thr) {
-                if (pos < p.capacity) p.pairs[pos] = make_int2((int)gq, col0 + j);
-                ++pos;
-              }
+              asm volatile(
+                  "{\n .reg .pred q;\n .reg .b64 a;\n"
+                  " setp.le.f32 q, %1, %2;\n"
+                  " mad.wide.s32 a, %0, 8, %3;\n"
+                  " @q st.global.v2.b32 [a], {%4, %5};\n"
+                  " @q add.s32 %0, %0, 1;\n}"
+                  : "+r"(k)
+                  : "f"(v[j]), "f"(lim), "l"(dst), "r"((int)gq), "r"(col0 + j)
+                  : "memory");
             }
           }
         }

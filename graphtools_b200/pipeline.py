@@ -14,7 +14,7 @@ import torch
 from . import _engine as E
 
 SYM_MODES = {"+": 0, "*": 1, "mnn": 2, None: 3}
-AUTO_TC = "tc"           # tensor-core flavour picked by impl="auto": "tc" (3xTF32) or "tc16" (bf16x3)
+AUTO_TC = "tc16"         # tensor-core flavour picked by impl="auto": "tc" (3xTF32) or "tc16" (bf16x3)
 BALL_CAP = 8192          # longest radius-pass row handled by refine_ball (shared-memory sort)
 _STATS = {}
 
