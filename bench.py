@@ -195,8 +195,8 @@ def run_gpu_arm(a):
     bounds = [gd.shard_bounds(n, world, r) for r in range(world)]
     impl = pipeline.default_impl()
     if impl == "auto":
-        impl = "tc" if d + 1 <= 104 else "simt"
-    SEARCH = "gtb_knn_topk_tc" if impl == "tc" else "gtb_knn_topk_simt"
+        impl = pipeline.AUTO_TC if d + 1 <= 104 else "simt"
+    SEARCH = "gtb_knn_topk_tc" if impl in ("tc", "tc16") else "gtb_knn_topk_simt"
 
     def step():
         """device-resident hot path; returns (K DeviceCSR, P values)."""
@@ -254,16 +254,35 @@ def run_gpu_arm(a):
     achieved = flop / (per_launch_ms / 1e3) / 1e12
     peaks, how = measured_peaks()
     peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    if impl == "tc16":
+        kp = (d + 1 + 15) // 16 * 16
+        kname = "search_tc_kernel<TOPK, CL=2, BF16> (%s): tcgen05.mma kind::f16 on bf16 hi/lo pairs (bf16x3), " \
+                "A in TMEM, TMA multicast, persistent" % SEARCH
+        issued, ceiling = achieved * 3.0 * kp / d, d / (3.0 * kp)
+        note = "the tensor pipe issues 3x that (bf16x3 split) on K padded to %d at the bf16 rate, so frac <= %.3f " \
+               "by construction" % (kp, ceiling)
+    elif impl == "tc":
+        kp = (d + 1 + 7) // 8 * 8
+        kname = "search_tc_kernel<TOPK, CL=2, TF32> (%s): tcgen05.mma kind::tf32, 3xTF32 split, A in TMEM, TMA " \
+                "multicast, persistent" % SEARCH
+        issued, ceiling = achieved * 3.0 * kp / d, d / (6.0 * kp)
+        note = "the tensor pipe issues 3x that (3xTF32) on K padded to %d at the TF32 rate = half the bf16 peak, " \
+               "so frac <= %.3f by construction" % (kp, ceiling)
+    else:
+        kname, issued, ceiling = "search_simt_kernel<48,false> (%s): fp32 CUDA cores" % SEARCH, achieved, None
+        note = "fp32 CUDA-core kernel; tensor peak kept as the denominator"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(impl if world == 1 else "", {}).get("dram_bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None,
-                "kernel": ("search_tc_kernel<0> (%s): tcgen05.mma kind::tf32, 3xTF32 split, TMA + TMEM" % SEARCH)
-                if impl == "tc" else ("search_simt_kernel<48,false> (%s)" % SEARCH),
-                "issued_tflops": achieved * 3.0 * ((d + 1 + 7) // 8 * 8) / d if impl == "tc" else achieved,
+                "traffic": traffic, "kernel": kname, "issued_tflops": issued, "frac_ceiling": ceiling,
+                "issued_frac_of_peak": issued / (peak if impl != "tc" else peak / 2.0),
                 "launch_ms": per_launch_ms, "share_of_step": per_launch_ms / ms_per_step,
                 "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step). achieved = algorithmic "
-                               "2*Nq*Nr*d FLOP/s; the tensor pipe issues 3x that (3xTF32) on K padded to %d, at the "
-                               "TF32 rate = half the bf16 peak, so frac <= %.3f by construction" % (
-                                   how, (d + 1 + 7) // 8 * 8, d / (6.0 * ((d + 1 + 7) // 8 * 8))),
+                               "2*Nq*Nr*d FLOP/s; %s. traffic = dram read+write bytes of one launch from the ncu "
+                               "--set full capture in profiles/ (1-GPU workload)" % (how, note),
                 "flops_per_launch": flop}
 
     # ---- end-to-end through the public API with host buffers (rank-sharded builds are not exposed
@@ -309,6 +328,7 @@ def run_gpu_arm(a):
             "config": {"workload": workload_name(a), "n": n, "d": d, "knn": KNN, "decay": DECAY, "thresh": THRESH,
                        "l2": "inputs (400 MB operand, 113 MB raw CSR) larger than the 126 MB L2; no explicit flush",
                        "sharding": "query rows over %d rank(s), reference set replicated" % world,
+                       "search_impl": impl,
                        "nnz_raw": stats.get("nnz_raw"), "nnz_sym": nnz_sym, "radius_rows": stats.get("radius_rows")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "stage_ms_per_step": {k: v[1] / a.steps for k, v in sorted(tm.items(), key=lambda kv: -kv[1][1])},
