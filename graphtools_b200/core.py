@@ -357,6 +357,14 @@ class BaseGraph(Base, metaclass=abc.ABCMeta):
     @property
     def diff_aff(self):
         """Symmetric diffusion affinity D^-1/2 K D^-1/2 (base.py:668-698)."""
+        self._ensure_built()
+        Kd = getattr(self, "_dev_kernel", None)
+        if isinstance(Kd, pipeline.DeviceCSR):
+            # K_ij / (d_i d_j)^(1/2) on the device: the anisotropy kernel with alpha = 1/2 on a copy of the values
+            from . import _engine as E
+            vals = Kd.data.clone()
+            E.call("gtb_anisotropy", Kd.indptr, Kd.indices, vals, self._dev_degree, 0.5, Kd.shape[0])
+            return Kd.to_scipy(vals)
         deg = self.kernel_degree
         K = self.kernel
         if sparse.issparse(K):

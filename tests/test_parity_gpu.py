@@ -178,3 +178,27 @@ def test_landmark_golden(name):
     compare_sparse(G.transitions, case.mat("transitions"), what=name + ".transitions")
     if "Y" in case.z.files:
         compare_sparse(G.extend_to_data(case.z["Y"]), case.mat("ext"), thresh=1e-4, what=name + ".ext")
+
+
+def test_diff_aff_and_interpolate():
+    """diff_aff (base.py:668-698) and interpolate (base.py:1195-1229) against the oracle."""
+    from oracle import graph_oracle as go
+    case = Case("mix_knn")
+    G = _build(case)
+    K_ref = case.mat("K")
+    compare_sparse(G.diff_aff, go.diff_aff(K_ref), what="diff_aff")
+    Y = case.z["Y"]
+    T = np.random.default_rng(0).normal(size=(K_ref.shape[0], 3))
+    ref = case.mat("ext").dot(T)
+    got = G.interpolate(T, Y=Y)
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-12)
+
+
+def test_pickle_roundtrip(tmp_path):
+    import pickle
+    case = Case("digits_knn5_decay40")
+    G = _build(case)
+    G.to_pickle(str(tmp_path / "g.pkl"))
+    with open(tmp_path / "g.pkl", "rb") as f:
+        G2 = pickle.load(f)
+    assert (G2.kernel != G.kernel).nnz == 0 and (G2.diff_op != G.diff_op).nnz == 0
