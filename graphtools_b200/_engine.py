@@ -63,6 +63,7 @@ _PLAIN = {
     "gtb_scan_ws_elems": ([c_int64], c_int64),
     "gtb_tc_max_kp": ([], c_int),
     "gtb_tc_set_cluster": ([c_int], c_int),
+    "gtb_tc_set_pacing": ([c_int], c_int),
     "gtb_tc_scratch_bytes": ([c_int64], c_int64),
 }
 

@@ -110,15 +110,33 @@ __global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Param
   // 1. exact distances
   const float* xq = rp.Xq + row * rp.d;
   int n_cand = 0;
-  for (int c = 0; c < S; ++c) {
-    int j = p.cand_idx[row * p.cand_stride + c];  // uniform load
-    if (j >= 0) {
-      double d2 = warp_dist2(xq, rp.Xr + (int64_t)j * rp.d, rp.d, lane);
-      if (lane == 0) { key[c] = d2; idx[c] = j; }
-      ++n_cand;
-    } else if (lane == 0) {
-      key[c] = DBL_MAX * 2.0;  // +inf
-      idx[c] = 0x7fffffff;
+  // four candidates in flight per pass: the row gathers are latency-bound, not bandwidth-bound
+  for (int c0 = 0; c0 < S; c0 += 4) {
+    int j[4];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) j[u] = (c0 + u < S) ? p.cand_idx[row * p.cand_stride + c0 + u] : -1;  // uniform loads
+    for (int k = lane; k < rp.d; k += 32) {
+      const double q = (double)xq[k];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j[u] >= 0) {
+          const double df = q - (double)rp.Xr[(int64_t)j[u] * rp.d + k];
+          acc[u] = fma(df, df, acc[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], off);
+      if (c0 + u < S) {
+        if (j[u] >= 0) ++n_cand;
+        if (lane == 0) {
+          key[c0 + u] = (j[u] >= 0) ? acc[u] : DBL_MAX * 2.0;  // +inf for empty slots
+          idx[c0 + u] = (j[u] >= 0) ? j[u] : 0x7fffffff;
+        }
+      }
     }
   }
   for (int t = S + lane; t < np2; t += 32) { key[t] = DBL_MAX * 2.0; idx[t] = 0x7fffffff; }

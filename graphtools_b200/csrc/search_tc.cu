@@ -157,6 +157,7 @@ struct TcParams {
   int64_t nq, nq_pad, nr, nr_pad;
   int nks;                                                 // 32-byte k-steps per operand row
   int64_t nrounds;
+  unsigned int* sync_ctr;                                  // grid-wide pacing counter (zeroed per launch)
   const float* qn2;
   int32_t* cand_idx; uint2* cand_buf; float* tau;          // TOPK: out [nq][2*TC_S], scratch [nq_pad][2][TC_CAP], tau [nq][2]
   const float* lim2; int2* pairs; unsigned long long capacity; unsigned long long* counter; int32_t* rowcnt;
@@ -220,6 +221,7 @@ __device__ __noinline__ float compact_row(uint2* buf, int cnt, int lane) {
 // TMEM column map (512 columns allocated): [0, 8*nks) A_hi, [8*nks, 16*nks) A_lo (nks <= 13),
 // [TC_ACC0 + s*TC_N, +TC_N) accumulator s.
 constexpr int TC_ACC0 = 256;
+constexpr int TC_SYNC_EVERY = 128;   // tiles between grid-wide pacing points of the TMA producers
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float4& a, const float4& b) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -323,6 +325,20 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         for (int64_t t = 0; t < ntiles; ++t, ++it) {
           const int s = (int)(it % TC_STAGES);
           const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+          if (p.sync_ctr != nullptr && (it % TC_SYNC_EVERY) == 0) {
+            // Pace the reference stream grid-wide: all producers enter tile `it` together, so one DRAM read
+            // of a reference tile serves every SM out of L2 (without this the 74 clusters drift apart by more
+            // than the 126 MB L2 window and each streams the operand from DRAM on its own: 2.1 TB instead of
+            // 44 GB per sweep set).  Performance only -- the wait is bounded, never a correctness dependency.
+            const unsigned int target = (unsigned int)(it / TC_SYNC_EVERY + 1) * gridDim.x;
+            atomicAdd(p.sync_ctr, 1u);
+            for (int polls = 0; polls < (1 << 16); ++polls) {
+              unsigned int seen;
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sync_ctr) : "memory");
+              if (seen >= target) break;
+              __nanosleep(64);
+            }
+          }
           mbar_wait(empty_b + 8 * s, ph ^ 1);      // every CTA of the cluster has consumed this stage
           mbar_arrive_expect_tx(full_b + 8 * s, 2 * sizeB);
           const int row0 = (int)(btile(round, t) * TC_N) + (int)crank * ROWS;
@@ -419,6 +435,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     // lists; every non-candidate of group g has approximate d2 >= tau[row][g].
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     const int grp = (warp - 2) >> 2;                 // 0 or 1
+    float* xpose = reinterpret_cast<float*>(gbase + (bar0 - base) + 128) + (warp - 2) * 32;   // 128-byte slot per warp
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     for (int64_t round = 0; round < nrounds; ++round) {
@@ -484,24 +501,43 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         float vmin = v[0];
 #pragma unroll
         for (int j = 1; j < 32; ++j) vmin = fminf(vmin, v[j]);
-        if (MODE == 0) {
-          if (vmin < thr) {
-            // branch-free append: predicated store + predicated counter bump per column (the compiler
-            // turns the plain C++ `if` into 32 BSSY/BRA/BSYNC regions, ~30 cycles each)
-            uint2* my = p.cand_buf + boff;
+        // Selection.  Lanes (= query rows) holding at least one qualifying column are rare (~1 per warp and
+        // batch), so they are served one at a time by the whole warp: the lane parks its 32 values in a
+        // 128-byte shared-memory slot, every lane tests ONE column, and the hits are written with their
+        // ballot-prefix positions.  ~25 instructions per serviced row instead of 32 predicated append slots.
+        unsigned hot = __ballot_sync(0xffffffffu, (MODE == 0) ? (vmin < thr) : (vmin <= thr));
+        while (hot) {
+          const int L = __ffs(hot) - 1;
+          hot &= hot - 1;
+          if (lane == L) {
+            float4* dst4 = reinterpret_cast<float4*>(xpose);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              asm volatile(
-                  "{\n .reg .pred q;\n .reg .b64 a;\n"
-                  " setp.lt.f32 q, %1, %2;\n"
-                  " mad.wide.s32 a, %0, 8, %3;\n"
-                  " @q st.global.v2.b32 [a], {%4, %5};\n"
-                  " @q add.s32 %0, %0, 1;\n}"
-                  : "+r"(cnt)
-                  : "f"(v[j]), "f"(thr), "l"(my), "r"(__float_as_uint(v[j])), "r"(col0 + j)
-                  : "memory");
-            }
+            for (int j = 0; j < 8; ++j) dst4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
+          __syncwarp();
+          const float x = xpose[lane];
+          const float tL = __shfl_sync(0xffffffffu, thr, L);
+          const bool pass = (MODE == 0) ? (x < tL) : (x <= tL);
+          const unsigned pm = __ballot_sync(0xffffffffu, pass);
+          const int npass = __popc(pm);
+          const int rank = __popc(pm & ((1u << lane) - 1u));
+          if (MODE == 0) {
+            const int cL = __shfl_sync(0xffffffffu, cnt, L);
+            if (pass) wbuf[(L * TC_GROUPS + grp) * TC_CAP + cL + rank] = make_uint2(__float_as_uint(x), (uint32_t)(col0 + lane));
+            if (lane == L) cnt += npass;
+          } else {
+            unsigned long long basepos = 0;
+            if (lane == L) {
+              basepos = atomicAdd(p.counter, (unsigned long long)npass);
+              atomicAdd(p.rowcnt + gq, npass);
+            }
+            basepos = __shfl_sync(0xffffffffu, basepos, L);
+            if (pass && basepos + (unsigned long long)rank < p.capacity)
+              p.pairs[basepos + rank] = make_int2((int)(q0 + quad * 32 + L), col0 + lane);
+          }
+          __syncwarp();
+        }
+        if (MODE == 0) {
           // keep >= 32 free slots for the next batch
           unsigned need = __ballot_sync(0xffffffffu, cnt > TC_CAP - 32);
           while (need) {
@@ -512,31 +548,6 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
             const float nt = compact_row(wbuf + (owner * TC_GROUPS + grp) * TC_CAP, ocnt, lane);
             __syncwarp();
             if (lane == owner) { thr = nt; cnt = TC_S; }
-          }
-        } else {
-          if (vmin <= thr) {
-            int c = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) c += (v[j] <= thr);
-            unsigned long long pos = atomicAdd(p.counter, (unsigned long long)c);
-            atomicAdd(p.rowcnt + gq, c);
-            // positions past the capacity are counted but not written (the host re-runs with a larger buffer)
-            const bool room = pos + (unsigned long long)c <= p.capacity;
-            int2* dst = p.pairs + (room ? pos : 0);
-            int k = 0;
-            const float lim = room ? thr : -gtb_inf_f();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              asm volatile(
-                  "{\n .reg .pred q;\n .reg .b64 a;\n"
-                  " setp.le.f32 q, %1, %2;\n"
-                  " mad.wide.s32 a, %0, 8, %3;\n"
-                  " @q st.global.v2.b32 [a], {%4, %5};\n"
-                  " @q add.s32 %0, %0, 1;\n}"
-                  : "+r"(k)
-                  : "f"(v[j]), "f"(lim), "l"(dst), "r"((int)gq), "r"(col0 + j)
-                  : "memory");
-            }
           }
         }
       }
@@ -680,6 +691,8 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int Kp, int box_k, i
   return GTB_OK;
 }
 
+int g_tc_pacing = 1;
+
 template <int MODE, int CL, bool BF16>
 int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, TcParams& p,
                  cudaStream_t st) {
@@ -701,6 +714,19 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
   const int64_t n_clusters = n_cluster_tiles < (nsm / CL) ? n_cluster_tiles : (nsm / CL);
   p.nrounds = gtb_cdiv(n_cluster_tiles, n_clusters);
   const unsigned nblk = (unsigned)(n_clusters * CL);
+  // pacing counter: a small ring of device words, one fresh (zeroed) slot per launch
+  static unsigned int* ring[64] = {nullptr};
+  static int ring_pos[64] = {0};
+  p.sync_ctr = nullptr;
+  if (dev < 64 && g_tc_pacing && nblk > (unsigned)CL) {
+    if (!ring[dev]) {
+      if (cudaMalloc(&ring[dev], 32 * 64) != cudaSuccess) { ring[dev] = nullptr; (void)cudaGetLastError(); }
+    }
+    if (ring[dev]) {
+      p.sync_ctr = ring[dev] + 16 * (ring_pos[dev]++ % 32);
+      GTB_CUDA(cudaMemsetAsync(p.sync_ctr, 0, sizeof(unsigned int), st));
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nblk);
   cfg.blockDim = dim3(TC_THREADS);
@@ -744,6 +770,9 @@ int launch_tc(const void* q_hi, const void* q_lo, const void* r_hi, const void* 
 extern "C" int gtb_tc_max_kp(void) { return 104; }
 
 // cluster size used by the tensor-core search (1, 2 or 4 CTAs sharing each reference tile via TMA multicast)
+// grid-wide pacing of the TMA producers (1 = on, default; 0 = off)
+extern "C" int gtb_tc_set_pacing(int on) { g_tc_pacing = on ? 1 : 0; return GTB_OK; }
+
 extern "C" int gtb_tc_set_cluster(int cl) {
   GTB_CHECK_ARG(cl == 1 || cl == 2 || cl == 4, "cluster size must be 1, 2 or 4");
   g_tc_cluster = cl;

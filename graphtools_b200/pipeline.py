@@ -46,6 +46,13 @@ def to_device_f32(X):
     return t.to(_dev(), non_blocking=False)
 
 
+def d2h_pinned(t):
+    """Device->host copy.  (A page-locked destination was measured slower end to end: cudaHostAlloc of the
+    ~350 MB result costs more than the pageable copy it saves, and the arrays are handed to the caller, so
+    the pinned blocks cannot be recycled.)"""
+    return t.cpu()
+
+
 class SearchOperand:
     """k-major centred copy of a point set + squared norms (csrc/prep.cu)."""
 
@@ -132,14 +139,24 @@ class DeviceCSR:
     def nnz(self):
         return int(self.indices.shape[0])
 
+    def _host_structure(self):
+        """(indices, indptr int32) as numpy arrays, copied device->host once through pinned buffers and
+        shared by every scipy view of this matrix (K, P, transitions...)."""
+        if getattr(self, "_host_struct", None) is None:
+            n1 = self.indptr.shape[0]
+            ip32 = _empty((n1,), torch.int32)
+            E.call("gtb_cast_indptr", self.indptr, n1, ip32)
+            idx_h, ip_h = d2h_pinned(self.indices), d2h_pinned(ip32)
+            torch.cuda.current_stream().synchronize()
+            self._host_struct = (idx_h.numpy(), ip_h.numpy())
+        return self._host_struct
+
     def to_scipy(self, data=None):
         from scipy import sparse
-        n1 = self.indptr.shape[0]
-        ip32 = _empty((n1,), torch.int32)
-        E.call("gtb_cast_indptr", self.indptr, n1, ip32)
-        vals = self.data if data is None else data
-        M = sparse.csr_matrix((vals.cpu().numpy(), self.indices.cpu().numpy(), ip32.cpu().numpy()),
-                              shape=self.shape)
+        vals = d2h_pinned(self.data if data is None else data)
+        indices, indptr = self._host_structure()
+        torch.cuda.current_stream().synchronize()
+        M = sparse.csr_matrix((vals.numpy(), indices, indptr), shape=self.shape)
         M.has_sorted_indices = True
         M.has_canonical_format = True
         return M
@@ -226,6 +243,8 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         if not ref.tc_ok(tcd):
             raise ValueError("tensor-core search: d = {} does not fit the resident query tile".format(d))
         S, stride, ntau = 64, 64, 2
+        import os
+        E.lib().gtb_tc_set_pacing(int(os.environ.get("GTB_TC_PACING", "1")))
         if E.lib().gtb_tc_set_cluster(min(tc_cluster(), 2) if tcd else tc_cluster()) != 0:
             raise ValueError("GTB_TC_CLUSTER must be 1, 2 or 4")
         if knn > 32:

@@ -67,6 +67,8 @@ int gtb_tc_max_kp(void);
 /* thread-block cluster size of the search kernel: 1, 2 (default) or 4 CTAs share each reference tile
  * through TMA multicast */
 int gtb_tc_set_cluster(int cl);
+/* grid-wide pacing of the TMA producers so that one DRAM read of a reference tile serves all SMs (default on) */
+int gtb_tc_set_pacing(int on);
 int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const float* mean, int role, void* hi, void* lo,
                            int64_t n_pad, int Kp, int dtype, float* norm2, float* maxnorm, void* stream);
 int gtb_knn_topk_tc(const void* q_hi, const void* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
