@@ -273,11 +273,14 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   const uint32_t sizeB = (uint32_t)TC_N * nks * 32;          // one part (hi or lo) of one stage
   const char* q_hi = reinterpret_cast<const char*>(q_hi_v);
   const char* q_lo = reinterpret_cast<const char*>(q_lo_v);
+  // shared-memory ring of NS reference stages (3 fit for bf16 operands, 2 for tf32); the two TMEM
+  // accumulators form an independent 2-deep ring
+  constexpr int NS = BF16 ? 3 : 2;
   const uint32_t B0 = base;                                  // stage s, part q at B0 + (2*s+q)*sizeB
-  const uint32_t bar0 = B0 + 2 * TC_STAGES * sizeB;
-  const uint32_t bar_a = bar0, full_b = bar0 + 8, empty_b = bar0 + 24, tm_full = bar0 + 40, tm_empty = bar0 + 56;
-  const uint32_t round_done = bar0 + 72;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (bar0 - base) + 96);
+  const uint32_t bar0 = B0 + 2 * NS * sizeB;
+  const uint32_t bar_a = bar0, full_b = bar0 + 8, empty_b = bar0 + 40, tm_full = bar0 + 72, tm_empty = bar0 + 88;
+  const uint32_t round_done = bar0 + 104;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (bar0 - base) + 112);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = p.nr_pad / TC_N;
@@ -297,9 +300,11 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   if (threadIdx.x == 0) {
     mbar_init(bar_a, 4);
     mbar_init(round_done, 1);
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(full_b + 8 * s, 1);
       mbar_init(empty_b + 8 * s, CL);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(tm_full + 8 * s, 1);
       mbar_init(tm_empty + 8 * s, 4);
     }
@@ -323,8 +328,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
       int64_t it = 0;                              // running stage counter across rounds
       for (int64_t round = 0; round < nrounds; ++round) {
         for (int64_t t = 0; t < ntiles; ++t, ++it) {
-          const int s = (int)(it % TC_STAGES);
-          const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+          const int s = (int)(it % NS);
+          const uint32_t ph = (uint32_t)((it / NS) & 1);
           if (p.sync_ctr != nullptr && (it % TC_SYNC_EVERY) == 0) {
             // Pace the reference stream grid-wide: all producers enter tile `it` together, so one DRAM read
             // of a reference tile serves every SM out of L2 (without this the 74 clusters drift apart by more
@@ -379,12 +384,14 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     mbar_wait(bar_a, (uint32_t)(round & 1));   // this round's A rows stored to TMEM by the epilogue warps
     tc_fence_after();
     for (int64_t tile = 0; tile < ntiles; ++tile, ++it) {
-      const int s = (int)(it % TC_STAGES);
-      const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
-      mbar_wait(tm_empty + 8 * s, ph ^ 1);   // accumulator index == stage index (both 2-deep)
+      const int s = (int)(it % NS);            // shared-memory stage
+      const uint32_t ph = (uint32_t)((it / NS) & 1);
+      const int ac_i = (int)(it & 1);          // TMEM accumulator
+      const uint32_t aph = (uint32_t)((it >> 1) & 1);
+      mbar_wait(tm_empty + 8 * ac_i, aph ^ 1);
       mbar_wait(full_b + 8 * s, ph);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC0 + s * TC_N);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC0 + ac_i * TC_N);
       uint32_t accum = 0;
 #pragma unroll 1
       for (int prod = 0; prod < 3; ++prod) {   // (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi)
@@ -420,7 +427,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         // smem stage free once these MMAs retire -- signalled to every CTA that multicasts into it
         if (CL > 1) tc_commit_mc(empty_b + 8 * s, cmask);
         else tc_commit(empty_b + 8 * s);
-        tc_commit(tm_full + 8 * s);   // accumulator ready for the epilogue
+        tc_commit(tm_full + 8 * ac_i);   // accumulator ready for the epilogue
       }
       __syncwarp();
     }
@@ -474,8 +481,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     for (int64_t t = (grp + (it0 & 1)) & 1; t < ntiles; t += TC_GROUPS) {
       const int64_t it = it0 + t;
       const int64_t tile = btile(round, t);
-      const int s = grp;                               // accumulator / smem stage of this iteration
-      const uint32_t ph = (uint32_t)((it / TC_STAGES) & 1);
+      const int s = grp;                               // accumulator of this iteration (it % 2 == grp)
+      const uint32_t ph = (uint32_t)((it >> 1) & 1);
       mbar_wait(tm_full + 8 * s, ph);
       tc_fence_after();
       // drain the whole accumulator into registers, hand it back to the MMA warp, THEN select: the
@@ -704,7 +711,7 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
   if ((rc = make_map(&mBht, r_hi, p.nr_pad, Kp, EPK, TC_N / CL, false, BF16))) return rc;
   if ((rc = make_map(&mBl, r_lo, p.nr_pad, Kp, 4 * EPK, TC_N / CL, true, BF16))) return rc;
   if ((rc = make_map(&mBlt, r_lo, p.nr_pad, Kp, EPK, TC_N / CL, false, BF16))) return rc;
-  size_t smem = 1024 + (size_t)2 * TC_STAGES * TC_N * p.nks * 32 + 128 + 1024;
+  size_t smem = 1024 + (size_t)2 * (BF16 ? 3 : 2) * TC_N * p.nks * 32 + 128 + 1024;
   auto kern = search_tc_kernel<MODE, CL, BF16>;
   GTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, nsm = 0;
