@@ -202,3 +202,37 @@ def test_pickle_roundtrip(tmp_path):
     with open(tmp_path / "g.pkl", "rb") as f:
         G2 = pickle.load(f)
     assert (G2.kernel != G.kernel).nnz == 0 and (G2.diff_op != G.diff_op).nnz == 0
+
+
+def test_duplicate_points_warn_and_match(impl):
+    """Exact duplicates: zero distances, bandwidth floor, RuntimeWarning (reference graphs.py:787-817,
+    test/test_knn.py:53-68)."""
+    from oracle import graph_oracle as go
+    X, _ = synth.gaussian_mixture(1500, 30, n_clusters=3, intrinsic_dim=6, seed=21)
+    X = np.vstack([X, X[:9]])
+    with pytest.warns(RuntimeWarning, match=r"Detected zero distance between samples ([0-9and,\s]*). Consider "
+                                            r"removing duplicates"):
+        G = gt.Graph(X, knn=5, decay=10, thresh=1e-4, verbose=0)
+    K_ref, P_ref = go.knn_graph(X.astype(np.float64), knn=5, decay=10, thresh=1e-4)
+    compare_sparse(G.kernel, K_ref, thresh=1e-4, what="K")
+    compare_sparse(G.diff_op, P_ref, what="P")
+    X2 = np.vstack([X, X[:30]])
+    with pytest.warns(RuntimeWarning, match=r"Detected zero distance between ([0-9]*) pairs of samples"):
+        gt.Graph(X2, knn=5, decay=10, thresh=1e-4, verbose=0)
+
+
+def test_bit_identical_across_search_implementations():
+    """The certified select-then-evaluate pipeline makes the result independent of the fast pass."""
+    import os
+    X, _ = synth.gaussian_mixture(30_000, 64, n_clusters=10, intrinsic_dim=8, seed=5)
+    out = {}
+    for impl in ("tc", "tc16", "simt"):
+        os.environ["GTB_SEARCH_IMPL"] = impl
+        try:
+            G = gt.Graph(X, knn=5, decay=40, verbose=0)
+            out[impl] = (G.kernel, G.diff_op)
+        finally:
+            os.environ.pop("GTB_SEARCH_IMPL", None)
+    for impl in ("tc16", "simt"):
+        assert (out[impl][0] != out["tc"][0]).nnz == 0
+        assert (out[impl][1] != out["tc"][1]).nnz == 0
