@@ -277,6 +277,16 @@ __global__ void __launch_bounds__(256) block_fill_kernel(
   if (sub == 0) cursor[grow] = cur + (int32_t)(e1 - e0);
 }
 
+// dense[row][idx[e]] = val[e]; the output was zero-filled by the caller (cudaMemsetAsync)
+__global__ void csr_to_dense_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx,
+                                    const double* __restrict__ val, int64_t n_rows, int64_t n_cols,
+                                    double* __restrict__ out) {
+  const int sub = threadIdx.x % SYM_GROUP;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / SYM_GROUP;
+  if (row >= n_rows) return;
+  for (int64_t e = indptr[row] + sub; e < indptr[row + 1]; e += SYM_GROUP) out[row * n_cols + idx[e]] = val[e];
+}
+
 __global__ void cast_indptr_kernel(const int64_t* __restrict__ in, int64_t n1, int32_t* __restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n1) out[i] = (int32_t)in[i];
@@ -359,6 +369,16 @@ extern "C" int gtb_block_fill(const int64_t* indptr, const int32_t* idx, const d
   GTB_CHECK_ARG(nb > 0, "empty block");
   block_fill_kernel<<<(unsigned)gtb_cdiv(nb * SYM_GROUP, 256), 256, 0, (cudaStream_t)stream>>>(
       indptr, idx, val, nb, row_map, col_map, within, between, beta, outptr, cursor, out_idx, out_val);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_csr_to_dense(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n_rows,
+                                int64_t n_cols, double* out, void* stream) {
+  GTB_CHECK_ARG(n_rows > 0 && n_cols > 0, "empty matrix");
+  cudaStream_t st = (cudaStream_t)stream;
+  GTB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)n_rows * (size_t)n_cols, st));
+  csr_to_dense_kernel<<<(unsigned)gtb_cdiv(n_rows * SYM_GROUP, 256), 256, 0, st>>>(indptr, idx, val, n_rows, n_cols, out);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }

@@ -120,9 +120,39 @@ class TraditionalGraph(DataGraph):
         K, _ = dense.dense_affinity(X, X, bw, None, self.decay, self.thresh, want_rowsum=False)
         return K
 
+    def _sparse_route_ok(self):
+        """With a positive threshold the exact kernel has the same support as the kNN-graph kernel without
+        knn_max (all j with exp(-(d/bw)^decay) >= thresh), so it is built sparse on the tensor-core
+        search path and densified once; thresh == 0 or a callable bandwidth need every pair -> dense kernel."""
+        return (self.thresh is not None and self.thresh > 0 and self.decay is not None
+                and not callable(self.bandwidth) and self.knn is not None and self.knn + 1 + 8 <= 128)
+
+    def _build_kernel_via_sparse(self):
+        from . import _engine as E
+        X = self._X()
+        n = X.shape[0]
+        op = pipeline.SearchOperand(X)
+        R, info = pipeline.knn_kernel(None, op, op, knn=self.knn + 1, knn_max=None, decay=self.decay,
+                                      thresh=self.thresh, bandwidth=self.bandwidth,
+                                      bandwidth_scale=self.bandwidth_scale)
+        self._dev_bandwidth = info["bandwidth"]
+        Ks, Pv, degree, flags = pipeline.symmetrize_normalize(R, self.kernel_symm, self.theta,
+                                                              float(self.anisotropy))
+        if flags & 1:
+            warnings.warn("K should be symmetric", RuntimeWarning)
+        K = pipeline._empty((n, n), torch.float64)
+        E.call("gtb_csr_to_dense", Ks.indptr, Ks.indices, Ks.data, n, n, K)
+        P = pipeline._empty((n, n), torch.float64)
+        E.call("gtb_csr_to_dense", Ks.indptr, Ks.indices, Pv, n, n, P)
+        self._dev_degree, self._dev_P = degree, P
+        return K
+
     def _build_kernel(self):
         if self.precomputed is not None:
             return self._build_precomputed()
+        if self._sparse_route_ok():
+            with _logger.log_task("affinities"):
+                return self._build_kernel_via_sparse()
         with _logger.log_task("affinities"):
             X = self._X()
             n = X.shape[0]

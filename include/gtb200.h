@@ -124,6 +124,11 @@ int gtb_row_finalize(const int64_t* ptr, const int32_t* tmp_idx, const double* t
                      int check_diag, void* stream);
 int gtb_anisotropy(const int64_t* indptr, const int32_t* idx, double* val, const double* deg, double alpha,
                    int64_t n, void* stream);
+/* out[n_rows][n_cols] (float64) = dense form of the CSR matrix (zero fill + scatter): exact graphs with a
+ * threshold are built sparse on the tensor-core path and densified once (reference container contract:
+ * TraditionalGraph.K is an ndarray, graphs.py:1594-1609) */
+int gtb_csr_to_dense(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n_rows, int64_t n_cols,
+                     double* out, void* stream);
 
 /* MNN block assembly: scatter a CSR block (local indices) into the global staging CSR.  Row i of the
  * block goes to global row row_map[i], column j to col_map[j], values scaled by
