@@ -187,6 +187,7 @@ def run_gpu_arm(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keeps NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     X = make_data(a)
     n, d = X.shape
