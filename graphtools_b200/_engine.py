@@ -46,6 +46,8 @@ _SIGS = {
     "gtb_row_finalize": ([_P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, c_int, _P], 1),
     "gtb_anisotropy": ([_P, _P, _P, _P, c_double, c_int64, _P], 1),
     "gtb_csr_to_dense": ([_P, _P, _P, c_int64, c_int64, _P, _P], 1),
+    "gtb_sym_merge_count": ([_P, _P, _P, _P, _P, _P, c_int64, c_int, c_double, _P, _P], 1),
+    "gtb_sym_merge_fill": ([_P, _P, _P, _P, _P, _P, c_int64, c_int, c_double, _P, _P, _P, _P, _P, _P], 1),
     "gtb_block_count": ([_P, c_int64, _P, _P, _P], 1),
     "gtb_block_fill": ([_P, _P, _P, c_int64, _P, _P, _P, _P, c_double, _P, _P, _P, _P, _P], 1),
     "gtb_cluster_aggregate_count": ([_P, _P, _P, c_int64, _P, _P, _P], 1),

@@ -277,6 +277,42 @@ __global__ void __launch_bounds__(256) block_fill_kernel(
   if (sub == 0) cursor[grow] = cur + (int32_t)(e1 - e0);
 }
 
+// ------------------------------------------- row-shard merge (multi-GPU symmetrisation)
+// Row r of A = this rank's raw kernel rows, row r of B = the transposed edges routed to this rank by
+// the all-to-all (both column-sorted).  Two-pointer merge per row: s(w, w') with w' = 0 where absent.
+// FILL = false: counts the non-zero results; FILL = true: writes K (sorted), P = K / rowsum and degree.
+template <bool FILL>
+__global__ void sym_merge_rows_kernel(const int64_t* __restrict__ pa, const int32_t* __restrict__ ia,
+                                      const double* __restrict__ va, const int64_t* __restrict__ pb,
+                                      const int32_t* __restrict__ ib, const double* __restrict__ vb, int64_t n_rows,
+                                      int mode, double theta, int32_t* __restrict__ newlen,
+                                      const int64_t* __restrict__ outptr, int32_t* __restrict__ out_idx,
+                                      double* __restrict__ out_val, double* __restrict__ p_val,
+                                      double* __restrict__ degree) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  int64_t a = pa[row], a1 = pa[row + 1], b = pb[row], b1 = pb[row + 1];
+  int64_t o = FILL ? outptr[row] : 0;
+  const int64_t o0 = o;
+  int cnt = 0;
+  double sum = 0.0;
+  while (a < a1 || b < b1) {
+    const int32_t ca = (a < a1) ? ia[a] : 0x7fffffff, cb = (b < b1) ? ib[b] : 0x7fffffff;
+    const int32_t c = ca < cb ? ca : cb;
+    const double w = (ca == c) ? va[a] : 0.0, wr = (cb == c) ? vb[b] : 0.0;
+    a += (ca == c);
+    b += (cb == c);
+    const double sv = sym_combine(mode, theta, w, wr);
+    if (sv != 0.0) {
+      if (FILL) { out_idx[o] = c; out_val[o] = sv; ++o; sum += fabs(sv); }
+      else ++cnt;
+    }
+  }
+  if (!FILL) { newlen[row] = cnt; return; }
+  if (p_val) for (int64_t e = o0; e < o; ++e) p_val[e] = (sum != 0.0) ? out_val[e] / sum : out_val[e];
+  if (degree) degree[row] = sum;
+}
+
 // dense[row][idx[e]] = val[e]; the output was zero-filled by the caller (cudaMemsetAsync)
 __global__ void csr_to_dense_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx,
                                     const double* __restrict__ val, int64_t n_rows, int64_t n_cols,
@@ -369,6 +405,27 @@ extern "C" int gtb_block_fill(const int64_t* indptr, const int32_t* idx, const d
   GTB_CHECK_ARG(nb > 0, "empty block");
   block_fill_kernel<<<(unsigned)gtb_cdiv(nb * SYM_GROUP, 256), 256, 0, (cudaStream_t)stream>>>(
       indptr, idx, val, nb, row_map, col_map, within, between, beta, outptr, cursor, out_idx, out_val);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_sym_merge_count(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pb,
+                                   const int32_t* ib, const double* vb, int64_t n_rows, int mode, double theta,
+                                   int32_t* newlen, void* stream) {
+  GTB_CHECK_ARG(n_rows > 0 && mode >= 0 && mode <= 2, "bad arguments");
+  sym_merge_rows_kernel<false><<<(unsigned)gtb_cdiv(n_rows, 128), 128, 0, (cudaStream_t)stream>>>(
+      pa, ia, va, pb, ib, vb, n_rows, mode, theta, newlen, nullptr, nullptr, nullptr, nullptr, nullptr);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_sym_merge_fill(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pb,
+                                  const int32_t* ib, const double* vb, int64_t n_rows, int mode, double theta,
+                                  const int64_t* outptr, int32_t* out_idx, double* out_val, double* p_val,
+                                  double* degree, void* stream) {
+  GTB_CHECK_ARG(n_rows > 0 && mode >= 0 && mode <= 2, "bad arguments");
+  sym_merge_rows_kernel<true><<<(unsigned)gtb_cdiv(n_rows, 128), 128, 0, (cudaStream_t)stream>>>(
+      pa, ia, va, pb, ib, vb, n_rows, mode, theta, nullptr, outptr, out_idx, out_val, p_val, degree);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }

@@ -54,3 +54,50 @@ def allgather_csr_rows(row_len, indices, data, n_rows_per_rank, scan_fn, group=N
     full_idx = _allgather_padded(indices, nnz_all, group)
     full_val = _allgather_padded(data, nnz_all, group)
     return scan_fn(full_len.contiguous()), full_idx, full_val
+
+
+def owner_of(cols, bounds):
+    """Rank that owns each column/row index under ``shard_bounds`` (bounds = [(lo, hi)] per rank)."""
+    world = len(bounds)
+    per = max(bounds[0][1] - bounds[0][0], 1)
+    return torch.clamp(cols.to(torch.int64) // per, max=world - 1)
+
+
+def route_edges_to_column_owner(row_len, indices, data, lo, bounds, group=None):
+    """The exchange step of the sharded symmetrisation: every raw edge (i, j, w) of this rank's rows is sent
+    to owner(j) with one NCCL all-to-all per field (variable splits).  Returns the edges received by this rank
+    as the TRANSPOSED entries of its own rows -- a CSR over the local rows (row_len_t [m] int32, cols [k] int32
+    = source row ids i, vals [k] float64), column-sorted -- ready to be merged with the local raw rows.
+
+    Pure plumbing on torch tensors (works on CPU tensors with gloo for the tests)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = indices.device
+    m = row_len.shape[0]
+    n_total = bounds[-1][1]
+    rows = torch.repeat_interleave(torch.arange(lo, lo + m, device=dev, dtype=torch.int64), row_len.to(torch.int64))
+    dest = owner_of(indices, bounds)
+    order = torch.argsort(dest, stable=True)
+    send_counts = torch.bincount(dest, minlength=world)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    in_split = send_counts.tolist()
+    out_split = recv_counts.tolist()
+    k = int(sum(out_split))
+
+    def a2a(t):
+        out = torch.empty((k,), dtype=t.dtype, device=dev)
+        dist.all_to_all_single(out, t[order].contiguous(), output_split_sizes=out_split, input_split_sizes=in_split,
+                               group=group)
+        return out
+
+    src_row = a2a(rows.to(torch.int32))          # i  (becomes the column of the transposed entry)
+    dst_col = a2a(indices.to(torch.int32))       # j  (a row of this rank)
+    val = a2a(data)
+    my_lo = bounds[rank][0]
+    my_m = bounds[rank][1] - my_lo
+    local_row = dst_col.to(torch.int64) - my_lo
+    key = local_row * n_total + src_row.to(torch.int64)
+    perm = torch.argsort(key)
+    row_len_t = torch.bincount(local_row, minlength=my_m).to(torch.int32)
+    return row_len_t, src_row[perm].contiguous(), val[perm].contiguous()

@@ -113,30 +113,91 @@ class kNNGraph(DataGraph):
         self._dev_bandwidth = info["bandwidth"]
         return R
 
-    def _build_kernel_sharded(self, ref, knn_max):
-        """One process per GPU: this rank builds the kernel rows of its contiguous query shard against the
-        replicated reference set, then the raw CSR shards are all-gathered (NCCL) so that symmetrisation
-        and normalisation are local.  Every rank ends up with the complete, identical kernel."""
+    def _local_raw_rows(self, ref, knn_max):
+        """(row_len int32 [m], indices, data) of this rank's raw kernel rows [lo, hi)."""
         import torch
         import torch.distributed as dist
         from . import distributed as gd
         world, rank = dist.get_world_size(), dist.get_rank()
-        n = ref.n
-        bounds = [gd.shard_bounds(n, world, r) for r in range(world)]
+        bounds = [gd.shard_bounds(ref.n, world, r) for r in range(world)]
         lo, hi = bounds[rank]
+        dev = ref.X.device
         if hi > lo:
             qry = pipeline.SearchOperand(ref.X[lo:hi], mean=ref.mean)
             Rl, _ = self._kernel_device(qry, ref, knn=self.knn + 1, knn_max=knn_max, bandwidth=self.bandwidth,
                                         bandwidth_scale=self.bandwidth_scale)
-            row_len = (Rl.indptr[1:] - Rl.indptr[:-1]).to(torch.int32)
-            idx, val = Rl.indices, Rl.data
-        else:
-            row_len = torch.zeros((0,), dtype=torch.int32, device=ref.X.device)
-            idx = torch.zeros((0,), dtype=torch.int32, device=ref.X.device)
-            val = torch.zeros((0,), dtype=torch.float64, device=ref.X.device)
+            return bounds, Rl.indptr, (Rl.indptr[1:] - Rl.indptr[:-1]).to(torch.int32), Rl.indices, Rl.data
+        z = torch.zeros((0,), dtype=torch.int32, device=dev)
+        return (bounds, torch.zeros((1,), dtype=torch.int64, device=dev), z, z,
+                torch.zeros((0,), dtype=torch.float64, device=dev))
+
+    def _build_kernel_sharded(self, ref, knn_max):
+        """One process per GPU, raw kernel only (used when the symmetrisation cannot be sharded): this rank
+        builds the rows of its contiguous query shard against the replicated reference set, the raw CSR
+        shards are all-gathered (NCCL) and every rank continues with the complete matrix."""
+        from . import distributed as gd
+        bounds, _, row_len, idx, val = self._local_raw_rows(ref, knn_max)
+        n = ref.n
         indptr, idx, val = gd.allgather_csr_rows(row_len, idx, val, [b[1] - b[0] for b in bounds],
                                                  pipeline.exclusive_scan)
         return pipeline.DeviceCSR(indptr, idx, val, (n, n))
+
+    def _build_kernel(self):
+        """Sharded build when torch.distributed is initialised: rows are sharded, every raw edge
+        (i, j, w) is routed to the owner of column j with an NCCL all-to-all, each rank merges its raw rows with
+        the transposed edges it received (csrc/sparse.cu sym_merge_rows), normalises its shard, and the K / P
+        shards are all-gathered so every rank returns the complete matrices (bit-identical for any rank count)."""
+        from . import distributed as gd
+        sharded = (gd.active() and np.ndim(self.bandwidth) == 0 and self.anisotropy == 0
+                   and self.kernel_symm in ("+", "*", "mnn"))
+        if not sharded:
+            return super()._build_kernel()
+        import torch
+        import torch.distributed as dist
+        from . import _engine as E
+        knn_max = self.knn_max + 1 if self.knn_max else None
+        ref = self.knn_tree
+        n = ref.n
+        with _logger.log_task("KNN search"):
+            bounds, indptr_a, row_len, idx, val = self._local_raw_rows(ref, knn_max)
+        rank = dist.get_rank()
+        lo, hi = bounds[rank]
+        m = hi - lo
+        row_len_t, idx_t, val_t = gd.route_edges_to_column_owner(row_len, idx, val, lo, bounds)
+        mode = pipeline.SYM_MODES[self.kernel_symm]
+        theta = 0.0 if self.theta is None else float(self.theta)
+        if m > 0:
+            indptr_b = pipeline.exclusive_scan(row_len_t)
+            newlen = pipeline._empty((m,), torch.int32)
+            E.call("gtb_sym_merge_count", indptr_a, idx, val, indptr_b, idx_t, val_t, m, mode, theta, newlen)
+            outptr = pipeline.exclusive_scan(newlen)
+            nnz = int(outptr[-1].item())
+            k_idx = pipeline._empty((nnz,), torch.int32)
+            k_val = pipeline._empty((nnz,), torch.float64)
+            p_val = pipeline._empty((nnz,), torch.float64)
+            deg = pipeline._empty((m,), torch.float64)
+            E.call("gtb_sym_merge_fill", indptr_a, idx, val, indptr_b, idx_t, val_t, m, mode, theta, outptr, k_idx,
+                   k_val, p_val, deg)
+        else:
+            newlen = torch.zeros((0,), dtype=torch.int32, device=idx.device)
+            k_idx = torch.zeros((0,), dtype=torch.int32, device=idx.device)
+            k_val = p_val = deg = torch.zeros((0,), dtype=torch.float64, device=idx.device)
+        heights = [b[1] - b[0] for b in bounds]
+        full_ptr, full_idx, full_val = gd.allgather_csr_rows(newlen, k_idx, k_val, heights, pipeline.exclusive_scan)
+        full_p = gd._allgather_padded(p_val, self._all_counts(k_idx.shape[0]))
+        full_deg = gd._allgather_padded(deg, heights)
+        K = pipeline.DeviceCSR(full_ptr, full_idx, full_val, (n, n))
+        self._dev_kernel, self._dev_P, self._dev_degree = K, full_p, full_deg
+        return K
+
+    @staticmethod
+    def _all_counts(local_count):
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([local_count], dtype=torch.int64, device="cuda")
+        out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(out, t)
+        return [int(x.item()) for x in out]
 
     def _kernel_device(self, qry, ref, knn, knn_max, bandwidth, bandwidth_scale):
         if self.decay is None or self.thresh == 1:

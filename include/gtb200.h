@@ -124,6 +124,15 @@ int gtb_row_finalize(const int64_t* ptr, const int32_t* tmp_idx, const double* t
                      int check_diag, void* stream);
 int gtb_anisotropy(const int64_t* indptr, const int32_t* idx, double* val, const double* deg, double alpha,
                    int64_t n, void* stream);
+/* Multi-GPU symmetrisation of a row shard: A = this rank's raw kernel rows, B = the transposed edges routed to
+ * it by the NCCL all-to-all (both CSR over the local rows, column-sorted).  count -> scan -> fill; fill also
+ * emits P = K / rowsum and the degree vector of the shard (base.py:557-577, :645 on a row partition). */
+int gtb_sym_merge_count(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pb,
+                        const int32_t* ib, const double* vb, int64_t n_rows, int mode, double theta,
+                        int32_t* newlen, void* stream);
+int gtb_sym_merge_fill(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pb, const int32_t* ib,
+                       const double* vb, int64_t n_rows, int mode, double theta, const int64_t* outptr,
+                       int32_t* out_idx, double* out_val, double* p_val, double* degree, void* stream);
 /* out[n_rows][n_cols] (float64) = dense form of the CSR matrix (zero fill + scatter): exact graphs with a
  * threshold are built sparse on the tensor-core path and densified once (reference container contract:
  * TraditionalGraph.K is an ndarray, graphs.py:1594-1609) */

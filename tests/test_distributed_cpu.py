@@ -52,3 +52,31 @@ def test_allgather_csr_rows_gloo_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, n, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+def _route_worker(rank, world, port, n, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    M = sparse.random(n, n, density=0.02, random_state=3, format="csr", dtype=np.float64)
+    M.setdiag(1.0); M = sparse.csr_matrix(M); M.sort_indices()
+    bounds = [gd.shard_bounds(n, world, r) for r in range(world)]
+    lo, hi = bounds[rank]
+    S = M[lo:hi]
+    row_len_t, cols_t, vals_t = gd.route_edges_to_column_owner(
+        torch.from_numpy(np.diff(S.indptr).astype(np.int32)), torch.from_numpy(S.indices.astype(np.int32)),
+        torch.from_numpy(S.data), lo, bounds)
+    T = sparse.csr_matrix(M.T)[lo:hi]          # what this rank must have received: rows lo:hi of M^T
+    T.sort_indices()
+    ok = (np.array_equal(row_len_t.numpy(), np.diff(T.indptr)) and np.array_equal(cols_t.numpy(), T.indices)
+          and np.array_equal(vals_t.numpy(), T.data))
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_route_edges_to_column_owner_gloo_world2():
+    world, n = 2, 300
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_route_worker, args=(world, port, n, out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world))

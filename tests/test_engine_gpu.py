@@ -201,3 +201,41 @@ def test_tc_radius_pairs_complete(dtype):
     assert want.issubset(got)
     assert len(got - want) < (0.5 if dtype else 0.05) * len(want) + 50
     assert np.array_equal(np.bincount(pr[:, 0], minlength=n), rowcnt[:n].cpu().numpy())
+
+
+@pytest.mark.parametrize("mode,theta", [("+", None), ("*", None), ("mnn", 0.3)])
+def test_sharded_symmetrise_merge_matches_global(mode, theta):
+    """gtb_sym_merge_* on two row shards (transposed edges prepared the way the all-to-all delivers them)
+    reproduces the single-GPU symmetrise + normalise bit for bit."""
+    from scipy import sparse
+    X, _ = synth.gaussian_mixture(3000, 20, n_clusters=4, intrinsic_dim=5, seed=9)
+    ref = pipeline.SearchOperand(_dev(X))
+    R, _ = pipeline.knn_kernel(None, ref, ref, knn=6, decay=10, thresh=1e-3)
+    K, P, deg, _ = pipeline.symmetrize_normalize(R, mode, theta, 0.0)
+    Kh, Ph = K.to_scipy(), K.to_scipy(P)
+    Rh = R.to_scipy()
+    RT = sparse.csr_matrix(Rh.T); RT.sort_indices()
+    n = 3000
+    smode = pipeline.SYM_MODES[mode]
+    for lo, hi in ((0, 1536), (1536, 3000)):
+        A, B = Rh[lo:hi], RT[lo:hi]
+        A.sort_indices(); B.sort_indices()
+        m = hi - lo
+        pa, ia, va = _dev(A.indptr.astype(np.int64)), _dev(A.indices.astype(np.int32)), _dev(A.data)
+        pb, ib, vb = _dev(B.indptr.astype(np.int64)), _dev(B.indices.astype(np.int32)), _dev(B.data)
+        newlen = torch.empty(m, dtype=torch.int32, device="cuda")
+        E.call("gtb_sym_merge_count", pa, ia, va, pb, ib, vb, m, smode, 0.0 if theta is None else theta, newlen)
+        outptr = pipeline.exclusive_scan(newlen)
+        nnz = int(outptr[-1])
+        oi = torch.empty(nnz, dtype=torch.int32, device="cuda")
+        ov = torch.empty(nnz, dtype=torch.float64, device="cuda")
+        pv = torch.empty(nnz, dtype=torch.float64, device="cuda")
+        dg = torch.empty(m, dtype=torch.float64, device="cuda")
+        E.call("gtb_sym_merge_fill", pa, ia, va, pb, ib, vb, m, smode, 0.0 if theta is None else theta, outptr, oi,
+               ov, pv, dg)
+        Ks, Ps = Kh[lo:hi], Ph[lo:hi]
+        assert np.array_equal(outptr.cpu().numpy(), Ks.indptr)
+        assert np.array_equal(oi.cpu().numpy(), Ks.indices)
+        assert np.array_equal(ov.cpu().numpy(), Ks.data)
+        assert np.allclose(pv.cpu().numpy(), Ps.data, rtol=1e-14, atol=0)
+        assert np.allclose(dg.cpu().numpy(), deg.cpu().numpy()[lo:hi], rtol=1e-14, atol=0)
