@@ -236,3 +236,85 @@ def test_bit_identical_across_search_implementations():
     for impl in ("tc16", "simt"):
         assert (out[impl][0] != out["tc"][0]).nnz == 0
         assert (out[impl][1] != out["tc"][1]).nnz == 0
+
+
+# ------------------------------------------------------------------ wider coverage of the class surface
+def test_per_row_bandwidth_and_knn_max_on_isotropic_data(impl):
+    """Vector bandwidth (graphs.py:895-897) and a knn_max cut that bites on rows going through the radius
+    pass (graphs.py:950-962)."""
+    from oracle import graph_oracle as go
+    X, _ = synth.gaussian_mixture(4000, 60, n_clusters=2, intrinsic_dim=None, seed=13)
+    bw = np.random.default_rng(1).uniform(9.5, 11.0, size=4000)
+    g = go.KnnOracle(X.astype(np.float64), knn=5, decay=20, thresh=1e-3, bandwidth=bw)
+    K_ref = go.finish_kernel(g.kernel(), "+")
+    G = gt.Graph(X, knn=5, decay=20, thresh=1e-3, bandwidth=bw, verbose=0)
+    compare_sparse(G.kernel, K_ref, thresh=1e-3, what="vector bandwidth")
+    K_ref2, _ = go.knn_graph(X.astype(np.float64), knn=5, decay=40, thresh=1e-4, knn_max=15)
+    G2 = gt.Graph(X, knn=5, decay=40, thresh=1e-4, knn_max=15, verbose=0)
+    compare_sparse(G2.kernel, K_ref2, thresh=1e-4, what="knn_max", tie=dict(X=X, knn=16))
+
+
+@pytest.mark.parametrize("precomputed", ["distance", "affinity", "adjacency"])
+def test_precomputed_exact_graphs(precomputed):
+    """graphs.py:1532-1549: element-wise kernels of user-supplied matrices."""
+    from scipy.spatial.distance import pdist, squareform
+    X, _ = synth.gaussian_mixture(300, 10, n_clusters=3, intrinsic_dim=4, seed=2)
+    D = squareform(pdist(X.astype(np.float64)))
+    if precomputed == "distance":
+        data = D
+        bw = np.max(np.partition(D, 6, axis=1)[:, :6], axis=1)
+        K = np.exp(-1 * np.power((D.T / bw).T, 40)); K[K < 1e-4] = 0
+    elif precomputed == "affinity":
+        data = np.exp(-D / D.mean()); K = data.copy(); K[K < 1e-4] = 0
+    else:
+        data = (D < np.percentile(D, 5)).astype(float); np.fill_diagonal(data, 0)
+        K = data.copy(); np.fill_diagonal(K, 1)
+    K = (K + K.T) / 2
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = gt.Graph(data, precomputed=precomputed, knn=5, decay=40 if precomputed == "distance" else None,
+                     verbose=0)
+    assert type(G).__name__ == "TraditionalGraph"
+    compare_dense(G.kernel, K, what=precomputed)
+    P = K / K.sum(1)[:, None]
+    compare_dense(G.diff_op, P, what=precomputed + ".P")
+    with pytest.raises(ValueError, match="Cannot extend kernel on precomputed graph"):
+        G.build_kernel_to_data(X)
+
+
+def test_exact_landmark_and_mnn_landmark_graphs():
+    """Composite classes (graphs.py:1969-1979): TraditionalLandmarkGraph and MNNLandmarkGraph."""
+    from oracle import graph_oracle as go
+    X, _ = synth.gaussian_mixture(900, 20, n_clusters=4, intrinsic_dim=5, seed=4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = gt.Graph(X, graphtype="exact", knn=5, decay=20, thresh=1e-3, n_landmark=60, random_landmarking=True,
+                     random_state=1, verbose=0)
+    assert type(G).__name__ == "TraditionalLandmarkGraph"
+    K_ref = go.finish_kernel(go.exact_kernel(X.astype(np.float64), knn=5, decay=20, thresh=1e-3))
+    clusters = go.random_landmark_clusters(X.astype(np.float64), 60, 1)
+    assert np.array_equal(G.clusters, clusters)
+    op, pnm = go.landmark_operator(K_ref, clusters)
+    compare_dense(G.landmark_op, op, what="exact landmark_op")
+    compare_dense(np.asarray(G.transitions), np.asarray(pnm), what="exact transitions")
+    idx = np.arange(900) % 3
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G2 = gt.Graph(X, sample_idx=idx, kernel_symm="mnn", theta=0.6, knn=5, decay=20, thresh=1e-3, n_landmark=50,
+                      random_landmarking=True, random_state=2, verbose=0)
+    assert type(G2).__name__ == "MNNLandmarkGraph"
+    K2 = go.finish_kernel(go.mnn_kernel(X.astype(np.float64), idx, knn=5, decay=20, thresh=1e-3), "mnn", 0.6)
+    compare_sparse(G2.kernel, K2, thresh=1e-3, what="mnn K")
+    op2, pnm2 = go.landmark_operator(K2, go.random_landmark_clusters(X.astype(np.float64), 50, 2))
+    compare_dense(G2.landmark_op, op2, what="mnn landmark_op")
+    compare_sparse(G2.transitions, pnm2, what="mnn transitions")
+
+
+def test_large_knn_uses_cuda_core_search():
+    """knn beyond the tensor-core candidate lists (2 x 32) falls back to the CUDA-core kernel (S = 128)."""
+    from oracle import graph_oracle as go
+    X, _ = synth.gaussian_mixture(3000, 30, n_clusters=3, intrinsic_dim=6, seed=8)
+    K_ref, _ = go.knn_graph(X.astype(np.float64), knn=40, decay=None)
+    G = gt.Graph(X, knn=40, decay=None, verbose=0)
+    assert pipeline.stats()["impl"] == "simt"
+    compare_sparse(G.kernel, K_ref, what="knn=40 binary", tie=dict(X=X, knn=41))
