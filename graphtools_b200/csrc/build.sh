@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")"
 OUT=../libgtb200.so
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -I../../include -I. --expt-relaxed-constexpr"
+FLAGS="${GTB_EXTRA_FLAGS} -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -I../../include -I. --expt-relaxed-constexpr"
 SRCS="api.cu prep.cu search_simt.cu refine.cu sparse.cu"
 for f in $(ls *.cu); do case " $SRCS " in *" $f "*) ;; *) SRCS="$SRCS $f";; esac; done
 mkdir -p ../../build

@@ -492,8 +492,13 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
       const uint32_t acc_addr = lane_addr + (uint32_t)(TC_ACC0 + s * TC_N);
       tmem_ld32_nowait(acc_addr, r0);
       tmem_ld32_nowait(acc_addr + 32, r1);
+#ifdef GTB_EXPERIMENT_HALF_DRAIN
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { r2[j] = 0x7f000000u; r3[j] = 0x7f000000u; }
+#else
       tmem_ld32_nowait(acc_addr + 64, r2);
       tmem_ld32_nowait(acc_addr + 96, r3);
+#endif
       tmem_wait_ld(r0, r1, r2, r3);
       tc_fence_before();
       __syncwarp();

@@ -94,7 +94,10 @@ class SearchOperand:
     # -- tensor-core operand: row-major [n_pad][Kp] hi/lo pair for one role (0 query, 1 reference);
     #    dtype 0 = tf32 pairs stored as float32 (3xTF32), dtype 1 = bfloat16 pairs (bf16x3)
     def kp(self, dtype=0):
-        step = 16 if dtype else 8
+        # bf16 rows are padded to whole 128-byte SWIZZLE_128B blocks (64 elements): MMAs fed from SWIZZLE_32B
+        # tail blocks were measured ~2.3x slower than from 128B-swizzled ones, and bf16 at d=100 would spend
+        # 9 of its 21 MMAs per tile on tails.  tf32 keeps its single 32-byte tail block (3 of 39 MMAs).
+        step = 64 if dtype else 8
         return (self.d + 1 + step - 1) // step * step
 
     @property
