@@ -218,9 +218,8 @@ __device__ __noinline__ float compact_row(uint2* buf, int cnt, int lane) {
 }
 
 // ---------------------------------------------------------------- the kernel
-// TMEM column map (512 columns allocated): [0, 8*nks) A_hi, [8*nks, 16*nks) A_lo (nks <= 13),
-// [TC_ACC0 + s*TC_N, +TC_N) accumulator s.
-constexpr int TC_ACC0 = 256;
+// TMEM column map (512 columns allocated): [0, 8*nks) A_hi, [8*nks, 16*nks) A_lo, then the accumulator
+// ring [ACC0 + a*TC_N, +TC_N): tf32 (nks <= 13) ACC0 = 256, 2 accumulators; bf16 (nks <= 8) ACC0 = 128, 3.
 constexpr int TC_SYNC_EVERY = 128;   // tiles between grid-wide pacing points of the TMA producers
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float4& a, const float4& b) {
@@ -253,6 +252,39 @@ __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem,
       : "memory");
 }
 
+// Predicated forms: issued from warp-uniform control flow with the election folded into the instruction
+// predicate, so there is no divergent region (BSSY/BSYNC) around the MMAs at all.
+__device__ __forceinline__ void tc_mma_ts_pred(bool bf16, uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
+                                               uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+  if (bf16) {
+    asm volatile(
+        "{\n .reg .pred p, q;\n setp.ne.b32 p, %4, 0;\n setp.ne.b32 q, %5, 0;\n"
+        " @q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n .reg .pred p, q;\n setp.ne.b32 p, %4, 0;\n setp.ne.b32 q, %5, 0;\n"
+        " @q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tc_commit_pred(uint32_t bar, uint32_t leader) {
+  asm volatile(
+      "{\n .reg .pred q;\n setp.ne.b32 q, %1, 0;\n"
+      " @q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}"
+      ::"r"(bar), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc_pred(uint32_t bar, uint16_t mask, uint32_t leader) {
+  asm volatile(
+      "{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n"
+      " @q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}"
+      ::"r"(bar), "h"(mask), "r"(leader)
+      : "memory");
+}
+
 // BF16 = false: operands are tf32 hi/lo float32 pairs (3xTF32, kind::tf32, 8 elements per 32-byte k-step);
 // BF16 = true : operands are bfloat16 hi/lo pairs (bf16x3, kind::f16, 16 elements per k-step, twice the MMA rate;
 //               the split keeps 16 mantissa bits -- still only used to SELECT candidates).
@@ -276,11 +308,15 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   // shared-memory ring of NS reference stages (3 fit for bf16 operands, 2 for tf32); the two TMEM
   // accumulators form an independent 2-deep ring
   constexpr int NS = BF16 ? 3 : 2;
+  // TMEM accumulator ring: bf16 query tiles need only 2 x 64 columns, leaving room for three 128-column
+  // accumulators (the MMA warp can run two tiles ahead of a busy epilogue group); tf32 has room for two.
+  constexpr int NA = BF16 ? 3 : 2;
+  constexpr int ACC0 = BF16 ? 128 : 256;
   const uint32_t B0 = base;                                  // stage s, part q at B0 + (2*s+q)*sizeB
   const uint32_t bar0 = B0 + 2 * NS * sizeB;
-  const uint32_t bar_a = bar0, full_b = bar0 + 8, empty_b = bar0 + 40, tm_full = bar0 + 72, tm_empty = bar0 + 88;
-  const uint32_t round_done = bar0 + 104;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (bar0 - base) + 112);
+  const uint32_t bar_a = bar0, full_b = bar0 + 8, empty_b = bar0 + 40, tm_full = bar0 + 72, tm_empty = bar0 + 104;
+  const uint32_t round_done = bar0 + 136;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (bar0 - base) + 144);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = p.nr_pad / TC_N;
@@ -304,7 +340,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
       mbar_init(full_b + 8 * s, 1);
       mbar_init(empty_b + 8 * s, CL);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NA; ++s) {
       mbar_init(tm_full + 8 * s, 1);
       mbar_init(tm_empty + 8 * s, 4);
     }
@@ -386,13 +422,14 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     for (int64_t tile = 0; tile < ntiles; ++tile, ++it) {
       const int s = (int)(it % NS);            // shared-memory stage
       const uint32_t ph = (uint32_t)((it / NS) & 1);
-      const int ac_i = (int)(it & 1);          // TMEM accumulator
-      const uint32_t aph = (uint32_t)((it >> 1) & 1);
+      const int ac_i = (int)(it % NA);         // TMEM accumulator
+      const uint32_t aph = (uint32_t)((it / NA) & 1);
       mbar_wait(tm_empty + 8 * ac_i, aph ^ 1);
       mbar_wait(full_b + 8 * s, ph);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(TC_ACC0 + ac_i * TC_N);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(ACC0 + ac_i * TC_N);
       uint32_t accum = 0;
+      const uint32_t lead = leader ? 1u : 0u;
 #pragma unroll 1
       for (int prod = 0; prod < 3; ++prod) {   // (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi)
         uint32_t ac = tmem_base + (uint32_t)((prod == 2) ? a_lo_col : 0);
@@ -402,10 +439,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         for (int blk = 0; blk < nfull; ++blk) {
 #pragma unroll
           for (int sub = 0; sub < 4; ++sub) {
-            if (leader) {
-              if (BF16) tc_mma_bf16_ts(d_tmem, ac + sub * 8, bd + sub * 2, idesc, accum);
-              else tc_mma_tf32_ts(d_tmem, ac + sub * 8, bd + sub * 2, idesc, accum);
-            }
+            tc_mma_ts_pred(BF16, d_tmem, ac + sub * 8, bd + sub * 2, idesc, accum, lead);
             accum = 1;
           }
           bd += (TC_N * 128) >> 4;
@@ -414,25 +448,18 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         bd = bd_tail0 + boff;
 #pragma unroll 1
         for (int t = 0; t < ntail; ++t) {
-          if (leader) {
-            if (BF16) tc_mma_bf16_ts(d_tmem, ac, bd, idesc, accum);
-            else tc_mma_tf32_ts(d_tmem, ac, bd, idesc, accum);
-          }
+          tc_mma_ts_pred(BF16, d_tmem, ac, bd, idesc, accum, lead);
           accum = 1;
           bd += (TC_N * 32) >> 4;
           ac += 8;
         }
       }
-      if (leader) {
-        // smem stage free once these MMAs retire -- signalled to every CTA that multicasts into it
-        if (CL > 1) tc_commit_mc(empty_b + 8 * s, cmask);
-        else tc_commit(empty_b + 8 * s);
-        tc_commit(tm_full + 8 * ac_i);   // accumulator ready for the epilogue
-      }
-      __syncwarp();
+      // smem stage free once these MMAs retire -- signalled to every CTA that multicasts into it
+      if (CL > 1) tc_commit_mc_pred(empty_b + 8 * s, cmask, lead);
+      else tc_commit_pred(empty_b + 8 * s, lead);
+      tc_commit_pred(tm_full + 8 * ac_i, lead);   // accumulator ready for the epilogue
     }
-    if (leader) tc_commit(round_done);       // every MMA that reads this round's A has retired
-    __syncwarp();
+    tc_commit_pred(round_done, leader ? 1u : 0u);   // every MMA that reads this round's A has retired
     }
   } else {
     // ===================== epilogue warps =====================
@@ -442,7 +469,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     // lists; every non-candidate of group g has approximate d2 >= tau[row][g].
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     const int grp = (warp - 2) >> 2;                 // 0 or 1
-    float* xpose = reinterpret_cast<float*>(gbase + (bar0 - base) + 128) + (warp - 2) * 32;   // 128-byte slot per warp
+    float* xpose = reinterpret_cast<float*>(gbase + (bar0 - base) + 256) + (warp - 2) * 32;   // 128-byte slot per warp
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     for (int64_t round = 0; round < nrounds; ++round) {
@@ -481,15 +508,15 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     for (int64_t t = (grp + (it0 & 1)) & 1; t < ntiles; t += TC_GROUPS) {
       const int64_t it = it0 + t;
       const int64_t tile = btile(round, t);
-      const int s = grp;                               // accumulator of this iteration (it % 2 == grp)
-      const uint32_t ph = (uint32_t)((it >> 1) & 1);
+      const int s = (int)(it % NA);                    // accumulator of this iteration
+      const uint32_t ph = (uint32_t)((it / NA) & 1);
       mbar_wait(tm_full + 8 * s, ph);
       tc_fence_after();
       // drain the whole accumulator into registers, hand it back to the MMA warp, THEN select: the
       // accumulator is held for four back-to-back tcgen05.ld only, never across the selection work
       uint32_t r0[32], r1[32], r2[32], r3[32];
       __syncwarp();
-      const uint32_t acc_addr = lane_addr + (uint32_t)(TC_ACC0 + s * TC_N);
+      const uint32_t acc_addr = lane_addr + (uint32_t)(ACC0 + s * TC_N);
       tmem_ld32_nowait(acc_addr, r0);
       tmem_ld32_nowait(acc_addr + 32, r1);
 #ifdef GTB_EXPERIMENT_HALF_DRAIN
@@ -716,7 +743,7 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
   if ((rc = make_map(&mBht, r_hi, p.nr_pad, Kp, EPK, TC_N / CL, false, BF16))) return rc;
   if ((rc = make_map(&mBl, r_lo, p.nr_pad, Kp, 4 * EPK, TC_N / CL, true, BF16))) return rc;
   if ((rc = make_map(&mBlt, r_lo, p.nr_pad, Kp, EPK, TC_N / CL, false, BF16))) return rc;
-  size_t smem = 1024 + (size_t)2 * (BF16 ? 3 : 2) * TC_N * p.nks * 32 + 128 + 1024;
+  size_t smem = 1024 + (size_t)2 * (BF16 ? 3 : 2) * TC_N * p.nks * 32 + 256 + 1024;
   auto kern = search_tc_kernel<MODE, CL, BF16>;
   GTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, nsm = 0;
@@ -797,7 +824,8 @@ extern "C" int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const fl
   GTB_CHECK_ARG(n > 0 && d > 0 && n_pad >= n && n_pad % 128 == 0, "bad shape");
   GTB_CHECK_ARG(dtype == 0 || dtype == 1, "dtype must be 0 (tf32 pairs in float32) or 1 (bfloat16 pairs)");
   const int epk = dtype ? 16 : 8;
-  GTB_CHECK_ARG(Kp % epk == 0 && Kp >= d + 1 && Kp / epk <= 13, "Kp must be a multiple of 8 (tf32) / 16 (bf16), >= d+1, <= 13 k-steps");
+  GTB_CHECK_ARG(Kp % epk == 0 && Kp >= d + 1 && Kp / epk <= (dtype ? 8 : 13),
+                "Kp must be a multiple of 8 (tf32, <= 104) / 16 (bf16, <= 128) and >= d+1");
   GTB_CHECK_ARG(role == 0 || role == 1, "role must be 0 (query) or 1 (reference)");
   cudaStream_t st = (cudaStream_t)stream;
   if (maxnorm) GTB_CUDA(cudaMemsetAsync(maxnorm, 0, sizeof(float), st));
@@ -819,7 +847,7 @@ static int tc_check(int64_t nq, int64_t nr, int64_t nq_pad, int64_t nr_pad, int 
   GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TC_M == 0 && nr_pad % TC_N == 0, "bad shape (pads must be x128)");
   GTB_CHECK_ARG(dtype == 0 || dtype == 1, "dtype must be 0 (tf32) or 1 (bf16)");
   const int epk = dtype ? 16 : 8;
-  GTB_CHECK_ARG(Kp % epk == 0 && Kp >= epk && Kp / epk <= 13, "Kp out of range");
+  GTB_CHECK_ARG(Kp % epk == 0 && Kp >= epk && Kp / epk <= (dtype ? 8 : 13), "Kp out of range");
   GTB_CHECK_ARG(nr_pad < (1ll << 31) && nq_pad < (1ll << 31), "too many rows for 32-bit TMA coordinates");
   return GTB_OK;
 }

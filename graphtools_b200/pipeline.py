@@ -94,10 +94,10 @@ class SearchOperand:
     # -- tensor-core operand: row-major [n_pad][Kp] hi/lo pair for one role (0 query, 1 reference);
     #    dtype 0 = tf32 pairs stored as float32 (3xTF32), dtype 1 = bfloat16 pairs (bf16x3)
     def kp(self, dtype=0):
-        # bf16 rows are padded to whole 128-byte SWIZZLE_128B blocks (64 elements): MMAs fed from SWIZZLE_32B
-        # tail blocks were measured ~2.3x slower than from 128B-swizzled ones, and bf16 at d=100 would spend
-        # 9 of its 21 MMAs per tile on tails.  tf32 keeps its single 32-byte tail block (3 of 39 MMAs).
-        step = 64 if dtype else 8
+        # rows are whole 32-byte k-steps (16 bf16 / 8 tf32 elements): SWIZZLE_128B blocks plus SWIZZLE_32B
+        # tail blocks.  (Padding bf16 rows to whole 128-byte blocks was measured slower: 699 vs 682 ms at
+        # d = 100 -- the extra MMAs cost more than the tail blocks.)
+        step = 16 if dtype else 8
         return (self.d + 1 + step - 1) // step * step
 
     @property
@@ -105,7 +105,7 @@ class SearchOperand:
         return self.kp(0)
 
     def tc_ok(self, dtype=0):
-        return self.kp(dtype) // (16 if dtype else 8) <= 13
+        return self.kp(dtype) // (16 if dtype else 8) <= (8 if dtype else 13)
 
     def tc(self, role, dtype=0):
         key = (role, dtype)
@@ -238,7 +238,12 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
     if impl is None:
         impl = default_impl()
     if impl == "auto":
-        impl = AUTO_TC if (ref.tc_ok(1 if AUTO_TC == "tc16" else 0) and knn + 8 <= 32 and S in (None, 64)) else "simt"
+        impl = "simt"
+        if knn + 8 <= 32 and S in (None, 64):
+            for cand_impl in (AUTO_TC, "tc16" if AUTO_TC == "tc" else "tc"):
+                if ref.tc_ok(1 if cand_impl == "tc16" else 0):
+                    impl = cand_impl
+                    break
     dev = _dev()
     ntau = 1
     tcd = 1 if impl == "tc16" else 0

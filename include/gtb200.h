@@ -60,7 +60,8 @@ int gtb_knn_radius_simt(const float* QT, const float* qn2, const float* lim2, in
  * row-major [n_pad][Kp] hi/lo pairs built by gtb_prepare_operand_tc: role 0 (query) = [x~, 1, 0..],
  * role 1 (reference) = [-2y~, |y~|^2, 0..].
  *   dtype 0: 3xTF32 -- float32 storage, hi = tf32(v), lo = tf32(v - hi), kind::tf32, Kp = roundup(d+1, 8) <= 104
- *   dtype 1: bf16x3 -- bfloat16 storage, hi = bf16(v), lo = bf16(v - hi), kind::f16,  Kp = roundup(d+1, 16) <= 208
+ *   dtype 1: bf16x3 -- bfloat16 storage, hi = bf16(v), lo = bf16(v - hi), kind::f16,  Kp multiple of 16, <= 128
+ *            (3 smem stages, 3 TMEM accumulators)
  * topk: cand_idx[nq][64] = two lists of 32 (disjoint halves of the reference tiles, -1 = empty) with their
  * thresholds tau[nq][2]; scratch = gtb_tc_scratch_bytes(nq_pad) bytes.  radius: contract of gtb_knn_radius_simt. */
 int gtb_tc_max_kp(void);
