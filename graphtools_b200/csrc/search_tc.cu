@@ -31,7 +31,7 @@
 
 namespace {
 
-constexpr int TC_M = 128, TC_N = 128, TC_STAGES = 2, TC_CAP = 96, TC_S = 32, TC_GROUPS = 2, TC_THREADS = 64 + 128 * TC_GROUPS;
+constexpr int TC_M = 128, TC_N = 128, TC_CAP = 96, TC_S = 32, TC_GROUPS = 2, TC_THREADS = 64 + 128 * TC_GROUPS;
 constexpr float TC_BIG = 1e29f;       // "no threshold yet"; padded reference rows carry |y|^2 = 1e30
 constexpr float TC_PAD_NORM = 1e30f;
 
