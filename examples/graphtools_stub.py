@@ -47,7 +47,7 @@ def knn_alpha_decay_kernel(X, Y, knn, decay, thresh, bandwidth_scale=1.0):
     n_keep, status, nzero = (e(ny, dt=torch.int32) for _ in range(3))
     bw = e(ny, dt=torch.float64); lim2 = e(ny)
     eps_rel = 4.0 * (d + 16) * 2.0 ** -24
-    _call("gtb_refine_topk", p(Yd), I64(ny), p(Xd), I(d), p(cand), I(64), I(64), p(tau), I(2), p(q_n2),
+    _call("gtb_refine_topk", p(Yd), I64(ny), p(Xd), I(d), I(0), p(cand), I(64), I(64), p(tau), I(2), p(q_n2),
           F(float(r_max.item())), D(eps_rel), I(knn), I64(0), D(decay), D(thresh), P(0), I(0), D(bandwidth_scale),
           p(st_idx), p(st_val), p(n_keep), p(bw), p(lim2), p(status), p(nzero))
     if int((status != 1).sum()):      # uncertified rows: radius pass, see graphtools_b200/pipeline.py:knn_kernel

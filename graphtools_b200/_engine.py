@@ -32,11 +32,11 @@ _SIGS = {
     "gtb_knn_topk_tc": ([_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P], 1),
     "gtb_knn_radius_tc": ([_P, _P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, _P,
                            _P, _P], 1),
-    "gtb_refine_topk": ([_P, c_int64, _P, c_int, _P, c_int, c_int, _P, c_int, _P, c_float, c_double, c_int, c_int64, c_double,
+    "gtb_refine_topk": ([_P, c_int64, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_float, c_double, c_int, c_int64, c_double,
                          c_double, _P, c_int, c_double, _P, _P, _P, _P, _P, _P, _P, _P], 1),
     "gtb_compact_todo": ([_P, c_int64, _P, _P, _P], 1),
     "gtb_scatter_pairs": ([_P, c_int64, _P, _P, c_int64, _P, _P], 1),
-    "gtb_refine_ball": ([_P, _P, _P, c_int64, _P, c_int, _P, _P, _P, c_int, c_int64, c_double, c_double, _P, c_int,
+    "gtb_refine_ball": ([_P, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, c_int, c_int64, c_double, c_double, _P, c_int,
                          c_double, _P, _P, _P, _P, _P, c_int, _P], 2),
     "gtb_csr_gather": ([_P, _P, _P, _P, _P, c_int64, c_int, _P, c_int64, _P, _P, _P, _P, _P, _P, _P], 2),
     "gtb_exclusive_scan": ([_P, c_int64, _P, _P, _P], 3),

@@ -462,10 +462,11 @@ class DataGraph(Data, BaseGraph, metaclass=abc.ABCMeta):
 
     # helper shared by the sparse graph types -------------------------------------------------
     def _dense_f32(self, A):
-        """Densify (scipy sparse -> ndarray) and hand to the device as float32."""
+        """Densify (scipy sparse -> ndarray) and hand to the device: float64 inputs stay float64 (exact
+        distances are evaluated on them), everything else becomes float32."""
         import torch
         if isinstance(A, torch.Tensor):
-            return pipeline.to_device_f32(A)
+            return pipeline.to_device(A)
         if sparse.issparse(A):
             A = A.toarray()
-        return pipeline.to_device_f32(np.asarray(A))
+        return pipeline.to_device(np.asarray(A))

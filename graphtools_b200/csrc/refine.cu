@@ -19,7 +19,7 @@
 namespace {
 
 struct RowParams {
-  const float* Xq; const float* Xr; int d;
+  const void* Xq; const void* Xr; int d;   // original rows, float32 or float64 (template T of the kernels)
   int knn; int64_t kmax;       // kmax = INT64_MAX when knn_max is None
   double decay;                // < 0: binary kNN (decay=None)
   double thresh; double rfac;  // rfac = (-ln thresh)^(1/decay)
@@ -28,8 +28,8 @@ struct RowParams {
 };
 
 // exact squared distance between query row xq and reference row xr, cooperatively by one warp
-__device__ __forceinline__ double warp_dist2(const float* __restrict__ xq, const float* __restrict__ xr,
-                                             int d, int lane) {
+template <typename T>
+__device__ __forceinline__ double warp_dist2(const T* __restrict__ xq, const T* __restrict__ xr, int d, int lane) {
   double s = 0.0;
   for (int k = lane; k < d; k += 32) {
     double df = (double)xq[k] - (double)xr[k];
@@ -93,6 +93,7 @@ struct Refine1Params {
   int32_t* status; int32_t* nzero;
 };
 
+template <typename T>
 __global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Params p) {
   __shared__ double key_s[R1_WARPS][R1_CAP];
   __shared__ int32_t idx_s[R1_WARPS][R1_CAP];
@@ -108,7 +109,8 @@ __global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Param
   auto sync = [] { __syncwarp(); };
 
   // 1. exact distances
-  const float* xq = rp.Xq + row * rp.d;
+  const T* xq = reinterpret_cast<const T*>(rp.Xq) + row * rp.d;
+  const T* Xr = reinterpret_cast<const T*>(rp.Xr);
   int n_cand = 0;
   // four candidates in flight per pass: the row gathers are latency-bound, not bandwidth-bound
   for (int c0 = 0; c0 < S; c0 += 4) {
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Param
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (j[u] >= 0) {
-          const double df = q - (double)rp.Xr[(int64_t)j[u] * rp.d + k];
+          const double df = q - (double)Xr[(int64_t)j[u] * rp.d + k];
           acc[u] = fma(df, df, acc[u]);
         }
       }
@@ -213,6 +215,7 @@ struct Refine2Params {
   int32_t* n_keep_t; double* bw_out; int32_t* nzero; int32_t* overflow; int cap;
 };
 
+template <typename T>
 __global__ void __launch_bounds__(R2_THREADS) refine_ball_kernel(Refine2Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* key = reinterpret_cast<double*>(smem_raw);               // [cap]
@@ -231,10 +234,11 @@ __global__ void __launch_bounds__(R2_THREADS) refine_ball_kernel(Refine2Params p
   }
   const int L = (int)L64;
   const int np2 = next_pow2(L < 2 ? 2 : L);
-  const float* xq = rp.Xq + row * rp.d;
+  const T* xq = reinterpret_cast<const T*>(rp.Xq) + row * rp.d;
+  const T* Xr = reinterpret_cast<const T*>(rp.Xr);
   for (int c = warp; c < L; c += R2_THREADS / 32) {
     int j = p.seg_idx[p0 + c];
-    double d2 = warp_dist2(xq, rp.Xr + (int64_t)j * rp.d, rp.d, lane);
+    double d2 = warp_dist2<T>(xq, Xr + (int64_t)j * rp.d, rp.d, lane);
     if (lane == 0) { key[c] = d2; idx[c] = j; }
   }
   for (int t = L + tid; t < np2; t += R2_THREADS) { key[t] = DBL_MAX * 2.0; idx[t] = 0x7fffffff; }
@@ -332,7 +336,7 @@ __global__ void compact_todo_kernel(const int32_t* __restrict__ status, int64_t 
   if (todo) todo_rows[base + __popc(m & ((1u << lane) - 1))] = (int32_t)i;
 }
 
-RowParams make_row_params(const float* Xq, const float* Xr, int d, int knn, int64_t kmax, double decay,
+RowParams make_row_params(const void* Xq, const void* Xr, int d, int knn, int64_t kmax, double decay,
                           double thresh, const double* bw_fixed, int bw_mode, double bw_scale) {
   RowParams rp;
   rp.Xq = Xq; rp.Xr = Xr; rp.d = d; rp.knn = knn; rp.kmax = kmax <= 0 ? INT64_MAX : kmax;
@@ -344,7 +348,8 @@ RowParams make_row_params(const float* Xq, const float* Xr, int d, int knn, int6
 
 }  // namespace
 
-extern "C" int gtb_refine_topk(const float* Xq, int64_t nq, const float* Xr, int d, const int32_t* cand_idx,
+extern "C" int gtb_refine_topk(const void* Xq, int64_t nq, const void* Xr, int d, int x_is_f64,
+                               const int32_t* cand_idx,
                                int S, int cand_stride, const float* tau, int ntau, const float* qn2, float maxrn2, double eps_rel,
                                int knn, int64_t kmax, double decay, double thresh, const double* bw_fixed,
                                int bw_mode, double bw_scale, int32_t* st_idx, double* st_val, int32_t* n_keep,
@@ -358,7 +363,10 @@ extern "C" int gtb_refine_topk(const float* Xq, int64_t nq, const float* Xr, int
   p.nq = nq; p.S = S; p.cand_stride = cand_stride; p.ntau = ntau < 1 ? 1 : ntau; p.cand_idx = cand_idx; p.tau = tau; p.qn2 = qn2; p.maxrn2 = maxrn2; p.eps_rel = eps_rel;
   p.st_idx = st_idx; p.st_val = st_val; p.n_keep = n_keep; p.bw_out = bw_out; p.lim2_out = lim2_out;
   p.status = status; p.nzero = nzero;
-  refine_topk_kernel<<<(unsigned)gtb_cdiv(nq, R1_WARPS), R1_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  if (x_is_f64)
+    refine_topk_kernel<double><<<(unsigned)gtb_cdiv(nq, R1_WARPS), R1_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+  else
+    refine_topk_kernel<float><<<(unsigned)gtb_cdiv(nq, R1_WARPS), R1_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }
@@ -383,7 +391,8 @@ extern "C" int gtb_scatter_pairs(const int32_t* pairs, int64_t npairs, const int
   return GTB_OK;
 }
 
-extern "C" int gtb_refine_ball(const float* Xq, const int32_t* todo_rows, const int32_t* status, int64_t nt, const float* Xr, int d,
+extern "C" int gtb_refine_ball(const void* Xq, const int32_t* todo_rows, const int32_t* status, int64_t nt,
+                               const void* Xr, int d, int x_is_f64,
                                const int64_t* seg_ptr, int32_t* seg_idx, double* seg_val, int knn, int64_t kmax,
                                double decay, double thresh, const double* bw_fixed, int bw_mode, double bw_scale,
                                int32_t* n_keep_t, int32_t* n_keep, double* bw_out, int32_t* nzero,
@@ -396,9 +405,14 @@ extern "C" int gtb_refine_ball(const float* Xq, const int32_t* todo_rows, const 
   p.todo_rows = todo_rows; p.status = status; p.nt = nt; p.seg_ptr = seg_ptr; p.seg_idx = seg_idx; p.seg_val = seg_val;
   p.n_keep_t = n_keep_t; p.bw_out = bw_out; p.nzero = nzero; p.overflow = overflow; p.cap = cap;
   size_t smem = (size_t)cap * 12;
-  GTB_CUDA(cudaFuncSetAttribute(refine_ball_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GTB_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int32_t), st));
-  refine_ball_kernel<<<(unsigned)nt, R2_THREADS, smem, st>>>(p);
+  if (x_is_f64) {
+    GTB_CUDA(cudaFuncSetAttribute(refine_ball_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    refine_ball_kernel<double><<<(unsigned)nt, R2_THREADS, smem, st>>>(p);
+  } else {
+    GTB_CUDA(cudaFuncSetAttribute(refine_ball_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    refine_ball_kernel<float><<<(unsigned)nt, R2_THREADS, smem, st>>>(p);
+  }
   GTB_CHECK_LAUNCH();
   scatter_counts_kernel<<<(unsigned)gtb_cdiv(nt, 256), 256, 0, st>>>(todo_rows, n_keep_t, nt, n_keep);
   GTB_CHECK_LAUNCH();

@@ -114,10 +114,11 @@ class TraditionalGraph(DataGraph):
                 self.kernel_symm, self.anisotropy = saved
         X = self._X()
         op = pipeline.SearchOperand(X)
-        bw = self._resolve_bandwidth(self.bandwidth, X.shape[0], lambda: dense.dense_distances(X, X), op, op,
+        Xf = X.float()
+        bw = self._resolve_bandwidth(self.bandwidth, X.shape[0], lambda: dense.dense_distances(Xf, Xf), op, op,
                                      (self.knn or 0) + 1)
         bw = (bw * float(self.bandwidth_scale)).contiguous()
-        K, _ = dense.dense_affinity(X, X, bw, None, self.decay, self.thresh, want_rowsum=False)
+        K, _ = dense.dense_affinity(Xf, Xf, bw, None, self.decay, self.thresh, want_rowsum=False)
         return K
 
     def _sparse_route_ok(self):
@@ -157,10 +158,11 @@ class TraditionalGraph(DataGraph):
             X = self._X()
             n = X.shape[0]
             op = pipeline.SearchOperand(X)
-            bw = self._resolve_bandwidth(self.bandwidth, n, lambda: dense.dense_distances(X, X), op, op,
+            bw = self._resolve_bandwidth(self.bandwidth, n, lambda: dense.dense_distances(X.float(), X.float()), op, op,
                                          (self.knn or 0) + 1)
             bw = (bw * float(self.bandwidth_scale)).contiguous()
             self._dev_bandwidth = bw
+            X = X.float()          # the dense fp64-accumulating kernel reads float32 rows
             if self.kernel_symm is None:
                 K, rowsum = dense.dense_affinity(X, X, bw, None, self.decay, self.thresh)
                 if float((K - K.T).max().item()) > 1e-5:
@@ -223,10 +225,11 @@ class TraditionalGraph(DataGraph):
             X = self._X()
             Yd = self._dense_f32(Y)
             ref = pipeline.SearchOperand(X)
-            qry = pipeline.SearchOperand(Yd, mean=ref.mean)
-            bw = self._resolve_bandwidth(bandwidth, Yd.shape[0], lambda: dense.dense_distances(Yd, X), qry, ref, knn)
+            qry = pipeline.SearchOperand(Yd.to(X.dtype), mean=ref.mean)
+            Xf, Yf = X.float(), Yd.float()
+            bw = self._resolve_bandwidth(bandwidth, Yd.shape[0], lambda: dense.dense_distances(Yf, Xf), qry, ref, knn)
             bw = (bw * float(bandwidth_scale)).contiguous()
-            K, _ = dense.dense_affinity(Yd, X, bw, None, self.decay, self.thresh, want_rowsum=False)
+            K, _ = dense.dense_affinity(Yf, Xf, bw, None, self.decay, self.thresh, want_rowsum=False)
         return K
 
     def build_kernel_to_data(self, Y, knn=None, bandwidth=None, bandwidth_scale=None):

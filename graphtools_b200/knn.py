@@ -244,7 +244,8 @@ class kNNGraph(DataGraph):
         Y = self._check_extension_shape(Y)
         ref = self.knn_tree
         with _logger.log_task("KNN search"):
-            qry = pipeline.SearchOperand(self._dense_f32(Y), mean=ref.mean)
+            Yd = self._dense_f32(Y)
+            qry = pipeline.SearchOperand(Yd.to(ref.X.dtype), mean=ref.mean)
             R, info = self._kernel_device(qry, ref, knn=knn, knn_max=knn_max, bandwidth=bandwidth,
                                           bandwidth_scale=bandwidth_scale)
         self._check_duplicates(info, qry, ref)

@@ -113,7 +113,7 @@ class LandmarkGraph(DataGraph):
         X = self._dense_f32(data)
         ref = pipeline.SearchOperand(X[torch.from_numpy(landmark_indices).to(X.device)].contiguous())
         qry = pipeline.SearchOperand(X, mean=ref.mean)
-        nearest, _ = pipeline.knn_kernel(None, ref, qry, knn=1, decay=None)
+        nearest, _ = pipeline.knn_kernel(None, ref, qry, knn=1, decay=None)   # exact float64 argmin per sample
         return nearest.indices.cpu().numpy().astype(np.int64)
 
     def _spectral_clusters(self):

@@ -46,6 +46,19 @@ def to_device_f32(X):
     return t.to(_dev(), non_blocking=False)
 
 
+def to_device(X):
+    """Host array / tensor -> contiguous CUDA tensor that keeps float64 inputs in float64 (the exact
+    distances are then evaluated on the original float64 rows, e.g. PCA output); everything else becomes
+    float32."""
+    E.require_cuda()
+    if isinstance(X, torch.Tensor):
+        dt = torch.float64 if X.dtype == torch.float64 else torch.float32
+        return X.to(device=_dev(), dtype=dt).contiguous()
+    X = np.asarray(X)
+    dt = np.float64 if X.dtype == np.float64 else np.float32
+    return torch.from_numpy(np.ascontiguousarray(X, dtype=dt)).to(_dev())
+
+
 def d2h_pinned(t):
     """Device->host copy.  (A page-locked destination was measured slower end to end: cudaHostAlloc of the
     ~350 MB result costs more than the pageable copy it saves, and the arrays are handed to the caller, so
@@ -57,14 +70,26 @@ class SearchOperand:
     """k-major centred copy of a point set + squared norms (csrc/prep.cu)."""
 
     def __init__(self, X, mean=None):
+        """X: the ORIGINAL rows on the device, float32 or float64 (kept for the exact distances).  The search
+        copy is always float32: float64 inputs are centred in float64 first and rounded once, so the
+        rounding error of the fast pass stays relative to the centred magnitudes (same bound E)."""
         n, d = X.shape
         self.X, self.n, self.d = X, n, d
+        self.is64 = X.dtype == torch.float64
         self.n_pad = (n + 127) // 128 * 128
         self.d_pad = (d + 7) // 8 * 8
-        if mean is None:
-            ws = _empty((E.lib().gtb_col_mean_ws_doubles(d),), torch.float64)
-            mean = _empty((d,), torch.float32)
-            E.call("gtb_col_mean", X, n, d, ws, mean)
+        if self.is64:
+            if mean is None:
+                mean = X.mean(dim=0)
+            self.Xs = (X - mean.to(torch.float64)).to(torch.float32).contiguous()
+            self._kmean = None                       # already centred
+        else:
+            if mean is None:
+                ws = _empty((E.lib().gtb_col_mean_ws_doubles(d),), torch.float64)
+                mean = _empty((d,), torch.float32)
+                E.call("gtb_col_mean", X, n, d, ws, mean)
+            self.Xs = X
+            self._kmean = mean.to(torch.float32)
         self.mean = mean
         self._simt = None
         self._tc = {}
@@ -77,7 +102,7 @@ class SearchOperand:
             XT = _empty((self.d_pad, self.n_pad), torch.float32)
             n2 = _empty((self.n_pad,), torch.float32)
             mx = _empty((1,), torch.float32)
-            E.call("gtb_prepare_operand", self.X, self.n, self.d, self.mean, XT, self.n_pad, self.d_pad, n2, mx)
+            E.call("gtb_prepare_operand", self.Xs, self.n, self.d, self._kmean, XT, self.n_pad, self.d_pad, n2, mx)
             self._simt = (XT, n2)
             if self._maxnorm is None:
                 self._maxnorm = mx
@@ -116,7 +141,7 @@ class SearchOperand:
             lo = _empty((self.n_pad, Kp), st)
             n2 = _empty((self.n_pad,), torch.float32)
             mx = _empty((1,), torch.float32)
-            E.call("gtb_prepare_operand_tc", self.X, self.n, self.d, self.mean, role, hi, lo, self.n_pad, Kp,
+            E.call("gtb_prepare_operand_tc", self.Xs, self.n, self.d, self._kmean, role, hi, lo, self.n_pad, Kp,
                    dtype, n2, mx)
             self._tc[key] = (hi, lo, n2)
             if self._maxnorm is None:
@@ -230,6 +255,9 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
     if qry is None:
         qry = ref
     nq, nr, d = qry.n, ref.n, ref.d
+    if qry.is64 != ref.is64:
+        raise ValueError("query and reference operands must have the same dtype")
+    x64 = int(ref.is64)
     binary = decay is None
     knn = int(min(knn, nr))
     kmax = 0 if knn_max is None else int(knn_max)
@@ -301,7 +329,7 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
     lim2 = _empty((nq,), torch.float32)
     status = _empty((nq,), torch.int32)
     nzero = _empty((nq,), torch.int32)
-    E.call("gtb_refine_topk", qry.X, nq, ref.X, d, cand, S, stride, tau, ntau, q_n2, ref.maxnorm, eps_rel, knn, kmax, decay_f,
+    E.call("gtb_refine_topk", qry.X, nq, ref.X, d, x64, cand, S, stride, tau, ntau, q_n2, ref.maxnorm, eps_rel, knn, kmax, decay_f,
            thresh_f, bw_fixed, bw_mode, float(bandwidth_scale), st_idx, st_val, n_keep, bw_out, lim2, status, nzero)
 
     todo_rows = _empty((nq,), torch.int32)
@@ -356,7 +384,7 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
             raise NotImplementedError(
                 "a row has {} neighbours inside the kernel radius; rows longer than {} are not supported "
                 "(use graphtype='exact' for such dense kernels)".format(longest, BALL_CAP))
-        E.call("gtb_refine_ball", qry.X, todo_rows, status, nt, ref.X, d, seg_ptr, seg_idx, seg_val, knn, kmax,
+        E.call("gtb_refine_ball", qry.X, todo_rows, status, nt, ref.X, d, x64, seg_ptr, seg_idx, seg_val, knn, kmax,
                decay_f, thresh_f, bw_fixed, bw_mode, float(bandwidth_scale), n_keep_t, n_keep, bw_out, nzero,
                overflow, cap)
 

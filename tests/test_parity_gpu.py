@@ -318,3 +318,22 @@ def test_large_knn_uses_cuda_core_search():
     G = gt.Graph(X, knn=40, decay=None, verbose=0)
     assert pipeline.stats()["impl"] == "simt"
     compare_sparse(G.kernel, K_ref, what="knn=40 binary", tie=dict(X=X, knn=41))
+
+
+def test_float64_inputs_are_evaluated_in_float64(impl):
+    """Inputs that are NOT float32-exact (here: PCA output, the usual PHATE entry n_pca=...): the fast pass
+    runs on a float32 copy centred in float64, every value that reaches the output is computed from the
+    float64 rows, so parity with the float64 reference path holds at rtol 1e-5."""
+    from oracle import graph_oracle as go
+    rng = np.random.default_rng(3)
+    X, _ = synth.gaussian_mixture(4000, 300, n_clusters=6, intrinsic_dim=12, seed=31)
+    X = X.astype(np.float64) * (1 + 1e-9 * rng.normal(size=X.shape))      # not representable in float32
+    G = gt.Graph(X, n_pca=30, random_state=5, knn=5, decay=40, thresh=1e-4, verbose=0)
+    assert G.data_nu.dtype == np.float64 and G.data_nu.shape == (4000, 30)
+    K_ref, P_ref = go.knn_graph(G.data_nu, knn=5, decay=40, thresh=1e-4)
+    r = compare_sparse(G.kernel, K_ref, thresh=1e-4, what="K (float64 input)")
+    assert r["max_rel"] < 1e-8
+    compare_sparse(G.diff_op, P_ref, what="P (float64 input)")
+    Y = G.data_nu[:50] + 1e-3
+    Kyx = go.KnnOracle(G.data_nu, knn=5, decay=40, thresh=1e-4).kernel_to_data(Y)
+    compare_sparse(G.build_kernel_to_data(Y), Kyx, thresh=1e-4, what="Kyx (float64 input)")
