@@ -337,3 +337,27 @@ def test_float64_inputs_are_evaluated_in_float64(impl):
     Y = G.data_nu[:50] + 1e-3
     Kyx = go.KnnOracle(G.data_nu, knn=5, decay=40, thresh=1e-4).kernel_to_data(Y)
     compare_sparse(G.build_kernel_to_data(Y), Kyx, thresh=1e-4, what="Kyx (float64 input)")
+
+
+@pytest.mark.parametrize("n,d,knn", [(12, 3, 3), (129, 1, 5), (257, 2, 10), (40, 7, 38), (1000, 103, 5), (600, 120, 4),
+                                     (500, 200, 5)])
+def test_edge_shapes(n, d, knn, impl):
+    """Tiny / ragged shapes: fewer points than a tile, one feature, knn at its n-2 ceiling, feature counts
+    at and beyond the tensor-core operand limits (falls back to the other kernel flavours)."""
+    from oracle import graph_oracle as go
+    rng = np.random.default_rng(n + d)
+    X = rng.normal(size=(n, d)).astype(np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = gt.Graph(X, knn=knn, decay=15, thresh=1e-3, verbose=0)
+        K_ref, P_ref = go.knn_graph(X.astype(np.float64), knn=knn, decay=15, thresh=1e-3)
+    compare_sparse(G.kernel, K_ref, thresh=1e-3, what="K %s" % ((n, d, knn),))
+    compare_sparse(G.diff_op, P_ref, what="P")
+    y = X[:1] + np.float32(0.1)
+    Kyx = go.KnnOracle(X.astype(np.float64), knn=knn, decay=15, thresh=1e-3).kernel_to_data(y.astype(np.float64))
+    compare_sparse(G.build_kernel_to_data(y), Kyx, thresh=1e-3, what="single query row")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Gb = gt.Graph(X, knn=min(knn, 5), decay=None, verbose=0)
+        Kb, _ = go.knn_graph(X.astype(np.float64), knn=min(knn, 5), decay=None)
+    compare_sparse(Gb.kernel, Kb, what="binary", tie=dict(X=X, knn=min(knn, 5) + 1))
