@@ -264,14 +264,19 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
     if kmax >= nr:
         kmax = 0
     if impl is None:
-        impl = default_impl()
-    if impl == "auto":
+        # GTB_SEARCH_IMPL is a preference: a flavour that cannot take this shape (feature count beyond the
+        # resident query tile, knn beyond the 2 x 32 candidate lists) hands over to the next one
+        want = default_impl()
+        order = {"auto": (AUTO_TC, "tc16" if AUTO_TC == "tc" else "tc", "simt"), "tc": ("tc", "tc16", "simt"),
+                 "tc16": ("tc16", "tc", "simt"), "simt": ("simt",)}.get(want)
+        if order is None:
+            raise ValueError("GTB_SEARCH_IMPL must be auto, tc, tc16 or simt (got %r)" % (want,))
         impl = "simt"
-        if knn + 8 <= 32 and S in (None, 64):
-            for cand_impl in (AUTO_TC, "tc16" if AUTO_TC == "tc" else "tc"):
-                if ref.tc_ok(1 if cand_impl == "tc16" else 0):
-                    impl = cand_impl
-                    break
+        for cand_impl in order:
+            if cand_impl == "simt" or (knn + 8 <= 32 and S in (None, 64)
+                                       and ref.tc_ok(1 if cand_impl == "tc16" else 0)):
+                impl = cand_impl
+                break
     dev = _dev()
     ntau = 1
     tcd = 1 if impl == "tc16" else 0
