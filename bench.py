@@ -334,10 +334,21 @@ def run_gpu_arm(a):
 
 def main():
     a = parse()
-    if a.impl == "reference":
-        run_reference_arm(a)
-    else:
-        run_gpu_arm(a)
+    # stdout carries exactly ONE line (the JSON): anything libraries print meanwhile (e.g. the NCCL version
+    # banner) is diverted to stderr at the file-descriptor level
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    py_stdout, sys.stdout = sys.stdout, real_stdout
+    try:
+        if a.impl == "reference":
+            run_reference_arm(a)
+        else:
+            run_gpu_arm(a)
+    finally:
+        real_stdout.flush()
+        sys.stdout = py_stdout
 
 
 if __name__ == "__main__":
