@@ -58,6 +58,8 @@ _SIGS = {
     "gtb_dense_row_scale": ([_P, _P, c_int64, c_int64, _P, _P], 1),
     "gtb_dense_anisotropy": ([_P, _P, c_double, c_int64, _P, _P], 1),
     "gtb_dense_rowsum": ([_P, c_int64, c_int64, _P, _P], 1),
+    "gtb_spmm_csr": ([_P, _P, _P, c_int64, _P, c_int64, c_int, _P, c_int64, _P], 1),
+    "gtb_row_scale": ([_P, _P, c_int64, c_int, c_int, _P, _P], 1),
 }
 _PLAIN = {
     "gtb_last_error": ([], ctypes.c_char_p),

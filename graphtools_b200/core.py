@@ -373,6 +373,31 @@ class BaseGraph(Base, metaclass=abc.ABCMeta):
             return D @ K @ D
         return (K / np.sqrt(deg)) / np.sqrt(deg.T)
 
+    def diffuse(self, signal, t=1, return_device=False):
+        """``P^t . signal`` by ``t`` repeated products with the device-resident diffusion operator -- what the
+        callers (MAGIC-style imputation) do with ``G.diff_op`` on the host, without materialising P there.
+        Each product is bit-identical to ``G.diff_op.dot(x)``."""
+        import torch
+        self._ensure_built()
+        K = self._dev_kernel
+        one_d = np.ndim(signal) == 1
+        if isinstance(signal, torch.Tensor):
+            x = signal.to(device=pipeline._dev(), dtype=torch.float64).reshape(signal.shape[0], -1).contiguous()
+        else:
+            x = pipeline.to_device(np.asarray(signal, dtype=np.float64).reshape(len(signal), -1))
+        if isinstance(K, pipeline.DeviceCSR):
+            if getattr(self, "_dev_P", None) is None:
+                self._dev_P = pipeline.row_normalize(K)
+            for _ in range(int(t)):
+                x = pipeline.spmm(K, x, self._dev_P)
+        else:
+            for _ in range(int(t)):
+                x = torch.matmul(self._dev_P, x)
+        if return_device:
+            return x[:, 0] if one_d else x
+        x = x.cpu().numpy()
+        return x[:, 0] if one_d else x
+
     @staticmethod
     def _materialize(dev):
         if isinstance(dev, pipeline.DeviceCSR):
@@ -433,23 +458,46 @@ class DataGraph(Data, BaseGraph, metaclass=abc.ABCMeta):
                 raise ValueError(msg)
         return Y
 
-    def extend_to_data(self, Y):
-        """Transition matrix from new points ``Y`` to the graph's samples (base.py:1166-1193):
-        out-of-sample kernel, L1-row-normalised on the device."""
+    def _extend_to_data_device(self, Y):
+        """Out-of-sample transition matrix kept in HBM: (DeviceCSR, normalised values) for sparse graphs,
+        a float64 CUDA tensor for dense graphs."""
         Y = self._check_extension_shape(Y)
         dev = self._kernel_to_data_device(Y)
         if isinstance(dev, pipeline.DeviceCSR):
-            return dev.to_scipy(pipeline.row_normalize(dev))
+            return dev, pipeline.row_normalize(dev)
         from .dense import row_normalize_dense
-        return row_normalize_dense(dev).cpu().numpy()
+        return row_normalize_dense(dev), None
+
+    def extend_to_data(self, Y):
+        """Transition matrix from new points ``Y`` to the graph's samples (base.py:1166-1193):
+        out-of-sample kernel, L1-row-normalised on the device."""
+        T, vals = self._extend_to_data_device(Y)
+        if vals is not None:
+            return T.to_scipy(vals)
+        return T.cpu().numpy()
 
     def interpolate(self, transform, transitions=None, Y=None):
-        """``transitions.dot(transform)`` (base.py:1195-1229)."""
+        """``transitions.dot(transform)`` (base.py:1195-1229) as a device-resident chain: the out-of-sample
+        kernel, its normalisation and the sparse x dense product (csrc/spmm.cu) never leave HBM; only the
+        interpolated [n_y, f] array is copied back.  A caller-supplied ``transitions`` (scipy / ndarray) is
+        uploaded and multiplied the same way; the product is bit-identical to scipy's."""
+        import torch
         if transitions is None:
             if Y is None:
                 raise ValueError("Either `transitions` or `Y` must be provided.")
-            transitions = self.extend_to_data(Y)
-        return transitions.dot(transform)
+            T, vals = self._extend_to_data_device(Y)
+        elif sparse.issparse(transitions):
+            T, vals = pipeline.csr_from_scipy(transitions), None
+        else:
+            T, vals = pipeline.to_device(np.asarray(transitions, dtype=np.float64)), None
+        one_d = np.ndim(transform) == 1
+        B = pipeline.to_device(np.asarray(transform, dtype=np.float64).reshape(len(transform), -1))
+        if isinstance(T, pipeline.DeviceCSR):
+            out = pipeline.spmm(T, B, vals)
+        else:
+            out = torch.matmul(T, B)          # dense transitions (exact graphs): plain library GEMM
+        out = out.cpu().numpy()
+        return out[:, 0] if one_d else out
 
     def set_params(self, **params):
         if "n_jobs" in params:

@@ -19,6 +19,13 @@ def active():
             and os.environ.get("GTB_DISTRIBUTED", "1") != "0")
 
 
+MIN_ROWS_PER_RANK = 128   # out-of-sample query sets smaller than this per rank are not worth sharding
+
+
+def world_size():
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
 def shard_bounds(n, world, rank):
     """Contiguous row range [lo, hi) owned by ``rank``; multiples of 128 rows so query tiles stay full."""
     tiles = (n + 127) // 128

@@ -113,30 +113,36 @@ class kNNGraph(DataGraph):
         self._dev_bandwidth = info["bandwidth"]
         return R
 
-    def _local_raw_rows(self, ref, knn_max):
-        """(row_len int32 [m], indices, data) of this rank's raw kernel rows [lo, hi)."""
+    def _local_raw_rows(self, ref, knn_max, Xq=None, knn=None, bandwidth=None, bandwidth_scale=None):
+        """(bounds, indptr, row_len int32 [m], indices, data, info) of this rank's raw kernel rows [lo, hi) of the
+        query set ``Xq`` (default: the reference set itself, i.e. the in-sample build)."""
         import torch
         import torch.distributed as dist
         from . import distributed as gd
         world, rank = dist.get_world_size(), dist.get_rank()
-        bounds = [gd.shard_bounds(ref.n, world, r) for r in range(world)]
+        Xq = ref.X if Xq is None else Xq
+        knn = self.knn + 1 if knn is None else knn
+        bandwidth = self.bandwidth if bandwidth is None else bandwidth
+        bandwidth_scale = self.bandwidth_scale if bandwidth_scale is None else bandwidth_scale
+        bounds = [gd.shard_bounds(Xq.shape[0], world, r) for r in range(world)]
         lo, hi = bounds[rank]
         dev = ref.X.device
         if hi > lo:
-            qry = pipeline.SearchOperand(ref.X[lo:hi], mean=ref.mean)
-            Rl, _ = self._kernel_device(qry, ref, knn=self.knn + 1, knn_max=knn_max, bandwidth=self.bandwidth,
-                                        bandwidth_scale=self.bandwidth_scale)
-            return bounds, Rl.indptr, (Rl.indptr[1:] - Rl.indptr[:-1]).to(torch.int32), Rl.indices, Rl.data
+            qry = pipeline.SearchOperand(Xq[lo:hi], mean=ref.mean)
+            Rl, info = self._kernel_device(qry, ref, knn=knn, knn_max=knn_max, bandwidth=bandwidth,
+                                           bandwidth_scale=bandwidth_scale)
+            return (bounds, Rl.indptr, (Rl.indptr[1:] - Rl.indptr[:-1]).to(torch.int32), Rl.indices, Rl.data,
+                    info)
         z = torch.zeros((0,), dtype=torch.int32, device=dev)
         return (bounds, torch.zeros((1,), dtype=torch.int64, device=dev), z, z,
-                torch.zeros((0,), dtype=torch.float64, device=dev))
+                torch.zeros((0,), dtype=torch.float64, device=dev), {"nzero": z, "bandwidth": None})
 
     def _build_kernel_sharded(self, ref, knn_max):
         """One process per GPU, raw kernel only (used when the symmetrisation cannot be sharded): this rank
         builds the rows of its contiguous query shard against the replicated reference set, the raw CSR
         shards are all-gathered (NCCL) and every rank continues with the complete matrix."""
         from . import distributed as gd
-        bounds, _, row_len, idx, val = self._local_raw_rows(ref, knn_max)
+        bounds, _, row_len, idx, val, _ = self._local_raw_rows(ref, knn_max)
         n = ref.n
         indptr, idx, val = gd.allgather_csr_rows(row_len, idx, val, [b[1] - b[0] for b in bounds],
                                                  pipeline.exclusive_scan)
@@ -159,7 +165,7 @@ class kNNGraph(DataGraph):
         ref = self.knn_tree
         n = ref.n
         with _logger.log_task("KNN search"):
-            bounds, indptr_a, row_len, idx, val = self._local_raw_rows(ref, knn_max)
+            bounds, indptr_a, row_len, idx, val, _ = self._local_raw_rows(ref, knn_max)
         rank = dist.get_rank()
         lo, hi = bounds[rank]
         m = hi - lo
@@ -243,13 +249,31 @@ class kNNGraph(DataGraph):
             knn = self.data_nu.shape[0]
         Y = self._check_extension_shape(Y)
         ref = self.knn_tree
+        from . import distributed as gd
         with _logger.log_task("KNN search"):
-            Yd = self._dense_f32(Y)
-            qry = pipeline.SearchOperand(Yd.to(ref.X.dtype), mean=ref.mean)
+            Yd = self._dense_f32(Y).to(ref.X.dtype)
+            if gd.active() and np.ndim(bandwidth) == 0 and Yd.shape[0] >= gd.MIN_ROWS_PER_RANK * gd.world_size():
+                return self._kernel_to_data_sharded(Yd, ref, knn, knn_max, bandwidth, bandwidth_scale)
+            qry = pipeline.SearchOperand(Yd, mean=ref.mean)
             R, info = self._kernel_device(qry, ref, knn=knn, knn_max=knn_max, bandwidth=bandwidth,
                                           bandwidth_scale=bandwidth_scale)
         self._check_duplicates(info, qry, ref)
         return R
+
+    def _kernel_to_data_sharded(self, Yd, ref, knn, knn_max, bandwidth, bandwidth_scale):
+        """Out-of-sample kernel with the query rows sharded over the ranks (MNN cross-batch blocks,
+        ``extend_to_data``): each rank searches its contiguous block of ``Y`` against the replicated reference
+        set, the CSR row shards are all-gathered (NCCL) and every rank returns the complete [n_y, n] matrix --
+        bit-identical to the single-GPU result because every row still sees the whole reference set."""
+        from . import distributed as gd
+        bounds, _, row_len, idx, val, info = self._local_raw_rows(ref, knn_max, Xq=Yd, knn=knn, bandwidth=bandwidth,
+                                                                  bandwidth_scale=bandwidth_scale)
+        heights = [b[1] - b[0] for b in bounds]
+        indptr, idx, val = gd.allgather_csr_rows(row_len, idx, val, heights, pipeline.exclusive_scan)
+        if not (self.decay is None or self.thresh == 1):
+            nzero = gd._allgather_padded(info["nzero"], heights)
+            self._check_duplicates({"nzero": nzero}, None, ref)
+        return pipeline.DeviceCSR(indptr, idx, val, (Yd.shape[0], ref.n))
 
     def build_kernel_to_data(self, Y, knn=None, knn_max=None, bandwidth=None, bandwidth_scale=None):
         """Kernel from new points ``Y`` to ``self.data`` as scipy CSR [n_y, n] (graphs.py:819-982)."""

@@ -74,7 +74,7 @@ class LandmarkGraph(DataGraph):
         return self
 
     def _reset_landmarks(self):
-        for name in ("_landmark_op", "_transitions", "_clusters", "_dev_labels", "_n_label"):
+        for name in ("_landmark_op", "_transitions", "_clusters", "_dev_labels", "_n_label", "_dev_transitions"):
             if hasattr(self, name):
                 delattr(self, name)
 
@@ -149,23 +149,40 @@ class LandmarkGraph(DataGraph):
                 E.call("gtb_landmark_op", pnm.indptr, pnm.indices, pnm.data, pnm_norm, colsum, K.shape[0], L, op)
                 self._landmark_op = op.cpu().numpy()
                 self._transitions = pnm.to_scipy(pnm_norm)
+                self._dev_transitions = (pnm, pnm_norm)
             else:
                 from .dense import dense_landmark
                 self._landmark_op, self._transitions = dense_landmark(K, labels, L)
 
-    def extend_to_data(self, data, **kwargs):
-        """Transition matrix from new points to the landmarks (graphs.py:1248-1288)."""
+    def _extend_to_data_device(self, data, **kwargs):
+        """(DeviceCSR [n_y, L], normalised values): out-of-sample kernel aggregated by landmark, in HBM."""
         self.clusters  # make sure labels exist
         if not hasattr(self, "_dev_labels"):
             self.build_landmark_op()
+        data = self._check_extension_shape(data)
         Kyx = self._kernel_to_data_device(data, **kwargs)
-        if isinstance(Kyx, pipeline.DeviceCSR):
-            agg, agg_norm, _ = aggregate_by_cluster(Kyx, self._dev_labels, self._n_label, want_colsum=False)
-            return agg.to_scipy(agg_norm)
-        from .dense import dense_landmark_extend
-        return dense_landmark_extend(Kyx, self._dev_labels, self._n_label)
+        if not isinstance(Kyx, pipeline.DeviceCSR):
+            from .dense import _dense_to_csr
+            Kyx = _dense_to_csr(Kyx)
+        agg, agg_norm, _ = aggregate_by_cluster(Kyx, self._dev_labels, self._n_label, want_colsum=False)
+        return agg, agg_norm
+
+    def extend_to_data(self, data, **kwargs):
+        """Transition matrix from new points to the landmarks (graphs.py:1248-1288)."""
+        agg, agg_norm = self._extend_to_data_device(data, **kwargs)
+        T = agg.to_scipy(agg_norm)
+        return T if isinstance(self._dev_kernel, pipeline.DeviceCSR) else T.toarray()
 
     def interpolate(self, transform, transitions=None, Y=None):
+        """Landmark -> sample interpolation (graphs.py:1290-1317): with neither ``transitions`` nor ``Y`` the
+        cached sample-to-landmark transitions are used straight from HBM."""
         if transitions is None and Y is None:
+            self.transitions
+            dev_t = getattr(self, "_dev_transitions", None)
+            if dev_t is not None:
+                one_d = np.ndim(transform) == 1
+                B = pipeline.to_device(np.asarray(transform, dtype=np.float64).reshape(len(transform), -1))
+                out = pipeline.spmm(dev_t[0], B, dev_t[1]).cpu().numpy()
+                return out[:, 0] if one_d else out
             transitions = self.transitions
         return super().interpolate(transform, transitions=transitions, Y=Y)

@@ -454,3 +454,34 @@ def row_normalize(K):
     flags = _zeros((1,), torch.int32)
     E.call("gtb_row_finalize", K.indptr, K.indices, K.data, K.shape[0], 0, None, None, P, None, flags, 0)
     return P
+
+
+def csr_from_scipy(M):
+    """scipy sparse -> DeviceCSR (canonical CSR: sorted columns, duplicates summed)."""
+    from scipy import sparse
+    M = sparse.csr_matrix(M, dtype=np.float64)
+    if not M.has_canonical_format:
+        M = M.copy()
+        M.sum_duplicates()
+    dev = _dev()
+    return DeviceCSR(torch.from_numpy(M.indptr.astype(np.int64)).to(dev),
+                     torch.from_numpy(M.indices.astype(np.int32)).to(dev),
+                     torch.from_numpy(np.ascontiguousarray(M.data)).to(dev), M.shape)
+
+
+def spmm(A, B, vals=None):
+    """``A.dot(B)`` on the device (csrc/spmm.cu): A = DeviceCSR (``vals`` substitutes its values, e.g. the
+    diffusion operator sharing K's structure), B = float64 CUDA tensor [n_cols, f] (row-major, any row
+    stride).  Accumulation order and rounding are scipy's, so the result is bit-identical to the host product
+    the reference computes (base.py:1229)."""
+    if B.dim() != 2 or B.shape[0] != A.shape[1]:
+        raise ValueError("shapes {} and {} not aligned".format(A.shape, tuple(B.shape)))
+    if B.dtype != torch.float64 or B.stride(1) != 1:
+        B = B.to(torch.float64).contiguous()
+    f = B.shape[1]
+    out = _empty((A.shape[0], f), torch.float64)
+    if A.shape[0] == 0 or f == 0:
+        return out
+    E.call("gtb_spmm_csr", A.indptr, A.indices, A.data if vals is None else vals, A.shape[0], B, B.stride(0), f,
+           out, f)
+    return out

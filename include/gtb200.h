@@ -178,6 +178,18 @@ int gtb_dense_row_scale(const double* in, const double* rowsum, int64_t nq, int6
 int gtb_dense_anisotropy(double* K, const double* deg, double alpha, int64_t n, double* newsum, void* stream);
 int gtb_dense_rowsum(const double* K, int64_t nq, int64_t nr, double* sum, void* stream);
 
+/* ---- sparse x dense product (section 8f "next" rows): replaces scipy csr_matvecs behind
+ * `transitions.dot(transform)` (DataGraph.interpolate, base.py:1195-1229), the callers' repeated
+ * `diff_op.dot(X)` diffusion, and the sparse products inside sklearn randomized_svd(diff_aff)
+ * (graphs.py:1216-1218) ---------------------------------------------------------------------- */
+/* out[n_rows][ldo] (first f columns) = A . B, A = CSR float64, B row-major [n_cols][ldb] float64; every element
+ * accumulated in stored order with separate multiply and add (bit-identical to scipy's A.dot(B)) */
+int gtb_spmm_csr(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n_rows, const double* B,
+                 int64_t ldb, int f, double* out, int64_t ldo, void* stream);
+/* out[i][:] = in[i][:] * s[i]   (power_neg_half = 0)   or   in[i][:] / sqrt(s[i])   (power_neg_half = 1) */
+int gtb_row_scale(const double* in, const double* s, int64_t n, int f, int power_neg_half, double* out,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif
