@@ -18,6 +18,9 @@ from .core import DataGraph
 from .logging_util import logger as _logger
 
 
+SPECTRAL_AUTO_N = 50_000   # GTB_SPECTRAL=auto: device-side SVD + k-means above this many samples
+
+
 def aggregate_by_cluster(K, labels_dev, n_label, want_colsum):
     """Row-wise aggregation of DeviceCSR ``K`` by ``labels[col]`` -> (DeviceCSR raw sums, normalised
     values, column sums | None)."""
@@ -116,7 +119,31 @@ class LandmarkGraph(DataGraph):
         nearest, _ = pipeline.knn_kernel(None, ref, qry, knn=1, decay=None)   # exact float64 argmin per sample
         return nearest.indices.cpu().numpy().astype(np.int64)
 
+    def _spectral_impl(self):
+        """GTB_SPECTRAL = host | device | auto (default).  ``host`` is the reference's own scikit-learn calls with
+        the same seeds (bit-identical clusters; minutes at 1M samples); ``device`` is graphtools_b200/spectral.py
+        (same algorithms in HBM, torch random streams); ``auto`` picks the device path for sparse kernels above
+        SPECTRAL_AUTO_N samples, where the host path stops being practical."""
+        import os
+        want = os.environ.get("GTB_SPECTRAL", "auto")
+        if want not in ("host", "device", "auto"):
+            raise ValueError("GTB_SPECTRAL must be host, device or auto (got %r)" % (want,))
+        sparse_kernel = isinstance(getattr(self, "_dev_kernel", None), pipeline.DeviceCSR)
+        if want == "auto":
+            want = "device" if (sparse_kernel and self.data.shape[0] > SPECTRAL_AUTO_N) else "host"
+        if want == "device" and not sparse_kernel:
+            raise NotImplementedError("device spectral landmarking needs a sparse (kNN / MNN) kernel")
+        return want
+
     def _spectral_clusters(self):
+        if self._spectral_impl() == "device":
+            from . import spectral
+            with _logger.log_task("SVD + KMeans (device)"):
+                K = self._dev_kernel
+                if getattr(self, "_dev_P", None) is None:
+                    self._dev_P = pipeline.row_normalize(K)
+                return spectral.spectral_clusters(K, self._dev_P, self._dev_degree, self.n_landmark, self.n_svd,
+                                                  self.random_state)
         from sklearn.cluster import MiniBatchKMeans
         from sklearn.utils.extmath import randomized_svd
         with _logger.log_task("SVD"):

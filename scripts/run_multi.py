@@ -62,16 +62,20 @@ def c4(n_per):
                 **checksum(G._dev_kernel))
 
 
-def c5(n, L):
+def c5(n, L, spectral=False):
     X, _ = synth.gaussian_mixture(n, 100, n_clusters=50, intrinsic_dim=10, seed=3)
     Xd = torch.from_numpy(X).cuda()
+    if spectral:
+        os.environ["GTB_SPECTRAL"] = "device"
 
     def build():
-        G = gt.Graph(Xd, knn=5, decay=40, n_landmark=L, random_landmarking=True, random_state=42, verbose=0)
+        G = gt.Graph(Xd, knn=5, decay=40, n_landmark=L, random_landmarking=not spectral, random_state=42, verbose=0)
         G.build_landmark_op()
         return G
     ms, G = timed(build)
-    return dict(config="C5 landmark %dx100 knn=5 decay=40 n_landmark=%d (random landmarking)" % (n, L), ms=ms,
+    how = "spectral landmarks: device SVD + mini-batch k-means" if spectral else "random landmarking"
+    return dict(config="C5 landmark %dx100 knn=5 decay=40 n_landmark=%d (%s)" % (n, L, how), ms=ms,
+                L_eff=int(G.landmark_op.shape[0]),
                 points_per_s=n / ms * 1e3, landmark_op_sum=float(np.sum(G.landmark_op)),
                 landmark_op_trace=float(np.trace(G.landmark_op)), **checksum(G._dev_kernel))
 
@@ -91,7 +95,7 @@ if __name__ == "__main__":
         if name == "c4":
             r = c4(20_000 if a.small else 250_000)
         else:
-            r = c5(100_000 if a.small else 1_000_000, 500 if a.small else 2000)
+            r = c5(100_000 if a.small else 1_000_000, 500 if a.small else 2000, spectral=(name == "c5s"))
         r["n_gpus"] = world
         if rank == 0:
             print(json.dumps(r), flush=True)
