@@ -9,7 +9,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgtb200.so")
+# GTB_LIB points the binding at another build of the same ABI (kernel experiments); default = the in-tree library
+LIB_PATH = os.environ.get("GTB_LIB") or os.path.join(_HERE, "libgtb200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gtb200.h")
 
 _lib = None
@@ -29,7 +30,7 @@ _SIGS = {
     "gtb_knn_radius_simt": ([_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, _P, c_int64, _P, _P,
                              _P], 1),
     "gtb_prepare_operand_tc": ([_P, c_int64, c_int, _P, c_int, _P, _P, c_int64, c_int, c_int, _P, _P, _P], 2),
-    "gtb_knn_topk_tc": ([_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P], 1),
+    "gtb_knn_topk_tc": ([_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P, _P, _P, _P], 1),
     "gtb_knn_radius_tc": ([_P, _P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, _P,
                            _P, _P], 1),
     "gtb_refine_topk": ([_P, c_int64, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_float, c_double, c_int, c_int64, c_double,

@@ -31,7 +31,14 @@
 
 namespace {
 
-constexpr int TC_M = 128, TC_N = 128, TC_CAP = 96, TC_S = 32, TC_GROUPS = 2, TC_THREADS = 64 + 128 * TC_GROUPS;
+#ifndef GTB_TC_CAP
+#define GTB_TC_CAP 96
+#endif
+#ifndef GTB_TC_HYBRID
+#define GTB_TC_HYBRID 4     // hot rows per batch from which the append switches to per-lane predicated stores (0 = never)
+#endif
+constexpr int TC_M = 128, TC_N = 128, TC_CAP = GTB_TC_CAP, TC_S = 32, TC_GROUPS = 2, TC_THREADS = 64 + 128 * TC_GROUPS;
+static_assert(TC_CAP % 32 == 0 && TC_CAP >= TC_S + 64 && TC_CAP <= 128, "candidate buffer: TC_S kept + two batches of 32");
 constexpr float TC_BIG = 1e29f;       // "no threshold yet"; padded reference rows carry |y|^2 = 1e30
 constexpr float TC_PAD_NORM = 1e30f;
 
@@ -157,6 +164,7 @@ struct TcParams {
   int64_t nq, nq_pad, nr, nr_pad;
   int nks;                                                 // 32-byte k-steps per operand row
   int64_t nrounds;
+  int64_t n_qclusters, tiles_per_split;                    // RADIUS with few query tiles: the reference range is split over CTAs
   unsigned int* sync_ctr;                                  // grid-wide pacing counter (zeroed per launch)
   const float* qn2;
   int32_t* cand_idx; uint2* cand_buf; float* tau;          // TOPK: out [nq][2*TC_S], scratch [nq_pad][2][TC_CAP], tau [nq][2]
@@ -164,57 +172,75 @@ struct TcParams {
 };
 
 // ---------------------------------------------------------------- warp-cooperative compaction
-// Sort the 128 (value, index) pairs held 4 per lane (element e = i*32 + lane) ascending.
-__device__ __forceinline__ void warp_bitonic128(float (&val)[4], int32_t (&idx)[4], int lane) {
-#pragma unroll
-  for (int k = 2; k <= 128; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= 32) {
-        const int jj = j >> 5;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int pnr = i ^ jj;
-          if (pnr > i) {
-            const bool up = (((i * 32 + lane) & k) == 0);
-            const bool gt = (val[i] > val[pnr]) || (val[i] == val[pnr] && idx[i] > idx[pnr]);
-            if (gt == up) {
-              float tv = val[i]; val[i] = val[pnr]; val[pnr] = tv;
-              int32_t ti = idx[i]; idx[i] = idx[pnr]; idx[pnr] = ti;
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool up = (((i * 32 + lane) & k) == 0);
-          const float ov = __shfl_xor_sync(0xffffffffu, val[i], j);
-          const int32_t oi = __shfl_xor_sync(0xffffffffu, idx[i], j);
-          const bool lower = ((lane & j) == 0);
-          const bool keep_min = (lower == up);
-          const bool mine_gt = (val[i] > ov) || (val[i] == ov && idx[i] > oi);
-          if (keep_min ? mine_gt : !mine_gt) { val[i] = ov; idx[i] = oi; }
-        }
-      }
-    }
-  }
+// order-preserving map float -> uint32 (and back): a < b  <=>  f2ord(a) < f2ord(b)
+__device__ __forceinline__ uint32_t f2ord(uint32_t bits) {
+  return bits ^ ((uint32_t)((int32_t)bits >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
 }
 
-// Compact one candidate buffer (TC_CAP (value, index) pairs owned by one thread): keep the TC_S smallest.
-// Returns the TC_S-th smallest value (the new threshold), uniform across the warp.
+// Compact one candidate buffer (<= TC_CAP (value, index) pairs owned by one row): keep the LS smallest and
+// return the LS-th smallest value (the row's new threshold), uniform across the warp.
+//
+// Selection instead of sorting: every pair becomes one unique 64-bit key (ordered value bits : index), held
+// TC_CAP/32 per lane; a warp-cooperative quickselect narrows (lo, hi) around the LS-th smallest key with one
+// pivot per step -- 64-bit compares, ballots and popcounts only, no data movement and no divergent branches
+// (the register bitonic sort this replaces compiled to ~100 shuffle stages of branchy compare-swaps, ~10k cycles
+// per call).  The survivors are written back in ballot-prefix order.
+template <int LS>
 __device__ __noinline__ float compact_row(uint2* buf, int cnt, int lane) {
-  float val[4];
-  int32_t idx[4];
+  constexpr int NSLOT = TC_CAP / 32;
+  constexpr unsigned long long NONE = ~0ull;
+  uint2 t[NSLOT];
+  unsigned long long key[NSLOT];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < NSLOT; ++i) {
     const int e = i * 32 + lane;
-    if (e < cnt) { uint2 t = buf[e]; val[i] = __uint_as_float(t.x); idx[i] = (int32_t)t.y; }
-    else { val[i] = gtb_inf_f(); idx[i] = 0x7fffffff; }
+    t[i] = make_uint2(0u, 0u);
+    key[i] = NONE;
+    if (e < cnt) {
+      t[i] = buf[e];
+      key[i] = ((unsigned long long)f2ord(t[i].x) << 32) | (unsigned long long)t[i].y;
+    }
   }
-  warp_bitonic128(val, idx, lane);
-  static_assert(TC_S == 32, "compact_row writes exactly one element per lane");
-  buf[lane] = make_uint2(__float_as_uint(val[0]), (uint32_t)idx[0]);
-  return __shfl_sync(0xffffffffu, val[0], 31);  // element TC_S - 1
+  unsigned long long lo = 0ull, hi = NONE, T = NONE;    // the LS-th smallest key lies strictly inside (lo, hi)
+  for (int iter = 0; iter < TC_CAP + 1; ++iter) {
+    // pivot = an element still inside the interval; slot and end of the lane scan rotate with the step so that no
+    // arrival order of the buffer is systematically bad
+    unsigned m[NSLOT];
+#pragma unroll
+    for (int i = 0; i < NSLOT; ++i) m[i] = __ballot_sync(0xffffffffu, key[i] > lo && key[i] < hi);
+    unsigned long long cand = 0ull;
+    unsigned mm = 0u;
+#pragma unroll
+    for (int i = 0; i < NSLOT; ++i) {
+      const int sl = (i + iter) % NSLOT;                 // iter is warp-uniform; first non-empty slot in rotated order
+      unsigned long long ks = key[0];
+      unsigned ms = m[0];
+#pragma unroll
+      for (int q = 1; q < NSLOT; ++q) { if (sl == q) { ks = key[q]; ms = m[q]; } }   // static indexing only
+      if (mm == 0u && ms != 0u) { cand = ks; mm = ms; }
+    }
+    if (mm == 0u) break;                                  // cannot happen while cnt >= LS
+    const int src = (iter & 2) ? (31 - __clz(mm)) : (__ffs(mm) - 1);
+    const unsigned long long pv = __shfl_sync(0xffffffffu, cand, src);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < NSLOT; ++i) c += __popc(__ballot_sync(0xffffffffu, key[i] < pv));
+    if (c == LS - 1) { T = pv; break; }
+    if (c >= LS) hi = pv; else lo = pv;
+  }
+  int base = 0;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < NSLOT; ++i) {
+    const bool keep = key[i] <= T;
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    if (keep) buf[base + __popc(km & lt)] = t[i];
+    base += __popc(km);
+  }
+  return ord2f((uint32_t)(T >> 32));
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -288,7 +314,7 @@ __device__ __forceinline__ void tc_commit_mc_pred(uint32_t bar, uint16_t mask, u
 // BF16 = false: operands are tf32 hi/lo float32 pairs (3xTF32, kind::tf32, 8 elements per 32-byte k-step);
 // BF16 = true : operands are bfloat16 hi/lo pairs (bf16x3, kind::f16, 16 elements per k-step, twice the MMA rate;
 //               the split keeps 16 mantissa bits -- still only used to SELECT candidates).
-template <int MODE, int CL, bool BF16>  // MODE 0 = TOPK, 1 = RADIUS
+template <int MODE, int CL, bool BF16, int LS>  // MODE 0 = TOPK (two lists of LS per row), 1 = RADIUS
 __global__ void __launch_bounds__(TC_THREADS, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBht,
                  const __grid_constant__ CUtensorMap mBl, const __grid_constant__ CUtensorMap mBlt,
@@ -319,16 +345,22 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (bar0 - base) + 144);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t ntiles = p.nr_pad / TC_N;
   // Persistent CTAs: cluster c sweeps the whole reference set once per ROUND for the query tiles
   // (c + round * n_clusters) * CL + rank.  All resident CTAs therefore stream the same reference tiles
   // at the same time (one DRAM read per round instead of one per CTA), and odd rounds sweep backwards so
   // the tail of the previous sweep is still in L2.
+  // RADIUS launches with fewer query tiles than SMs run one round and split the reference range instead
+  // (cluster c = query cluster c % n_qclusters, tile range c / n_qclusters): the output is an append list,
+  // so the pieces need no merge.
   const int64_t n_clusters = gridDim.x / CL;
   const int64_t cluster_id = blockIdx.x / CL;
   const int64_t nrounds = p.nrounds;
-  auto q0_of = [&](int64_t round) { return ((cluster_id + round * n_clusters) * CL + (blockIdx.x % CL)) * TC_M; };
-  auto btile = [&](int64_t round, int64_t t) { return (round & 1) ? (ntiles - 1 - t) : t; };
+  const int64_t qcluster = cluster_id % p.n_qclusters;
+  const int64_t tile0 = (cluster_id / p.n_qclusters) * p.tiles_per_split;
+  const int64_t tiles_left = p.nr_pad / TC_N - tile0;
+  const int64_t ntiles = tiles_left < p.tiles_per_split ? tiles_left : p.tiles_per_split;
+  auto q0_of = [&](int64_t round) { return ((qcluster + round * n_clusters) * CL + (blockIdx.x % CL)) * TC_M; };
+  auto btile = [&](int64_t round, int64_t t) { return tile0 + ((round & 1) ? (ntiles - 1 - t) : t); };
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
   constexpr int ROWS = TC_N / CL;                            // rows of each B block this CTA loads
@@ -502,6 +534,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     // this thread's candidate buffer: uniform base + per-thread offset (rows past nq never append)
     const int64_t boff = valid ? (gq * TC_GROUPS + grp) * TC_CAP : 0;
     uint2* wbuf = p.cand_buf + (q0 + quad * 32) * TC_GROUPS * TC_CAP;   // warp-uniform: first row of this quadrant
+    uint2* mybuf = p.cand_buf + boff;                                     // this row's buffer (never written when !valid)
 
     // this group's tiles: running iteration index it = round * ntiles + t with it % 2 == grp
     const int64_t it0 = round * ntiles;
@@ -530,6 +563,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tm_empty + 8 * s);
+#ifdef GTB_EXP_NOSELECT
+      continue;
+#endif
 #pragma unroll
       for (int part = 0; part < TC_N / 32; ++part) {
         float v[32];
@@ -540,11 +576,33 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         float vmin = v[0];
 #pragma unroll
         for (int j = 1; j < 32; ++j) vmin = fminf(vmin, v[j]);
-        // Selection.  Lanes (= query rows) holding at least one qualifying column are rare (~1 per warp and
-        // batch), so they are served one at a time by the whole warp: the lane parks its 32 values in a
-        // 128-byte shared-memory slot, every lane tests ONE column, and the hits are written with their
-        // ballot-prefix positions.  ~25 instructions per serviced row instead of 32 predicated append slots.
+        // Selection.  A batch in which no lane (= query row) has a qualifying column -- the common case once the
+        // thresholds have tightened -- costs the min tree and one ballot.
         unsigned hot = __ballot_sync(0xffffffffu, (MODE == 0) ? (vmin < thr) : (vmin <= thr));
+#ifdef GTB_EXP_NOSERVICE
+        hot = 0;
+#endif
+        if (MODE == 0) {
+#if GTB_TC_HYBRID > 0
+          // Burst regime (round start: most rows hit in every batch): every lane appends its own hits to its own
+          // row buffer with predicated stores behind one warp-uniform branch -- a fixed ~130 issue slots instead
+          // of ~350 cycles per hot row.  With few hot rows the cooperative path below is cheaper.
+          if (__popc(hot) >= GTB_TC_HYBRID) {
+            uint2* wp = mybuf + cnt;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              asm volatile(
+                  "{\n .reg .pred p;\n setp.lt.f32 p, %1, %2;\n @p st.global.v2.b32 [%0], {%3, %4};\n"
+                  " @p add.u64 %0, %0, 8;\n}"
+                  : "+l"(wp)
+                  : "f"(v[j]), "f"(thr), "r"(__float_as_uint(v[j])), "r"(col0 + j)
+                  : "memory");
+            }
+            cnt = (int)(wp - mybuf);
+            hot = 0;
+          }
+#endif
+        }
         while (hot) {
           const int L = __ffs(hot) - 1;
           hot &= hot - 1;
@@ -584,9 +642,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
             need &= need - 1;
             const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
             __syncwarp();
-            const float nt = compact_row(wbuf + (owner * TC_GROUPS + grp) * TC_CAP, ocnt, lane);
+            const float nt = compact_row<LS>(wbuf + (owner * TC_GROUPS + grp) * TC_CAP, ocnt, lane);
             __syncwarp();
-            if (lane == owner) { thr = nt; cnt = TC_S; }
+            if (lane == owner) { thr = nt; cnt = LS; }
           }
         }
       }
@@ -594,21 +652,21 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
 
     if (MODE == 0) {
       // final compaction of every buffer still holding more than TC_S candidates
-      unsigned need = __ballot_sync(0xffffffffu, cnt > TC_S);
+      unsigned need = __ballot_sync(0xffffffffu, cnt > LS);
       while (need) {
         const int owner = __ffs(need) - 1;
         need &= need - 1;
         const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
         __syncwarp();
-        const float nt = compact_row(wbuf + (owner * TC_GROUPS + grp) * TC_CAP, ocnt, lane);
+        const float nt = compact_row<LS>(wbuf + (owner * TC_GROUPS + grp) * TC_CAP, ocnt, lane);
         __syncwarp();
-        if (lane == owner) { thr = nt; cnt = TC_S; }
+        if (lane == owner) { thr = nt; cnt = LS; }
       }
       __syncwarp();
       if (valid) {
-        int32_t* out = p.cand_idx + gq * (TC_GROUPS * TC_S) + grp * TC_S;
-        for (int e = 0; e < TC_S; ++e) out[e] = (e < cnt) ? (int32_t)p.cand_buf[boff + e].y : -1;
-        p.tau[gq * TC_GROUPS + grp] = (cnt < TC_S || thr >= TC_BIG) ? gtb_inf_f() : thr + nx;
+        int32_t* out = p.cand_idx + gq * (TC_GROUPS * LS) + grp * LS;
+        for (int e = 0; e < LS; ++e) out[e] = (e < cnt) ? (int32_t)p.cand_buf[boff + e].y : -1;
+        p.tau[gq * TC_GROUPS + grp] = (cnt < LS || thr >= TC_BIG) ? gtb_inf_f() : thr + nx;
       }
     }
     }  // rounds
@@ -732,7 +790,7 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int Kp, int box_k, i
 
 int g_tc_pacing = 1;
 
-template <int MODE, int CL, bool BF16>
+template <int MODE, int CL, bool BF16, int LS>
 int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, TcParams& p,
                  cudaStream_t st) {
   CUtensorMap mBh, mBht, mBl, mBlt;
@@ -744,20 +802,31 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
   if ((rc = make_map(&mBl, r_lo, p.nr_pad, Kp, 4 * EPK, TC_N / CL, true, BF16))) return rc;
   if ((rc = make_map(&mBlt, r_lo, p.nr_pad, Kp, EPK, TC_N / CL, false, BF16))) return rc;
   size_t smem = 1024 + (size_t)2 * (BF16 ? 3 : 2) * TC_N * p.nks * 32 + 256 + 1024;
-  auto kern = search_tc_kernel<MODE, CL, BF16>;
+  auto kern = search_tc_kernel<MODE, CL, BF16, LS>;
   GTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, nsm = 0;
   GTB_CUDA(cudaGetDevice(&dev));
   GTB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   const int64_t n_cluster_tiles = gtb_cdiv(p.nq_pad / TC_M, CL);
-  const int64_t n_clusters = n_cluster_tiles < (nsm / CL) ? n_cluster_tiles : (nsm / CL);
+  int64_t n_clusters = n_cluster_tiles < (nsm / CL) ? n_cluster_tiles : (nsm / CL);
   p.nrounds = gtb_cdiv(n_cluster_tiles, n_clusters);
+  const int64_t total_tiles = p.nr_pad / TC_N;
+  p.n_qclusters = n_clusters;
+  p.tiles_per_split = total_tiles;
+  int64_t splits = 1;
+  if (MODE == 1 && n_cluster_tiles * 2 <= nsm / CL && total_tiles >= 16) {
+    splits = (nsm / CL) / n_cluster_tiles;
+    if (splits > total_tiles / 8) splits = total_tiles / 8;
+    p.tiles_per_split = gtb_cdiv(total_tiles, splits);
+    splits = gtb_cdiv(total_tiles, p.tiles_per_split);
+    n_clusters = n_cluster_tiles * splits;
+  }
   const unsigned nblk = (unsigned)(n_clusters * CL);
   // pacing counter: a small ring of device words, one fresh (zeroed) slot per launch
   static unsigned int* ring[64] = {nullptr};
   static int ring_pos[64] = {0};
   p.sync_ctr = nullptr;
-  if (dev < 64 && g_tc_pacing && nblk > (unsigned)CL) {
+  if (dev < 64 && g_tc_pacing && nblk > (unsigned)CL && splits == 1) {
     if (!ring[dev]) {
       if (cudaMalloc(&ring[dev], 32 * 64) != cudaSuccess) { ring[dev] = nullptr; (void)cudaGetLastError(); }
     }
@@ -784,21 +853,27 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
 }
 
 int g_tc_cluster = 2;
+int g_tc_list = 32;
 
 template <int MODE>
 int launch_tc(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, bool bf16, TcParams& p,
               cudaStream_t st) {
+  const bool short_list = (MODE == 0) && g_tc_list == 16;
   if (bf16) {
     switch (g_tc_cluster) {
-      case 1: return launch_tc_cl<MODE, 1, true>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
-      case 2: return launch_tc_cl<MODE, 2, true>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+      case 1: return short_list ? launch_tc_cl<MODE, 1, true, (MODE == 0 ? 16 : 32)>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
+                                : launch_tc_cl<MODE, 1, true, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+      case 2: return short_list ? launch_tc_cl<MODE, 2, true, (MODE == 0 ? 16 : 32)>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
+                                : launch_tc_cl<MODE, 2, true, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
       default: gtb_set_error("cluster size must be 1 or 2 for the bf16 variant"); return GTB_ERR_ARG;
     }
   }
   switch (g_tc_cluster) {
-    case 1: return launch_tc_cl<MODE, 1, false>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
-    case 2: return launch_tc_cl<MODE, 2, false>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
-    case 4: return launch_tc_cl<MODE, 4, false>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+    case 1: return short_list ? launch_tc_cl<MODE, 1, false, (MODE == 0 ? 16 : 32)>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
+                              : launch_tc_cl<MODE, 1, false, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+    case 2: return short_list ? launch_tc_cl<MODE, 2, false, (MODE == 0 ? 16 : 32)>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
+                              : launch_tc_cl<MODE, 2, false, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+    case 4: return launch_tc_cl<MODE, 4, false, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
     default: gtb_set_error("cluster size must be 1, 2 or 4"); return GTB_ERR_ARG;
   }
 }
@@ -854,9 +929,11 @@ static int tc_check(int64_t nq, int64_t nr, int64_t nq_pad, int64_t nr_pad, int 
 
 extern "C" int gtb_knn_topk_tc(const void* q_hi, const void* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
                                const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp, int dtype,
-                               int32_t* cand_idx, void* scratch, float* tau, void* stream) {
+                               int list, int32_t* cand_idx, void* scratch, float* tau, void* stream) {
   int rc = tc_check(nq, nr, nq_pad, nr_pad, Kp, dtype);
   if (rc) return rc;
+  GTB_CHECK_ARG(list == 16 || list == 32, "list size must be 16 or 32");
+  g_tc_list = list;
   TcParams p{};
   p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.qn2 = qn2;
   p.cand_idx = cand_idx; p.cand_buf = reinterpret_cast<uint2*>(scratch); p.tau = tau;

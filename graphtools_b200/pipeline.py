@@ -122,7 +122,9 @@ class SearchOperand:
         # rows are whole 32-byte k-steps (16 bf16 / 8 tf32 elements): SWIZZLE_128B blocks plus SWIZZLE_32B
         # tail blocks.  (Padding bf16 rows to whole 128-byte blocks was measured slower: 699 vs 682 ms at
         # d = 100 -- the extra MMAs cost more than the tail blocks.)
+        import os
         step = 16 if dtype else 8
+        step = int(os.environ.get("GTB_KP_STEP", step))      # experiments: 64 (bf16) / 32 (tf32) = whole 128-byte blocks
         return (self.d + 1 + step - 1) // step * step
 
     @property
@@ -273,7 +275,7 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
             raise ValueError("GTB_SEARCH_IMPL must be auto, tc, tc16 or simt (got %r)" % (want,))
         impl = "simt"
         for cand_impl in order:
-            if cand_impl == "simt" or (knn + 8 <= 32 and S in (None, 64)
+            if cand_impl == "simt" or (knn + 8 <= 32 and S in (None, 32, 64)
                                        and ref.tc_ok(1 if cand_impl == "tc16" else 0)):
                 impl = cand_impl
                 break
@@ -283,8 +285,14 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
     if impl in ("tc", "tc16"):
         if not ref.tc_ok(tcd):
             raise ValueError("tensor-core search: d = {} does not fit the resident query tile".format(d))
-        S, stride, ntau = 64, 64, 2
         import os
+        # two candidate lists per row (one per epilogue group) of `ls` entries each.  Short lists (16) halve the
+        # selection work of the sweep; they are used when the neighbourhood asked for is small (knn + 8 <= 16) --
+        # rows whose kernel support is wider fail certification and are finished by the radius pass.
+        ls = int(os.environ.get("GTB_TC_LIST", "16" if knn + 8 <= 16 else "32"))
+        if ls not in (16, 32) or knn > ls:
+            raise ValueError("GTB_TC_LIST must be 16 or 32 and >= knn")
+        S, stride, ntau = 2 * ls, 2 * ls, 2
         E.lib().gtb_tc_set_pacing(int(os.environ.get("GTB_TC_PACING", "1")))
         if E.lib().gtb_tc_set_cluster(min(tc_cluster(), 2) if tcd else tc_cluster()) != 0:
             raise ValueError("GTB_TC_CLUSTER must be 1, 2 or 4")
@@ -297,7 +305,7 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         cand = _empty((nq, stride), torch.int32)
         tau = _empty((nq, ntau), torch.float32)
         scratch = _empty((E.lib().gtb_tc_scratch_bytes(qry.n_pad),), torch.uint8)
-        E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, nq, qry.n_pad, r_hi, r_lo, nr, ref.n_pad, Kp, tcd, cand,
+        E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, nq, qry.n_pad, r_hi, r_lo, nr, ref.n_pad, Kp, tcd, ls, cand,
                scratch, tau)
         del scratch
     elif impl == "simt":

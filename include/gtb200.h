@@ -62,7 +62,9 @@ int gtb_knn_radius_simt(const float* QT, const float* qn2, const float* lim2, in
  *   dtype 0: 3xTF32 -- float32 storage, hi = tf32(v), lo = tf32(v - hi), kind::tf32, Kp = roundup(d+1, 8) <= 104
  *   dtype 1: bf16x3 -- bfloat16 storage, hi = bf16(v), lo = bf16(v - hi), kind::f16,  Kp multiple of 16, <= 128
  *            (3 smem stages, 3 TMEM accumulators)
- * topk: cand_idx[nq][64] = two lists of 32 (disjoint halves of the reference tiles, -1 = empty) with their
+ * topk: cand_idx[nq][2 * list] = two lists of `list` = 32 or 16 entries (disjoint halves of the reference tiles, -1 = empty; shorter
+ * lists halve the selection work -- rows whose kernel support they do not cover fail certification in gtb_refine_topk and are
+ * completed by the radius pass, so the result does not depend on `list`) with their
  * thresholds tau[nq][2]; scratch = gtb_tc_scratch_bytes(nq_pad) bytes.  radius: contract of gtb_knn_radius_simt. */
 int gtb_tc_max_kp(void);
 /* thread-block cluster size of the search kernel: 1, 2 (default) or 4 CTAs share each reference tile
@@ -74,7 +76,7 @@ int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const float* mean, 
                            int64_t n_pad, int Kp, int dtype, float* norm2, float* maxnorm, void* stream);
 int gtb_knn_topk_tc(const void* q_hi, const void* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
                     const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp, int dtype,
-                    int32_t* cand_idx, void* scratch, float* tau, void* stream);
+                    int list, int32_t* cand_idx, void* scratch, float* tau, void* stream);
 int64_t gtb_tc_scratch_bytes(int64_t nq_pad);
 int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float* qn2, const float* lim2, int64_t nq,
                       int64_t nq_pad, const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp,

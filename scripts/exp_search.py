@@ -1,0 +1,42 @@
+"""Times the tensor-core search kernel alone (gtb_knn_topk_tc) on the headline shape -- kernel experiments.
+    GTB_LIB=path/to/variant.so python scripts/exp_search.py [--n 1000000] [--d 100] [--dtype 1] [--reps 2]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from graphtools_b200 import _engine as E, pipeline, synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=1_000_000)
+ap.add_argument("--d", type=int, default=100)
+ap.add_argument("--dtype", type=int, default=1)
+ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--tag", default="")
+a = ap.parse_args()
+X, _ = synth.gaussian_mixture(a.n, a.d, n_clusters=50, intrinsic_dim=10, seed=3)
+ref = pipeline.SearchOperand(torch.from_numpy(X).cuda())
+q_hi, q_lo, q_n2 = ref.tc(0, a.dtype)
+r_hi, r_lo, _ = ref.tc(1, a.dtype)
+Kp = ref.kp(a.dtype)
+E.lib().gtb_tc_set_pacing(int(os.environ.get("GTB_TC_PACING", "1")))
+E.lib().gtb_tc_set_cluster(int(os.environ.get("GTB_TC_CLUSTER", "2")))
+ls = int(os.environ.get("GTB_TC_LIST", "32"))
+cand = torch.empty((a.n, 2 * ls), dtype=torch.int32, device="cuda")
+tau = torch.empty((a.n, 2), dtype=torch.float32, device="cuda")
+scratch = torch.empty((E.lib().gtb_tc_scratch_bytes(ref.n_pad),), dtype=torch.uint8, device="cuda")
+times = []
+for rep in range(a.reps + 1):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, a.n, ref.n_pad, r_hi, r_lo, a.n, ref.n_pad, Kp, a.dtype, ls, cand, scratch,
+           tau)
+    e1.record()
+    torch.cuda.synchronize()
+    times.append(e0.elapsed_time(e1))
+best = min(times[1:])
+print("EXP %s list=%d lib=%s n=%d d=%d Kp=%d dtype=%d: %s ms (best %.1f) -> %.1f TFLOP/s algorithmic; cand checksum %d" % (
+    a.tag, ls, os.path.basename(E.LIB_PATH), a.n, a.d, Kp, a.dtype, ["%.1f" % t for t in times], best,
+    2.0 * a.n * a.n * a.d / best / 1e9, int(cand.clamp(min=0).to(torch.int64).sum().item())), flush=True)

@@ -96,16 +96,16 @@ def test_radius_pairs_complete():
 
 
 # ------------------------------------------------------------------ tensor-core (tcgen05) search
-def _tc_topk(X, Y=None, dtype=0):
+def _tc_topk(X, Y=None, dtype=0, ls=32):
     ref = pipeline.SearchOperand(_dev(X))
     qry = ref if Y is None else pipeline.SearchOperand(_dev(Y), mean=ref.mean)
     q_hi, q_lo, q_n2 = qry.tc(0, dtype)
     r_hi, r_lo, _ = ref.tc(1, dtype)
-    cand = torch.full((qry.n, 64), -7, dtype=torch.int32, device="cuda")
+    cand = torch.full((qry.n, 2 * ls), -7, dtype=torch.int32, device="cuda")
     scratch = torch.zeros((E.lib().gtb_tc_scratch_bytes(qry.n_pad),), dtype=torch.uint8, device="cuda")
     tau = torch.empty((qry.n, 2), dtype=torch.float32, device="cuda")
     E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, qry.n, qry.n_pad, r_hi, r_lo, ref.n, ref.n_pad, ref.kp(dtype),
-           dtype, cand, scratch, tau)
+           dtype, ls, cand, scratch, tau)
     torch.cuda.synchronize()
     return cand.cpu().numpy(), tau.cpu().numpy().min(axis=1), qry, ref
 
@@ -127,19 +127,20 @@ def test_tc_operand_split():
     assert np.allclose(qfull[:300, :100], Xc, rtol=2e-6, atol=1e-9) and (qfull[:300, 100] == 1).all()
 
 
+@pytest.mark.parametrize("ls", [32, 16])
 @pytest.mark.parametrize("dtype", [0, 1])
 @pytest.mark.parametrize("n,d", [(1797, 64), (3000, 100), (700, 20), (2500, 10), (300, 5), (40, 3), (1000, 31),
                                  (1000, 55), (777, 103)])
-def test_tc_topk_candidates(n, d, dtype):
+def test_tc_topk_candidates(n, d, dtype, ls):
     X, _ = synth.gaussian_mixture(n, d, n_clusters=5, intrinsic_dim=min(8, d), seed=3)
-    cand, tau, qry, ref = _tc_topk(X, dtype=dtype)
+    cand, tau, qry, ref = _tc_topk(X, dtype=dtype, ls=ls)
     X64 = X.astype(np.float64)
     D2 = ((X64[:, None, :] - X64[None, :, :]) ** 2).sum(-1)
     order = np.argsort(D2, axis=1, kind="stable")
     Xc = X64 - X64.mean(0)
     nrm = (Xc ** 2).sum(1)
     eps = pipeline.eps_rel_tc16(d) if dtype else pipeline.eps_rel_tc(d)
-    # two lists of 32: references in even / odd 128-row tiles
+    # two lists of ls: references in even / odd 128-row tiles
     tile_par = (np.arange(n) // 128) % 2
     n_even, n_odd = int((tile_par == 0).sum()), int((tile_par == 1).sum())
     for i in range(0, n, max(1, n // 300)):
@@ -147,18 +148,18 @@ def test_tc_topk_candidates(n, d, dtype):
         c = cand[i][cand[i] >= 0]
         assert (c < n).all(), "padded reference leaked into the candidates"
         assert len(np.unique(c)) == len(c), "duplicate candidate"
-        assert len(c) == min(32, n_even) + min(32, n_odd), (i, len(c))
-        assert (tile_par[cand[i][:32][cand[i][:32] >= 0]] == 0).all() and \
-            (tile_par[cand[i][32:][cand[i][32:] >= 0]] == 1).all()
+        assert len(c) == min(ls, n_even) + min(ls, n_odd), (i, len(c))
+        assert (tile_par[cand[i][:ls][cand[i][:ls] >= 0]] == 0).all() and \
+            (tile_par[cand[i][ls:][cand[i][ls:] >= 0]] == 1).all()
         bound = eps * (nrm[i] + nrm.max())
-        # the true nearest 24 are present unless the fast pass cannot tell them apart from the 25th+
-        sure = [j for j in order[i, :min(24, n)] if D2[i, j] + 2 * bound < D2[i, order[i, min(31, n - 1)]]]
+        # the true nearest ls - 8 are present unless the fast pass cannot tell them apart from the ls-th
+        sure = [j for j in order[i, :min(ls - 8, n)] if D2[i, j] + 2 * bound < D2[i, order[i, min(ls - 1, n - 1)]]]
         assert set(sure).issubset(set(c)), "row %d misses a true neighbour" % i
         non = np.setdiff1d(np.arange(n), c)
         if len(non):
             assert np.isfinite(tau[i])
             assert D2[i, non].min() >= tau[i] - bound
-        if n_even <= 32 and n_odd <= 32:
+        if n_even <= ls and n_odd <= ls:
             assert np.isinf(tau[i])
 
 
