@@ -28,12 +28,32 @@ struct RowParams {
 };
 
 // exact squared distance between query row xq and reference row xr, cooperatively by one warp
+// (float32 rows made of whole, 16-byte aligned float4s are read as float4 -- the same element-to-lane assignment and
+// summation order as the gather loop of refine_topk_kernel, so both refine stages return identical bits)
 template <typename T>
 __device__ __forceinline__ double warp_dist2(const T* __restrict__ xq, const T* __restrict__ xr, int d, int lane) {
   double s = 0.0;
-  for (int k = lane; k < d; k += 32) {
-    double df = (double)xq[k] - (double)xr[k];
-    s = fma(df, df, s);
+  bool vec = false;
+  if constexpr (sizeof(T) == 4) {
+    vec = ((d & 3) == 0) && (((reinterpret_cast<uintptr_t>(xq) | reinterpret_cast<uintptr_t>(xr)) & 15) == 0);
+  }
+  if (vec) {
+    if constexpr (sizeof(T) == 4) {
+      const float4* q4 = reinterpret_cast<const float4*>(xq);
+      const float4* r4 = reinterpret_cast<const float4*>(xr);
+      for (int kv = lane; kv < (d >> 2); kv += 32) {
+        const float4 q = q4[kv], r = r4[kv];
+        double df = (double)q.x - (double)r.x; s = fma(df, df, s);
+        df = (double)q.y - (double)r.y; s = fma(df, df, s);
+        df = (double)q.z - (double)r.z; s = fma(df, df, s);
+        df = (double)q.w - (double)r.w; s = fma(df, df, s);
+      }
+    }
+  } else {
+    for (int k = lane; k < d; k += 32) {
+      double df = (double)xq[k] - (double)xr[k];
+      s = fma(df, df, s);
+    }
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -112,6 +132,58 @@ __global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Param
   const T* xq = reinterpret_cast<const T*>(rp.Xq) + row * rp.d;
   const T* Xr = reinterpret_cast<const T*>(rp.Xr);
   int n_cand = 0;
+  bool vec = false;
+  if constexpr (sizeof(T) == 4) {
+    vec = ((rp.d & 3) == 0) && (((reinterpret_cast<uintptr_t>(rp.Xq) | reinterpret_cast<uintptr_t>(rp.Xr)) & 15) == 0);
+  }
+  if (vec) {
+    if constexpr (sizeof(T) == 4) {
+      // float32 rows of whole float4s: one 16-byte load per lane covers a 400-byte row with 25 lanes, and eight
+      // candidate rows are gathered per pass -- the gathers are latency-bound, so bytes in flight are what counts
+      const int nv = rp.d >> 2;
+      const float4* xq4 = reinterpret_cast<const float4*>(xq);
+      const float4* Xr4 = reinterpret_cast<const float4*>(Xr);
+      for (int c0 = 0; c0 < S; c0 += 8) {
+        int j[8];
+        double acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          acc[u] = 0.0;
+          j[u] = (c0 + u < S) ? p.cand_idx[row * p.cand_stride + c0 + u] : -1;  // uniform loads
+        }
+        for (int kv = lane; kv < nv; kv += 32) {
+          const float4 q = xq4[kv];
+          float4 r[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j[u] >= 0) r[u] = Xr4[(int64_t)j[u] * nv + kv];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (j[u] >= 0) {
+              double df = (double)q.x - (double)r[u].x; acc[u] = fma(df, df, acc[u]);
+              df = (double)q.y - (double)r[u].y; acc[u] = fma(df, df, acc[u]);
+              df = (double)q.z - (double)r[u].z; acc[u] = fma(df, df, acc[u]);
+              df = (double)q.w - (double)r[u].w; acc[u] = fma(df, df, acc[u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], off);
+          if (c0 + u < S) {
+            if (j[u] >= 0) ++n_cand;
+            if (lane == 0) {
+              key[c0 + u] = (j[u] >= 0) ? acc[u] : DBL_MAX * 2.0;  // +inf for empty slots
+              idx[c0 + u] = (j[u] >= 0) ? j[u] : 0x7fffffff;
+            }
+          }
+        }
+      }
+    }
+  } else {
   // four candidates in flight per pass: the row gathers are latency-bound, not bandwidth-bound
   for (int c0 = 0; c0 < S; c0 += 4) {
     int j[4];
@@ -140,6 +212,7 @@ __global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Param
         }
       }
     }
+  }
   }
   for (int t = S + lane; t < np2; t += 32) { key[t] = DBL_MAX * 2.0; idx[t] = 0x7fffffff; }
   __syncwarp();

@@ -55,14 +55,27 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+#ifndef GTB_TC_WAIT_HINT
+#define GTB_TC_WAIT_HINT 0      // suspend-time hint (ns) of the mbarrier waits; 0 = the implementation default
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {
+#if GTB_TC_WAIT_HINT > 0
+    // the waiting warp is suspended by the hardware for up to the hint instead of re-issuing the poll: under
+    // the power cap every spin instruction costs clock
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"((uint32_t)GTB_TC_WAIT_HINT)
+        : "memory");
+#else
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
   } while (!ok);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {

@@ -59,11 +59,73 @@ def to_device(X):
     return torch.from_numpy(np.ascontiguousarray(X, dtype=dt)).to(_dev())
 
 
+_D2H_CHUNK = 32 << 20      # bytes per staging buffer
+_D2H_RING = 3
+_d2h_state = {}
+
+
+def _d2h_ring():
+    """Page-locked staging ring, a side stream and a small thread pool, created once per process: the result
+    arrays (K / P values, indices: ~350 MB at 1M samples) are handed to the caller, so they must live in ordinary
+    pageable memory, but a direct pageable cudaMemcpy runs at ~2.6 GB/s (first-touch page faults serialised with
+    the copy)."""
+    if not _d2h_state:
+        from concurrent.futures import ThreadPoolExecutor
+        _d2h_state["bufs"] = [torch.empty((_D2H_CHUNK,), dtype=torch.uint8, pin_memory=True) for _ in range(_D2H_RING)]
+        _d2h_state["stream"] = torch.cuda.Stream()
+        _d2h_state["pool"] = ThreadPoolExecutor(max_workers=4)
+    return _d2h_state["bufs"], _d2h_state["stream"], _d2h_state["pool"]
+
+
 def d2h_pinned(t):
-    """Device->host copy.  (A page-locked destination was measured slower end to end: cudaHostAlloc of the
-    ~350 MB result costs more than the pageable copy it saves, and the arrays are handed to the caller, so
-    the pinned blocks cannot be recycled.)"""
-    return t.cpu()
+    """Device->host copy into a fresh pageable tensor.  Large tensors go through the pinned staging ring in
+    32 MB chunks: the DMA of chunk i+1 overlaps the host-side copy of chunk i, which four threads perform in
+    parallel (so the first-touch page faults of the destination are taken in parallel too)."""
+    nbytes = t.numel() * t.element_size()
+    if nbytes < (8 << 20) or not t.is_cuda:
+        return t.cpu()
+    bufs, side, pool = _d2h_ring()
+    src = t.contiguous().view(-1).view(torch.uint8)
+    out = torch.empty(t.shape, dtype=t.dtype)
+    dst = out.view(-1).view(torch.uint8).numpy()
+    side.wait_stream(torch.cuda.current_stream())
+    chunks = [(off, min(_D2H_CHUNK, nbytes - off)) for off in range(0, nbytes, _D2H_CHUNK)]
+    events = [None] * len(chunks)
+    pending = [[] for _ in range(_D2H_RING)]           # host copies still reading staging buffer r
+
+    def issue(i):
+        off, n = chunks[i]
+        r = i % _D2H_RING
+        for f in pending[r]:
+            f.result()
+        pending[r] = []
+        with torch.cuda.stream(side):
+            bufs[r][:n].copy_(src[off:off + n], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        events[i] = ev
+
+    def drain(i):
+        off, n = chunks[i]
+        r = i % _D2H_RING
+        events[i].synchronize()
+        hb = bufs[r].numpy()
+        step = (n + 3) // 4
+        for a in range(0, n, step):
+            b = min(n, a + step)
+            pending[r].append(pool.submit(np.copyto, dst[off + a:off + b], hb[a:b]))
+
+    for i in range(min(_D2H_RING - 1, len(chunks))):
+        issue(i)
+    for i in range(len(chunks)):
+        if i + _D2H_RING - 1 < len(chunks):
+            issue(i + _D2H_RING - 1)
+        drain(i)
+    for r in range(_D2H_RING):
+        for f in pending[r]:
+            f.result()
+    t.record_stream(side)
+    return out
 
 
 class SearchOperand:
