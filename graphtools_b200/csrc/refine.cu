@@ -25,6 +25,7 @@ struct RowParams {
   double thresh; double rfac;  // rfac = (-ln thresh)^(1/decay)
   const double* bw_fixed; int bw_mode;  // 0 adaptive (k-th neighbour), 1 scalar, 2 per-row
   double bw_scale; double bw_floor;     // bw_floor = eps (np.finfo(float).eps)
+  int metric;                           // 0 euclidean, 1 cosine (1 - x.y / (|x||y|), sklearn cosine_distances)
 };
 
 // exact squared distance between query row xq and reference row xr, cooperatively by one warp
@@ -58,6 +59,31 @@ __device__ __forceinline__ double warp_dist2(const T* __restrict__ xq, const T* 
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
   return s;
+}
+
+// Cosine metric.  The fast pass runs on the row-normalised copies, where |x^ - y^|^2 = 2 (1 - cos) = 2 d_cos: same
+// ordering, and the certification arithmetic below converts between the metric's own units (in which key[] holds the
+// SQUARED exact distance, so sqrt(key) is the distance for both metrics) and search-space squared distances.
+__device__ __forceinline__ double search2_of_key(double key, int metric) { return metric == 0 ? key : 2.0 * sqrt(key); }
+__device__ __forceinline__ double search2_of_radius(double r, int metric) { return metric == 0 ? r * r : 2.0 * r; }
+
+// squared cosine distance between two rows of the ORIGINAL data, float64, one warp
+template <typename T>
+__device__ __forceinline__ double warp_cos2(const T* __restrict__ xq, const T* __restrict__ xr, int d, int lane) {
+  double dot = 0.0, nx = 0.0, ny = 0.0;
+  for (int k = lane; k < d; k += 32) {
+    const double a = (double)xq[k], b = (double)xr[k];
+    dot = fma(a, b, dot); nx = fma(a, a, nx); ny = fma(b, b, ny);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    nx += __shfl_xor_sync(0xffffffffu, nx, off);
+    ny += __shfl_xor_sync(0xffffffffu, ny, off);
+  }
+  double dc = 1.0 - dot / (sqrt(nx) * sqrt(ny));
+  dc = fmin(fmax(dc, 0.0), 2.0);          // np.clip(S, 0, 2) in sklearn cosine_distances
+  return dc * dc;
 }
 
 __device__ __forceinline__ int next_pow2(int x) {
@@ -133,10 +159,20 @@ __global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Param
   const T* Xr = reinterpret_cast<const T*>(rp.Xr);
   int n_cand = 0;
   bool vec = false;
+  if (rp.metric == 1) {
+    for (int c0 = 0; c0 < S; ++c0) {
+      const int j = p.cand_idx[row * p.cand_stride + c0];
+      const double v = (j >= 0) ? warp_cos2<T>(xq, Xr + (int64_t)j * rp.d, rp.d, lane) : DBL_MAX * 2.0;
+      if (j >= 0) ++n_cand;
+      if (lane == 0) { key[c0] = v; idx[c0] = (j >= 0) ? j : 0x7fffffff; }
+    }
+  } else
   if constexpr (sizeof(T) == 4) {
     vec = ((rp.d & 3) == 0) && (((reinterpret_cast<uintptr_t>(rp.Xq) | reinterpret_cast<uintptr_t>(rp.Xr)) & 15) == 0);
   }
-  if (vec) {
+  if (rp.metric == 1) {
+    // done above
+  } else if (vec) {
     if constexpr (sizeof(T) == 4) {
       // float32 rows of whole float4s: one 16-byte load per lane covers a 400-byte row with 25 lanes, and eight
       // candidate rows are gathered per pass -- the gathers are latency-bound, so bytes in flight are what counts
@@ -235,20 +271,20 @@ __global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Param
   bool done, bw_cert = true;
   if (rp.decay < 0) {
     double dk2 = key[rp.knn - 1];
-    done = all_found || dk2 < rho2;
+    done = all_found || search2_of_key(dk2, rp.metric) < rho2;
     r_search = sqrt(dk2);
   } else {
     if (rp.bw_mode == 0) {
       double dk2 = key[rp.knn - 1];
       dk = sqrt(dk2);
       bw = fmax(dk * rp.bw_scale, rp.bw_floor);
-      bw_cert = all_found || dk2 < rho2;
+      bw_cert = all_found || search2_of_key(dk2, rp.metric) < rho2;
     } else {
       bw = fmax((rp.bw_mode == 1 ? rp.bw_fixed[0] : rp.bw_fixed[row]) * rp.bw_scale, rp.bw_floor);
     }
     double r = bw * rp.rfac;
-    bool ball_cert = all_found || r * r < rho2;
-    bool kmax_cert = (rp.kmax <= (int64_t)n_cand) && key[rp.kmax - 1] < rho2;
+    bool ball_cert = all_found || search2_of_radius(r, rp.metric) < rho2;
+    bool kmax_cert = (rp.kmax <= (int64_t)n_cand) && search2_of_key(key[rp.kmax - 1], rp.metric) < rho2;
     done = bw_cert && (ball_cert || kmax_cert);
     // an uncertified bandwidth is only an upper bound: the search ball must then also hold the
     // true knn nearest (radius >= bw) so stage 2 can recompute it
@@ -260,7 +296,7 @@ __global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Param
     p.status[row] = done ? 1 : (bw_cert ? 0 : 2);
     p.nzero[row] = nz;
     if (!done) {
-      double l2 = r_search * r_search * (1.0 + 1e-6) + E;
+      double l2 = search2_of_radius(r_search, rp.metric) * (1.0 + 1e-6) + E;
       p.lim2_out[row] = __double2float_ru(l2);
       p.n_keep[row] = 0;
     } else {
@@ -311,7 +347,8 @@ __global__ void __launch_bounds__(R2_THREADS) refine_ball_kernel(Refine2Params p
   const T* Xr = reinterpret_cast<const T*>(rp.Xr);
   for (int c = warp; c < L; c += R2_THREADS / 32) {
     int j = p.seg_idx[p0 + c];
-    double d2 = warp_dist2<T>(xq, Xr + (int64_t)j * rp.d, rp.d, lane);
+    double d2 = (rp.metric == 1) ? warp_cos2<T>(xq, Xr + (int64_t)j * rp.d, rp.d, lane)
+                                 : warp_dist2<T>(xq, Xr + (int64_t)j * rp.d, rp.d, lane);
     if (lane == 0) { key[c] = d2; idx[c] = j; }
   }
   for (int t = L + tid; t < np2; t += R2_THREADS) { key[t] = DBL_MAX * 2.0; idx[t] = 0x7fffffff; }
@@ -410,8 +447,9 @@ __global__ void compact_todo_kernel(const int32_t* __restrict__ status, int64_t 
 }
 
 RowParams make_row_params(const void* Xq, const void* Xr, int d, int knn, int64_t kmax, double decay,
-                          double thresh, const double* bw_fixed, int bw_mode, double bw_scale) {
+                          double thresh, const double* bw_fixed, int bw_mode, double bw_scale, int metric) {
   RowParams rp;
+  rp.metric = metric;
   rp.Xq = Xq; rp.Xr = Xr; rp.d = d; rp.knn = knn; rp.kmax = kmax <= 0 ? INT64_MAX : kmax;
   rp.decay = decay; rp.thresh = thresh;
   rp.rfac = decay >= 0 ? pow(-log(thresh), 1.0 / decay) : 0.0;
@@ -421,7 +459,7 @@ RowParams make_row_params(const void* Xq, const void* Xr, int d, int knn, int64_
 
 }  // namespace
 
-extern "C" int gtb_refine_topk(const void* Xq, int64_t nq, const void* Xr, int d, int x_is_f64,
+extern "C" int gtb_refine_topk(const void* Xq, int64_t nq, const void* Xr, int d, int x_kind,
                                const int32_t* cand_idx,
                                int S, int cand_stride, const float* tau, int ntau, const float* qn2, float maxrn2, double eps_rel,
                                int knn, int64_t kmax, double decay, double thresh, const double* bw_fixed,
@@ -430,8 +468,10 @@ extern "C" int gtb_refine_topk(const void* Xq, int64_t nq, const void* Xr, int d
   GTB_CHECK_ARG(nq > 0 && S > 0 && S <= R1_CAP, "S out of range");
   GTB_CHECK_ARG(knn >= 1 && knn <= S, "knn must be in [1, S]");
   GTB_CHECK_ARG(decay < 0 || (thresh > 0 && thresh <= 1), "thresh must be in (0, 1]");
+  GTB_CHECK_ARG(x_kind >= 0 && x_kind <= 3, "x_kind: bit 0 = float64 rows, bit 1 = cosine metric");
+  const int x_is_f64 = x_kind & 1;
   Refine1Params p;
-  p.rp = make_row_params(Xq, Xr, d, knn, kmax, decay, thresh, bw_fixed, bw_mode, bw_scale);
+  p.rp = make_row_params(Xq, Xr, d, knn, kmax, decay, thresh, bw_fixed, bw_mode, bw_scale, x_kind >> 1);
   GTB_CHECK_ARG(cand_stride >= S, "cand_stride must be >= S");
   p.nq = nq; p.S = S; p.cand_stride = cand_stride; p.ntau = ntau < 1 ? 1 : ntau; p.cand_idx = cand_idx; p.tau = tau; p.qn2 = qn2; p.maxrn2 = maxrn2; p.eps_rel = eps_rel;
   p.st_idx = st_idx; p.st_val = st_val; p.n_keep = n_keep; p.bw_out = bw_out; p.lim2_out = lim2_out;
@@ -465,7 +505,7 @@ extern "C" int gtb_scatter_pairs(const int32_t* pairs, int64_t npairs, const int
 }
 
 extern "C" int gtb_refine_ball(const void* Xq, const int32_t* todo_rows, const int32_t* status, int64_t nt,
-                               const void* Xr, int d, int x_is_f64,
+                               const void* Xr, int d, int x_kind,
                                const int64_t* seg_ptr, int32_t* seg_idx, double* seg_val, int knn, int64_t kmax,
                                double decay, double thresh, const double* bw_fixed, int bw_mode, double bw_scale,
                                int32_t* n_keep_t, int32_t* n_keep, double* bw_out, int32_t* nzero,
@@ -473,8 +513,10 @@ extern "C" int gtb_refine_ball(const void* Xq, const int32_t* todo_rows, const i
   GTB_CHECK_ARG(nt > 0, "no rows");
   GTB_CHECK_ARG(cap >= 2 && (cap & (cap - 1)) == 0 && cap <= 8192, "cap must be a power of two <= 8192");
   cudaStream_t st = (cudaStream_t)stream;
+  GTB_CHECK_ARG(x_kind >= 0 && x_kind <= 3, "x_kind: bit 0 = float64 rows, bit 1 = cosine metric");
+  const int x_is_f64 = x_kind & 1;
   Refine2Params p;
-  p.rp = make_row_params(Xq, Xr, d, knn, kmax, decay, thresh, bw_fixed, bw_mode, bw_scale);
+  p.rp = make_row_params(Xq, Xr, d, knn, kmax, decay, thresh, bw_fixed, bw_mode, bw_scale, x_kind >> 1);
   p.todo_rows = todo_rows; p.status = status; p.nt = nt; p.seg_ptr = seg_ptr; p.seg_idx = seg_idx; p.seg_val = seg_val;
   p.n_keep_t = n_keep_t; p.bw_out = bw_out; p.nzero = nzero; p.overflow = overflow; p.cap = cap;
   size_t smem = (size_t)cap * 12;

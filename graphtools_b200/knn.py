@@ -45,9 +45,9 @@ class kNNGraph(DataGraph):
         if n_pca in [None, 0, False] and data.shape[1] > 500:
             warnings.warn("Building a kNNGraph on data of shape {} is "
                           "expensive. Consider setting n_pca.".format(data.shape), UserWarning)
-        if distance != "euclidean":
+        if distance not in ("euclidean", "cosine"):
             raise NotImplementedError(
-                "graphtools_b200 accelerates the Euclidean metric only (got distance={!r})".format(distance))
+                "graphtools_b200 accelerates the euclidean and cosine metrics (got distance={!r})".format(distance))
         self.knn = knn
         self.knn_max = knn_max
         self.search_multiplier = search_multiplier
@@ -95,7 +95,7 @@ class kNNGraph(DataGraph):
         try:
             return self._ref_operand
         except AttributeError:
-            self._ref_operand = pipeline.SearchOperand(self._dense_f32(self.data_nu))
+            self._ref_operand = pipeline.SearchOperand(self._dense_f32(self.data_nu), metric=self.distance)
             return self._ref_operand
 
     def build_kernel(self):
@@ -128,7 +128,7 @@ class kNNGraph(DataGraph):
         lo, hi = bounds[rank]
         dev = ref.X.device
         if hi > lo:
-            qry = pipeline.SearchOperand(Xq[lo:hi], mean=ref.mean)
+            qry = pipeline.SearchOperand(Xq[lo:hi], mean=ref.mean, metric=ref.metric)
             Rl, info = self._kernel_device(qry, ref, knn=knn, knn_max=knn_max, bandwidth=bandwidth,
                                            bandwidth_scale=bandwidth_scale)
             return (bounds, Rl.indptr, (Rl.indptr[1:] - Rl.indptr[:-1]).to(torch.int32), Rl.indices, Rl.data,
@@ -254,7 +254,7 @@ class kNNGraph(DataGraph):
             Yd = self._dense_f32(Y).to(ref.X.dtype)
             if gd.active() and np.ndim(bandwidth) == 0 and Yd.shape[0] >= gd.MIN_ROWS_PER_RANK * gd.world_size():
                 return self._kernel_to_data_sharded(Yd, ref, knn, knn_max, bandwidth, bandwidth_scale)
-            qry = pipeline.SearchOperand(Yd, mean=ref.mean)
+            qry = pipeline.SearchOperand(Yd, mean=ref.mean, metric=ref.metric)
             R, info = self._kernel_device(qry, ref, knn=knn, knn_max=knn_max, bandwidth=bandwidth,
                                           bandwidth_scale=bandwidth_scale)
         self._check_duplicates(info, qry, ref)

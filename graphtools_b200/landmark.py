@@ -114,8 +114,9 @@ class LandmarkGraph(DataGraph):
         landmark_indices = rng.choice(n, self.n_landmark, replace=False)
         data = self.data if not hasattr(self, "data_nu") else self.data_nu
         X = self._dense_f32(data)
-        ref = pipeline.SearchOperand(X[torch.from_numpy(landmark_indices).to(X.device)].contiguous())
-        qry = pipeline.SearchOperand(X, mean=ref.mean)
+        metric = getattr(self, "distance", "euclidean")          # cdist(..., metric=self.distance), graphs.py:1212
+        ref = pipeline.SearchOperand(X[torch.from_numpy(landmark_indices).to(X.device)].contiguous(), metric=metric)
+        qry = pipeline.SearchOperand(X, mean=ref.mean, metric=metric)
         nearest, _ = pipeline.knn_kernel(None, ref, qry, knn=1, decay=None)   # exact float64 argmin per sample
         return nearest.indices.cpu().numpy().astype(np.int64)
 

@@ -131,20 +131,31 @@ def d2h_pinned(t):
 class SearchOperand:
     """k-major centred copy of a point set + squared norms (csrc/prep.cu)."""
 
-    def __init__(self, X, mean=None):
+    def __init__(self, X, mean=None, metric="euclidean"):
         """X: the ORIGINAL rows on the device, float32 or float64 (kept for the exact distances).  The search
         copy is always float32: float64 inputs are centred in float64 first and rounded once, so the
-        rounding error of the fast pass stays relative to the centred magnitudes (same bound E)."""
+        rounding error of the fast pass stays relative to the centred magnitudes (same bound E).
+
+        metric="cosine": the search copy is built from the row-normalised data (normalised and centred in float64,
+        rounded once), on which squared Euclidean distance = 2 x cosine distance; the exact stage evaluates
+        1 - x.y / (|x||y|) on the original rows."""
         n, d = X.shape
         self.X, self.n, self.d = X, n, d
+        self.metric = metric
         self.is64 = X.dtype == torch.float64
         self.n_pad = (n + 127) // 128 * 128
         self.d_pad = (d + 7) // 8 * 8
-        if self.is64:
+        if metric not in ("euclidean", "cosine"):
+            raise NotImplementedError("metric {!r} is not supported by the CUDA search".format(metric))
+        if self.is64 or metric == "cosine":
+            rows = X.to(torch.float64)
+            if metric == "cosine":
+                rows = rows / rows.norm(dim=1, keepdim=True)
             if mean is None:
-                mean = X.mean(dim=0)
-            self.Xs = (X - mean.to(torch.float64)).to(torch.float32).contiguous()
+                mean = rows.mean(dim=0)
+            self.Xs = (rows - mean.to(torch.float64)).to(torch.float32).contiguous()
             self._kmean = None                       # already centred
+            del rows
         else:
             if mean is None:
                 ws = _empty((E.lib().gtb_col_mean_ws_doubles(d),), torch.float64)
@@ -319,9 +330,9 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
     if qry is None:
         qry = ref
     nq, nr, d = qry.n, ref.n, ref.d
-    if qry.is64 != ref.is64:
-        raise ValueError("query and reference operands must have the same dtype")
-    x64 = int(ref.is64)
+    if qry.is64 != ref.is64 or qry.metric != ref.metric:
+        raise ValueError("query and reference operands must have the same dtype and metric")
+    x64 = int(ref.is64) | (2 if ref.metric == "cosine" else 0)      # x_kind of the refine entry points
     binary = decay is None
     knn = int(min(knn, nr))
     kmax = 0 if knn_max is None else int(knn_max)
@@ -421,7 +432,7 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         lim_t[:nt] = lim2[todo_rows.long()]
         if impl in ("tc", "tc16"):
             # the radius rows form their own (small) query operand; build it from the gathered rows
-            sub = SearchOperand(qry.X[todo_rows.long()].contiguous(), mean=ref.mean)
+            sub = SearchOperand(qry.X[todo_rows.long()].contiguous(), mean=ref.mean, metric=ref.metric)
             s_hi, s_lo, s_n2 = sub.tc(0, tcd)
             r_hi, r_lo, _ = ref.tc(1, tcd)
         else:

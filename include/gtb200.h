@@ -85,13 +85,15 @@ int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float* qn2, cons
 
 /* ---- K3 float64 re-evaluation, bandwidth, affinities, CSR emission: replaces graphs.py:886-911
  * and _build_csr_from_neighbors (graphs.py:450-559) ------------------------------------------ */
-/* Xq / Xr are the ORIGINAL rows (float32, or float64 when x_is_f64 != 0: e.g. PCA output) used for the exact
- * distances.  decay < 0 means binary kNN (decay=None); kmax <= 0 means knn_max=None;
+/* Xq / Xr are the ORIGINAL rows used for the exact distances; x_kind bit 0: rows are float64 (e.g. PCA output)
+ * instead of float32; bit 1: cosine metric -- exact distances 1 - x.y/(|x||y|) (sklearn cosine_distances, the metric
+ * behind knn_tree for distance="cosine", graphs.py:763-768) while the fast pass ran on the row-normalised copies,
+ * where |x^ - y^|^2 = 2 d_cos.  decay < 0 means binary kNN (decay=None); kmax <= 0 means knn_max=None;
  * bw_mode 0: bandwidth = distance to the knn-th candidate (graphs.py:892), 1: scalar bw_fixed[0],
  * 2: per-row bw_fixed[nq].  cand_idx rows are cand_stride apart (first S entries used); tau holds ntau
  * thresholds per row (lists built over disjoint reference subsets), the row's bound is their minimum.  status: 1 done, 0 needs radius pass, 2 needs radius pass and its
  * bandwidth is not yet certified.  st_idx/st_val[nq][S]: kept entries sorted by column. */
-int gtb_refine_topk(const void* Xq, int64_t nq, const void* Xr, int d, int x_is_f64, const int32_t* cand_idx, int S,
+int gtb_refine_topk(const void* Xq, int64_t nq, const void* Xr, int d, int x_kind, const int32_t* cand_idx, int S,
                     int cand_stride, const float* tau, int ntau, const float* qn2, float maxrn2, double eps_rel, int knn, int64_t kmax,
                     double decay, double thresh, const double* bw_fixed, int bw_mode, double bw_scale,
                     int32_t* st_idx, double* st_val, int32_t* n_keep, double* bw_out, float* lim2_out,
@@ -101,7 +103,7 @@ int gtb_scatter_pairs(const int32_t* pairs, int64_t npairs, const int64_t* seg_p
                       int64_t nt, int32_t* seg_idx, void* stream);
 /* block per radius-pass row; *overflow receives the longest row length that exceeded `cap` */
 int gtb_refine_ball(const void* Xq, const int32_t* todo_rows, const int32_t* status, int64_t nt,
-                    const void* Xr, int d, int x_is_f64, const int64_t* seg_ptr, int32_t* seg_idx, double* seg_val, int knn,
+                    const void* Xr, int d, int x_kind, const int64_t* seg_ptr, int32_t* seg_idx, double* seg_val, int knn,
                     int64_t kmax, double decay, double thresh, const double* bw_fixed, int bw_mode,
                     double bw_scale, int32_t* n_keep_t, int32_t* n_keep, double* bw_out, int32_t* nzero,
                     int32_t* overflow, int cap, void* stream);

@@ -71,15 +71,24 @@ def cases():
     c["mnn_decay"] = dict(X=mnnX, params=dict(knn=5, decay=40, sample_idx=mnn_idx, kernel_symm="mnn", theta=0.5))
     c["mnn_binary"] = dict(X=mnnX, params=dict(knn=4, decay=None, sample_idx=mnn_idx, kernel_symm="mnn", theta=0.9,
                                                 beta=0.5))
+    # cosine metric (sklearn brute-force cosine_distances behind knn_tree)
+    c["mix_cosine"] = dict(X=mix, params=dict(knn=5, decay=40, distance="cosine"), Y=Yq)
+    c["digits_cosine_binary"] = dict(X="digits700", params=dict(knn=5, decay=None, distance="cosine"))
+    c["iso_cosine_refine"] = dict(X=iso, params=dict(knn=5, decay=20, distance="cosine", thresh=1e-3))
+    c["mix_cosine_landmark_random"] = dict(X=mix, X_from="mix_knn", params=dict(
+        knn=5, decay=40, distance="cosine", n_landmark=100, random_landmarking=True, random_state=7))
     return c
 
 
 def main():
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
     gt = load_reference()
     assert gt is not None, "reference not available"
     import scipy, sklearn
     os.makedirs(OUT, exist_ok=True)
     for name, case in cases().items():
+        if only and name not in only:
+            continue
         X32 = case["X"]
         if isinstance(X32, str):
             X32 = digits(int(X32[6:]) if len(X32) > 6 else None)

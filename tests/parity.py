@@ -16,11 +16,16 @@ def _coo_keys(M):
     return M.row.astype(np.int64) * M.shape[1] + M.col.astype(np.int64), M.data
 
 
-def _tie_exempt(rows, cols, X, knn_eff, Y=None):
+def _tie_exempt(rows, cols, X, knn_eff, Y=None, metric="euclidean"):
     """True where entry (i, j) sits on a k-th / (k+1)-th neighbour tie (north_star: distances within
-    1e-6 relative) in row i -- or in row j for symmetrised in-sample graphs (Y is None)."""
+    1e-6 relative) in row i -- or in row j for symmetrised in-sample graphs (Y is None).  Cosine ties are
+    ties of the Euclidean distance between the normalised rows (d_euc^2 = 2 d_cos)."""
     X = np.asarray(X, dtype=np.float64)
     Q = X if Y is None else np.asarray(Y, dtype=np.float64)
+    if metric == "cosine":
+        Xn = X / np.linalg.norm(X, axis=1, keepdims=True)
+        Q = Xn if Y is None else Q / np.linalg.norm(Q, axis=1, keepdims=True)
+        X = Xn
     ok = np.zeros(len(rows), dtype=bool)
     cache = {}
 
@@ -63,7 +68,7 @@ def compare_sparse(gpu, ref, rtol=RTOL, thresh=None, max_exempt_frac=1e-5, atol=
     if (len(only_g) or len(only_r)) and tie is not None:
         ncol = gpu.shape[1]
         keys = np.concatenate([kg[only_g], kr[only_r]])
-        ok = _tie_exempt(keys // ncol, keys % ncol, tie["X"], tie["knn"], tie.get("Y"))
+        ok = _tie_exempt(keys // ncol, keys % ncol, tie["X"], tie["knn"], tie.get("Y"), tie.get("metric", "euclidean"))
         n_tie = int(ok.sum())
         only_g = only_g[~ok[:len(only_g)]]
         only_r = only_r[~ok[len(ok) - len(only_r):]] if len(only_r) else only_r
@@ -86,7 +91,7 @@ def compare_sparse(gpu, ref, rtol=RTOL, thresh=None, max_exempt_frac=1e-5, atol=
         # a tie decides whether an edge is one- or two-directional, which changes its symmetrised value
         ncol = gpu.shape[1]
         keys = common[bad]
-        ok = _tie_exempt(keys // ncol, keys % ncol, tie["X"], tie["knn"], tie.get("Y"))
+        ok = _tie_exempt(keys // ncol, keys % ncol, tie["X"], tie["knn"], tie.get("Y"), tie.get("metric", "euclidean"))
         n_tie += int(ok.sum())
         bad[np.flatnonzero(bad)[ok]] = False
         worst = float((err[~bad] / np.maximum(np.abs(b[~bad]), 1e-300)).max()) if (~bad).any() else 0.0

@@ -151,9 +151,11 @@ def test_pca_reduction_on_host():
         G._check_extension_shape(rng.normal(size=(3, 9)))
 
 
-def test_non_euclidean_metric_is_rejected_loudly():
+def test_unsupported_metric_is_rejected_loudly():
+    with pytest.raises(NotImplementedError, match="euclidean and cosine"):
+        build(distance="manhattan")
     with pytest.raises(NotImplementedError, match="Euclidean"):
-        build(distance="cosine")
+        build(distance="cosine", graphtype="exact")
 
 
 def test_mnn_to_data_not_implemented():

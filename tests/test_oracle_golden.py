@@ -14,7 +14,7 @@ def _raw_kernel(case):
     if case.cls.startswith("kNN"):
         g = go.KnnOracle(X, knn=p.get("knn", 5), decay=p.get("decay", 40), knn_max=p.get("knn_max"),
                          bandwidth=p.get("bandwidth"), bandwidth_scale=p.get("bandwidth_scale", 1.0),
-                         thresh=p.get("thresh", 1e-4))
+                         thresh=p.get("thresh", 1e-4), distance=p.get("distance", "euclidean"))
         return g.kernel(), g
     if case.cls.startswith("Traditional"):
         return go.exact_kernel(X, knn=p.get("knn", 5), decay=p.get("decay", 40), bandwidth=p.get("bandwidth"),
@@ -46,7 +46,8 @@ def test_oracle_reproduces_reference(name):
     if "clusters" in case.z.files:
         X = case.X.astype(np.float64)
         if p.get("random_landmarking"):
-            clusters = go.random_landmark_clusters(X, p["n_landmark"], p["random_state"])
+            clusters = go.random_landmark_clusters(X, p["n_landmark"], p["random_state"],
+                                                   distance=p.get("distance", "euclidean"))
         else:
             clusters = go.spectral_clusters(K, p["n_landmark"], p.get("n_svd", 100), p["random_state"])
         assert np.array_equal(clusters, case.z["clusters"])

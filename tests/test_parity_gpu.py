@@ -41,7 +41,7 @@ def test_knn_golden(name, impl):
     tie = None
     if p.get("decay", 40) is None or p.get("knn_max") is not None:
         k_eff = (p["knn"] if p.get("decay", 40) is None else p["knn_max"]) + 1
-        tie = dict(X=case.X, knn=k_eff)
+        tie = dict(X=case.X, knn=k_eff, metric=p.get("distance", "euclidean"))
     r = compare_sparse(K, case.mat("K"), thresh=thresh, what=name + ".K", tie=tie)
     if r["n_exempt"] == 0:
         compare_sparse(G.diff_op, case.mat("P"), what=name + ".P")
