@@ -143,15 +143,34 @@ class Data(Base):
                 data_nu = data_nu.tocsr()
             return data_nu
         from sklearn.decomposition import PCA, TruncatedSVD
+        import os
+        impl = os.environ.get("GTB_PCA", "auto")
+        if impl not in ("auto", "device", "host"):
+            raise ValueError("GTB_PCA must be auto, device or host (got %r)" % (impl,))
+        if impl == "auto":
+            # the front-end is not part of the accelerated contract: without a GPU (host-side API use with
+            # initialize=False) it stays the reference's own scikit-learn call
+            import torch
+            impl = "device" if torch.cuda.is_available() else "host"
         with _logger.log_task("PCA"):
             k = self.data.shape[1] - 1 if self.n_pca == "auto" else self.n_pca
             if sparse.issparse(self.data):
                 if isinstance(self.data, (sparse.coo_matrix, sparse.lil_matrix, sparse.dok_matrix)):
                     self.data = self.data.tocsr()
-                self.data_pca = TruncatedSVD(k, random_state=self.random_state)
+            dev_nu = None
+            if impl == "device":
+                # same randomized SVD as sklearn's PCA / TruncatedSVD, in HBM (graphtools_b200/pca.py)
+                from . import pca
+                if sparse.issparse(self.data):
+                    self.data_pca, dev_nu = pca.fit_transform_sparse(self.data, k, self.random_state)
+                else:
+                    self.data_pca, dev_nu = pca.fit_transform_dense(self.data, k, self.random_state)
             else:
-                self.data_pca = PCA(k, svd_solver="randomized", random_state=self.random_state)
-            self.data_pca.fit(self.data)
+                if sparse.issparse(self.data):
+                    self.data_pca = TruncatedSVD(k, random_state=self.random_state)
+                else:
+                    self.data_pca = PCA(k, svd_solver="randomized", random_state=self.random_state)
+                self.data_pca.fit(self.data)
             if self.n_pca == "auto":
                 s = self.data_pca.singular_values_
                 if self.rank_threshold == "auto":
@@ -167,6 +186,13 @@ class Data(Base):
                 op.explained_variance_ = op.explained_variance_[gate]
                 op.explained_variance_ratio_ = op.explained_variance_ratio_[gate]
                 op.singular_values_ = op.singular_values_[gate]
+                if dev_nu is not None:
+                    import torch
+                    dev_nu = dev_nu[:, torch.from_numpy(gate).to(dev_nu.device)].contiguous()
+            if dev_nu is not None:
+                # the reduced data stays in HBM for the graph build; the host copy is the public ``data_nu``
+                self._dev_data_nu = dev_nu
+                return pipeline.d2h_pinned(dev_nu).numpy()
             return self.data_pca.transform(self.data)
 
     def get_params(self):
@@ -513,6 +539,8 @@ class DataGraph(Data, BaseGraph, metaclass=abc.ABCMeta):
         """Densify (scipy sparse -> ndarray) and hand to the device: float64 inputs stay float64 (exact
         distances are evaluated on them), everything else becomes float32."""
         import torch
+        if A is getattr(self, "data_nu", None) and getattr(self, "_dev_data_nu", None) is not None:
+            return self._dev_data_nu
         if isinstance(A, torch.Tensor):
             return pipeline.to_device(A)
         if sparse.issparse(A):
