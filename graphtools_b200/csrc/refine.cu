@@ -127,6 +127,52 @@ __device__ int finalize_sorted_row(double* key, int32_t* idx, int n_cand, double
   return n_keep;
 }
 
+// Reduce eight per-lane partial sums acc[0..7] across the warp with a halving exchange: at offsets 16, 8, 4 every lane
+// keeps half of its accumulators and hands the other half to its partner (4 + 2 + 1 exchanges), then two butterfly
+// steps finish the single value left per lane -- 9 shuffles instead of 40.  Every partial sum is formed from the same
+// pairs as in the plain butterfly of warp_dist2 (a + b == b + a), so the bits agree.  Lane l ends with the sum of
+// candidate u = 4*bit4 + 2*bit3 + bit2 of l; lanes with l % 4 == 0 store key[] / idx[].  Uses acc, j, c0, S, lane,
+// key, idx, n_cand of the enclosing scope.
+#define GTB_REDUCE8_AND_STORE() do { \
+        double h4[4], h2[2], h1; \
+        { \
+          const bool up = (lane & 16) != 0; \
+    _Pragma("unroll") \
+          for (int u = 0; u < 4; ++u) { \
+            const double keep = up ? acc[u + 4] : acc[u]; \
+            const double give = up ? acc[u] : acc[u + 4]; \
+            h4[u] = keep + __shfl_xor_sync(0xffffffffu, give, 16); \
+          } \
+        } \
+        { \
+          const bool up = (lane & 8) != 0; \
+    _Pragma("unroll") \
+          for (int u = 0; u < 2; ++u) { \
+            const double keep = up ? h4[u + 2] : h4[u]; \
+            const double give = up ? h4[u] : h4[u + 2]; \
+            h2[u] = keep + __shfl_xor_sync(0xffffffffu, give, 8); \
+          } \
+        } \
+        { \
+          const bool up = (lane & 4) != 0; \
+          const double keep = up ? h2[1] : h2[0]; \
+          const double give = up ? h2[0] : h2[1]; \
+          h1 = keep + __shfl_xor_sync(0xffffffffu, give, 4); \
+        } \
+        h1 += __shfl_xor_sync(0xffffffffu, h1, 2); \
+        h1 += __shfl_xor_sync(0xffffffffu, h1, 1); \
+        const int myu = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); \
+        int myj = j[0]; \
+    _Pragma("unroll") \
+        for (int u = 1; u < 8; ++u) myj = (myu == u) ? j[u] : myj; \
+    _Pragma("unroll") \
+        for (int u = 0; u < 8; ++u) n_cand += (c0 + u < S && j[u] >= 0) ? 1 : 0; \
+        if ((lane & 3) == 0 && c0 + myu < S) { \
+          key[c0 + myu] = (myj >= 0) ? h1 : DBL_MAX * 2.0; \
+          idx[c0 + myu] = (myj >= 0) ? myj : 0x7fffffff; \
+        } \
+  } while (0)
+
 // ------------------------------------------------------------------ stage 1: warp per row
 constexpr int R1_WARPS = 4;
 constexpr int R1_CAP = 128;  // max candidates per row handled by the warp kernel
@@ -137,10 +183,11 @@ struct Refine1Params {
   const int32_t* cand_idx; const float* tau; const float* qn2; float maxrn2; double eps_rel;
   int32_t* st_idx; double* st_val; int32_t* n_keep; double* bw_out; float* lim2_out;
   int32_t* status; int32_t* nzero;
+  int staged;                  // 1: candidate rows are staged through shared memory with cp.async (float32, d % 4 == 0, d <= 128)
 };
 
 template <typename T>
-__global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Params p) {
+__global__ void __launch_bounds__(R1_WARPS * 32, 6) refine_topk_kernel(Refine1Params p) {
   __shared__ double key_s[R1_WARPS][R1_CAP];
   __shared__ int32_t idx_s[R1_WARPS][R1_CAP];
   __shared__ int scratch_s[R1_WARPS];
@@ -172,6 +219,59 @@ __global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Param
   }
   if (rp.metric == 1) {
     // done above
+  } else if (p.staged && sizeof(T) == 4) {
+    if constexpr (sizeof(T) == 4) {
+      // Candidate rows stream through a two-deep shared-memory ring of eight rows per warp with cp.async (L2 -> smem,
+      // no registers held while in flight): sixteen 400-byte row gathers per warp are outstanding while the previous
+      // eight are reduced -- the gathers are latency-bound (~2 us under load), so bytes in flight set the rate.
+      // Lane l copies and later reads float4 l of every row, so no cross-lane visibility is needed.
+      extern __shared__ __align__(16) float stage_all[];
+      const int nv = rp.d >> 2;                                  // <= 32
+      float* stage = stage_all + (size_t)warp * (2 * 8 * rp.d);
+      const float4* Xr4 = reinterpret_cast<const float4*>(Xr);
+      const int ngroups = (S + 7) >> 3;
+      const bool on = lane < nv;
+      auto issue = [&](int g) {
+        float* dst = stage + (g & 1) * 8 * rp.d;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c = g * 8 + u;
+          const int jj = (c < S) ? p.cand_idx[row * p.cand_stride + c] : -1;
+          if (on) {
+            const float4* src = Xr4 + (int64_t)(jj >= 0 ? jj : 0) * nv + lane;
+            const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst + u * rp.d + lane * 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32), "l"(src) : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      issue(0);
+      if (ngroups > 1) issue(1);
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (on) q = reinterpret_cast<const float4*>(xq)[lane];
+      for (int g = 0; g < ngroups; ++g) {
+        if (g + 1 < ngroups) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const int c0 = g * 8;
+        const float* src = stage + (g & 1) * 8 * rp.d + lane * 4;
+        int j[8];
+        double acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          j[u] = (c0 + u < S) ? p.cand_idx[row * p.cand_stride + c0 + u] : -1;  // uniform loads
+          acc[u] = 0.0;
+          if (on) {
+            const float4 r = *reinterpret_cast<const float4*>(src + u * rp.d);
+            double df = (double)q.x - (double)r.x; acc[u] = fma(df, df, acc[u]);
+            df = (double)q.y - (double)r.y; acc[u] = fma(df, df, acc[u]);
+            df = (double)q.z - (double)r.z; acc[u] = fma(df, df, acc[u]);
+            df = (double)q.w - (double)r.w; acc[u] = fma(df, df, acc[u]);
+          }
+        }
+        if (g + 2 < ngroups) issue(g + 2);       // this lane has consumed its part of ring slot g & 1
+        GTB_REDUCE8_AND_STORE();
+      }
+    }
   } else if (vec) {
     if constexpr (sizeof(T) == 4) {
       // float32 rows of whole float4s: one 16-byte load per lane covers a 400-byte row with 25 lanes, and eight
@@ -205,18 +305,7 @@ __global__ void __launch_bounds__(R1_WARPS * 32) refine_topk_kernel(Refine1Param
             }
           }
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], off);
-          if (c0 + u < S) {
-            if (j[u] >= 0) ++n_cand;
-            if (lane == 0) {
-              key[c0 + u] = (j[u] >= 0) ? acc[u] : DBL_MAX * 2.0;  // +inf for empty slots
-              idx[c0 + u] = (j[u] >= 0) ? j[u] : 0x7fffffff;
-            }
-          }
-        }
+        GTB_REDUCE8_AND_STORE();
       }
     }
   } else {
@@ -476,10 +565,14 @@ extern "C" int gtb_refine_topk(const void* Xq, int64_t nq, const void* Xr, int d
   p.nq = nq; p.S = S; p.cand_stride = cand_stride; p.ntau = ntau < 1 ? 1 : ntau; p.cand_idx = cand_idx; p.tau = tau; p.qn2 = qn2; p.maxrn2 = maxrn2; p.eps_rel = eps_rel;
   p.st_idx = st_idx; p.st_val = st_val; p.n_keep = n_keep; p.bw_out = bw_out; p.lim2_out = lim2_out;
   p.status = status; p.nzero = nzero;
+  // float32 rows of whole, 16-byte aligned float4s no longer than one warp-wide load: stage the gathers through smem
+  p.staged = (!x_is_f64 && (x_kind >> 1) == 0 && (d & 3) == 0 && d <= 128 &&
+              (((uintptr_t)Xq | (uintptr_t)Xr) & 15) == 0) ? 1 : 0;
+  const size_t smem = p.staged ? (size_t)R1_WARPS * 2 * 8 * d * sizeof(float) : 0;
   if (x_is_f64)
     refine_topk_kernel<double><<<(unsigned)gtb_cdiv(nq, R1_WARPS), R1_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
   else
-    refine_topk_kernel<float><<<(unsigned)gtb_cdiv(nq, R1_WARPS), R1_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+    refine_topk_kernel<float><<<(unsigned)gtb_cdiv(nq, R1_WARPS), R1_WARPS * 32, smem, (cudaStream_t)stream>>>(p);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }
