@@ -4,23 +4,27 @@
 //   d~2(i,j) - |x_i|^2  =  |y_j|^2 - 2 x_i.y_j  =  sum_k A[i,k] * B[j,k]
 //       A (query role) = [ x~_1 .. x~_d , 1 , 0.. ]        B (ref role) = [ -2y~_1 .. -2y~_d , |y~|^2 , 0.. ]
 //
-// Every float32 operand value v is split v = hi + lo with hi = tf32(v), lo = tf32(v - hi) and the tile
-// is accumulated as A_hi.B_hi + A_hi.B_lo + A_lo.B_hi with tcgen05.mma.kind::tf32 into a float32 TMEM
-// accumulator (3xTF32: ~2^-21 relative to |x||y|, enough to SELECT candidates; every value that
-// reaches the output is re-evaluated in float64 by refine.cu).
+// Every float32 operand value v is split v = hi + lo and the tile is accumulated as A_hi.B_hi + A_hi.B_lo + A_lo.B_hi
+// into a float32 TMEM accumulator, in one of two flavours: bf16x3 (hi = bf16(v), lo = bf16(v - hi), kind::f16,
+// 16 elements per 32-byte k-step; the default) or 3xTF32 (hi = tf32(v), lo = tf32(v - hi), kind::tf32, 8 per
+// k-step).  Either keeps >= 16 mantissa bits -- enough to SELECT candidates; every value that reaches the output
+// is re-evaluated in float64 by refine.cu.
 //
-// CTA = 128 query rows (UMMA M=128, cta_group::1).  The query tile (A_hi, A_lo) lives in TENSOR MEMORY for
-// the whole sweep (tcgen05.st by the epilogue warps, 2 x Kp columns; the MMA reads A from TMEM, so
-// shared-memory bandwidth is spent on B only); reference tiles of 128 rows (B_hi, B_lo) stream through
-// a 2-stage TMA/mbarrier ring that owns all of shared memory; two 128-column TMEM accumulators let the
-// epilogue of tile t overlap the MMAs of tile t+1.  Warp roles: warp 0 = TMA producer, warp 1 = MMA
-// issuer (+TMEM alloc), warps 2-5 = epilogue (tcgen05.ld 32x32b: thread == query row).  Shared-memory B
-// tiles are K-major: floor(Kp/32) SWIZZLE_128B blocks (32 floats per row) then (Kp%32)/8 SWIZZLE_32B blocks.
+// CTA = 128 query rows (UMMA M=128, cta_group::1), persistent: cluster c sweeps the whole reference set once per
+// round for its next pair of query tiles.  The query tile (A_hi, A_lo) lives in TENSOR MEMORY for the whole sweep
+// (tcgen05.st by the epilogue warps; the MMA reads A from TMEM, so shared-memory bandwidth is spent on B only);
+// reference tiles of 128 rows (B_hi, B_lo) stream through a 3-stage (bf16) / 2-stage (tf32) TMA ring, multicast to
+// the CTAs of the cluster; a ring of three (bf16) / two (tf32) 128-column TMEM accumulators lets the epilogue of
+// tile t overlap the MMAs of tiles t+1, t+2.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+// alloc), warps 2-9 = two epilogue groups of four (tcgen05.ld 32x32b: thread == query row), alternating tiles.
+// Shared-memory B tiles are K-major: SWIZZLE_128B blocks of four k-steps, then SWIZZLE_32B tail blocks.
 //
-// Epilogue, TOPK mode: each thread keeps a running threshold; values under it are appended to the
-// row's 128-slot candidate buffer in global memory (L2 resident); when a buffer nears capacity the
-// warp cooperatively bitonic-sorts it in registers, keeps the 64 smallest and tightens the
-// threshold.  RADIUS mode: values under the row's limit are appended to the global pair list.
+// Epilogue, TOPK mode: each thread keeps a running threshold; per 32-column batch a 3-input-min tree and one
+// ballot decide whether any row of the warp has a value under its threshold.  Hits are appended to the row's
+// 96-slot candidate buffer in global memory (L2 resident) -- rows served one at a time by the whole warp, or by
+// per-lane predicated stores when many rows hit; a buffer that nears capacity is compacted to its LS smallest by
+// a warp-cooperative quickselect on 64-bit ordered keys (ballots and popcounts only) and the threshold tightens.
+// RADIUS mode: values under the row's limit are appended to the global pair list.
 //
 // Replaces sklearn ArgKmin / RadiusNeighbors behind knn_tree.kneighbors / radius_neighbors
 // (reference graphtools/graphs.py:883, :922, :957, :966).
@@ -92,12 +96,6 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
       ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(bar), "h"(mask)
-      : "memory");
-}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -114,17 +112,6 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
-      " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -145,23 +132,6 @@ __device__ __forceinline__ void tmem_wait_ld(uint32_t (&a)[32], uint32_t (&b)[32
     asm volatile("" : "+r"(a[i]), "+r"(b[i]), "+r"(c[i]), "+r"(d[i]));
   }
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 // shared-memory matrix descriptor, K-major, dense 8-row groups (SBO = 8 * row bytes)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
@@ -268,29 +238,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float4& a, const 
                "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w))
                : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem]   (A: lane = row, one 32-bit column per K element)
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate) {
-  asm volatile(
-      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
-      " tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 // CL = thread-block cluster size: the CL CTAs of a cluster sweep the same reference tiles for CL different
 // query tiles; each loads 1/CL of every B stage and TMA-multicasts it to all of them, so the L2 -> SM
 // traffic per output drops by CL.  A stage is recycled once every CTA's MMAs have retired (commit
 // multicast to all empty barriers).
-__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate) {
-  asm volatile(
-      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
-      " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 // Predicated forms: issued from warp-uniform control flow with the election folded into the instruction
 // predicate, so there is no divergent region (BSSY/BSYNC) around the MMAs at all.
 __device__ __forceinline__ void tc_mma_ts_pred(bool bf16, uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
@@ -565,19 +516,14 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
       const uint32_t acc_addr = lane_addr + (uint32_t)(ACC0 + s * TC_N);
       tmem_ld32_nowait(acc_addr, r0);
       tmem_ld32_nowait(acc_addr + 32, r1);
-#ifdef GTB_EXPERIMENT_HALF_DRAIN
-#pragma unroll
-      for (int j = 0; j < 32; ++j) { r2[j] = 0x7f000000u; r3[j] = 0x7f000000u; }
-#else
       tmem_ld32_nowait(acc_addr + 64, r2);
       tmem_ld32_nowait(acc_addr + 96, r3);
-#endif
       tmem_wait_ld(r0, r1, r2, r3);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tm_empty + 8 * s);
 #ifdef GTB_EXP_NOSELECT
-      continue;
+      continue;                                   // experiment build: the sweep without any selection work
 #endif
 #pragma unroll
       for (int part = 0; part < TC_N / 32; ++part) {

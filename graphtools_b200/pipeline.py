@@ -362,7 +362,8 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         # two candidate lists per row (one per epilogue group) of `ls` entries each.  Short lists (16) halve the
         # selection work of the sweep; they are used when the neighbourhood asked for is small (knn + 8 <= 16) --
         # rows whose kernel support is wider fail certification and are finished by the radius pass.
-        ls = int(os.environ.get("GTB_TC_LIST", "16" if knn + 8 <= 16 else "32"))
+        want = max(knn, kmax)                                   # knn_max neighbours must fit the lists as well
+        ls = int(os.environ.get("GTB_TC_LIST", "16" if want + 8 <= 16 else "32"))
         if ls not in (16, 32) or knn > ls:
             raise ValueError("GTB_TC_LIST must be 16 or 32 and >= knn")
         S, stride, ntau = 2 * ls, 2 * ls, 2

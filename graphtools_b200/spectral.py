@@ -41,14 +41,19 @@ def _seed_of(random_state):
 def _cholesky_qr(A, passes=2):
     """Orthonormal basis of the columns of tall-skinny ``A`` [n, k] (k ~ 110): Q = A R^-1 with R from the Cholesky
     factor of the k x k Gram matrix, applied twice (CholeskyQR2) so the loss of orthogonality of the first pass
-    (kappa^2 eps) is removed.  Falls back to Householder QR when the Gram matrix is numerically singular."""
+    (kappa^2 eps) is removed.  R^-1 is formed explicitly (k x k triangular solve against the identity) so the tall
+    operand only ever goes through GEMMs.  Falls back to Householder QR when the Gram matrix is numerically
+    singular."""
     Q = A
+    k = A.shape[1]
+    eye = torch.eye(k, dtype=A.dtype, device=A.device)
     for _ in range(passes):
         G = Q.T @ Q
         L, info = torch.linalg.cholesky_ex(G)
         if int(info.item()) != 0:
             return torch.linalg.qr(A, mode="reduced")[0]
-        Q = torch.linalg.solve_triangular(L.T, Q, upper=True, left=False)
+        Rinv = torch.linalg.solve_triangular(L.T, eye, upper=True)        # R = L^T, Q = A R^-1
+        Q = Q @ Rinv
     return Q
 
 
