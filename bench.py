@@ -316,7 +316,7 @@ def run_gpu_arm(a):
         line = {
             "metric": "graph build points/sec (kernel+diff_op)", "value": value, "unit": "points/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 select / f64 values",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16x3 tensor-core select (f32 accumulate) / f64 values",
             "data": "synthetic",
             "config": {"workload": workload_name(a), "n": n, "d": d, "knn": KNN, "decay": DECAY, "thresh": THRESH,
                        "l2": "inputs (400 MB operand, 113 MB raw CSR) larger than the 126 MB L2; no explicit flush",

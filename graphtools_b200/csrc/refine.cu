@@ -173,6 +173,27 @@ __device__ int finalize_sorted_row(double* key, int32_t* idx, int n_cand, double
         } \
   } while (0)
 
+// Bitonic sort of 32 (key, value) pairs held one per lane, ascending by (key, value), entirely in registers: fifteen
+// compare-exchange steps of three shuffles each -- no shared memory, no barriers, no divergent branches (the
+// comparisons are combined with bitwise operators so that ptxas emits predicates, not BSSY/BRA regions).
+template <typename K, typename V>
+__device__ __forceinline__ void warp_sort32(K& k, V& v, int lane) {
+#pragma unroll
+  for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      const K ok = __shfl_xor_sync(0xffffffffu, k, j);
+      const V ov = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool keep_min = (((lane & kk) == 0) == ((lane & j) == 0));
+      const bool gt = (k > ok) | ((k == ok) & (v > ov));
+      const bool lt = (k < ok) | ((k == ok) & (v < ov));
+      const bool take = keep_min ? gt : lt;
+      k = take ? ok : k;
+      v = take ? ov : v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ stage 1: warp per row
 constexpr int R1_WARPS = 4;
 constexpr int R1_CAP = 128;  // max candidates per row handled by the warp kernel
@@ -339,16 +360,27 @@ __global__ void __launch_bounds__(R1_WARPS * 32, 6) refine_topk_kernel(Refine1Pa
     }
   }
   }
-  for (int t = S + lane; t < np2; t += 32) { key[t] = DBL_MAX * 2.0; idx[t] = 0x7fffffff; }
-  __syncwarp();
-  // 2. sort by (d2, idx)
-  GTB_BITONIC_SORT(key, idx, np2, lane, 32, sync, double, int32_t);
-
-  // 3. zero-distance count (duplicate detection, graphs.py:787-817)
+  // 2. sort by (d2, idx); 3. zero-distance count (duplicate detection, graphs.py:787-817)
+  const bool small = S <= 32;            // one candidate per lane: both sorts of the row run in registers
+  double mk = DBL_MAX * 2.0;
+  int32_t mi = 0x7fffffff;
   int nz = 0;
-  for (int t = lane; t < n_cand; t += 32) nz += (key[t] == 0.0);
+  if (small) {
+    __syncwarp();
+    if (lane < S) { mk = key[lane]; mi = idx[lane]; }
+    warp_sort32<double, int32_t>(mk, mi, lane);
+    __syncwarp();
+    key[lane] = mk; idx[lane] = mi;      // the certification below reads order statistics by position
+    __syncwarp();
+    nz = __popc(__ballot_sync(0xffffffffu, lane < n_cand && mk == 0.0));
+  } else {
+    for (int t = S + lane; t < np2; t += 32) { key[t] = DBL_MAX * 2.0; idx[t] = 0x7fffffff; }
+    __syncwarp();
+    GTB_BITONIC_SORT(key, idx, np2, lane, 32, sync, double, int32_t);
+    for (int t = lane; t < n_cand; t += 32) nz += (key[t] == 0.0);
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, off);
+    for (int off = 16; off > 0; off >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, off);
+  }
 
   // 4. bandwidth + certification
   float tau = p.tau[row * p.ntau];
@@ -395,6 +427,31 @@ __global__ void __launch_bounds__(R1_WARPS * 32, 6) refine_topk_kernel(Refine1Pa
   if (!done) return;
   __syncwarp();
   // 5. affinities, threshold, column sort, staging
+  if (small) {
+    // lane t holds the t-th nearest candidate: keep the leading entries with affinity >= thresh among the first
+    // min(n_cand, kmax) (finalize_sorted_row's rule), then order the survivors by column in registers
+    const int64_t m64 = rp.kmax < (int64_t)n_cand ? rp.kmax : (int64_t)n_cand;
+    const int m = (int)m64;
+    double w = 0.0;
+    int n_keep;
+    if (rp.decay < 0) {
+      n_keep = rp.knn < m ? rp.knn : m;            // binary kNN: the knn nearest, weight 1 (graphs.py:872-877)
+      w = 1.0;
+    } else {
+      const bool inm = lane < m;
+      if (inm) w = gtb_affinity(sqrt(mk), bw, rp.decay);
+      const unsigned fail = __ballot_sync(0xffffffffu, inm && !(w >= rp.thresh));
+      n_keep = fail ? (__ffs(fail) - 1) : m;
+    }
+    int32_t ci = (lane < n_keep) ? mi : 0x7fffffff;
+    warp_sort32<int32_t, double>(ci, w, lane);
+    if (lane < n_keep) {
+      p.st_idx[row * S + lane] = ci;
+      p.st_val[row * S + lane] = w;
+    }
+    if (lane == 0) p.n_keep[row] = n_keep;
+    return;
+  }
   int n_keep = finalize_sorted_row<32>(key, idx, n_cand, bw, rp, lane, &scratch_s[warp], sync);
   for (int t = lane; t < n_keep; t += 32) {
     p.st_idx[row * S + t] = idx[t];
