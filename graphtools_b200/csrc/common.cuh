@@ -48,6 +48,27 @@ __device__ __forceinline__ double gtb_affinity(double dist, double bw, double de
   return (w != w) ? 1.0 : w;
 }
 
+// Bitonic sort of 32 (key, value) pairs held one per lane, ascending by (key, value), entirely in registers: fifteen
+// compare-exchange steps of three shuffles each -- no shared memory, no barriers, no divergent branches (the
+// comparisons are combined with bitwise operators so that ptxas emits predicates, not BSSY/BRA regions).
+template <typename K, typename V>
+__device__ __forceinline__ void warp_sort32(K& k, V& v, int lane) {
+#pragma unroll
+  for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      const K ok = __shfl_xor_sync(0xffffffffu, k, j);
+      const V ov = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool keep_min = (((lane & kk) == 0) == ((lane & j) == 0));
+      const bool gt = (k > ok) | ((k == ok) & (v > ov));
+      const bool lt = (k < ok) | ((k == ok) & (v < ov));
+      const bool take = keep_min ? gt : lt;
+      k = take ? ok : k;
+      v = take ? ov : v;
+    }
+  }
+}
+
 // Bitonic sort of n_pow2 (key, payload) pairs living in shared memory, ascending by
 // (key, idx).  Executed by `nthreads` cooperating threads whose rank is `tid`;
 // SYNC() must be a barrier over exactly those threads.

@@ -173,27 +173,6 @@ __device__ int finalize_sorted_row(double* key, int32_t* idx, int n_cand, double
         } \
   } while (0)
 
-// Bitonic sort of 32 (key, value) pairs held one per lane, ascending by (key, value), entirely in registers: fifteen
-// compare-exchange steps of three shuffles each -- no shared memory, no barriers, no divergent branches (the
-// comparisons are combined with bitwise operators so that ptxas emits predicates, not BSSY/BRA regions).
-template <typename K, typename V>
-__device__ __forceinline__ void warp_sort32(K& k, V& v, int lane) {
-#pragma unroll
-  for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-    for (int j = kk >> 1; j > 0; j >>= 1) {
-      const K ok = __shfl_xor_sync(0xffffffffu, k, j);
-      const V ov = __shfl_xor_sync(0xffffffffu, v, j);
-      const bool keep_min = (((lane & kk) == 0) == ((lane & j) == 0));
-      const bool gt = (k > ok) | ((k == ok) & (v > ov));
-      const bool lt = (k < ok) | ((k == ok) & (v < ov));
-      const bool take = keep_min ? gt : lt;
-      k = take ? ok : k;
-      v = take ? ov : v;
-    }
-  }
-}
-
 // ------------------------------------------------------------------ stage 1: warp per row
 constexpr int R1_WARPS = 4;
 constexpr int R1_CAP = 128;  // max candidates per row handled by the warp kernel

@@ -188,6 +188,18 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) row_finalize_kernel(
       sum += fabs(tmp_val[p0 + t]);
       has_diag |= (tmp_idx[p0 + t] == row);
     }
+  } else if (L <= 32) {
+    // the common case (a kNN kernel row): one entry per lane, sorted by column in registers
+    int32_t c = 0x7fffffff;
+    double w = 0.0;
+    if (lane < L) { c = tmp_idx[p0 + lane]; w = tmp_val[p0 + lane]; }
+    warp_sort32<int32_t, double>(c, w, lane);
+    if (lane < L) {
+      out_idx[p0 + lane] = c;
+      out_val[p0 + lane] = w;
+      sum += fabs(w);
+      has_diag |= (c == row);
+    }
   } else if (L <= FIN_CAP) {
     int32_t* k = ks[warp];
     double* v = vs[warp];
