@@ -54,8 +54,8 @@ _SIGS = {
     "gtb_cluster_aggregate_count": ([_P, _P, _P, c_int64, _P, _P, _P], 1),
     "gtb_cluster_aggregate_fill": ([_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, _P], 1),
     "gtb_landmark_op": ([_P, _P, _P, _P, _P, c_int64, c_int, _P, _P], 1),
-    "gtb_dense_kernel": ([_P, c_int64, _P, c_int64, c_int, c_int, _P, _P, c_double, c_double, c_int, c_double, _P,
-                          _P, _P], 1),
+    "gtb_dense_kernel": ([_P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, _P, c_double, c_double, c_int, c_double,
+                          _P, _P, _P], 1),
     "gtb_dense_row_scale": ([_P, _P, c_int64, c_int64, _P, _P], 1),
     "gtb_dense_anisotropy": ([_P, _P, c_double, c_int64, _P, _P], 1),
     "gtb_dense_rowsum": ([_P, c_int64, c_int64, _P, _P], 1),

@@ -26,7 +26,7 @@ __device__ __forceinline__ double sym_dense(int mode, double theta, double a, do
 // out[i][j] for i in query rows (Xq), j in reference rows (Xr).
 __global__ void __launch_bounds__(256) dense_kernel(const float* __restrict__ Xq, int64_t nq,
                                                     const float* __restrict__ Xr, int64_t nr, int d, int what,
-                                                    const double* __restrict__ bw_q, const double* __restrict__ bw_r,
+                                                    int metric, const double* __restrict__ bw_q, const double* __restrict__ bw_r,
                                                     double decay, double thresh, double rfac, int symm,
                                                     double theta, double* __restrict__ out,
                                                     double* __restrict__ rowsum) {
@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) dense_kernel(const float* __restrict__ Xq
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x 4 outputs each
   const int64_t i0 = (int64_t)blockIdx.y * DT, j0 = (int64_t)blockIdx.x * DT;
   double acc[4][4];
+  double qn[4] = {0.0, 0.0, 0.0, 0.0}, rn[4] = {0.0, 0.0, 0.0, 0.0};   // squared row norms (cosine metric)
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -54,13 +55,24 @@ __global__ void __launch_bounds__(256) dense_kernel(const float* __restrict__ Xq
       double qv[4], rv[4];
 #pragma unroll
       for (int a = 0; a < 4; ++a) { qv[a] = qs[k][ty * 4 + a]; rv[a] = rs[k][tx * 4 + a]; }
+      if (metric == 1) {
+        // cosine: accumulate the dot products and the squared norms (scipy cdist / pdist "cosine")
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a) {
+          qn[a] = fma(qv[a], qv[a], qn[a]);
+          rn[a] = fma(rv[a], rv[a], rn[a]);
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          double df = qv[a] - rv[b];
-          acc[a][b] = fma(df, df, acc[a][b]);
+          for (int b = 0; b < 4; ++b) acc[a][b] = fma(qv[a], rv[b], acc[a][b]);
         }
+      } else {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            double df = qv[a] - rv[b];
+            acc[a][b] = fma(df, df, acc[a][b]);
+          }
+      }
     }
     __syncthreads();
   }
@@ -75,7 +87,14 @@ __global__ void __launch_bounds__(256) dense_kernel(const float* __restrict__ Xq
       for (int b = 0; b < 4; ++b) {
         const int64_t j = j0 + tx * 4 + b;
         if (j >= nr) continue;
-        const double dist = sqrt(acc[a][b]);
+        double dist;
+        if (metric == 1) {
+          double c = acc[a][b] / (sqrt(qn[a]) * sqrt(rn[b]));
+          if (fabs(c) > 1.0) c = copysign(1.0, c);
+          dist = 1.0 - c;
+        } else {
+          dist = sqrt(acc[a][b]);
+        }
         double v;
         if (what == DENSE_DIST) {
           v = dist;
@@ -152,10 +171,11 @@ __global__ void dense_rowsum_kernel(const double* __restrict__ K, int64_t nq, in
 }  // namespace
 
 extern "C" int gtb_dense_kernel(const float* Xq, int64_t nq, const float* Xr, int64_t nr, int d, int what,
-                                const double* bw_q, const double* bw_r, double decay, double thresh, int symm,
+                                int metric, const double* bw_q, const double* bw_r, double decay, double thresh, int symm,
                                 double theta, double* out, double* rowsum, void* stream) {
   GTB_CHECK_ARG(nq > 0 && nr > 0 && d > 0, "empty input");
   GTB_CHECK_ARG(what >= 0 && what <= 2, "bad mode");
+  GTB_CHECK_ARG(metric == 0 || metric == 1, "metric must be 0 (euclidean) or 1 (cosine)");
   GTB_CHECK_ARG(what == 0 || bw_q != nullptr, "bandwidth required");
   GTB_CHECK_ARG(what != 2 || (bw_r != nullptr && nq == nr), "symmetric mode needs a square problem");
   cudaStream_t st = (cudaStream_t)stream;
@@ -164,7 +184,7 @@ extern "C" int gtb_dense_kernel(const float* Xq, int64_t nq, const float* Xr, in
   // support radius factor; +inf when nothing is thresholded away (thresh <= 0) or in distance mode
   double rfac = INFINITY;
   if (what != DENSE_DIST && thresh > 0 && thresh < 1 && decay > 0) rfac = pow(-log(thresh), 1.0 / decay) * (1.0 + 1e-9);
-  dense_kernel<<<grid, 256, 0, st>>>(Xq, nq, Xr, nr, d, what, bw_q, bw_r, decay, thresh, rfac, symm, theta, out,
+  dense_kernel<<<grid, 256, 0, st>>>(Xq, nq, Xr, nr, d, what, metric, bw_q, bw_r, decay, thresh, rfac, symm, theta, out,
                                      rowsum);
   GTB_CHECK_LAUNCH();
   return GTB_OK;

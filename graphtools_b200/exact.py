@@ -43,9 +43,9 @@ class TraditionalGraph(DataGraph):
                     precomputed, data.shape))
             elif (data < 0).sum() > 0:
                 raise ValueError("Precomputed {} should be non-negative".format(precomputed))
-        if precomputed is None and distance != "euclidean":
+        if precomputed is None and distance not in ("euclidean", "cosine"):
             raise NotImplementedError(
-                "graphtools_b200 accelerates the Euclidean metric only (got distance={!r})".format(distance))
+                "graphtools_b200 accelerates the euclidean and cosine metrics (got distance={!r})".format(distance))
         self.knn = knn
         self.decay = decay
         self.bandwidth = bandwidth
@@ -74,6 +74,9 @@ class TraditionalGraph(DataGraph):
         return self
 
     # ------------------------------------------------------------------ device side
+    def _metric(self):
+        return self.distance if self.precomputed is None else "euclidean"
+
     def _X(self):
         if not hasattr(self, "_dev_X"):
             if sparse.issparse(self.data_nu):
@@ -113,12 +116,12 @@ class TraditionalGraph(DataGraph):
             finally:
                 self.kernel_symm, self.anisotropy = saved
         X = self._X()
-        op = pipeline.SearchOperand(X)
+        op = pipeline.SearchOperand(X, metric=self._metric())
         Xf = X.float()
-        bw = self._resolve_bandwidth(self.bandwidth, X.shape[0], lambda: dense.dense_distances(Xf, Xf), op, op,
+        bw = self._resolve_bandwidth(self.bandwidth, X.shape[0], lambda: dense.dense_distances(Xf, Xf, self._metric()), op, op,
                                      (self.knn or 0) + 1)
         bw = (bw * float(self.bandwidth_scale)).contiguous()
-        K, _ = dense.dense_affinity(Xf, Xf, bw, None, self.decay, self.thresh, want_rowsum=False)
+        K, _ = dense.dense_affinity(Xf, Xf, bw, None, self.decay, self.thresh, want_rowsum=False, metric=self._metric())
         return K
 
     def _sparse_route_ok(self):
@@ -132,7 +135,7 @@ class TraditionalGraph(DataGraph):
         from . import _engine as E
         X = self._X()
         n = X.shape[0]
-        op = pipeline.SearchOperand(X)
+        op = pipeline.SearchOperand(X, metric=self._metric())
         R, info = pipeline.knn_kernel(None, op, op, knn=self.knn + 1, knn_max=None, decay=self.decay,
                                       thresh=self.thresh, bandwidth=self.bandwidth,
                                       bandwidth_scale=self.bandwidth_scale)
@@ -157,18 +160,19 @@ class TraditionalGraph(DataGraph):
         with _logger.log_task("affinities"):
             X = self._X()
             n = X.shape[0]
-            op = pipeline.SearchOperand(X)
-            bw = self._resolve_bandwidth(self.bandwidth, n, lambda: dense.dense_distances(X.float(), X.float()), op, op,
+            op = pipeline.SearchOperand(X, metric=self._metric())
+            bw = self._resolve_bandwidth(self.bandwidth, n, lambda: dense.dense_distances(X.float(), X.float(), self._metric()), op, op,
                                          (self.knn or 0) + 1)
             bw = (bw * float(self.bandwidth_scale)).contiguous()
             self._dev_bandwidth = bw
             X = X.float()          # the dense fp64-accumulating kernel reads float32 rows
             if self.kernel_symm is None:
-                K, rowsum = dense.dense_affinity(X, X, bw, None, self.decay, self.thresh)
+                K, rowsum = dense.dense_affinity(X, X, bw, None, self.decay, self.thresh, metric=self._metric())
                 if float((K - K.T).max().item()) > 1e-5:
                     warnings.warn("K should be symmetric", RuntimeWarning)
             else:
-                K, rowsum = dense.dense_affinity(X, X, bw, bw, self.decay, self.thresh, self.kernel_symm, self.theta)
+                K, rowsum = dense.dense_affinity(X, X, bw, bw, self.decay, self.thresh, self.kernel_symm, self.theta,
+                                                 metric=self._metric())
             if self.anisotropy != 0:
                 dense.anisotropy_dense(K, self.anisotropy, rowsum)
                 rowsum = dense.rowsum_dense(K)
@@ -224,12 +228,12 @@ class TraditionalGraph(DataGraph):
             Y = self._check_extension_shape(Y)
             X = self._X()
             Yd = self._dense_f32(Y)
-            ref = pipeline.SearchOperand(X)
-            qry = pipeline.SearchOperand(Yd.to(X.dtype), mean=ref.mean)
+            ref = pipeline.SearchOperand(X, metric=self._metric())
+            qry = pipeline.SearchOperand(Yd.to(X.dtype), mean=ref.mean, metric=self._metric())
             Xf, Yf = X.float(), Yd.float()
-            bw = self._resolve_bandwidth(bandwidth, Yd.shape[0], lambda: dense.dense_distances(Yf, Xf), qry, ref, knn)
+            bw = self._resolve_bandwidth(bandwidth, Yd.shape[0], lambda: dense.dense_distances(Yf, Xf, self._metric()), qry, ref, knn)
             bw = (bw * float(bandwidth_scale)).contiguous()
-            K, _ = dense.dense_affinity(Yf, Xf, bw, None, self.decay, self.thresh, want_rowsum=False)
+            K, _ = dense.dense_affinity(Yf, Xf, bw, None, self.decay, self.thresh, want_rowsum=False, metric=self._metric())
         return K
 
     def build_kernel_to_data(self, Y, knn=None, bandwidth=None, bandwidth_scale=None):

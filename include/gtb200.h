@@ -174,8 +174,9 @@ int gtb_landmark_op(const int64_t* ptr, const int32_t* lab, const double* raw, c
  * (graphs.py:1546-1609, :1651-1677) and the dense branches of base.py:557-592, :645 ---------- */
 /* what 0: out = distances; 1: out = thresholded affinities exp(-(d/bw_q[i])^decay);
  * 2: additionally symmetrised with the transposed entry (symm 0 '+', 1 '*', 2 'mnn', 3 none);
- * rowsum (optional) receives the row L1 sums */
-int gtb_dense_kernel(const float* Xq, int64_t nq, const float* Xr, int64_t nr, int d, int what,
+ * rowsum (optional) receives the row L1 sums.  metric 0: Euclidean distances; 1: cosine distances
+ * 1 - x.y/(|x||y|) with |cos| clamped to 1 (scipy pdist / cdist "cosine", graphs.py:1552, :1653) */
+int gtb_dense_kernel(const float* Xq, int64_t nq, const float* Xr, int64_t nr, int d, int what, int metric,
                      const double* bw_q, const double* bw_r, double decay, double thresh, int symm, double theta,
                      double* out, double* rowsum, void* stream);
 int gtb_dense_row_scale(const double* in, const double* rowsum, int64_t nq, int64_t nr, double* out, void* stream);

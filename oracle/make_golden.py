@@ -77,6 +77,10 @@ def cases():
     c["iso_cosine_refine"] = dict(X=iso, params=dict(knn=5, decay=20, distance="cosine", thresh=1e-3))
     c["mix_cosine_landmark_random"] = dict(X=mix, X_from="mix_knn", params=dict(
         knn=5, decay=40, distance="cosine", n_landmark=100, random_landmarking=True, random_state=7))
+    c["small_exact_cosine"] = dict(X=small, params=dict(knn=5, decay=40, graphtype="exact", distance="cosine"),
+                                   Y=small[:97] + np.float32(0.02))
+    c["small_exact_cosine_thresh0"] = dict(X=small[:250], params=dict(knn=3, decay=10, thresh=0, distance="cosine",
+                                                                      kernel_symm="mnn", theta=0.3))
     return c
 
 

@@ -154,8 +154,8 @@ def test_pca_reduction_on_host():
 def test_unsupported_metric_is_rejected_loudly():
     with pytest.raises(NotImplementedError, match="euclidean and cosine"):
         build(distance="manhattan")
-    with pytest.raises(NotImplementedError, match="Euclidean"):
-        build(distance="cosine", graphtype="exact")
+    with pytest.raises(NotImplementedError, match="euclidean and cosine"):
+        build(distance="chebyshev", graphtype="exact")
 
 
 def test_mnn_to_data_not_implemented():

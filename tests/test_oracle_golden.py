@@ -18,7 +18,8 @@ def _raw_kernel(case):
         return g.kernel(), g
     if case.cls.startswith("Traditional"):
         return go.exact_kernel(X, knn=p.get("knn", 5), decay=p.get("decay", 40), bandwidth=p.get("bandwidth"),
-                               bandwidth_scale=p.get("bandwidth_scale", 1.0), thresh=p.get("thresh", 1e-4)), None
+                               bandwidth_scale=p.get("bandwidth_scale", 1.0), thresh=p.get("thresh", 1e-4),
+                               distance=p.get("distance", "euclidean")), None
     if case.cls.startswith("MNN"):
         return go.mnn_kernel(X, p["sample_idx"], knn=p.get("knn", 5), decay=p.get("decay", 40),
                              thresh=p.get("thresh", 1e-4), beta=p.get("beta", 1)), None
@@ -60,7 +61,8 @@ def test_oracle_reproduces_reference(name):
             Kyx = g.kernel_to_data(Y)
         else:
             Kyx = go.exact_kernel_to_data(case.X.astype(np.float64), Y, knn=p.get("knn", 5),
-                                          decay=p.get("decay", 40), thresh=p.get("thresh", 1e-4))
+                                          decay=p.get("decay", 40), thresh=p.get("thresh", 1e-4),
+                                          distance=p.get("distance", "euclidean"))
         assert _same(Kyx, case.mat("Kyx"))
         if "clusters" in case.z.files:
             assert _same(go.landmark_extend(Kyx, case.z["clusters"]), case.mat("ext"))
