@@ -249,8 +249,8 @@ def run_gpu_arm(a):
     peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
     if impl == "tc16":
         kp = (d + 1 + 15) // 16 * 16
-        kname = "search_tc_kernel<TOPK, CL=2, BF16> (%s): tcgen05.mma kind::f16 on bf16 hi/lo pairs (bf16x3), " \
-                "A in TMEM, TMA multicast, persistent" % SEARCH
+        kname = "search_tc_kernel<TOPK, CL=2, BF16, LS=16> (%s): tcgen05.mma kind::f16 on bf16 hi/lo pairs " \
+                "(bf16x3), A in TMEM, TMA multicast, persistent, quickselect epilogue" % SEARCH
         issued, ceiling = achieved * 3.0 * kp / d, d / (3.0 * kp)
         note = "the tensor pipe issues 3x that (bf16x3 split) on K padded to %d at the bf16 rate, so frac <= %.3f " \
                "by construction" % (kp, ceiling)

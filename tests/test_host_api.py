@@ -164,3 +164,53 @@ def test_mnn_to_data_not_implemented():
         G = build(sample_idx=np.arange(60) % 2, kernel_symm="mnn", theta=0.5)
     with pytest.raises(NotImplementedError):
         G.build_kernel_to_data(DATA)
+
+
+# ------------------------------------------------------------------ switches added with the widened rows
+def test_pca_front_end_without_gpu_is_the_reference_call(monkeypatch):
+    """GTB_PCA=auto keeps scikit-learn's PCA when no GPU is present (host-side API use); values = sklearn's."""
+    from sklearn.decomposition import PCA
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("covers the host-only container")
+    X = rng.normal(size=(80, 20))
+    G = build(X, n_pca=5, random_state=3)
+    ref = PCA(5, svd_solver="randomized", random_state=3).fit(X)
+    assert np.array_equal(G.data_nu, ref.transform(X))
+    assert np.array_equal(G.transform(X[:4]), ref.transform(X[:4]))
+    monkeypatch.setenv("GTB_PCA", "bogus")
+    with pytest.raises(ValueError, match="GTB_PCA"):
+        build(X, n_pca=5)
+
+
+def test_spectral_switch_validation(monkeypatch):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = build(n_landmark=20)
+    monkeypatch.setenv("GTB_SPECTRAL", "bogus")
+    with pytest.raises(ValueError, match="GTB_SPECTRAL"):
+        G._spectral_impl()
+    monkeypatch.setenv("GTB_SPECTRAL", "auto")
+    assert G._spectral_impl() == "host"            # small input, no device kernel yet
+    monkeypatch.setenv("GTB_SPECTRAL", "device")
+    with pytest.raises(NotImplementedError):
+        G._spectral_impl()                         # needs a built sparse kernel in HBM
+
+
+def test_cosine_is_accepted_by_every_graph_type():
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert build(distance="cosine").distance == "cosine"
+        assert build(distance="cosine", graphtype="exact").distance == "cosine"
+        assert build(distance="cosine", sample_idx=np.arange(60) % 2).distance == "cosine"
+        assert build(distance="cosine", n_landmark=10, random_landmarking=True).distance == "cosine"
+
+
+def test_tie_exemption_uses_the_graph_metric():
+    """The comparator's k-th neighbour tie test must run in the metric of the graph (tests/parity.py)."""
+    from tests.parity import _tie_exempt
+    X = np.array([[1.0, 0.0], [2.0, 0.0], [0.0, 3.0], [1.0, 1.0]])
+    # rows 0 and 1 point the same way: cosine distance 0 -- a tie with the self distance for k = 2
+    ok_cos = _tie_exempt(np.array([0]), np.array([1]), X, 2, metric="cosine")
+    ok_euc = _tie_exempt(np.array([0]), np.array([1]), X, 1, metric="euclidean")
+    assert ok_cos[0] and not ok_euc[0]
