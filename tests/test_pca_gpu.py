@@ -82,3 +82,20 @@ def test_graph_with_n_pca_matches_oracle_on_sklearn_reduced_data(monkeypatch):
         warnings.simplefilter("ignore")
         Gh = gt.Graph(X, n_pca=30, knn=5, decay=40, random_state=1, verbose=0)
     assert np.array_equal(Gh.data_nu, Z_ref)
+
+
+def test_graph_on_sparse_input_with_n_pca():
+    """Sparse data goes through TruncatedSVD (base.py:251-256): device path = sklearn's values, graph builds."""
+    from sklearn.decomposition import TruncatedSVD
+    rng = np.random.default_rng(8)
+    X = sparse.random(1500, 400, density=0.05, random_state=2, format="csr", data_rvs=lambda k: rng.gamma(2.0, size=k))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = gt.Graph(X, n_pca=20, knn=5, decay=40, random_state=5, verbose=0)
+    Z_ref = TruncatedSVD(20, random_state=5).fit_transform(X)
+    assert np.allclose(G.data_nu, Z_ref, rtol=0, atol=1e-8 * np.abs(Z_ref).max())
+    K_ref, _ = go.knn_graph(Z_ref, knn=5, decay=40)
+    compare_sparse(G.kernel, K_ref, thresh=1e-4, what="K on TruncatedSVD-reduced data")
+    # new points in the ambient (sparse) space are reduced by the fitted estimator on the host
+    T = G.extend_to_data(X[:20])
+    assert T.shape == (20, 1500)
