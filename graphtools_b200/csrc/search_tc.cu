@@ -812,12 +812,11 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
 }
 
 int g_tc_cluster = 2;
-int g_tc_list = 32;
 
 template <int MODE>
-int launch_tc(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, bool bf16, TcParams& p,
-              cudaStream_t st) {
-  const bool short_list = (MODE == 0) && g_tc_list == 16;
+int launch_tc(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, bool bf16, int list,
+              TcParams& p, cudaStream_t st) {
+  const bool short_list = (MODE == 0) && list == 16;
   if (bf16) {
     switch (g_tc_cluster) {
       case 1: return short_list ? launch_tc_cl<MODE, 1, true, (MODE == 0 ? 16 : 32)>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
@@ -892,11 +891,10 @@ extern "C" int gtb_knn_topk_tc(const void* q_hi, const void* q_lo, const float* 
   int rc = tc_check(nq, nr, nq_pad, nr_pad, Kp, dtype);
   if (rc) return rc;
   GTB_CHECK_ARG(list == 16 || list == 32, "list size must be 16 or 32");
-  g_tc_list = list;
   TcParams p{};
   p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.qn2 = qn2;
   p.cand_idx = cand_idx; p.cand_buf = reinterpret_cast<uint2*>(scratch); p.tau = tau;
-  return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, Kp, dtype == 1, p, (cudaStream_t)stream);
+  return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, Kp, dtype == 1, list, p, (cudaStream_t)stream);
 }
 
 extern "C" int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float* qn2, const float* lim2,
@@ -909,5 +907,5 @@ extern "C" int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float
   p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.qn2 = qn2; p.lim2 = lim2;
   p.pairs = reinterpret_cast<int2*>(pairs); p.capacity = (unsigned long long)capacity; p.counter = counter;
   p.rowcnt = rowcnt;
-  return launch_tc<1>(q_hi, q_lo, r_hi, r_lo, Kp, dtype == 1, p, (cudaStream_t)stream);
+  return launch_tc<1>(q_hi, q_lo, r_hi, r_lo, Kp, dtype == 1, 32, p, (cudaStream_t)stream);
 }
