@@ -80,3 +80,29 @@ def test_route_edges_to_column_owner_gloo_world2():
     out = mgr.dict()
     mp.spawn(_route_worker, args=(world, port, n, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+def test_uneven_and_empty_shards_gloo_world2():
+    """Query sets that do not fill every rank (out-of-sample extension with few rows): rank 1 owns 44 rows of 300,
+    and nothing at all of a 100-row set -- the all-gather and the edge routing must still assemble the full matrix."""
+    for n in (300, 100):
+        port = _free_port()
+        mgr = mp.Manager()
+        out = mgr.dict()
+        mp.spawn(_worker, args=(2, port, n, out), nprocs=2, join=True)
+        assert all(out[r] for r in range(2)), n
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_route_worker, args=(2, port, 100, out), nprocs=2, join=True)
+    assert all(out[r] for r in range(2))
+
+
+def test_owner_of_matches_bounds():
+    for n, world in ((1000, 2), (1000, 8), (100, 4), (1_000_000, 8)):
+        bounds = [gd.shard_bounds(n, world, r) for r in range(world)]
+        cols = torch.arange(0, n, max(1, n // 997))
+        own = gd.owner_of(cols, bounds).numpy()
+        for c, o in zip(cols.numpy(), own):
+            lo, hi = bounds[o]
+            assert lo <= c < hi, (n, world, c, o, bounds)
