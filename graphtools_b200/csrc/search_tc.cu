@@ -831,7 +831,8 @@ int launch_tc(const void* q_hi, const void* q_lo, const void* r_hi, const void* 
                               : launch_tc_cl<MODE, 1, false, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
     case 2: return short_list ? launch_tc_cl<MODE, 2, false, (MODE == 0 ? 16 : 32)>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
                               : launch_tc_cl<MODE, 2, false, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
-    case 4: return launch_tc_cl<MODE, 4, false, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+    case 4: return short_list ? launch_tc_cl<MODE, 4, false, (MODE == 0 ? 16 : 32)>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
+                              : launch_tc_cl<MODE, 4, false, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
     default: gtb_set_error("cluster size must be 1, 2 or 4"); return GTB_ERR_ARG;
   }
 }

@@ -72,7 +72,7 @@ def cases():
     c["mnn_binary"] = dict(X=mnnX, params=dict(knn=4, decay=None, sample_idx=mnn_idx, kernel_symm="mnn", theta=0.9,
                                                 beta=0.5))
     # cosine metric (sklearn brute-force cosine_distances behind knn_tree)
-    c["mix_cosine"] = dict(X=mix, params=dict(knn=5, decay=40, distance="cosine"), Y=Yq)
+    c["mix_cosine"] = dict(X=mix, X_ref="mix_knn", params=dict(knn=5, decay=40, distance="cosine"), Y=Yq)
     c["digits_cosine_binary"] = dict(X="digits700", params=dict(knn=5, decay=None, distance="cosine"))
     c["iso_cosine_refine"] = dict(X=iso, params=dict(knn=5, decay=20, distance="cosine", thresh=1e-3))
     c["mix_cosine_landmark_random"] = dict(X=mix, X_from="mix_knn", params=dict(
@@ -101,6 +101,8 @@ def main():
         meta = {k: (v if not isinstance(v, np.ndarray) else "array") for k, v in params.items()}
         if "X_from" in case:
             meta["X_from"] = case["X_from"]
+        elif "X_ref" in case:
+            meta["X_from"] = case["X_ref"]          # same input as another fixture: stored once, outputs stored here
         elif not isinstance(case["X"], str):
             out["X"] = X32
         if "sample_idx" in params:
