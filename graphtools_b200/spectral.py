@@ -155,8 +155,16 @@ def minibatch_kmeans(X, n_clusters, init_size=None, batch_size=10000, max_iter=1
         labels, d2 = assign_nearest(Xb, centers)
         batch_inertia = float(d2.sum().item()) / batch_size
         # centre update: running mean weighted by the number of samples each centre has seen
-        bc = torch.bincount(labels, minlength=n_clusters).to(torch.float64)
-        sums = torch.zeros_like(centers).index_add_(0, labels, Xb)
+        bc_i = torch.bincount(labels, minlength=n_clusters)
+        bc = bc_i.to(torch.float64)
+        # per-centre sums of the batch rows as a CSR x dense product (rows = centres, entries = the batch members in
+        # batch order): sequential accumulation, so the update is reproducible run to run -- an atomic scatter-add is not
+        order = torch.argsort(labels, stable=True).to(torch.int32)
+        member_ptr = torch.zeros((n_clusters + 1,), dtype=torch.int64, device=dev)
+        member_ptr[1:] = torch.cumsum(bc_i, 0)
+        members = pipeline.DeviceCSR(member_ptr, order, torch.ones((batch_size,), dtype=torch.float64, device=dev),
+                                     (n_clusters, batch_size))
+        sums = pipeline.spmm(members, Xb)
         new_counts = counts + bc
         hit = bc > 0
         centers[hit] = (centers[hit] * counts[hit, None] + sums[hit]) / new_counts[hit, None]
