@@ -229,12 +229,18 @@ class Data(Base):
                                                                     self.data.shape[1]))
 
     def inverse_transform(self, Y, columns=None):
-        """Map ``Y`` from the reduced space back to the ambient space."""
+        """Map ``Y`` from the reduced space back to the ambient space (base.py:368-424)."""
         try:
             if not hasattr(self, "data_pca"):
-                if Y.shape[1] != self.data_nu.shape[1]:
+                try:
+                    if Y.shape[1] != self.data_nu.shape[1]:
+                        raise ValueError
+                except IndexError:              # len(Y.shape) < 2
                     raise ValueError
-                return Y if columns is None else Y[:, columns]
+                if columns is None:
+                    return Y
+                columns = np.array([columns]).flatten()
+                return Y[:, columns]
             if columns is None:
                 return self.data_pca.inverse_transform(Y)
             columns = np.array([columns]).flatten()
