@@ -4,11 +4,11 @@
     G = graphtools.Graph(X, knn=5, decay=40)
     G.kernel, G.diff_op
 """
-from .factory import Graph
+from .factory import Graph, from_igraph, read_pickle
 from . import graphs
 from .graphs import (kNNGraph, TraditionalGraph, MNNGraph, LandmarkGraph, kNNLandmarkGraph, MNNLandmarkGraph,
                      TraditionalLandmarkGraph)
 
 __version__ = "0.1.0"
-__all__ = ["Graph", "graphs", "kNNGraph", "TraditionalGraph", "MNNGraph", "LandmarkGraph", "kNNLandmarkGraph",
+__all__ = ["Graph", "from_igraph", "read_pickle", "graphs", "kNNGraph", "TraditionalGraph", "MNNGraph", "LandmarkGraph", "kNNLandmarkGraph",
            "MNNLandmarkGraph", "TraditionalLandmarkGraph"]

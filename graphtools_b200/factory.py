@@ -83,3 +83,32 @@ def Graph(data, n_pca=None, rank_threshold=None, knn=5, decay=40, bandwidth=None
     _logger.log_debug("Initializing {} with arguments {}".format(
         parents, ", ".join("{}='{}'".format(k, v) for k, v in params.items() if k != "data")))
     return cls(**params)
+
+
+def from_igraph(G, attribute="weight", **kwargs):
+    """igraph.Graph -> TraditionalGraph on its (weighted) adjacency matrix (reference api.py:298-336)."""
+    from scipy import sparse
+    if "precomputed" in kwargs:
+        if kwargs["precomputed"] != "adjacency":
+            warnings.warn("Cannot build graph from igraph with precomputed={}. Use 'adjacency' instead.".format(
+                kwargs["precomputed"]), UserWarning)
+        del kwargs["precomputed"]
+    try:
+        K = G.get_adjacency(attribute=attribute).data
+    except ValueError as e:
+        if str(e) == "Attribute does not exist":
+            warnings.warn("Edge attribute {} not found. Returning unweighted graph".format(attribute), UserWarning)
+        K = G.get_adjacency(attribute=None).data
+    return Graph(sparse.coo_matrix(K), precomputed="adjacency", **kwargs)
+
+
+def read_pickle(path):
+    """Load a pickled graph (or any object) from ``path`` (reference api.py:339-354).  Graphs are pickled with their
+    host-side results (``BaseGraph.__getstate__`` materialises K / P and drops the device handles)."""
+    import pickle
+    from .core import BaseGraph
+    with open(path, "rb") as f:
+        G = pickle.load(f)
+    if not isinstance(G, BaseGraph):
+        warnings.warn("Returning object that is not a graphtools.base.BaseGraph")
+    return G

@@ -214,3 +214,44 @@ def test_tie_exemption_uses_the_graph_metric():
     ok_cos = _tie_exempt(np.array([0]), np.array([1]), X, 2, metric="cosine")
     ok_euc = _tie_exempt(np.array([0]), np.array([1]), X, 1, metric="euclidean")
     assert ok_cos[0] and not ok_euc[0]
+
+
+def test_pickle_round_trip_and_read_pickle(tmp_path):
+    """to_pickle / read_pickle (reference api.py:339-354, test_api.py:89-137) on graphs without device state."""
+    import pickle
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = build(knn=4, decay=20, n_landmark=10)
+    path = str(tmp_path / "graph.pkl")
+    G.to_pickle(path)
+    G2 = gt.read_pickle(path)
+    assert type(G2).__name__ == type(G).__name__ and G2.get_params() == G.get_params()
+    assert np.array_equal(G2.data, G.data)
+    other = str(tmp_path / "other.pkl")
+    with open(other, "wb") as f:
+        pickle.dump("hello world", f)
+    with pytest.warns(UserWarning, match="Returning object that is not a graphtools.base.BaseGraph"):
+        assert gt.read_pickle(other) == "hello world"
+
+
+def test_from_igraph_contract():
+    """from_igraph (reference api.py:298-336) with a minimal stand-in for igraph.Graph.get_adjacency."""
+    A = (np.abs(rng.normal(size=(12, 12))) > 1.0).astype(float)
+    A = np.maximum(A, A.T)
+
+    class _Adj:
+        def __init__(self, data):
+            self.data = data
+
+    class _IG:
+        def get_adjacency(self, attribute=None):
+            if attribute not in (None, "weight"):
+                raise ValueError("Attribute does not exist")
+            return _Adj(A.tolist())
+
+    G = gt.from_igraph(_IG(), initialize=False, verbose=0)
+    assert type(G).__name__ == "TraditionalGraph" and G.precomputed == "adjacency"
+    with pytest.warns(UserWarning, match="Cannot build graph from igraph with precomputed=affinity"):
+        gt.from_igraph(_IG(), precomputed="affinity", initialize=False, verbose=0)
+    with pytest.warns(UserWarning, match="Edge attribute nope not found. Returning unweighted graph"):
+        gt.from_igraph(_IG(), attribute="nope", initialize=False, verbose=0)
