@@ -51,6 +51,15 @@ def workload_name(a):
            "thresh=1e-4, kernel + diff_op".format(a.n, a.d, a.clusters, a.seed)
 
 
+METRIC = "graph build points/sec (kernel+diff_op)"
+
+
+def bench_config(a):
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": workload_name(a), "n": a.n, "d": a.d, "knn": KNN, "decay": DECAY, "thresh": THRESH,
+            "l2": "inputs (400 MB operand, 113 MB raw CSR) larger than the 126 MB L2; no explicit flush"}
+
+
 def make_data(a):
     from graphtools_b200 import synth
     X, _ = synth.gaussian_mixture(a.n, a.d, n_clusters=a.clusters, intrinsic_dim=10, seed=a.seed)
@@ -58,18 +67,66 @@ def make_data(a):
 
 
 # ------------------------------------------------------------------------------ CPU arm
-def cpu_sample_rate(X, seconds, fixed_rows=None):
-    """Times the oracle (restatement of the reference's sklearn/numpy path, float64, all host threads) on a
-    bounded sample: `m` query rows of the workload searched against the FULL reference set and turned into
-    kernel rows (kneighbors + bandwidth + affinity CSR; graphs.py:819-982).  Per-row cost equals the full
-    job's per-point cost, so points/s = m / t.  Symmetrise + normalise (<1% of CPU time) are
-    not in the sample."""
-    from oracle import graph_oracle as go
+REF_SIZES = (25_000, 50_000, 100_000, 200_000)      # fit t = a N^2 + b N, quote N = 1M
+
+
+def load_reference():
+    """The UNMODIFIED reference installed under baseline/_ref (baseline/install_ref.sh), float64 path
+    (NUMBA_AVAILABLE = False), with the three stand-ins for its uninstalled dependencies
+    (tasklogger, future, pygsp) from oracle/shims.  None when the install is missing."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "graphtools")):
+        return None
+    for p in (os.path.join(ROOT, "oracle", "shims"), ref):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import graphtools
+    import graphtools.graphs
+    graphtools.graphs.NUMBA_AVAILABLE = False
+    return graphtools
+
+
+def _all_threads():
     try:
         from threadpoolctl import threadpool_limits
         threadpool_limits(limits=os.cpu_count())
     except Exception:
         pass
+
+
+def reference_build_seconds(graphtools, X, n_sub):
+    """One run of the reference's own public API on an n_sub-point subsample of the workload (every
+    (n / n_sub)-th point, so the mixture proportions are kept): Graph(...) builds the kernel, .diff_op the
+    diffusion operator (graphs.py:819-982, base.py:534-646)."""
+    rows = np.linspace(0, X.shape[0] - 1, n_sub).astype(np.int64)
+    Xs = X[rows].astype(np.float64)
+    t0 = time.perf_counter()
+    G = graphtools.Graph(Xs, knn=KNN, decay=DECAY, thresh=THRESH, n_jobs=-1, verbose=0)
+    K = G.kernel
+    P = G.diff_op
+    dt = time.perf_counter() - t0
+    return dt, int(K.nnz), int(P.nnz)
+
+
+def fit_quadratic(sizes, times):
+    """Least-squares t = a N^2 + b N (relative residuals), as BASELINE.md section 3 prescribes."""
+    N = np.asarray(sizes, dtype=np.float64)
+    t = np.asarray(times, dtype=np.float64)
+    if len(set(sizes)) < 2:
+        return float(t.mean() / N.mean() ** 2), 0.0
+    A = np.stack([N * N, N], axis=1) / t[:, None]
+    (a, b), *_ = np.linalg.lstsq(A, np.ones_like(t), rcond=None)
+    if a <= 0 or b < 0:                      # degenerate fit (noise): pure quadratic through the largest size
+        i = int(np.argmax(N))
+        return float(t[i] / N[i] ** 2), 0.0
+    return float(a), float(b)
+
+
+def cpu_sample_rate(X, seconds, fixed_rows=None):
+    """Cross-check leg: the oracle port (restatement of graphs.py:819-982, float64, all host threads) on `m` query
+    rows of the workload searched against the FULL reference set; per-row cost = per-point cost of the full job."""
+    from oracle import graph_oracle as go
+    _all_threads()
     X64 = X.astype(np.float64)
     g = go.KnnOracle(X64, knn=KNN, decay=DECAY, thresh=THRESH, n_jobs=-1)
     g.tree  # fit (brute force: keeps a pointer)
@@ -78,17 +135,17 @@ def cpu_sample_rate(X, seconds, fixed_rows=None):
     def run(m):
         rows = np.linspace(0, n - 1, m).astype(np.int64)
         t0 = time.perf_counter()
-        g.kernel_to_data(X64[rows], knn=KNN + 1)
-        return time.perf_counter() - t0
+        R = g.kernel_to_data(X64[rows], knn=KNN + 1)
+        return time.perf_counter() - t0, rows, R
 
     if fixed_rows is None:
         m0 = min(n, 512)
-        t0 = run(m0)
+        t0, _, _ = run(m0)
         m = int(min(n, max(m0, m0 * seconds / max(t0, 1e-3))))
     else:
         m = fixed_rows
-    t = run(m)
-    return m / t, m, t
+    t, rows, R = run(m)
+    return m / t, m, t, rows, R
 
 
 def cpu_threads():
@@ -99,31 +156,82 @@ def cpu_threads():
         return os.cpu_count()
 
 
+def reference_schedule(steps):
+    """Subsample size of each timed step: the four sizes of BASELINE.md section 3, the large ones less often so that
+    a 20-step run still ends within a few minutes (200k twice, 100k four times, ...)."""
+    out = []
+    for i in range(steps):
+        if i % 10 == 5:
+            out.append(REF_SIZES[3])
+        elif i % 5 == 2:
+            out.append(REF_SIZES[2])
+        elif i % 2 == 1:
+            out.append(REF_SIZES[1])
+        else:
+            out.append(REF_SIZES[0])
+    return out
+
+
+def reference_fit(graphtools, X, sizes, n_target):
+    times, nnz = [], []
+    for m in sizes:
+        dt, nk, _ = reference_build_seconds(graphtools, X, min(m, X.shape[0]))
+        times.append(dt); nnz.append(nk)
+    a, b = fit_quadratic([min(m, X.shape[0]) for m in sizes], times)
+    t_target = a * n_target ** 2 + b * n_target
+    return {"a_s_per_point2": a, "b_s_per_point": b, "sizes": [int(min(m, X.shape[0])) for m in sizes],
+            "seconds": times, "nnz_K": nnz, "extrapolated_seconds_at_n": t_target, "n": int(n_target)}
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    _all_threads()
     X = make_data(a)
-    rate, m, _ = cpu_sample_rate(X, a.cpu_seconds)      # sizing pass (also a warm-up)
-    for _ in range(max(0, a.warmup - 1)):
-        cpu_sample_rate(X, 0, fixed_rows=min(m, 2048))
-    rates, times = [], []
-    for _ in range(a.steps):
-        r, _, t = cpu_sample_rate(X, 0, fixed_rows=m)
-        rates.append(r); times.append(t)
+    graphtools = load_reference()
+    cfg = bench_config(a)
+    if graphtools is None:
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is missing (run baseline/install_ref.sh "
+                          "in the build container)"}))
+        return
+    for _ in range(a.warmup):
+        reference_build_seconds(graphtools, X, min(a.n, 12_500))
+    sched = reference_schedule(a.steps)
+    sched = [min(m, a.n) for m in sched]
+    times = []
+    for m in sched:
+        dt, _, _ = reference_build_seconds(graphtools, X, m)
+        times.append(dt)
     total_t = sum(times)
-    value = m * a.steps / total_t
-    sample = "{} of {} query rows vs the full {}-point reference set per step (oracle port of graphs.py:819-982, " \
-             "float64, sklearn brute kneighbors + affinity CSR)".format(m, a.n, a.n)
+    fa, fb = fit_quadratic(sched, times)
+    t_full = fa * a.n ** 2 + fb * a.n
+    value = a.n / t_full
+    per_size = {}
+    for m, t in zip(sched, times):
+        per_size.setdefault(int(m), []).append(t)
+    # port-vs-reference cross-check: the oracle port's per-point rate on rows searched against the full set
+    port_rate, port_m, port_t, _, _ = cpu_sample_rate(X, min(a.cpu_seconds, 8.0))
+    sample = "unmodified graphtools.Graph(X_sub, knn=5, decay=40, thresh=1e-4, n_jobs=-1).kernel/.diff_op from " \
+             "baseline/_ref on subsamples of the workload, one size per step from {}; value = n / (a n^2 + b n) at " \
+             "n = {} (extrapolated)".format(sorted(per_size), a.n)
     line = {
-        "impl": "reference", "metric": "graph build points/sec (kernel+diff_op)", "value": value,
+        "impl": "reference", "metric": METRIC, "value": value,
         "unit": "points/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1e3 * total_t / a.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a)},
-        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cpu_threads(), "kind": "port",
+        "ms_per_step": 1e3 * total_t / max(a.steps, 1), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "extrapolated": True,
+        "fit": {"model": "t = a N^2 + b N", "a_s_per_point2": fa, "b_s_per_point": fb,
+                "seconds_by_size": {str(k): v for k, v in sorted(per_size.items())},
+                "points_per_s_by_size": {str(k): k / float(np.mean(v)) for k, v in sorted(per_size.items())},
+                "extrapolated_seconds_at_n": t_full},
+        "port_check": {"port_points_per_s_full_set_rows": port_rate, "rows": port_m, "seconds": port_t,
+                       "reference_over_port": value / port_rate,
+                       "note": "oracle port (graphs.py:819-982 restated) on sampled rows against the full 1M set"},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cpu_threads(), "kind": "reference",
                          "sample": sample},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host": {"cpu_count": os.cpu_count(), "numba": False},
     }
     print(json.dumps(line))
 

@@ -40,15 +40,21 @@ _SIGS = {
     "gtb_refine_ball": ([_P, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, c_int, c_int64, c_double, c_double, _P, c_int,
                          c_double, _P, _P, _P, _P, _P, c_int, _P], 2),
     "gtb_csr_gather": ([_P, _P, _P, _P, _P, c_int64, c_int, _P, c_int64, _P, _P, _P, _P, _P, _P, _P], 2),
-    "gtb_exclusive_scan": ([_P, c_int64, _P, _P, _P], 3),
+    "gtb_exclusive_scan": ([_P, c_int64, _P, _P, _P], 1),
     "gtb_cast_indptr": ([_P, c_int64, _P, _P], 1),
-    "gtb_sym_count": ([_P, _P, _P, c_int64, c_int, c_double, _P, _P, _P], 1),
-    "gtb_sym_fill": ([_P, _P, _P, c_int64, c_int, c_double, _P, _P, _P, _P, _P], 1),
-    "gtb_row_finalize": ([_P, _P, _P, c_int64, c_int, _P, _P, _P, _P, _P, c_int, _P], 1),
-    "gtb_anisotropy": ([_P, _P, _P, _P, c_double, c_int64, _P], 1),
-    "gtb_csr_to_dense": ([_P, _P, _P, c_int64, c_int64, _P, _P], 1),
+    "gtb_transpose_count": ([_P, c_int64, c_int, _P, c_int64, _P], 1),
+    "gtb_transpose_scatter": ([_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P], 1),
+    "gtb_csr_sort_rows": ([_P, _P, _P, c_int64, _P, _P], 2),
+    "gtb_records_count": ([_P, c_int64, c_int, _P, c_int64, _P], 1),
+    "gtb_records_scatter": ([_P, c_int64, c_int, _P, _P, _P, _P, _P], 1),
     "gtb_sym_merge_count": ([_P, _P, _P, _P, _P, _P, c_int64, c_int, c_double, _P, _P], 1),
-    "gtb_sym_merge_fill": ([_P, _P, _P, _P, _P, _P, c_int64, c_int, c_double, _P, _P, _P, _P, _P, _P], 1),
+    "gtb_sym_merge_fill": ([_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_double, _P, _P, _P, _P, _P, _P, _P], 1),
+    "gtb_asym_check": ([_P, _P, _P, c_int64, _P, _P], 1),
+    "gtb_row_finalize": ([_P, _P, _P, c_int64, _P, _P, _P, c_int, _P], 1),
+    "gtb_anisotropy": ([_P, _P, _P, _P, c_double, c_int64, _P], 1),
+    "gtb_route_count": ([_P, _P, c_int64, c_int, c_int, _P, _P], 1),
+    "gtb_route_fill": ([_P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P], 1),
+    "gtb_csr_to_dense": ([_P, _P, _P, c_int64, c_int64, _P, _P], 1),
     "gtb_block_count": ([_P, c_int64, _P, _P, _P], 1),
     "gtb_block_fill": ([_P, _P, _P, c_int64, _P, _P, _P, _P, c_double, _P, _P, _P, _P, _P], 1),
     "gtb_cluster_aggregate_count": ([_P, _P, _P, c_int64, _P, _P, _P], 1),

@@ -317,8 +317,99 @@ class BaseGraph(Base, metaclass=abc.ABCMeta):
         raise NotImplementedError
 
     def _ensure_built(self):
-        if not hasattr(self, "_dev_kernel") and not hasattr(self, "_kernel"):
-            self._dev_kernel = self._build_kernel()
+        d = self.__dict__
+        if "_dev_kernel" in d or "_dev_shard" in d:
+            return
+        if "_kernel" in d:
+            # host views only (an unpickled graph): put the kernel back into HBM so that every device-side
+            # consumer (diffuse, landmark operator, extension, spectral clusters) keeps working
+            self._restore_device_state()
+            return
+        K = self._build_kernel()
+        if K is not None:
+            self._dev_kernel = K
+
+    def _restore_device_state(self):
+        K = self._kernel
+        if sparse.issparse(K):
+            Kd = pipeline.csr_from_scipy(K)
+            self._dev_kernel = Kd
+            self._dev_degree = pipeline.row_sums(Kd)
+            self._dev_P = pipeline.row_normalize(Kd)
+        else:
+            import torch
+            from . import dense
+            Kd = torch.from_numpy(np.ascontiguousarray(K, dtype=np.float64)).to(pipeline._dev())
+            self._dev_kernel = Kd
+            self._dev_degree = dense.rowsum_dense(Kd)
+            self._dev_P = dense.row_normalize_dense(Kd, self._dev_degree)
+
+    def __getattr__(self, name):
+        # A row-sharded multi-GPU build keeps only this rank's rows of K / P in HBM (``_dev_shard``); the first
+        # consumer that needs the complete device matrices triggers one NCCL all-gather (collective: every rank
+        # reaches it, because every rank runs the same program).
+        if name in ("_dev_kernel", "_dev_P", "_dev_degree") and "_dev_shard" in self.__dict__:
+            self._gather_shards()
+            return self.__dict__[name]
+        raise AttributeError("'{}' object has no attribute '{}'".format(type(self).__name__, name))
+
+    def _gather_shards(self):
+        from . import distributed as gd
+        sh = self.__dict__["_dev_shard"]
+        heights = [b[1] - b[0] for b in sh["bounds"]]
+        full_ptr, full_idx, full_val = gd.allgather_csr_rows(sh["row_len"], sh["indices"], sh["data"], heights,
+                                                             pipeline.exclusive_scan)
+        nnz_all = gd.allgather_counts(sh["indices"].shape[0], sh["indices"].device)
+        n = sh["n"]
+        self.__dict__["_dev_kernel"] = pipeline.DeviceCSR(full_ptr, full_idx, full_val, (n, n))
+        self.__dict__["_dev_P"] = gd._allgather_padded(sh["P"], nnz_all)
+        self.__dict__["_dev_degree"] = gd._allgather_padded(sh["degree"], heights)
+
+    def _materialize_shards(self):
+        """Host K and P of a row-sharded build: every rank copies ITS rows device->host into a shared-memory segment
+        (parallel PCIe links, parallel first-touch), then all ranks view the complete scipy matrices zero-copy.
+        Collective."""
+        import torch
+        from . import _engine as E
+        from . import distributed as gd
+        sh = self.__dict__["_dev_shard"]
+        bounds, n = sh["bounds"], sh["n"]
+        rank = gd.dist.get_rank()
+        lo, hi = bounds[rank]
+        nnz_all = gd.allgather_counts(sh["indices"].shape[0], sh["indices"].device)
+        nnz = int(sum(nnz_all))
+        off = int(sum(nnz_all[:rank]))
+        if not gd.SharedResult.available(24 * nnz + 4 * (n + 1)):
+            # no room in /dev/shm: assemble on the device, copy the whole matrix on every rank
+            self._kernel = self._dev_kernel.to_scipy()
+            self._diff_op = self._dev_kernel.to_scipy(self._dev_P)
+            self._kernel_degree = self._dev_degree.cpu().numpy().reshape(-1, 1)
+            return
+        res = gd.SharedResult()
+        arr = res.create({"indptr": (n + 1, np.int32), "indices": (nnz, np.int32), "K": (nnz, np.float64),
+                          "P": (nnz, np.float64), "degree": (n, np.float64)})
+        m = hi - lo
+        if m > 0:
+            ip32 = pipeline._empty((m + 1,), torch.int32)
+            E.call("gtb_cast_indptr", sh["indptr"], m + 1, ip32)
+            ip32 += off
+            # slice [lo, hi) of the global row pointers; the entry at `hi` is written by the next rank (or below)
+            pipeline.d2h_into(ip32[:m], arr["indptr"][lo:hi])
+            pipeline.d2h_into(sh["indices"], arr["indices"][off:off + nnz_all[rank]])
+            pipeline.d2h_into(sh["data"], arr["K"][off:off + nnz_all[rank]])
+            pipeline.d2h_into(sh["P"], arr["P"][off:off + nnz_all[rank]])
+            pipeline.d2h_into(sh["degree"], arr["degree"][lo:hi])
+        if rank == 0:
+            arr["indptr"][bounds[-1][1]:] = nnz            # rows past the last non-empty shard, and the end marker
+        torch.cuda.current_stream().synchronize()
+        arr = res.finish(arr)
+        K = sparse.csr_matrix((arr["K"], arr["indices"], arr["indptr"]), shape=(n, n), copy=False)
+        P = sparse.csr_matrix((arr["P"], arr["indices"], arr["indptr"]), shape=(n, n), copy=False)
+        for M in (K, P):
+            M.has_sorted_indices = True
+            M.has_canonical_format = True
+        self._kernel, self._diff_op = K, P
+        self._kernel_degree = arr["degree"].reshape(-1, 1)
 
     def symmetrize_kernel(self, K):
         """Host-callable symmetrisation of an arbitrary scipy / numpy kernel on the GPU."""
@@ -345,12 +436,13 @@ class BaseGraph(Base, metaclass=abc.ABCMeta):
     @property
     def K(self):
         """Kernel matrix (scipy CSR or ndarray), materialised from HBM on first access."""
-        try:
-            return self._kernel
-        except AttributeError:
+        if "_kernel" not in self.__dict__:
             self._ensure_built()
-            self._kernel = self._materialize(self._dev_kernel)
-            return self._kernel
+            if "_dev_shard" in self.__dict__ and "_dev_kernel" not in self.__dict__:
+                self._materialize_shards()
+            else:
+                self._kernel = self._materialize(self._dev_kernel)
+        return self._kernel
 
     @property
     def kernel(self):
@@ -359,10 +451,11 @@ class BaseGraph(Base, metaclass=abc.ABCMeta):
     @property
     def P(self):
         """Diffusion operator = row-L1-normalised kernel (base.py:629-646)."""
-        try:
-            return self._diff_op
-        except AttributeError:
+        if "_diff_op" not in self.__dict__:
             self._ensure_built()
+            if "_dev_shard" in self.__dict__ and "_dev_kernel" not in self.__dict__:
+                self._materialize_shards()
+                return self._diff_op
             K = self._dev_kernel
             if isinstance(K, pipeline.DeviceCSR):
                 if getattr(self, "_dev_P", None) is None:
@@ -370,7 +463,7 @@ class BaseGraph(Base, metaclass=abc.ABCMeta):
                 self._diff_op = K.to_scipy(self._dev_P)
             else:
                 self._diff_op = self._dev_P.cpu().numpy()
-            return self._diff_op
+        return self._diff_op
 
     @property
     def diff_op(self):
@@ -379,12 +472,10 @@ class BaseGraph(Base, metaclass=abc.ABCMeta):
     @property
     def kernel_degree(self):
         """Row sums of the kernel, shape [N, 1] (base.py:648-666)."""
-        try:
-            return self._kernel_degree
-        except AttributeError:
+        if "_kernel_degree" not in self.__dict__:
             self._ensure_built()
             self._kernel_degree = self._dev_degree.cpu().numpy().reshape(-1, 1)
-            return self._kernel_degree
+        return self._kernel_degree
 
     @property
     def diff_aff(self):

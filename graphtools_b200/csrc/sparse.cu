@@ -1,29 +1,34 @@
-// K4: sparse symmetrisation (+, *, mnn), anisotropy and row-normalisation into the diffusion
-// operator, plus the exclusive scan used to size every CSR in the engine.
+// Sparse helpers shared by every stage that sizes or finishes a CSR: the single-pass exclusive scan, per-row
+// normalisation (P = K / rowsum, degree, diagonal check), anisotropy, MNN block assembly, densification.
+// The symmetrisation itself (sort-based transpose + merge) lives in symm.cu.
 //
-// Replaces scipy's csr binops behind BaseGraph.symmetrize_kernel (reference graphtools/base.py:557-577,
-// matrix.py:16-29), apply_anisotropy (base.py:579-592), sklearn normalize(K, "l1") (base.py:645) and
-// kernel_degree (base.py:648-666).
-//
-// Symmetrisation never materialises K^T: every edge (i,j,w) binary-searches row j for column i
-// (rows are column-sorted), which yields the reverse weight w' (0 when absent).  All three merge
-// rules are symmetric functions s(w,w'), so an edge whose reverse is absent contributes the same
-// value s to row j.  Pass 1 counts the new row lengths, pass 2 scatters (atomic cursor per row),
-// pass 3 sorts each row by column and emits K, P = K / rowsum and the degree vector in one sweep.
+// Replaces sklearn normalize(K, "l1") (reference graphtools/base.py:645), kernel_degree (base.py:648-666),
+// apply_anisotropy (base.py:579-592), the np.cumsum of _build_csr_from_neighbors (graphs.py:519-551) and
+// matrix.set_submatrix (matrix.py:49-51).
 #include "common.cuh"
 #include "gtb200.h"
 
 namespace {
 
 // ------------------------------------------------------------------------------ scan
+// Single-pass exclusive scan (int32 -> int64) with decoupled look-back: every tile publishes its aggregate, then
+// its inclusive prefix, in one 64-bit word (2 flag bits : 62 value bits) and resolves its own prefix by walking
+// back over its predecessors' words.  Tile ids are handed out by an atomic ticket, so a tile's predecessors have
+// always started -- no dependence on block scheduling order.  ws[0] = ticket, ws[1 + t] = state of tile t.
 constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr unsigned long long SCAN_AGG = 1ull << 62, SCAN_PRE = 2ull << 62, SCAN_VAL = (1ull << 62) - 1;
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_block_kernel(const int32_t* __restrict__ in, int64_t n,
-                                                                  int64_t* __restrict__ out,
-                                                                  int64_t* __restrict__ blocksum) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(const int32_t* __restrict__ in, int64_t n,
+                                                                     int64_t* __restrict__ out,
+                                                                     unsigned long long* __restrict__ ws) {
   __shared__ int64_t warp_tot[SCAN_THREADS / 32];
+  __shared__ int64_t tile_s, prefix_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)tid * SCAN_ITEMS;
+  if (tid == 0) tile_s = (int64_t)atomicAdd(ws, 1ull);
+  __syncthreads();
+  const int64_t tile = tile_s;
+  unsigned long long* state = ws + 1;
+  const int64_t base = tile * SCAN_TILE + (int64_t)tid * SCAN_ITEMS;
   int32_t v[SCAN_ITEMS];
   int64_t tsum = 0;
 #pragma unroll
@@ -34,69 +39,59 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_kernel(const int32_t*
   int64_t incl = tsum;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
-    int64_t o = __shfl_up_sync(0xffffffffu, incl, off);
+    const int64_t o = __shfl_up_sync(0xffffffffu, incl, off);
     if (lane >= off) incl += o;
   }
   if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
-  int64_t wbase = 0;
-  for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
-  int64_t run = wbase + incl - tsum;
+  int64_t wbase = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+    const int64_t x = warp_tot[w];
+    if (w < warp) wbase += x;
+    total += x;
+  }
+  if (warp == 0) {
+    int64_t excl = 0;
+    if (tile > 0) {
+      if (lane == 0) atomicExch(state + tile, SCAN_AGG | (unsigned long long)total);
+      int64_t look = tile - 1;
+      while (true) {
+        const int64_t t = look - lane;
+        unsigned long long word = SCAN_PRE;                       // tiles before 0: prefix 0
+        if (t >= 0) {
+          do {
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(word) : "l"(state + t) : "memory");
+          } while ((word >> 62) == 0);
+        }
+        const unsigned pre = __ballot_sync(0xffffffffu, (word >> 62) == 2);
+        const int first = pre ? (__ffs(pre) - 1) : 32;             // nearest predecessor that already has a prefix
+        int64_t part = (lane <= first) ? (int64_t)(word & SCAN_VAL) : 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        excl += part;
+        if (pre) break;
+        look -= 32;
+      }
+    }
+    if (lane == 0) {
+      atomicExch(state + tile, SCAN_PRE | (unsigned long long)(excl + total));
+      prefix_s = excl;
+    }
+  }
+  __syncthreads();
+  int64_t run = prefix_s + wbase + incl - tsum;
 #pragma unroll
   for (int i = 0; i < SCAN_ITEMS; ++i) {
     if (base + i < n) out[base + i] = run;
     run += v[i];
   }
-  if (tid == SCAN_THREADS - 1) blocksum[blockIdx.x] = wbase + incl;
+  if (base <= n - 1 && n - 1 < base + SCAN_ITEMS) out[n] = run;   // the thread that owns the last element
 }
 
-// single block: exclusive scan of blocksum[0..nblk) in place; blocksum[nblk] = total
-__global__ void scan_top_kernel(int64_t* __restrict__ blocksum, int64_t nblk) {
-  __shared__ int64_t warp_tot[32];
-  __shared__ int64_t carry_s;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) carry_s = 0;
-  __syncthreads();
-  for (int64_t start = 0; start < nblk; start += blockDim.x) {
-    int64_t i = start + tid;
-    int64_t v = (i < nblk) ? blocksum[i] : 0;
-    int64_t incl = v;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      int64_t o = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += o;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    int64_t wbase = 0;
-    for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
-    int64_t carry = carry_s;
-    if (i < nblk) blocksum[i] = carry + wbase + incl - v;
-    __syncthreads();
-    if (tid == blockDim.x - 1) carry_s = carry + wbase + incl;
-    __syncthreads();
-  }
-  if (tid == 0) blocksum[nblk] = carry_s;
-}
-
-__global__ void scan_add_kernel(int64_t* __restrict__ out, int64_t n, const int64_t* __restrict__ blocksum,
-                                int64_t nblk) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] += blocksum[i / SCAN_TILE];
-  if (i == 0) out[n] = blocksum[nblk];
-}
-
-// ------------------------------------------------------------------------ symmetrise
-enum { SYM_PLUS = 0, SYM_MULT = 1, SYM_MNN = 2, SYM_NONE = 3 };
-
-__device__ __forceinline__ double sym_combine(int mode, double theta, double w, double wr) {
-  if (mode == SYM_PLUS) return (w + wr) / 2;
-  if (mode == SYM_MULT) return w * wr;
-  double lo = fmin(w, wr), hi = fmax(w, wr);
-  return theta * lo + (1 - theta) * hi;
-}
-
-// position of column `c` in the column-sorted slice idx[lo, hi), or -1
+// ------------------------------------------------------------------------ asymmetry check
+// kernel_symm=None: the reference warns when max(K - K^T) > 1e-5 (base.py:551-552).  Every edge binary-searches
+// row j for column i (rows are column-sorted); an absent reverse edge counts as 0.
 __device__ __forceinline__ int64_t find_col(const int32_t* __restrict__ idx, int64_t lo, int64_t hi, int32_t c) {
   while (lo < hi) {
     int64_t mid = (lo + hi) >> 1;
@@ -110,135 +105,49 @@ __device__ __forceinline__ int64_t find_col(const int32_t* __restrict__ idx, int
 
 constexpr int SYM_GROUP = 8;  // lanes cooperating on one row (raw rows hold ~10 edges)
 
-template <bool FILL>
-__global__ void __launch_bounds__(256) sym_pass_kernel(const int64_t* __restrict__ indptr,
-                                                       const int32_t* __restrict__ idx,
-                                                       const double* __restrict__ val, int64_t n, int mode,
-                                                       double theta, int32_t* __restrict__ newlen,
-                                                       int32_t* __restrict__ flags,
-                                                       const int64_t* __restrict__ outptr,
-                                                       int32_t* __restrict__ cursor, int32_t* __restrict__ tmp_idx,
-                                                       double* __restrict__ tmp_val) {
+__global__ void __launch_bounds__(256) asym_check_kernel(const int64_t* __restrict__ indptr,
+                                                         const int32_t* __restrict__ idx,
+                                                         const double* __restrict__ val, int64_t n,
+                                                         int32_t* __restrict__ flags) {
   const int sub = threadIdx.x % SYM_GROUP;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / SYM_GROUP;
-  const bool active = row < n;
-  int self_cnt = 0;
+  if (row >= n) return;
   bool asym = false;
-  if (active) {
-    const int64_t e0 = indptr[row], e1 = indptr[row + 1];
-    for (int64_t e = e0 + sub; e < e1; e += SYM_GROUP) {
-      const int32_t j = idx[e];
-      const double w = val[e];
-      double wr = w;
-      int64_t pos = e;
-      if (j != row) {
-        pos = find_col(idx, indptr[j], indptr[j + 1], (int32_t)row);
-        wr = pos >= 0 ? val[pos] : 0.0;
-      }
-      if (mode == SYM_NONE) {
-        if (w - wr > 1e-5) asym = true;
-        continue;
-      }
-      const double s = sym_combine(mode, theta, w, wr);
-      if (s != 0.0) {
-        if (FILL) {
-          int64_t o = outptr[row] + atomicAdd(cursor + row, 1);
-          tmp_idx[o] = j; tmp_val[o] = s;
-          if (pos < 0) {
-            int64_t o2 = outptr[j] + atomicAdd(cursor + j, 1);
-            tmp_idx[o2] = (int32_t)row; tmp_val[o2] = s;
-          }
-        } else {
-          ++self_cnt;
-          if (pos < 0) atomicAdd(newlen + j, 1);
-        }
-      }
-    }
+  for (int64_t e = indptr[row] + sub; e < indptr[row + 1]; e += SYM_GROUP) {
+    const int32_t j = idx[e];
+    if (j == row) continue;
+    const int64_t pos = find_col(idx, indptr[j], indptr[j + 1], (int32_t)row);
+    const double wr = pos >= 0 ? val[pos] : 0.0;
+    if (val[e] - wr > 1e-5) asym = true;
   }
-  if (!FILL) {
-#pragma unroll
-    for (int off = SYM_GROUP / 2; off > 0; off >>= 1) self_cnt += __shfl_xor_sync(0xffffffffu, self_cnt, off);
-    if (active && sub == 0 && self_cnt) atomicAdd(newlen + row, self_cnt);
-    if (asym) atomicOr(flags, 1);
-  }
+  if (asym) atomicOr(flags, 1);
 }
 
-// ------------------------------------------------- per-row sort + normalise (warp per row)
-constexpr int FIN_WARPS = 4, FIN_CAP = 64;
+// ------------------------------------------------- per-row normalise (warp per row)
+constexpr int FIN_WARPS = 4;
 
-// SORT: rows of (tmp_idx,tmp_val) are unsorted -> sort by column.  Writes K (idx,val), P = val/rowsum,
-// degree = rowsum; flags bit 1 set when a row of a square matrix has no diagonal entry.
-template <bool SORT>
+// P = val / rowsum (sklearn normalize(K, "l1"): rows summing to zero are left as they are), degree = rowsum;
+// flags bit 1 set when a row of a square matrix has no diagonal entry.
 __global__ void __launch_bounds__(FIN_WARPS * 32) row_finalize_kernel(
-    const int64_t* __restrict__ ptr, const int32_t* __restrict__ tmp_idx, const double* __restrict__ tmp_val,
-    int64_t n, int32_t* __restrict__ out_idx, double* __restrict__ out_val, double* __restrict__ p_val,
-    double* __restrict__ degree, int32_t* __restrict__ flags, int check_diag) {
-  __shared__ int32_t ks[FIN_WARPS][FIN_CAP];
-  __shared__ double vs[FIN_WARPS][FIN_CAP];
+    const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const double* __restrict__ val, int64_t n,
+    double* __restrict__ p_val, double* __restrict__ degree, int32_t* __restrict__ flags, int check_diag) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = (int64_t)blockIdx.x * FIN_WARPS + warp;
   if (row >= n) return;
   const int64_t p0 = ptr[row], p1 = ptr[row + 1];
   const int64_t L = p1 - p0;
-  auto sync = [] { __syncwarp(); };
   double sum = 0.0;
   bool has_diag = false;
-  if (!SORT) {
-    for (int64_t t = lane; t < L; t += 32) {
-      sum += fabs(tmp_val[p0 + t]);
-      has_diag |= (tmp_idx[p0 + t] == row);
-    }
-  } else if (L <= 32) {
-    // the common case (a kNN kernel row): one entry per lane, sorted by column in registers
-    int32_t c = 0x7fffffff;
-    double w = 0.0;
-    if (lane < L) { c = tmp_idx[p0 + lane]; w = tmp_val[p0 + lane]; }
-    warp_sort32<int32_t, double>(c, w, lane);
-    if (lane < L) {
-      out_idx[p0 + lane] = c;
-      out_val[p0 + lane] = w;
-      sum += fabs(w);
-      has_diag |= (c == row);
-    }
-  } else if (L <= FIN_CAP) {
-    int32_t* k = ks[warp];
-    double* v = vs[warp];
-    int np2 = 2;
-    while (np2 < L) np2 <<= 1;
-    for (int t = lane; t < np2; t += 32) {
-      if (t < L) { k[t] = tmp_idx[p0 + t]; v[t] = tmp_val[p0 + t]; }
-      else { k[t] = 0x7fffffff; v[t] = 0.0; }
-    }
-    __syncwarp();
-    GTB_BITONIC_SORT(k, v, np2, lane, 32, sync, int32_t, double);
-    for (int t = lane; t < L; t += 32) {
-      out_idx[p0 + t] = k[t];
-      out_val[p0 + t] = v[t];
-      sum += fabs(v[t]);
-      has_diag |= (k[t] == row);
-    }
-  } else {
-    // long (hub) rows: rank by counting, columns are unique within a row
-    for (int64_t t = lane; t < L; t += 32) {
-      const int32_t c = tmp_idx[p0 + t];
-      const double w = tmp_val[p0 + t];
-      int64_t rank = 0;
-      for (int64_t u = 0; u < L; ++u) rank += (tmp_idx[p0 + u] < c);
-      out_idx[p0 + rank] = c;
-      out_val[p0 + rank] = w;
-      sum += fabs(w);
-      has_diag |= (c == row);
-    }
+  for (int64_t t = lane; t < L; t += 32) {
+    sum += fabs(val[p0 + t]);
+    has_diag |= (idx[p0 + t] == row);
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
   has_diag = __any_sync(0xffffffffu, has_diag);
-  __syncwarp();
   if (p_val) {
-    const double* src = SORT ? out_val : tmp_val;
-    if (SORT && L > FIN_CAP) __threadfence_block();
     for (int64_t t = lane; t < L; t += 32) {
-      double w = src[p0 + t];
+      const double w = val[p0 + t];
       p_val[p0 + t] = (sum != 0.0) ? w / sum : w;
     }
   }
@@ -289,42 +198,6 @@ __global__ void __launch_bounds__(256) block_fill_kernel(
   if (sub == 0) cursor[grow] = cur + (int32_t)(e1 - e0);
 }
 
-// ------------------------------------------- row-shard merge (multi-GPU symmetrisation)
-// Row r of A = this rank's raw kernel rows, row r of B = the transposed edges routed to this rank by
-// the all-to-all (both column-sorted).  Two-pointer merge per row: s(w, w') with w' = 0 where absent.
-// FILL = false: counts the non-zero results; FILL = true: writes K (sorted), P = K / rowsum and degree.
-template <bool FILL>
-__global__ void sym_merge_rows_kernel(const int64_t* __restrict__ pa, const int32_t* __restrict__ ia,
-                                      const double* __restrict__ va, const int64_t* __restrict__ pb,
-                                      const int32_t* __restrict__ ib, const double* __restrict__ vb, int64_t n_rows,
-                                      int mode, double theta, int32_t* __restrict__ newlen,
-                                      const int64_t* __restrict__ outptr, int32_t* __restrict__ out_idx,
-                                      double* __restrict__ out_val, double* __restrict__ p_val,
-                                      double* __restrict__ degree) {
-  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n_rows) return;
-  int64_t a = pa[row], a1 = pa[row + 1], b = pb[row], b1 = pb[row + 1];
-  int64_t o = FILL ? outptr[row] : 0;
-  const int64_t o0 = o;
-  int cnt = 0;
-  double sum = 0.0;
-  while (a < a1 || b < b1) {
-    const int32_t ca = (a < a1) ? ia[a] : 0x7fffffff, cb = (b < b1) ? ib[b] : 0x7fffffff;
-    const int32_t c = ca < cb ? ca : cb;
-    const double w = (ca == c) ? va[a] : 0.0, wr = (cb == c) ? vb[b] : 0.0;
-    a += (ca == c);
-    b += (cb == c);
-    const double sv = sym_combine(mode, theta, w, wr);
-    if (sv != 0.0) {
-      if (FILL) { out_idx[o] = c; out_val[o] = sv; ++o; sum += fabs(sv); }
-      else ++cnt;
-    }
-  }
-  if (!FILL) { newlen[row] = cnt; return; }
-  if (p_val) for (int64_t e = o0; e < o; ++e) p_val[e] = (sum != 0.0) ? out_val[e] / sum : out_val[e];
-  if (degree) degree[row] = sum;
-}
-
 // dense[row][idx[e]] = val[e]; the output was zero-filled by the caller (cudaMemsetAsync)
 __global__ void csr_to_dense_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx,
                                     const double* __restrict__ val, int64_t n_rows, int64_t n_cols,
@@ -347,12 +220,9 @@ extern "C" int64_t gtb_scan_ws_elems(int64_t n) { return gtb_cdiv(n > 0 ? n : 1,
 extern "C" int gtb_exclusive_scan(const int32_t* in, int64_t n, int64_t* out, int64_t* ws, void* stream) {
   GTB_CHECK_ARG(n > 0, "empty scan");
   cudaStream_t st = (cudaStream_t)stream;
-  int64_t nblk = gtb_cdiv(n, SCAN_TILE);
-  scan_block_kernel<<<(unsigned)nblk, SCAN_THREADS, 0, st>>>(in, n, out, ws);
-  GTB_CHECK_LAUNCH();
-  scan_top_kernel<<<1, 1024, 0, st>>>(ws, nblk);
-  GTB_CHECK_LAUNCH();
-  scan_add_kernel<<<(unsigned)gtb_cdiv(n, 256), 256, 0, st>>>(out, n, ws, nblk);
+  const int64_t nblk = gtb_cdiv(n, SCAN_TILE);
+  GTB_CUDA(cudaMemsetAsync(ws, 0, sizeof(int64_t) * (size_t)(nblk + 1), st));
+  scan_lookback_kernel<<<(unsigned)nblk, SCAN_THREADS, 0, st>>>(in, n, out, reinterpret_cast<unsigned long long*>(ws));
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }
@@ -363,41 +233,20 @@ extern "C" int gtb_cast_indptr(const int64_t* in, int64_t n1, int32_t* out, void
   return GTB_OK;
 }
 
-extern "C" int gtb_sym_count(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n, int mode,
-                             double theta, int32_t* newlen, int32_t* flags, void* stream) {
-  GTB_CHECK_ARG(n > 0 && mode >= 0 && mode <= 3, "bad arguments");
-  cudaStream_t st = (cudaStream_t)stream;
-  GTB_CUDA(cudaMemsetAsync(newlen, 0, sizeof(int32_t) * n, st));
-  sym_pass_kernel<false><<<(unsigned)gtb_cdiv(n * SYM_GROUP, 256), 256, 0, st>>>(
-      indptr, idx, val, n, mode, theta, newlen, flags, nullptr, nullptr, nullptr, nullptr);
-  GTB_CHECK_LAUNCH();
-  return GTB_OK;
-}
-
-extern "C" int gtb_sym_fill(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n, int mode,
-                            double theta, const int64_t* outptr, int32_t* cursor, int32_t* tmp_idx,
-                            double* tmp_val, void* stream) {
-  GTB_CHECK_ARG(n > 0 && mode >= 0 && mode <= 2, "bad arguments");
-  cudaStream_t st = (cudaStream_t)stream;
-  GTB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * n, st));
-  sym_pass_kernel<true><<<(unsigned)gtb_cdiv(n * SYM_GROUP, 256), 256, 0, st>>>(
-      indptr, idx, val, n, mode, theta, nullptr, nullptr, outptr, cursor, tmp_idx, tmp_val);
-  GTB_CHECK_LAUNCH();
-  return GTB_OK;
-}
-
-extern "C" int gtb_row_finalize(const int64_t* ptr, const int32_t* tmp_idx, const double* tmp_val, int64_t n,
-                                int sort, int32_t* out_idx, double* out_val, double* p_val, double* degree,
-                                int32_t* flags, int check_diag, void* stream) {
+extern "C" int gtb_asym_check(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n,
+                              int32_t* flags, void* stream) {
   GTB_CHECK_ARG(n > 0, "empty matrix");
-  cudaStream_t st = (cudaStream_t)stream;
-  unsigned grid = (unsigned)gtb_cdiv(n, FIN_WARPS);
-  if (sort)
-    row_finalize_kernel<true><<<grid, FIN_WARPS * 32, 0, st>>>(ptr, tmp_idx, tmp_val, n, out_idx, out_val, p_val,
-                                                               degree, flags, check_diag);
-  else
-    row_finalize_kernel<false><<<grid, FIN_WARPS * 32, 0, st>>>(ptr, tmp_idx, tmp_val, n, out_idx, out_val, p_val,
-                                                                degree, flags, check_diag);
+  asym_check_kernel<<<(unsigned)gtb_cdiv(n * SYM_GROUP, 256), 256, 0, (cudaStream_t)stream>>>(indptr, idx, val, n,
+                                                                                            flags);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_row_finalize(const int64_t* ptr, const int32_t* idx, const double* val, int64_t n, double* p_val,
+                                double* degree, int32_t* flags, int check_diag, void* stream) {
+  GTB_CHECK_ARG(n > 0, "empty matrix");
+  row_finalize_kernel<<<(unsigned)gtb_cdiv(n, FIN_WARPS), FIN_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      ptr, idx, val, n, p_val, degree, flags, check_diag);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }
@@ -417,27 +266,6 @@ extern "C" int gtb_block_fill(const int64_t* indptr, const int32_t* idx, const d
   GTB_CHECK_ARG(nb > 0, "empty block");
   block_fill_kernel<<<(unsigned)gtb_cdiv(nb * SYM_GROUP, 256), 256, 0, (cudaStream_t)stream>>>(
       indptr, idx, val, nb, row_map, col_map, within, between, beta, outptr, cursor, out_idx, out_val);
-  GTB_CHECK_LAUNCH();
-  return GTB_OK;
-}
-
-extern "C" int gtb_sym_merge_count(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pb,
-                                   const int32_t* ib, const double* vb, int64_t n_rows, int mode, double theta,
-                                   int32_t* newlen, void* stream) {
-  GTB_CHECK_ARG(n_rows > 0 && mode >= 0 && mode <= 2, "bad arguments");
-  sym_merge_rows_kernel<false><<<(unsigned)gtb_cdiv(n_rows, 128), 128, 0, (cudaStream_t)stream>>>(
-      pa, ia, va, pb, ib, vb, n_rows, mode, theta, newlen, nullptr, nullptr, nullptr, nullptr, nullptr);
-  GTB_CHECK_LAUNCH();
-  return GTB_OK;
-}
-
-extern "C" int gtb_sym_merge_fill(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pb,
-                                  const int32_t* ib, const double* vb, int64_t n_rows, int mode, double theta,
-                                  const int64_t* outptr, int32_t* out_idx, double* out_val, double* p_val,
-                                  double* degree, void* stream) {
-  GTB_CHECK_ARG(n_rows > 0 && mode >= 0 && mode <= 2, "bad arguments");
-  sym_merge_rows_kernel<true><<<(unsigned)gtb_cdiv(n_rows, 128), 128, 0, (cudaStream_t)stream>>>(
-      pa, ia, va, pb, ib, vb, n_rows, mode, theta, nullptr, outptr, out_idx, out_val, p_val, degree);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }

@@ -1,0 +1,497 @@
+// K4: sort-based sparse transpose + symmetrisation (+, *, mnn) + row normalisation into the diffusion
+// operator, in streaming passes over the CSR -- and the bucketing kernels of the multi-GPU edge exchange.
+//
+// Replaces scipy's csr binops behind BaseGraph.symmetrize_kernel (reference graphtools/base.py:557-577,
+// matrix.py:16-29), sklearn normalize(K, "l1") (base.py:645), kernel_degree (base.py:648-666) and the diagonal
+// check of BaseGraph._build_kernel (base.py:553-554).
+//
+//   transpose_count   histogram of the column indices                        (thread per edge)
+//   scan              row pointers of R^T                                    (sparse.cu, single pass)
+//   transpose_scatter every edge (i, j, w) -> slot of row j of R^T           (8 lanes per row, atomic cursor)
+//   csr_sort_rows     rows of R^T ordered by column (= source row i)         (tiered segmented sort, in place)
+//   sym_merge<count>  |row i of R  UNION  row i of R^T| under the merge rule (warp per row)
+//   scan
+//   sym_merge<fill>   K row (column-sorted), P = K / rowsum, degree, diagonal flag, one sweep
+//
+// Both inputs of the merge are column-sorted with unique columns, so the result does not depend on the order
+// in which the atomics of the scatter landed: K, P and the degree vector are bit-reproducible, and identical
+// between the single-GPU build and the row-sharded multi-GPU build (same kernels, same per-row order).
+// All three merge rules are symmetric functions s(w, w'), hence K is bitwise symmetric.
+#include "common.cuh"
+#include "gtb200.h"
+
+namespace {
+
+enum { SYM_PLUS = 0, SYM_MULT = 1, SYM_MNN = 2 };
+
+__device__ __forceinline__ double sym_combine(int mode, double theta, double w, double wr) {
+  if (mode == SYM_PLUS) return (w + wr) / 2;
+  if (mode == SYM_MULT) return w * wr;
+  const double lo = fmin(w, wr), hi = fmax(w, wr);
+  return theta * lo + (1 - theta) * hi;
+}
+
+constexpr int GRP = 8;  // lanes cooperating on one raw row (~9 edges)
+
+// ------------------------------------------------------------------------------ transpose
+__global__ void __launch_bounds__(256) transpose_count_kernel(const int32_t* __restrict__ idx, int64_t nnz,
+                                                              int32_t col0, int32_t* __restrict__ cnt) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(cnt + (idx[e] - col0), 1);
+}
+
+// cnt[] holds the row lengths of R^T on entry and is counted down to zero: slot = ptr_t[j] + (--cnt[j])
+__global__ void __launch_bounds__(256) transpose_scatter_kernel(
+    const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+    int64_t n_rows, int32_t row0, int32_t col0, const int64_t* __restrict__ ptr_t, int32_t* __restrict__ cnt,
+    int32_t* __restrict__ t_idx, double* __restrict__ t_val) {
+  const int sub = threadIdx.x % GRP;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GRP;
+  if (row >= n_rows) return;
+  const int64_t e1 = indptr[row + 1];
+  for (int64_t e = indptr[row] + sub; e < e1; e += GRP) {
+    const int32_t j = idx[e] - col0;
+    const int64_t o = ptr_t[j] + (atomicSub(cnt + j, 1) - 1);
+    t_idx[o] = (int32_t)row + row0;
+    t_val[o] = val[e];
+  }
+}
+
+// the same two steps for a list of packed edge records {i, j, w} (what the all-to-all delivers)
+struct __align__(16) EdgeRec { int32_t i, j; double w; };
+
+__global__ void __launch_bounds__(256) records_count_kernel(const EdgeRec* __restrict__ rec, int64_t k, int32_t col0,
+                                                            int32_t* __restrict__ cnt) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < k; e += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(cnt + (rec[e].j - col0), 1);
+}
+
+__global__ void __launch_bounds__(256) records_scatter_kernel(const EdgeRec* __restrict__ rec, int64_t k, int32_t col0,
+                                                              const int64_t* __restrict__ ptr_t,
+                                                              int32_t* __restrict__ cnt, int32_t* __restrict__ t_idx,
+                                                              double* __restrict__ t_val) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < k; e += (int64_t)gridDim.x * blockDim.x) {
+    const EdgeRec r = rec[e];
+    const int32_t j = r.j - col0;
+    const int64_t o = ptr_t[j] + (atomicSub(cnt + j, 1) - 1);
+    t_idx[o] = r.i;
+    t_val[o] = r.w;
+  }
+}
+
+// ------------------------------------------------------------------------------ segmented sort (in place)
+// Rows of a CSR ordered by column; columns are unique within a row.  Tiers: <= 32 entries: one per lane, rank by
+// counting (3 instructions per entry, no network); <= SORT_WARP_CAP: warp bitonic in shared memory; longer rows
+// are left to csr_sort_long_kernel (block per row: shared memory up to SORT_BLOCK_CAP, global memory beyond).
+constexpr int SORT_WARPS = 4, SORT_WARP_CAP = 256, SORT_BLOCK_CAP = 4096, SORT_BLOCK_THREADS = 256;
+
+__global__ void __launch_bounds__(SORT_WARPS * 32) csr_sort_rows_kernel(const int64_t* __restrict__ ptr,
+                                                                        int32_t* __restrict__ idx,
+                                                                        double* __restrict__ val, int64_t n,
+                                                                        int32_t* __restrict__ has_long) {
+  __shared__ int32_t ks[SORT_WARPS][SORT_WARP_CAP];
+  __shared__ double vs[SORT_WARPS][SORT_WARP_CAP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * SORT_WARPS + warp;
+  if (row >= n) return;
+  const int64_t p0 = ptr[row];
+  const int64_t L = ptr[row + 1] - p0;
+  if (L <= 1) return;
+  if (L <= 32) {
+    int32_t c = 0x7fffffff;
+    double w = 0.0;
+    if (lane < L) { c = idx[p0 + lane]; w = val[p0 + lane]; }
+    int rank = 0;
+    for (int k = 0; k < (int)L; ++k) rank += (__shfl_sync(0xffffffffu, c, k) < c);
+    __syncwarp();
+    if (lane < L) { idx[p0 + rank] = c; val[p0 + rank] = w; }
+  } else if (L <= SORT_WARP_CAP) {
+    int32_t* k = ks[warp];
+    double* v = vs[warp];
+    int np2 = 64;
+    while (np2 < L) np2 <<= 1;
+    for (int t = lane; t < np2; t += 32) {
+      if (t < L) { k[t] = idx[p0 + t]; v[t] = val[p0 + t]; }
+      else { k[t] = 0x7fffffff; v[t] = 0.0; }
+    }
+    __syncwarp();
+    auto sync = [] { __syncwarp(); };
+    GTB_BITONIC_SORT(k, v, np2, lane, 32, sync, int32_t, double);
+    for (int t = lane; t < L; t += 32) { idx[p0 + t] = k[t]; val[p0 + t] = v[t]; }
+  } else if (lane == 0) {
+    *has_long = 1;
+  }
+}
+
+__global__ void __launch_bounds__(SORT_BLOCK_THREADS) csr_sort_long_kernel(const int64_t* __restrict__ ptr,
+                                                                           int32_t* __restrict__ idx,
+                                                                           double* __restrict__ val, int64_t n,
+                                                                           const int32_t* __restrict__ has_long) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  double* v = reinterpret_cast<double*>(sort_smem);                    // [SORT_BLOCK_CAP]
+  int32_t* k = reinterpret_cast<int32_t*>(v + SORT_BLOCK_CAP);         // [SORT_BLOCK_CAP]
+  __shared__ unsigned int long_mask[SORT_BLOCK_THREADS / 32];
+  if (*has_long == 0) return;
+  const int tid = threadIdx.x;
+  auto sync = [] { __syncthreads(); };
+  for (int64_t base = (int64_t)blockIdx.x * SORT_BLOCK_THREADS; base < n; base += (int64_t)gridDim.x * SORT_BLOCK_THREADS) {
+    const int64_t r = base + tid;
+    const bool is_long = (r < n) && (ptr[r + 1] - ptr[r] > SORT_WARP_CAP);
+    const unsigned m = __ballot_sync(0xffffffffu, is_long);
+    if ((tid & 31) == 0) long_mask[tid >> 5] = m;
+    __syncthreads();
+    for (int w = 0; w < SORT_BLOCK_THREADS / 32; ++w) {
+      unsigned mm = long_mask[w];
+      while (mm) {
+        const int b = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const int64_t row = base + w * 32 + b;
+        const int64_t p0 = ptr[row];
+        const int64_t L = ptr[row + 1] - p0;
+        if (L <= SORT_BLOCK_CAP) {
+          int np2 = 512;
+          while (np2 < L) np2 <<= 1;
+          for (int t = tid; t < np2; t += SORT_BLOCK_THREADS) {
+            if (t < L) { k[t] = idx[p0 + t]; v[t] = val[p0 + t]; }
+            else { k[t] = 0x7fffffff; v[t] = 0.0; }
+          }
+          __syncthreads();
+          GTB_BITONIC_SORT(k, v, np2, tid, SORT_BLOCK_THREADS, sync, int32_t, double);
+          for (int t = tid; t < L; t += SORT_BLOCK_THREADS) { idx[p0 + t] = k[t]; val[p0 + t] = v[t]; }
+          __syncthreads();
+        } else {
+          // hub rows beyond the shared-memory tile: bitonic network straight on global memory, in the form whose
+          // compare-exchanges all point the same way (first step of a stage pairs t with its mirror t ^ (kk - 1)):
+          // virtual +infinity padding past L then never has to move, so no scratch row is needed
+          int64_t np2 = SORT_BLOCK_CAP;
+          while (np2 < L) np2 <<= 1;
+          int32_t* gk = idx + p0;
+          double* gv = val + p0;
+          for (int64_t kk = 2; kk <= np2; kk <<= 1) {
+            for (int64_t j = kk >> 1; j > 0; j >>= 1) {
+              for (int64_t t = tid; t < L; t += SORT_BLOCK_THREADS) {
+                const int64_t q = (j == (kk >> 1)) ? (t ^ (kk - 1)) : (t ^ j);
+                if (q > t && q < L) {
+                  const int32_t a = gk[t], b2 = gk[q];
+                  if (a > b2) {
+                    const double va = gv[t], vb = gv[q];
+                    gk[t] = b2; gk[q] = a; gv[t] = vb; gv[q] = va;
+                  }
+                }
+              }
+              __threadfence_block();
+              __syncthreads();
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------ merge
+// Row r of A = raw kernel rows [pa, ia, va] (columns global), row r of T = rows of the transposed matrix
+// [pt, it, vt]; both column-sorted.  FILL = false: newlen[r] = number of non-zero results; FILL = true: K row,
+// P = K / sum|K|, degree, flags bit 1 when the row has no diagonal entry (global row id = row0 + r).
+constexpr int MRG_WARPS = 8;
+
+// number of entries of the sorted slice a[0, n) that are < c
+__device__ __forceinline__ int lower_bound_g(const int32_t* __restrict__ a, int n, int32_t c) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < c) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(MRG_WARPS * 32) sym_merge_kernel(
+    const int64_t* __restrict__ pa, const int32_t* __restrict__ ia, const double* __restrict__ va,
+    const int64_t* __restrict__ pt, const int32_t* __restrict__ it, const double* __restrict__ vt, int64_t n_rows,
+    int32_t row0, int mode, double theta, int32_t* __restrict__ newlen, const int64_t* __restrict__ outptr,
+    int32_t* __restrict__ out_idx, double* __restrict__ out_val, double* __restrict__ p_val,
+    double* __restrict__ degree, int32_t* __restrict__ flags) {
+  __shared__ double sv[MRG_WARPS][32];
+  __shared__ int32_t sc[MRG_WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * MRG_WARPS + warp;
+  if (row >= n_rows) return;
+  const int64_t a0 = pa[row], t0 = pt[row];
+  const int la = (int)(pa[row + 1] - a0), lt = (int)(pt[row + 1] - t0);
+  const int L = la + lt;
+  const int32_t grow = (int32_t)row + row0;
+  if (L <= 32) {
+    // ---- the common case (a kNN kernel row and its transpose): one element per lane, A in lanes [0, la), T in
+    //      lanes [la, L); no sort, no loop -- lookups are binary searches over lanes, output order by popcounts
+    const bool isA = lane < la, isT = (lane >= la) && (lane < L);
+    int32_t c = 0x7fffffff;
+    double w = 0.0;
+    if (isA) { c = ia[a0 + lane]; w = va[a0 + lane]; }
+    else if (isT) { c = it[t0 + lane - la]; w = vt[t0 + lane - la]; }
+    // position of this element's column in the OTHER list (binary search over lanes; both lists sorted)
+    int lo = isA ? la : 0, hi = isA ? L : la;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      const int mid = (lo + hi) >> 1;
+      const int32_t cm = __shfl_sync(0xffffffffu, c, mid & 31);
+      const bool go = (lo < hi) && (cm < c);
+      const bool stay = (lo < hi) && !(cm < c);
+      lo = go ? mid + 1 : lo;
+      hi = stay ? mid : hi;
+    }
+    // one more step covers lists of 17..32 entries (2^5 = 32 needs ceil(log2(33)) = 6 probes)
+    {
+      const int mid = (lo + hi) >> 1;
+      const int32_t cm = __shfl_sync(0xffffffffu, c, mid & 31);
+      const bool go = (lo < hi) && (cm < c);
+      const bool stay = (lo < hi) && !(cm < c);
+      lo = go ? mid + 1 : lo;
+      hi = stay ? mid : hi;
+    }
+    const int pos = lo;                                  // absolute lane of the first entry >= c in the other list
+    const int32_t c_at = __shfl_sync(0xffffffffu, c, pos & 31);
+    const double w_at = __shfl_sync(0xffffffffu, w, pos & 31);
+    const bool in_other = isA ? (pos < L) : (pos < la);
+    const bool mutual = (isA || isT) && in_other && (c_at == c);
+    const double s = sym_combine(mode, theta, w, mutual ? w_at : 0.0);
+    const bool emit = (isA || isT) && (s != 0.0) && !(mutual && isT);   // a mutual pair is emitted by its A copy
+    const unsigned em = __ballot_sync(0xffffffffu, emit);
+    const int cnt = __popc(em);
+    if (!FILL) {
+      if (lane == 0) newlen[row] = cnt;
+      return;
+    }
+    // rank among the emitted entries = emitted entries of my own list before me + emitted entries of the other
+    // list with a smaller column (those sit before `pos`)
+    const unsigned mA = (la >= 32) ? 0xffffffffu : ((1u << la) - 1u);
+    const unsigned below_me = (1u << lane) - 1u;
+    const unsigned below_pos = (pos >= 32) ? 0xffffffffu : ((1u << pos) - 1u);
+    const unsigned own = isA ? (em & mA & below_me) : (em & ~mA & below_me);
+    const unsigned oth = isA ? (em & ~mA & below_pos) : (em & mA & below_pos);
+    const int rank = __popc(own) + __popc(oth);
+    if (emit) { sv[warp][rank] = s; sc[warp][rank] = c; }
+    __syncwarp();
+    const bool on = lane < cnt;
+    const double v = on ? sv[warp][lane] : 0.0;
+    const int32_t cc = on ? sc[warp][lane] : -1;
+    double sum = fabs(v);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const bool has_diag = __any_sync(0xffffffffu, on && cc == grow);
+    const int64_t o0 = outptr[row];
+    if (on) {
+      out_idx[o0 + lane] = cc;
+      out_val[o0 + lane] = v;
+      if (p_val) p_val[o0 + lane] = (sum != 0.0) ? v / sum : v;
+    }
+    if (lane == 0) {
+      if (degree) degree[row] = sum;
+      if (flags && !has_diag) atomicOr(flags, 2);
+    }
+    return;
+  }
+  // ---- rows with more than 32 entries (hub rows; every row of an isotropic, high-intrinsic-dimension data set)
+  const int32_t* A = ia + a0;
+  const int32_t* T = it + t0;
+  if (!FILL) {
+    // count: every element looks its column up in the other (sorted) list
+    int cnt = 0;
+    for (int t = lane; t < la; t += 32) {
+      const int32_t c = A[t];
+      const int p = lower_bound_g(T, lt, c);
+      const bool mutual = (p < lt) && (T[p] == c);
+      cnt += (sym_combine(mode, theta, va[a0 + t], mutual ? vt[t0 + p] : 0.0) != 0.0);
+    }
+    for (int t = lane; t < lt; t += 32) {
+      const int32_t c = T[t];
+      const int p = lower_bound_g(A, la, c);
+      const bool mutual = (p < la) && (A[p] == c);
+      if (!mutual) cnt += (sym_combine(mode, theta, 0.0, vt[t0 + t]) != 0.0);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    if (lane == 0) newlen[row] = cnt;
+    return;
+  }
+  // fill: sequential two-pointer merge by one lane (O(L), any length, fixed order); the row sum runs in column
+  // order, which is sklearn's own summation order (sparsefuncs_fast.pyx:_inplace_csr_row_normalize_l1)
+  const int64_t o0 = outptr[row];
+  int o = 0;
+  double sum = 0.0;
+  if (lane == 0) {
+    bool has_diag = false;
+    int a = 0, b = 0;
+    while (a < la || b < lt) {
+      const int32_t ca = (a < la) ? A[a] : 0x7fffffff, cb = (b < lt) ? T[b] : 0x7fffffff;
+      const int32_t c = ca < cb ? ca : cb;
+      const double w = (ca == c) ? va[a0 + a] : 0.0, wr = (cb == c) ? vt[t0 + b] : 0.0;
+      a += (ca == c);
+      b += (cb == c);
+      const double sv2 = sym_combine(mode, theta, w, wr);
+      if (sv2 != 0.0) {
+        out_idx[o0 + o] = c; out_val[o0 + o] = sv2; ++o;
+        sum += fabs(sv2);
+        has_diag |= (c == grow);
+      }
+    }
+    if (degree) degree[row] = sum;
+    if (flags && !has_diag) atomicOr(flags, 2);
+  }
+  o = __shfl_sync(0xffffffffu, o, 0);
+  sum = __shfl_sync(0xffffffffu, sum, 0);
+  __syncwarp();
+  if (p_val)
+    for (int e = lane; e < o; e += 32) { const double v = out_val[o0 + e]; p_val[o0 + e] = (sum != 0.0) ? v / sum : v; }
+}
+
+// ------------------------------------------------------------------------------ edge routing (multi-GPU)
+// Column owner under the block row partition: owner(j) = min(j / per, world - 1).  Rows are column-sorted, so the
+// entries of a row bound for one owner are contiguous: cnt[o * m + r] = how many of row r go to rank o
+// (destination-major, so one exclusive scan of cnt yields every send-buffer position).
+__global__ void __launch_bounds__(256) route_count_kernel(const int64_t* __restrict__ indptr,
+                                                          const int32_t* __restrict__ idx, int64_t m, int32_t per,
+                                                          int world, int32_t* __restrict__ cnt) {
+  const int sub = threadIdx.x % GRP;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GRP;
+  if (row >= m) return;
+  const int64_t e1 = indptr[row + 1];
+  for (int64_t e = indptr[row] + sub; e < e1; e += GRP) {
+    int o = idx[e] / per;
+    o = o < world ? o : world - 1;
+    atomicAdd(cnt + (int64_t)o * m + row, 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) route_fill_kernel(const int64_t* __restrict__ indptr,
+                                                         const int32_t* __restrict__ idx,
+                                                         const double* __restrict__ val, int64_t m, int32_t row0,
+                                                         int32_t per, int world, const int32_t* __restrict__ cnt,
+                                                         const int64_t* __restrict__ pos, EdgeRec* __restrict__ send) {
+  const int sub = threadIdx.x % GRP;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GRP;
+  if (row >= m) return;
+  const int64_t e0 = indptr[row], e1 = indptr[row + 1];
+  for (int64_t e = e0 + sub; e < e1; e += GRP) {
+    const int32_t j = idx[e];
+    int o = j / per;
+    o = o < world ? o : world - 1;
+    int64_t before = 0;                           // entries of this row bound for lower ranks
+    for (int q = 0; q < o; ++q) before += cnt[(int64_t)q * m + row];
+    EdgeRec r;
+    r.i = (int32_t)row + row0; r.j = j; r.w = val[e];
+    send[pos[(int64_t)o * m + row] + ((e - e0) - before)] = r;
+  }
+}
+
+}  // namespace
+
+extern "C" int gtb_transpose_count(const int32_t* idx, int64_t nnz, int32_t col0, int32_t* cnt, int64_t n_cols,
+                                   void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  GTB_CHECK_ARG(n_cols > 0 && nnz >= 0, "bad shape");
+  GTB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * n_cols, st));
+  if (nnz > 0) {
+    const int64_t blocks = gtb_cdiv(nnz, 256);
+    transpose_count_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(idx, nnz, col0, cnt);
+    GTB_CHECK_LAUNCH();
+  }
+  return GTB_OK;
+}
+
+extern "C" int gtb_transpose_scatter(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n_rows,
+                                     int32_t row0, int32_t col0, const int64_t* ptr_t, int32_t* cnt, int32_t* t_idx,
+                                     double* t_val, void* stream) {
+  GTB_CHECK_ARG(n_rows > 0, "empty matrix");
+  transpose_scatter_kernel<<<(unsigned)gtb_cdiv(n_rows * GRP, 256), 256, 0, (cudaStream_t)stream>>>(
+      indptr, idx, val, n_rows, row0, col0, ptr_t, cnt, t_idx, t_val);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_records_count(const void* rec, int64_t k, int32_t col0, int32_t* cnt, int64_t n_cols,
+                                 void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  GTB_CHECK_ARG(n_cols > 0 && k >= 0, "bad shape");
+  GTB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * n_cols, st));
+  if (k > 0) {
+    const int64_t blocks = gtb_cdiv(k, 256);
+    records_count_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
+        reinterpret_cast<const EdgeRec*>(rec), k, col0, cnt);
+    GTB_CHECK_LAUNCH();
+  }
+  return GTB_OK;
+}
+
+extern "C" int gtb_records_scatter(const void* rec, int64_t k, int32_t col0, const int64_t* ptr_t, int32_t* cnt,
+                                   int32_t* t_idx, double* t_val, void* stream) {
+  if (k > 0) {
+    const int64_t blocks = gtb_cdiv(k, 256);
+    records_scatter_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const EdgeRec*>(rec), k, col0, ptr_t, cnt, t_idx, t_val);
+    GTB_CHECK_LAUNCH();
+  }
+  return GTB_OK;
+}
+
+extern "C" int gtb_csr_sort_rows(const int64_t* ptr, int32_t* idx, double* val, int64_t n, int32_t* has_long,
+                                 void* stream) {
+  GTB_CHECK_ARG(n > 0, "empty matrix");
+  cudaStream_t st = (cudaStream_t)stream;
+  GTB_CUDA(cudaMemsetAsync(has_long, 0, sizeof(int32_t), st));
+  csr_sort_rows_kernel<<<(unsigned)gtb_cdiv(n, SORT_WARPS), SORT_WARPS * 32, 0, st>>>(ptr, idx, val, n, has_long);
+  GTB_CHECK_LAUNCH();
+  const size_t smem = (size_t)SORT_BLOCK_CAP * 12;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GTB_CUDA(cudaFuncSetAttribute(csr_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int64_t blocks = gtb_cdiv(n, SORT_BLOCK_THREADS);
+  csr_sort_long_kernel<<<(unsigned)(blocks < 148 * 4 ? blocks : 148 * 4), SORT_BLOCK_THREADS, smem, st>>>(
+      ptr, idx, val, n, has_long);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_sym_merge_count(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pt,
+                                   const int32_t* it, const double* vt, int64_t n_rows, int mode, double theta,
+                                   int32_t* newlen, void* stream) {
+  GTB_CHECK_ARG(n_rows > 0 && mode >= 0 && mode <= 2, "bad arguments");
+  sym_merge_kernel<false><<<(unsigned)gtb_cdiv(n_rows, MRG_WARPS), MRG_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      pa, ia, va, pt, it, vt, n_rows, 0, mode, theta, newlen, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_sym_merge_fill(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pt,
+                                  const int32_t* it, const double* vt, int64_t n_rows, int32_t row0, int mode,
+                                  double theta, const int64_t* outptr, int32_t* out_idx, double* out_val,
+                                  double* p_val, double* degree, int32_t* flags, void* stream) {
+  GTB_CHECK_ARG(n_rows > 0 && mode >= 0 && mode <= 2, "bad arguments");
+  sym_merge_kernel<true><<<(unsigned)gtb_cdiv(n_rows, MRG_WARPS), MRG_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      pa, ia, va, pt, it, vt, n_rows, row0, mode, theta, nullptr, outptr, out_idx, out_val, p_val, degree, flags);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_route_count(const int64_t* indptr, const int32_t* idx, int64_t m, int32_t per, int world,
+                               int32_t* cnt, void* stream) {
+  GTB_CHECK_ARG(m > 0 && per > 0 && world > 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  GTB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)m * world, st));
+  route_count_kernel<<<(unsigned)gtb_cdiv(m * GRP, 256), 256, 0, st>>>(indptr, idx, m, per, world, cnt);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
+extern "C" int gtb_route_fill(const int64_t* indptr, const int32_t* idx, const double* val, int64_t m, int32_t row0,
+                              int32_t per, int world, const int32_t* cnt, const int64_t* pos, void* send,
+                              void* stream) {
+  GTB_CHECK_ARG(m > 0 && per > 0 && world > 0, "bad arguments");
+  route_fill_kernel<<<(unsigned)gtb_cdiv(m * GRP, 256), 256, 0, (cudaStream_t)stream>>>(
+      indptr, idx, val, m, row0, per, world, cnt, pos, reinterpret_cast<EdgeRec*>(send));
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}

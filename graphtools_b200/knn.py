@@ -92,11 +92,23 @@ class kNNGraph(DataGraph):
         """The fitted search structure: the device-resident search operand of ``data_nu``
         (centred k-major copy + norms).  Stands in for the reference's sklearn NearestNeighbors
         (graphs.py:748-769)."""
-        try:
-            return self._ref_operand
-        except AttributeError:
-            self._ref_operand = pipeline.SearchOperand(self._dense_f32(self.data_nu), metric=self.distance)
-            return self._ref_operand
+        if "_ref_operand" not in self.__dict__:
+            self._ref_operand = pipeline.SearchOperand(self._reference_rows(), metric=self.distance)
+        return self._ref_operand
+
+    def _reference_rows(self):
+        """``data_nu`` in HBM.  One process per GPU: every rank uploads its own row block of the host array and the
+        blocks are assembled by an NCCL all-gather (collective 1) instead of every rank copying all
+        of X across its PCIe link."""
+        import torch
+        from . import distributed as gd
+        A = self.data_nu
+        host_dense = isinstance(A, np.ndarray) or (isinstance(A, torch.Tensor) and not A.is_cuda)
+        if (gd.active() and host_dense and getattr(self, "_dev_data_nu", None) is None
+                and A.shape[0] >= gd.MIN_ROWS_PER_RANK * gd.world_size()):
+            is64 = (A.dtype == np.float64) if isinstance(A, np.ndarray) else (A.dtype == torch.float64)
+            return gd.upload_sharded(A, torch.float64 if is64 else torch.float32, pipeline._dev())
+        return self._dense_f32(A)
 
     def build_kernel(self):
         """Raw in-sample kernel: every sample queried against all samples with knn+1 neighbours
@@ -150,9 +162,12 @@ class kNNGraph(DataGraph):
 
     def _build_kernel(self):
         """Sharded build when torch.distributed is initialised: rows are sharded, every raw edge
-        (i, j, w) is routed to the owner of column j with an NCCL all-to-all, each rank merges its raw rows with
-        the transposed edges it received (csrc/sparse.cu sym_merge_rows), normalises its shard, and the K / P
-        shards are all-gathered so every rank returns the complete matrices (bit-identical for any rank count)."""
+        (i, j, w) is routed to the owner of column j with one NCCL all-to-all of packed records (bucketed by kernels,
+        csrc/symm.cu route_count / route_fill), each rank turns what it received into the rows of the transposed matrix
+        (records_count / scan / records_scatter / csr_sort_rows), merges them with its raw rows and normalises its
+        shard with the same kernel as the single-GPU build (sym_merge) -- bit-identical for any rank count.  The
+        result stays row-sharded in HBM (``_dev_shard``); the complete K / P are assembled on demand
+        (core.BaseGraph._gather_shards on the device, _materialize_shards on the host)."""
         from . import distributed as gd
         sharded = (gd.active() and np.ndim(self.bandwidth) == 0 and self.anisotropy == 0
                    and self.kernel_symm in ("+", "*", "mnn"))
@@ -165,45 +180,37 @@ class kNNGraph(DataGraph):
         ref = self.knn_tree
         n = ref.n
         with _logger.log_task("KNN search"):
-            bounds, indptr_a, row_len, idx, val, _ = self._local_raw_rows(ref, knn_max)
+            bounds, indptr_a, row_len, idx, val, info = self._local_raw_rows(ref, knn_max)
         rank = dist.get_rank()
         lo, hi = bounds[rank]
         m = hi - lo
-        row_len_t, idx_t, val_t = gd.route_edges_to_column_owner(row_len, idx, val, lo, bounds)
+        dev = idx.device
+        rec = gd.exchange_edges(indptr_a, idx, val, lo, bounds)
         mode = pipeline.SYM_MODES[self.kernel_symm]
         theta = 0.0 if self.theta is None else float(self.theta)
+        flags = pipeline._zeros((1,), torch.int32)
         if m > 0:
-            indptr_b = pipeline.exclusive_scan(row_len_t)
-            newlen = pipeline._empty((m,), torch.int32)
-            E.call("gtb_sym_merge_count", indptr_a, idx, val, indptr_b, idx_t, val_t, m, mode, theta, newlen)
-            outptr = pipeline.exclusive_scan(newlen)
-            nnz = int(outptr[-1].item())
-            k_idx = pipeline._empty((nnz,), torch.int32)
-            k_val = pipeline._empty((nnz,), torch.float64)
-            p_val = pipeline._empty((nnz,), torch.float64)
-            deg = pipeline._empty((m,), torch.float64)
-            E.call("gtb_sym_merge_fill", indptr_a, idx, val, indptr_b, idx_t, val_t, m, mode, theta, outptr, k_idx,
-                   k_val, p_val, deg)
+            k = rec.shape[0]
+            cnt = pipeline._empty((m,), torch.int32)
+            E.call("gtb_records_count", rec, k, lo, cnt, m)
+            ptr_t = pipeline.exclusive_scan(cnt)
+            t_idx = pipeline._empty((k,), torch.int32)
+            t_val = pipeline._empty((k,), torch.float64)
+            E.call("gtb_records_scatter", rec, k, lo, ptr_t, cnt, t_idx, t_val)
+            pipeline.sort_rows(ptr_t, t_idx, t_val, m)
+            outptr, k_idx, k_val, p_val, deg, newlen = pipeline.merge_with_transpose(
+                indptr_a, idx, val, ptr_t, t_idx, t_val, m, lo, mode, theta, want_p=True, flags=flags)
         else:
-            newlen = torch.zeros((0,), dtype=torch.int32, device=idx.device)
-            k_idx = torch.zeros((0,), dtype=torch.int32, device=idx.device)
-            k_val = p_val = deg = torch.zeros((0,), dtype=torch.float64, device=idx.device)
-        heights = [b[1] - b[0] for b in bounds]
-        full_ptr, full_idx, full_val = gd.allgather_csr_rows(newlen, k_idx, k_val, heights, pipeline.exclusive_scan)
-        full_p = gd._allgather_padded(p_val, self._all_counts(k_idx.shape[0]))
-        full_deg = gd._allgather_padded(deg, heights)
-        K = pipeline.DeviceCSR(full_ptr, full_idx, full_val, (n, n))
-        self._dev_kernel, self._dev_P, self._dev_degree = K, full_p, full_deg
-        return K
-
-    @staticmethod
-    def _all_counts(local_count):
-        import torch
-        import torch.distributed as dist
-        t = torch.tensor([local_count], dtype=torch.int64, device="cuda")
-        out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
-        dist.all_gather(out, t)
-        return [int(x.item()) for x in out]
+            newlen = torch.zeros((0,), dtype=torch.int32, device=dev)
+            outptr = torch.zeros((1,), dtype=torch.int64, device=dev)
+            k_idx = torch.zeros((0,), dtype=torch.int32, device=dev)
+            k_val = p_val = deg = torch.zeros((0,), dtype=torch.float64, device=dev)
+        self._dev_shard = {"bounds": bounds, "n": n, "lo": lo, "hi": hi, "indptr": outptr, "row_len": newlen,
+                           "indices": k_idx, "data": k_val, "P": p_val, "degree": deg, "flags": flags}
+        if info.get("bandwidth") is not None:
+            self._dev_bandwidth_shard = info["bandwidth"]
+        pipeline._STATS.update(nnz_sym_local=int(k_idx.shape[0]))
+        return None
 
     def _kernel_device(self, qry, ref, knn, knn_max, bandwidth, bandwidth_scale):
         if self.decay is None or self.thresh == 1:

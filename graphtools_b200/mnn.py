@@ -102,10 +102,7 @@ class MNNGraph(DataGraph):
                         continue
                     with _logger.log_task("kernel from sample {} to {}".format(self.samples[i], self.samples[j])):
                         Kij = gj._kernel_to_data_device(gi.data_nu, knn=self.knn)
-                        between = pipeline._empty((Kij.shape[0],), torch.float64)
-                        flags = pipeline._zeros((1,), torch.int32)
-                        E.call("gtb_row_finalize", Kij.indptr, Kij.indices, Kij.data, Kij.shape[0], 0, None, None,
-                               None, between, flags, 0)
+                        between = pipeline.row_sums(Kij)
                         blocks.append((Kij, members[i], members[j], gi._dev_degree, between))
             for (B, rmap, cmap, within, between) in blocks:
                 E.call("gtb_block_count", B.indptr, B.shape[0], rmap, rowlen)
@@ -117,11 +114,8 @@ class MNNGraph(DataGraph):
             for (B, rmap, cmap, within, between) in blocks:
                 E.call("gtb_block_fill", B.indptr, B.indices, B.data, B.shape[0], rmap, cmap, within, between,
                        float(self.beta), outptr, cursor, tmp_idx, tmp_val)
-            k_idx = pipeline._empty((nnz,), torch.int32)
-            k_val = pipeline._empty((nnz,), torch.float64)
-            flags = pipeline._zeros((1,), torch.int32)
-            E.call("gtb_row_finalize", outptr, tmp_idx, tmp_val, n, 1, k_idx, k_val, None, None, flags, 0)
-        return pipeline.DeviceCSR(outptr, k_idx, k_val, (n, n))
+            pipeline.sort_rows(outptr, tmp_idx, tmp_val, n)      # blocks land in batch order -> column order
+        return pipeline.DeviceCSR(outptr, tmp_idx, tmp_val, (n, n))
 
     def _kernel_to_data_device(self, Y, theta=None):
         raise NotImplementedError

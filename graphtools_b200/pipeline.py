@@ -77,17 +77,32 @@ def _d2h_ring():
     return _d2h_state["bufs"], _d2h_state["stream"], _d2h_state["pool"]
 
 
-def d2h_pinned(t):
-    """Device->host copy into a fresh pageable tensor.  Large tensors go through the pinned staging ring in
-    32 MB chunks: the DMA of chunk i+1 overlaps the host-side copy of chunk i, which four threads perform in
-    parallel (so the first-touch page faults of the destination are taken in parallel too)."""
+def d2h_into(t, dst_array):
+    """Device tensor -> an existing host numpy array of the same size and dtype (e.g. a slice of a shared-memory
+    segment), through the pinned staging ring."""
+    assert dst_array.nbytes == t.numel() * t.element_size(), (dst_array.nbytes, t.numel(), t.element_size())
+    if t.numel() == 0:
+        return
+    d2h_pinned(t, dst_array.reshape(-1).view(np.uint8))
+
+
+def d2h_pinned(t, dst=None):
+    """Device->host copy into a fresh pageable tensor (or into ``dst``, a uint8 numpy view of the destination).
+    Large tensors go through the pinned staging ring in 32 MB chunks: the DMA of chunk i+1 overlaps the host-side
+    copy of chunk i, which four threads perform in parallel (so the first-touch page faults of the destination are
+    taken in parallel too)."""
     nbytes = t.numel() * t.element_size()
     if nbytes < (8 << 20) or not t.is_cuda:
-        return t.cpu()
+        if dst is None:
+            return t.cpu()
+        dst[:] = t.contiguous().view(-1).view(torch.uint8).cpu().numpy()
+        return None
     bufs, side, pool = _d2h_ring()
     src = t.contiguous().view(-1).view(torch.uint8)
-    out = torch.empty(t.shape, dtype=t.dtype)
-    dst = out.view(-1).view(torch.uint8).numpy()
+    out = None
+    if dst is None:
+        out = torch.empty(t.shape, dtype=t.dtype)
+        dst = out.view(-1).view(torch.uint8).numpy()
     side.wait_stream(torch.cuda.current_stream())
     chunks = [(off, min(_D2H_CHUNK, nbytes - off)) for off in range(0, nbytes, _D2H_CHUNK)]
     events = [None] * len(chunks)
@@ -486,6 +501,43 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
     return csr, {"bandwidth": bw_out, "nzero": nzero}
 
 
+def sort_rows(ptr, idx, val, n):
+    """Order every row of a CSR by column, in place (csrc/symm.cu: tiered segmented sort)."""
+    if n == 0 or idx.shape[0] == 0:
+        return
+    E.call("gtb_csr_sort_rows", ptr, idx, val, n, _empty((1,), torch.int32))
+
+
+def transpose_csr(R):
+    """R^T as a DeviceCSR with column-sorted rows: histogram of the columns -> scan -> scatter -> per-row sort."""
+    n_rows, n_cols = R.shape
+    cnt = _empty((n_cols,), torch.int32)
+    E.call("gtb_transpose_count", R.indices, R.nnz, 0, cnt, n_cols)
+    ptr_t = exclusive_scan(cnt)
+    t_idx = _empty((R.nnz,), torch.int32)
+    t_val = _empty((R.nnz,), torch.float64)
+    if R.nnz:
+        E.call("gtb_transpose_scatter", R.indptr, R.indices, R.data, n_rows, 0, 0, ptr_t, cnt, t_idx, t_val)
+        sort_rows(ptr_t, t_idx, t_val, n_cols)
+    return DeviceCSR(ptr_t, t_idx, t_val, (n_cols, n_rows))
+
+
+def merge_with_transpose(A_ptr, A_idx, A_val, T_ptr, T_idx, T_val, n_rows, row0, mode, theta, want_p=True,
+                         flags=None):
+    """sym(A, T) row by row (csrc/symm.cu sym_merge): returns (outptr, k_idx, k_val, p_val | None, degree, newlen)."""
+    newlen = _empty((n_rows,), torch.int32)
+    E.call("gtb_sym_merge_count", A_ptr, A_idx, A_val, T_ptr, T_idx, T_val, n_rows, mode, theta, newlen)
+    outptr = exclusive_scan(newlen)
+    nnz = int(outptr[-1].item())
+    k_idx = _empty((nnz,), torch.int32)
+    k_val = _empty((nnz,), torch.float64)
+    p_val = _empty((nnz,), torch.float64) if want_p else None
+    degree = _empty((n_rows,), torch.float64)
+    E.call("gtb_sym_merge_fill", A_ptr, A_idx, A_val, T_ptr, T_idx, T_val, n_rows, row0, mode, theta, outptr,
+           k_idx, k_val, p_val, degree, flags)
+    return outptr, k_idx, k_val, p_val, degree, newlen
+
+
 def symmetrize_normalize(R, kernel_symm="+", theta=None, anisotropy=0.0, want_p=True):
     """``BaseGraph._build_kernel`` post-processing (base.py:534-592) + ``P`` (base.py:645).
 
@@ -500,32 +552,22 @@ def symmetrize_normalize(R, kernel_symm="+", theta=None, anisotropy=0.0, want_p=
         raise ValueError("symmetrisation needs a square kernel")
     if mode == 3:
         if square:
-            dummy = _empty((n,), torch.int32)
-            E.call("gtb_sym_count", R.indptr, R.indices, R.data, n, 3, 0.0, dummy, flags)
+            E.call("gtb_asym_check", R.indptr, R.indices, R.data, n, flags)
         K = R
         P = _empty((R.nnz,), torch.float64) if want_p else None
         degree = _empty((n,), torch.float64)
-        E.call("gtb_row_finalize", K.indptr, K.indices, K.data, n, 0, None, None, P, degree, flags, int(square))
+        E.call("gtb_row_finalize", K.indptr, K.indices, K.data, n, P, degree, flags, int(square))
     else:
-        newlen = _empty((n,), torch.int32)
         th = 0.0 if theta is None else float(theta)
-        E.call("gtb_sym_count", R.indptr, R.indices, R.data, n, mode, th, newlen, flags)
-        outptr = exclusive_scan(newlen)
-        nnz = int(outptr[-1].item())
-        tmp_idx = _empty((nnz,), torch.int32)
-        tmp_val = _empty((nnz,), torch.float64)
-        cursor = newlen  # reuse as the per-row cursor (zeroed by sym_fill)
-        E.call("gtb_sym_fill", R.indptr, R.indices, R.data, n, mode, th, outptr, cursor, tmp_idx, tmp_val)
-        k_idx = _empty((nnz,), torch.int32)
-        k_val = _empty((nnz,), torch.float64)
-        P = _empty((nnz,), torch.float64) if (want_p and anisotropy == 0) else None
-        degree = _empty((n,), torch.float64)
-        E.call("gtb_row_finalize", outptr, tmp_idx, tmp_val, n, 1, k_idx, k_val, P, degree, flags, 1)
+        T = transpose_csr(R)
+        outptr, k_idx, k_val, P, degree, _ = merge_with_transpose(
+            R.indptr, R.indices, R.data, T.indptr, T.indices, T.data, n, 0, mode, th,
+            want_p=want_p and anisotropy == 0, flags=flags)
         K = DeviceCSR(outptr, k_idx, k_val, R.shape)
     if anisotropy != 0:
         E.call("gtb_anisotropy", K.indptr, K.indices, K.data, degree, float(anisotropy), n)
         P = _empty((K.nnz,), torch.float64) if want_p else None
-        E.call("gtb_row_finalize", K.indptr, K.indices, K.data, n, 0, None, None, P, degree, flags, 0)
+        E.call("gtb_row_finalize", K.indptr, K.indices, K.data, n, P, degree, flags, 0)
     _STATS.update(nnz_sym=K.nnz)
     return K, P, degree, int(flags.item())
 
@@ -534,8 +576,17 @@ def row_normalize(K):
     """sklearn ``normalize(K, 'l1', axis=1)`` on a DeviceCSR -> values tensor."""
     P = _empty((K.nnz,), torch.float64)
     flags = _zeros((1,), torch.int32)
-    E.call("gtb_row_finalize", K.indptr, K.indices, K.data, K.shape[0], 0, None, None, P, None, flags, 0)
+    if K.shape[0]:
+        E.call("gtb_row_finalize", K.indptr, K.indices, K.data, K.shape[0], P, None, flags, 0)
     return P
+
+
+def row_sums(K):
+    """Row L1 sums of a DeviceCSR (``np.sum(K, 1)`` for the non-negative kernels of this package)."""
+    deg = _empty((K.shape[0],), torch.float64)
+    flags = _zeros((1,), torch.int32)
+    E.call("gtb_row_finalize", K.indptr, K.indices, K.data, K.shape[0], None, deg, flags, 0)
+    return deg
 
 
 def csr_from_scipy(M):

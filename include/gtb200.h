@@ -114,31 +114,53 @@ int gtb_csr_gather(const int32_t* st_idx, const double* st_val, const int32_t* n
 
 /* ---- K4 sparse symmetrise / normalise: replaces base.py:557-577, :579-592, :645, :648-666 --- */
 int64_t gtb_scan_ws_elems(int64_t n);
-/* out[n+1] = exclusive prefix sums of in[n] (int32 -> int64); ws: gtb_scan_ws_elems(n) int64 */
+/* out[n+1] = exclusive prefix sums of in[n] (int32 -> int64), one launch (decoupled look-back);
+ * ws: gtb_scan_ws_elems(n) int64 of scratch */
 int gtb_exclusive_scan(const int32_t* in, int64_t n, int64_t* out, int64_t* ws, void* stream);
 int gtb_cast_indptr(const int64_t* in, int64_t n1, int32_t* out, void* stream);
-/* mode 0 '+', 1 '*', 2 'mnn' (theta), 3 none (only sets flags bit 0 when max(K - K^T) > 1e-5) */
-int gtb_sym_count(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n, int mode,
-                  double theta, int32_t* newlen, int32_t* flags, void* stream);
-int gtb_sym_fill(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n, int mode,
-                 double theta, const int64_t* outptr, int32_t* cursor, int32_t* tmp_idx, double* tmp_val,
-                 void* stream);
-/* sort != 0: rows of tmp are unsorted -> write column-sorted K (out_idx/out_val); always (when
- * non-NULL) p_val = val / sum|val| and degree = sum|val|; flags bit 1: a row lacks its diagonal */
-int gtb_row_finalize(const int64_t* ptr, const int32_t* tmp_idx, const double* tmp_val, int64_t n, int sort,
-                     int32_t* out_idx, double* out_val, double* p_val, double* degree, int32_t* flags,
-                     int check_diag, void* stream);
+/* Sort-based transpose of a CSR (K^T of base.py:561-571 without scipy's csr_tocsc):
+ * cnt[n_cols] = histogram of (idx - col0); after gtb_exclusive_scan(cnt) -> ptr_t, scatter writes every edge
+ * (row0 + r, j, w) into row j - col0 of the transposed matrix (cnt is consumed as the per-row cursor); the rows
+ * come out in arrival order -> gtb_csr_sort_rows orders them by column, in place (has_long: one int of scratch) */
+int gtb_transpose_count(const int32_t* idx, int64_t nnz, int32_t col0, int32_t* cnt, int64_t n_cols, void* stream);
+int gtb_transpose_scatter(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n_rows, int32_t row0,
+                          int32_t col0, const int64_t* ptr_t, int32_t* cnt, int32_t* t_idx, double* t_val,
+                          void* stream);
+int gtb_csr_sort_rows(const int64_t* ptr, int32_t* idx, double* val, int64_t n, int32_t* has_long, void* stream);
+/* The same transpose for a list of k packed 16-byte edge records {int32 i, int32 j, float64 w} (what the
+ * multi-GPU all-to-all delivers): row j - col0 of the result receives (i, w) */
+int gtb_records_count(const void* rec, int64_t k, int32_t col0, int32_t* cnt, int64_t n_cols, void* stream);
+int gtb_records_scatter(const void* rec, int64_t k, int32_t col0, const int64_t* ptr_t, int32_t* cnt, int32_t* t_idx,
+                        double* t_val, void* stream);
+/* Merge of the raw kernel rows A = (pa, ia, va) with the rows T = (pt, it, vt) of the transposed matrix, both
+ * column-sorted, under mode 0 '+' ((w + w')/2), 1 '*' (w w'), 2 'mnn' (theta min + (1 - theta) max):
+ * count -> gtb_exclusive_scan -> fill.  fill emits the column-sorted K row, P = K / sum|K| (base.py:645), the degree
+ * vector (base.py:648-666) and sets flags bit 1 when a row lacks its diagonal (base.py:553-554; global row id =
+ * row0 + r, columns are global).  Used on the whole matrix (one GPU) and on a row shard (multi-GPU, after the
+ * all-to-all) alike, so the two builds agree bit for bit. */
+int gtb_sym_merge_count(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pt,
+                        const int32_t* it, const double* vt, int64_t n_rows, int mode, double theta,
+                        int32_t* newlen, void* stream);
+int gtb_sym_merge_fill(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pt, const int32_t* it,
+                       const double* vt, int64_t n_rows, int32_t row0, int mode, double theta, const int64_t* outptr,
+                       int32_t* out_idx, double* out_val, double* p_val, double* degree, int32_t* flags,
+                       void* stream);
+/* kernel_symm=None: flags bit 0 set when max(K - K^T) > 1e-5 (base.py:551-552) */
+int gtb_asym_check(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n, int32_t* flags,
+                   void* stream);
+/* p_val = val / sum|val| and degree = sum|val| per row (each optional); flags bit 1: a row lacks its diagonal */
+int gtb_row_finalize(const int64_t* ptr, const int32_t* idx, const double* val, int64_t n, double* p_val,
+                     double* degree, int32_t* flags, int check_diag, void* stream);
 int gtb_anisotropy(const int64_t* indptr, const int32_t* idx, double* val, const double* deg, double alpha,
                    int64_t n, void* stream);
-/* Multi-GPU symmetrisation of a row shard: A = this rank's raw kernel rows, B = the transposed edges routed to
- * it by the NCCL all-to-all (both CSR over the local rows, column-sorted).  count -> scan -> fill; fill also
- * emits P = K / rowsum and the degree vector of the shard (base.py:557-577, :645 on a row partition). */
-int gtb_sym_merge_count(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pb,
-                        const int32_t* ib, const double* vb, int64_t n_rows, int mode, double theta,
-                        int32_t* newlen, void* stream);
-int gtb_sym_merge_fill(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pb, const int32_t* ib,
-                       const double* vb, int64_t n_rows, int mode, double theta, const int64_t* outptr,
-                       int32_t* out_idx, double* out_val, double* p_val, double* degree, void* stream);
+/* Multi-GPU edge exchange (SURVEY 8e collective 2): bucket the raw edges of a row shard by the rank that owns their
+ * column, owner(j) = min(j / per, world - 1).  count: cnt[o * m + r] = entries of local row r bound for rank o
+ * (destination-major); after gtb_exclusive_scan(cnt) -> pos, fill packs the 16-byte records {row0 + r, j, w} into
+ * the send buffer in (destination, row, column) order -- the layout ncclAllToAll consumes, no sort. */
+int gtb_route_count(const int64_t* indptr, const int32_t* idx, int64_t m, int32_t per, int world, int32_t* cnt,
+                    void* stream);
+int gtb_route_fill(const int64_t* indptr, const int32_t* idx, const double* val, int64_t m, int32_t row0, int32_t per,
+                   int world, const int32_t* cnt, const int64_t* pos, void* send, void* stream);
 /* out[n_rows][n_cols] (float64) = dense form of the CSR matrix (zero fill + scatter): exact graphs with a
  * threshold are built sparse on the tensor-core path and densified once (reference container contract:
  * TraditionalGraph.K is an ndarray, graphs.py:1594-1609) */

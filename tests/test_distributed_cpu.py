@@ -1,4 +1,5 @@
-"""world_size-2 gloo test of the multi-GPU host logic (row sharding + CSR shard all-gather)."""
+"""world_size-2 gloo tests of the multi-GPU host logic: row sharding, CSR shard all-gather, the edge exchange
+(split-size exchange + one all-to-all of packed records) and the shared-memory result assembly."""
 import os
 import socket
 
@@ -54,6 +55,18 @@ def test_allgather_csr_rows_gloo_world2():
     assert all(out[r] for r in range(world))
 
 
+def _torch_bucket(indptr, indices, data, lo, per, world):
+    """torch restatement of csrc/symm.cu route_count / route_fill (test helper: the product path buckets with the
+    CUDA kernels): records {int32 i, int32 j, float64 w} in (destination, row, column) order + per-rank counts."""
+    m = indptr.shape[0] - 1
+    rows = torch.repeat_interleave(torch.arange(lo, lo + m, dtype=torch.int64), indptr[1:] - indptr[:-1])
+    dest = torch.clamp(indices.to(torch.int64) // per, max=world - 1)
+    order = torch.argsort(dest, stable=True)
+    ij = torch.stack([rows.to(torch.int32), indices.to(torch.int32)], 1)[order].contiguous().view(torch.int64).view(-1)
+    w = data[order].contiguous().view(torch.int64)
+    return torch.stack([ij, w], 1).contiguous(), torch.bincount(dest, minlength=world)
+
+
 def _route_worker(rank, world, port, n, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -62,18 +75,51 @@ def _route_worker(rank, world, port, n, out):
     bounds = [gd.shard_bounds(n, world, r) for r in range(world)]
     lo, hi = bounds[rank]
     S = M[lo:hi]
-    row_len_t, cols_t, vals_t = gd.route_edges_to_column_owner(
-        torch.from_numpy(np.diff(S.indptr).astype(np.int32)), torch.from_numpy(S.indices.astype(np.int32)),
-        torch.from_numpy(S.data), lo, bounds)
-    T = sparse.csr_matrix(M.T)[lo:hi]          # what this rank must have received: rows lo:hi of M^T
+    rec = gd.exchange_edges(torch.from_numpy(S.indptr.astype(np.int64)), torch.from_numpy(S.indices.astype(np.int32)),
+                            torch.from_numpy(S.data), lo, bounds, bucket_fn=_torch_bucket)
+    i, j, w = (t.numpy() for t in gd.unpack_records(rec))
+    # what this rank must have received: the entries of rows lo:hi of M^T, i.e. (j - lo, i) -> w
+    got = sparse.csr_matrix((w, (j - lo, i)), shape=(hi - lo, n)) if hi > lo else None
+    T = sparse.csr_matrix(M.T)[lo:hi]
     T.sort_indices()
-    ok = (np.array_equal(row_len_t.numpy(), np.diff(T.indptr)) and np.array_equal(cols_t.numpy(), T.indices)
-          and np.array_equal(vals_t.numpy(), T.data))
-    out[rank] = ok
+    ok = len(i) == T.nnz and ((j >= lo) & (j < hi)).all()
+    if hi > lo:
+        got.sort_indices()
+        ok = ok and (np.array_equal(got.indptr, T.indptr) and np.array_equal(got.indices, T.indices)
+                     and np.array_equal(got.data, T.data))
+    out[rank] = bool(ok)
     dist.destroy_process_group()
 
 
-def test_route_edges_to_column_owner_gloo_world2():
+def _shared_worker(rank, world, port, out):
+    """SharedResult: every rank fills its slice of a shared-memory array; all ranks then see the whole array."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = gd.SharedResult()
+    arr = res.create({"a": (1000, np.float64), "b": (10, np.int32)})
+    per = 1000 // world
+    arr["a"][rank * per:(rank + 1) * per] = np.arange(rank * per, (rank + 1) * per, dtype=np.float64)
+    if rank == 0:
+        arr["b"][:] = 7
+    arr = res.finish(arr)
+    ok = np.array_equal(arr["a"], np.arange(1000, dtype=np.float64)) and (arr["b"] == 7).all()
+    ok = ok and (arr["a"].flags.writeable == (rank == 0))
+    import glob
+    dist.barrier()
+    ok = ok and not glob.glob(res.prefix + "*")        # unlinked: nothing left in /dev/shm
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_shared_result_gloo_world2():
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_shared_worker, args=(2, port, out), nprocs=2, join=True)
+    assert all(out[r] for r in range(2))
+
+
+def test_exchange_edges_gloo_world2():
     world, n = 2, 300
     port = _free_port()
     mgr = mp.Manager()
