@@ -57,9 +57,9 @@ _SIGS = {
     "gtb_csr_to_dense": ([_P, _P, _P, c_int64, c_int64, _P, _P], 1),
     "gtb_block_count": ([_P, c_int64, _P, _P, _P], 1),
     "gtb_block_fill": ([_P, _P, _P, c_int64, _P, _P, _P, _P, c_double, _P, _P, _P, _P, _P], 1),
-    "gtb_cluster_aggregate_count": ([_P, _P, _P, c_int64, _P, _P, _P], 1),
-    "gtb_cluster_aggregate_fill": ([_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_int, _P], 1),
-    "gtb_landmark_op": ([_P, _P, _P, _P, _P, c_int64, c_int, _P, _P], 1),
+    "gtb_cluster_aggregate_count": ([_P, _P, _P, c_int64, _P, c_int, _P, _P, _P], 2),
+    "gtb_cluster_aggregate_fill": ([_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P], 3),
+    "gtb_landmark_op": ([_P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P], 2),
     "gtb_dense_kernel": ([_P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, _P, c_double, c_double, c_int, c_double,
                           _P, _P, _P], 1),
     "gtb_dense_row_scale": ([_P, _P, c_int64, c_int64, _P, _P], 1),
@@ -73,6 +73,7 @@ _PLAIN = {
     "gtb_version": ([], c_int),
     "gtb_col_mean_ws_doubles": ([c_int], c_int64),
     "gtb_scan_ws_elems": ([c_int64], c_int64),
+    "gtb_cluster_aggregate_ws_elems": ([c_int], c_int64),
     "gtb_tc_max_kp": ([], c_int),
     "gtb_tc_set_cluster": ([c_int], c_int),
     "gtb_tc_set_pacing": ([c_int], c_int),

@@ -73,16 +73,29 @@ def _dense_to_csr(K):
     return pipeline.DeviceCSR(indptr, cols, K[nz].contiguous(), tuple(K.shape))
 
 
+def _one_hot(labels, L):
+    C = torch.zeros((labels.shape[0], L), dtype=torch.float64, device=labels.device)
+    C[torch.arange(labels.shape[0], device=labels.device), labels.long()] = 1.0
+    return C
+
+
 def dense_landmark(K, labels, L):
-    from .landmark import aggregate_by_cluster
-    csr = _dense_to_csr(K)
-    pnm, pnm_norm, colsum = aggregate_by_cluster(csr, labels, L, want_colsum=True)
-    op = pipeline._empty((L, L), torch.float64)
-    E.call("gtb_landmark_op", pnm.indptr, pnm.indices, pnm.data, pnm_norm, colsum, K.shape[0], L, op)
-    return op.cpu().numpy(), pnm.to_scipy(pnm_norm).toarray()
+    """Landmark operator of a DENSE kernel (graphs.py:1169-1246 on an ndarray K): two plain float64 library GEMMs --
+    pmn = C^T K, op = rownorm(pmn) rownorm(pmn^T).  (Going through the sparse aggregation kernels would turn every
+    row of the n x n matrix into a "hub row".)  Plumbing, not a hot path: dense graphs are the small-n case."""
+    C = _one_hot(labels, L)
+    pmn = C.T @ K                                   # [L, n]: sum of the kernel rows of each cluster
+    pnm = pmn.T.contiguous()                        # [n, L]
+    rs_m = pmn.abs().sum(1, keepdim=True)
+    rs_n = pnm.abs().sum(1, keepdim=True)
+    pmn_n = torch.where(rs_m != 0, pmn / rs_m, pmn)
+    pnm_n = torch.where(rs_n != 0, pnm / rs_n, pnm)
+    op = pmn_n @ pnm_n
+    return op.cpu().numpy(), pnm_n.cpu().numpy()
 
 
 def dense_landmark_extend(Kyx, labels, L):
-    from .landmark import aggregate_by_cluster
-    agg, agg_norm, _ = aggregate_by_cluster(_dense_to_csr(Kyx), labels, L, want_colsum=False)
-    return agg.to_scipy(agg_norm).toarray()
+    """rownorm(Kyx C) for a dense out-of-sample kernel (graphs.py:1272-1288)."""
+    agg = Kyx @ _one_hot(labels, L)
+    rs = agg.abs().sum(1, keepdim=True)
+    return torch.where(rs != 0, agg / rs, agg).cpu().numpy()

@@ -23,19 +23,29 @@ SPECTRAL_AUTO_N = 50_000   # GTB_SPECTRAL=auto: device-side SVD + k-means above 
 
 def aggregate_by_cluster(K, labels_dev, n_label, want_colsum):
     """Row-wise aggregation of DeviceCSR ``K`` by ``labels[col]`` -> (DeviceCSR raw sums, normalised
-    values, column sums | None)."""
+    values, column sums | None).  Column sums are accumulated in fixed point (csrc/landmark.cu): bit-reproducible."""
     n = K.shape[0]
     cnt = pipeline._empty((n,), torch.int32)
-    E.call("gtb_cluster_aggregate_count", K.indptr, K.indices, K.data, n, labels_dev, cnt)
+    ws = pipeline._empty((E.lib().gtb_cluster_aggregate_ws_elems(n_label),), torch.int64)
+    E.call("gtb_cluster_aggregate_count", K.indptr, K.indices, K.data, n, labels_dev, n_label, cnt, ws)
     outptr = pipeline.exclusive_scan(cnt)
     nnz = int(outptr[-1].item())
     out_idx = pipeline._empty((nnz,), torch.int32)
     out_raw = pipeline._empty((nnz,), torch.float64)
     out_norm = pipeline._empty((nnz,), torch.float64)
     colsum = pipeline._empty((n_label,), torch.float64) if want_colsum else None
+    colsum_fx = pipeline._empty((2 * n_label,), torch.int64) if want_colsum else None
     E.call("gtb_cluster_aggregate_fill", K.indptr, K.indices, K.data, n, labels_dev, outptr, out_idx, out_raw,
-           out_norm, colsum, n_label)
+           out_norm, colsum, colsum_fx, n_label, ws)
     return pipeline.DeviceCSR(outptr, out_idx, out_raw, (n, n_label)), out_norm, colsum
+
+
+def landmark_operator(pnm, pnm_norm, colsum, n, L):
+    """Dense [L, L] operator rownorm(pnm^T) . rownorm(pnm), accumulated in fixed point (order independent)."""
+    op = pipeline._empty((L, L), torch.float64)
+    op_fx = pipeline._empty((2 * L * L,), torch.int64)
+    E.call("gtb_landmark_op", pnm.indptr, pnm.indices, pnm.data, pnm_norm, colsum, n, L, op, op_fx)
+    return op
 
 
 class LandmarkGraph(DataGraph):
@@ -170,11 +180,11 @@ class LandmarkGraph(DataGraph):
             labels = torch.from_numpy(inv.astype(np.int32)).to(pipeline._dev())
             self._dev_labels, self._n_label = labels, L
             if isinstance(K, pipeline.DeviceCSR):
-                if self.kernel_symm is None:
-                    raise NotImplementedError("landmark operator needs a symmetric kernel (kernel_symm=None given)")
-                pnm, pnm_norm, colsum = aggregate_by_cluster(K, labels, L, want_colsum=True)
-                op = pipeline._empty((L, L), torch.float64)
-                E.call("gtb_landmark_op", pnm.indptr, pnm.indices, pnm.data, pnm_norm, colsum, K.shape[0], L, op)
+                # pnm[j, l] = sum_{i in l} K[i, j] (graphs.py:1169-1182): rows of K^T aggregated by the label of the
+                # column.  K is symmetric unless kernel_symm=None, where the transpose is formed explicitly.
+                Kt = K if self.kernel_symm is not None else pipeline.transpose_csr(K)
+                pnm, pnm_norm, colsum = aggregate_by_cluster(Kt, labels, L, want_colsum=True)
+                op = landmark_operator(pnm, pnm_norm, colsum, K.shape[0], L)
                 self._landmark_op = op.cpu().numpy()
                 self._transitions = pnm.to_scipy(pnm_norm)
                 self._dev_transitions = (pnm, pnm_norm)

@@ -180,17 +180,23 @@ int gtb_block_fill(const int64_t* indptr, const int32_t* idx, const double* val,
 
 /* ---- K6 landmark operator: replaces LandmarkGraph._landmarks_to_data, build_landmark_op and
  * extend_to_data (graphs.py:1169-1182, :1232-1246, :1272-1288) ------------------------------- */
-/* per row: aggregate entries by label[col]; cnt[row] = number of distinct labels */
+/* per row: aggregate entries by label[col]; cnt[row] = number of distinct labels.  ws: gtb_cluster_aggregate_ws_elems
+ * 8-byte words of scratch (long-row flag + dense per-label tables for rows longer than 256 entries) */
+int64_t gtb_cluster_aggregate_ws_elems(int n_label);
 int gtb_cluster_aggregate_count(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n,
-                                const int32_t* label, int32_t* cnt, void* stream);
-/* out rows sorted by label: out_raw = sums, out_norm = sums / row L1 norm (optional),
- * colsum[n_label] = column L1 sums of out_raw (optional) */
+                                const int32_t* label, int n_label, int32_t* cnt, void* ws, void* stream);
+/* out rows sorted by label: out_raw = sums (column order inside a label, as the reference's
+ * kernel[clusters == l, :].sum(axis=0)), out_norm = sums / row L1 norm (optional), colsum[n_label] = column L1 sums
+ * of out_raw (optional; accumulated in 96-bit fixed point in colsum_fx[2 * n_label] -- order independent, hence
+ * bit-reproducible) */
 int gtb_cluster_aggregate_fill(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n,
                                const int32_t* label, const int64_t* outptr, int32_t* out_idx, double* out_raw,
-                               double* out_norm, double* colsum, int n_label, void* stream);
-/* op[L][L] = rownorm(pnm^T) . rownorm(pnm) from the aggregated rows */
+                               double* out_norm, double* colsum, void* colsum_fx, int n_label, void* ws,
+                               void* stream);
+/* op[L][L] = rownorm(pnm^T) . rownorm(pnm) from the aggregated rows; op_fx: 2 * L * L 8-byte words of scratch (the
+ * fixed-point accumulator: integer atomics, so the operator is identical from run to run and for any row split) */
 int gtb_landmark_op(const int64_t* ptr, const int32_t* lab, const double* raw, const double* nrm,
-                    const double* colsum, int64_t n, int L, double* op, void* stream);
+                    const double* colsum, int64_t n, int L, double* op, void* op_fx, void* stream);
 
 /* ---- K5 dense exact graph: replaces TraditionalGraph.build_kernel / build_kernel_to_data
  * (graphs.py:1546-1609, :1651-1677) and the dense branches of base.py:557-592, :645 ---------- */

@@ -204,39 +204,137 @@ def test_tc_radius_pairs_complete(dtype):
     assert np.array_equal(np.bincount(pr[:, 0], minlength=n), rowcnt[:n].cpu().numpy())
 
 
+def _csr_dev(M):
+    M = M.tocsr(); M.sort_indices()
+    return _dev(M.indptr.astype(np.int64)), _dev(M.indices.astype(np.int32)), _dev(M.data.astype(np.float64))
+
+
+def _random_kernel(n, density, seed, hub=None):
+    """Random non-symmetric sparse matrix with a unit diagonal; ``hub`` = (row, count) adds a long row / column."""
+    from scipy import sparse
+    rng = np.random.default_rng(seed)
+    M = sparse.random(n, n, density=density, random_state=seed, format="lil", dtype=np.float64)
+    if hub is not None:
+        r, cnt = hub
+        cols = rng.choice(n, cnt, replace=False)
+        M[r, cols] = rng.uniform(0.1, 1.0, cnt)
+        rows = rng.choice(n, cnt, replace=False)
+        M[rows, r] = rng.uniform(0.1, 1.0, cnt)
+    M.setdiag(1.0)
+    M = M.tocsr(); M.sort_indices()
+    return M
+
+
+@pytest.mark.parametrize("n,density,hub", [(500, 0.01, None), (3000, 0.004, (7, 200)), (6000, 0.002, (11, 5000)),
+                                            (1, 1.0, None), (33, 0.5, None)])
+def test_transpose_and_row_sort(n, density, hub):
+    """csrc/symm.cu transpose_count / scan / transpose_scatter / csr_sort_rows against scipy's CSR transpose:
+    short rows (register tier), rows of 33..256 (warp shared-memory tier), 257..4096 (block tier) and a 5000-entry
+    hub row (global-memory tier)."""
+    from scipy import sparse
+    M = _random_kernel(n, density, 5, hub)
+    R = pipeline.DeviceCSR(*_csr_dev(M), M.shape)
+    T = pipeline.transpose_csr(R)
+    want = sparse.csr_matrix(M.T); want.sort_indices()
+    assert np.array_equal(T.indptr.cpu().numpy(), want.indptr)
+    assert np.array_equal(T.indices.cpu().numpy(), want.indices)
+    assert np.array_equal(T.data.cpu().numpy(), want.data)
+
+
+@pytest.mark.parametrize("mode,theta", [("+", None), ("*", None), ("mnn", 0.3), ("mnn", 1.0)])
+@pytest.mark.parametrize("n,density,hub", [(800, 0.01, None), (3000, 0.004, (7, 300)), (2000, 0.03, None)])
+def test_symmetrize_normalize_matches_scipy(mode, theta, n, density, hub):
+    """The whole K4 chain (transpose + merge count / scan / fill) against scipy's own binops (the reference's
+    base.py:557-577) and sklearn's normalize: structure and K values bit-exact, P within 1e-15, on rows of every
+    length tier; flags report a missing diagonal."""
+    from oracle import graph_oracle as go
+    M = _random_kernel(n, density, 9, hub)
+    K_ref = go.symmetrize(M, mode, theta).tocsr()
+    K_ref.eliminate_zeros(); K_ref.sort_indices()
+    K, P, deg, flags = pipeline.symmetrize_normalize(pipeline.DeviceCSR(*_csr_dev(M), M.shape), mode, theta, 0.0)
+    Kh = K.to_scipy()
+    assert np.array_equal(Kh.indptr, K_ref.indptr) and np.array_equal(Kh.indices, K_ref.indices)
+    assert np.array_equal(Kh.data, K_ref.data)
+    P_ref = go.diff_op(K_ref)
+    assert np.allclose(P.cpu().numpy(), P_ref.data, rtol=1e-14, atol=0)
+    assert np.allclose(deg.cpu().numpy(), np.asarray(K_ref.sum(1)).ravel(), rtol=1e-14, atol=0)
+    assert flags == 0
+    M2 = M.tolil(); M2[3, 3] = 0; M2 = M2.tocsr(); M2.eliminate_zeros()
+    _, _, _, flags = pipeline.symmetrize_normalize(pipeline.DeviceCSR(*_csr_dev(M2), M2.shape), mode, theta, 0.0)
+    assert flags == 2
+
+
 @pytest.mark.parametrize("mode,theta", [("+", None), ("*", None), ("mnn", 0.3)])
 def test_sharded_symmetrise_merge_matches_global(mode, theta):
-    """gtb_sym_merge_* on two row shards (transposed edges prepared the way the all-to-all delivers them)
-    reproduces the single-GPU symmetrise + normalise bit for bit."""
-    from scipy import sparse
+    """The multi-GPU path on one device: the rows of two shards are bucketed by route_count / route_fill, the
+    records a rank would receive are turned into the transposed rows (records_count / scatter / sort) and merged --
+    bit-identical to the single-GPU symmetrise + normalise."""
+    from graphtools_b200 import distributed as gd
     X, _ = synth.gaussian_mixture(3000, 20, n_clusters=4, intrinsic_dim=5, seed=9)
     ref = pipeline.SearchOperand(_dev(X))
     R, _ = pipeline.knn_kernel(None, ref, ref, knn=6, decay=10, thresh=1e-3)
     K, P, deg, _ = pipeline.symmetrize_normalize(R, mode, theta, 0.0)
     Kh, Ph = K.to_scipy(), K.to_scipy(P)
     Rh = R.to_scipy()
-    RT = sparse.csr_matrix(Rh.T); RT.sort_indices()
-    n = 3000
+    n, world = 3000, 2
+    per = gd.rows_per_rank(n, world)
+    bounds = [gd.shard_bounds(n, world, r) for r in range(world)]
     smode = pipeline.SYM_MODES[mode]
-    for lo, hi in ((0, 1536), (1536, 3000)):
-        A, B = Rh[lo:hi], RT[lo:hi]
-        A.sort_indices(); B.sort_indices()
+    sends = []
+    for lo, hi in bounds:
+        pa, ia, va = _csr_dev(Rh[lo:hi])
+        send, counts = gd.cuda_bucket_edges(pa, ia, va, lo, per, world)
+        counts = counts.cpu().numpy()
+        i, j, w = (t.cpu().numpy() for t in gd.unpack_records(send))
+        assert counts.sum() == len(i)
+        assert (np.diff(np.minimum(j // per, world - 1)) >= 0).all()       # destination-major
+        sends.append((send, np.concatenate([[0], np.cumsum(counts)])))
+    for r, (lo, hi) in enumerate(bounds):
         m = hi - lo
-        pa, ia, va = _dev(A.indptr.astype(np.int64)), _dev(A.indices.astype(np.int32)), _dev(A.data)
-        pb, ib, vb = _dev(B.indptr.astype(np.int64)), _dev(B.indices.astype(np.int32)), _dev(B.data)
-        newlen = torch.empty(m, dtype=torch.int32, device="cuda")
-        E.call("gtb_sym_merge_count", pa, ia, va, pb, ib, vb, m, smode, 0.0 if theta is None else theta, newlen)
-        outptr = pipeline.exclusive_scan(newlen)
-        nnz = int(outptr[-1])
-        oi = torch.empty(nnz, dtype=torch.int32, device="cuda")
-        ov = torch.empty(nnz, dtype=torch.float64, device="cuda")
-        pv = torch.empty(nnz, dtype=torch.float64, device="cuda")
-        dg = torch.empty(m, dtype=torch.float64, device="cuda")
-        E.call("gtb_sym_merge_fill", pa, ia, va, pb, ib, vb, m, smode, 0.0 if theta is None else theta, outptr, oi,
-               ov, pv, dg)
+        rec = torch.cat([s[o[r]:o[r + 1]] for s, o in sends]).contiguous()   # what rank r receives (rank-major)
+        k = rec.shape[0]
+        cnt = torch.empty(m, dtype=torch.int32, device="cuda")
+        E.call("gtb_records_count", rec, k, lo, cnt, m)
+        ptr_t = pipeline.exclusive_scan(cnt)
+        t_idx = torch.empty(k, dtype=torch.int32, device="cuda")
+        t_val = torch.empty(k, dtype=torch.float64, device="cuda")
+        E.call("gtb_records_scatter", rec, k, lo, ptr_t, cnt, t_idx, t_val)
+        pipeline.sort_rows(ptr_t, t_idx, t_val, m)
+        pa, ia, va = _csr_dev(Rh[lo:hi])
+        flags = torch.zeros(1, dtype=torch.int32, device="cuda")
+        outptr, oi, ov, pv, dg, _ = pipeline.merge_with_transpose(pa, ia, va, ptr_t, t_idx, t_val, m, lo, smode,
+                                                                  0.0 if theta is None else theta, True, flags)
         Ks, Ps = Kh[lo:hi], Ph[lo:hi]
         assert np.array_equal(outptr.cpu().numpy(), Ks.indptr)
         assert np.array_equal(oi.cpu().numpy(), Ks.indices)
         assert np.array_equal(ov.cpu().numpy(), Ks.data)
-        assert np.allclose(pv.cpu().numpy(), Ps.data, rtol=1e-14, atol=0)
-        assert np.allclose(dg.cpu().numpy(), deg.cpu().numpy()[lo:hi], rtol=1e-14, atol=0)
+        assert np.array_equal(pv.cpu().numpy(), Ps.data)
+        assert np.array_equal(dg.cpu().numpy(), deg.cpu().numpy()[lo:hi])
+        assert int(flags.item()) == 0
+
+
+def test_landmark_operator_is_reproducible_and_handles_long_rows():
+    """csrc/landmark.cu: fixed-point accumulation makes landmark_op / column sums bit-identical from run to run;
+    rows of every tier (<= 32, <= 256, longer) agree with the oracle's C^T K aggregation."""
+    from oracle import graph_oracle as go
+    from graphtools_b200 import landmark as lm
+    n, L = 4000, 300
+    M = _random_kernel(n, 0.004, 2, (5, 900))
+    K = go.symmetrize(M, "+").tocsr(); K.sort_indices()
+    clusters = np.random.default_rng(0).integers(0, L, size=n)
+    clusters[:L] = np.arange(L)
+    op_ref, pnm_ref = go.landmark_operator(K, clusters)
+    labels = _dev(clusters.astype(np.int32))
+    Kd = pipeline.DeviceCSR(*_csr_dev(K), K.shape)
+    outs = []
+    for _ in range(3):
+        pnm, pnm_norm, colsum = lm.aggregate_by_cluster(Kd, labels, L, want_colsum=True)
+        op = lm.landmark_operator(pnm, pnm_norm, colsum, n, L)
+        outs.append((op.cpu().numpy(), colsum.cpu().numpy(), pnm.to_scipy(pnm_norm)))
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+    assert np.allclose(outs[0][0], op_ref, rtol=1e-10, atol=0)
+    T = outs[0][2]
+    pnm_ref = pnm_ref.tocsr(); pnm_ref.sort_indices()
+    assert np.array_equal(T.indptr, pnm_ref.indptr) and np.array_equal(T.indices, pnm_ref.indices)
+    assert np.allclose(T.data, pnm_ref.data, rtol=1e-12, atol=0)
