@@ -43,12 +43,13 @@ _SIGS = {
     "gtb_exclusive_scan": ([_P, c_int64, _P, _P, _P], 1),
     "gtb_cast_indptr": ([_P, c_int64, _P, _P], 1),
     "gtb_transpose_count": ([_P, c_int64, c_int, _P, c_int64, _P], 1),
-    "gtb_transpose_scatter": ([_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P], 1),
+    "gtb_transpose_scatter": ([_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P], 1),
     "gtb_csr_sort_rows": ([_P, _P, _P, c_int64, _P, _P], 2),
+    "gtb_rec_sort_rows": ([_P, _P, c_int64, _P, c_int, _P, _P], 2),
     "gtb_records_count": ([_P, c_int64, c_int, _P, c_int64, _P], 1),
-    "gtb_records_scatter": ([_P, c_int64, c_int, _P, _P, _P, _P, _P], 1),
-    "gtb_sym_merge_count": ([_P, _P, _P, _P, _P, _P, c_int64, c_int, c_double, _P, _P], 1),
-    "gtb_sym_merge_fill": ([_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_double, _P, _P, _P, _P, _P, _P, _P], 1),
+    "gtb_records_scatter": ([_P, c_int64, c_int, _P, _P, _P], 1),
+    "gtb_sym_merge_count": ([_P, _P, _P, _P, _P, c_int64, c_int, c_double, _P, _P], 1),
+    "gtb_sym_merge_fill": ([_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_double, _P, _P, _P, _P, _P, _P, _P], 1),
     "gtb_asym_check": ([_P, _P, _P, c_int64, _P, _P], 1),
     "gtb_row_finalize": ([_P, _P, _P, c_int64, _P, _P, _P, c_int, _P], 1),
     "gtb_anisotropy": ([_P, _P, _P, _P, c_double, c_int64, _P], 1),
@@ -60,8 +61,10 @@ _SIGS = {
     "gtb_cluster_aggregate_count": ([_P, _P, _P, c_int64, _P, c_int, _P, _P, _P], 2),
     "gtb_cluster_aggregate_fill": ([_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P], 3),
     "gtb_landmark_op": ([_P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P], 2),
-    "gtb_dense_kernel": ([_P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, _P, c_double, c_double, c_int, c_double,
-                          _P, _P, _P], 1),
+    "gtb_dense_kernel": ([_P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_double, c_double, c_int,
+                          c_double, _P, _P, _P], 1),
+    "gtb_knn_topk_simt_l1": ([_P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P], 1),
+    "gtb_knn_radius_simt_l1": ([_P, _P, c_int64, c_int64, _P, c_int64, c_int64, c_int, _P, c_int64, _P, _P, _P], 1),
     "gtb_dense_row_scale": ([_P, _P, c_int64, c_int64, _P, _P], 1),
     "gtb_dense_anisotropy": ([_P, _P, c_double, c_int64, _P, _P], 1),
     "gtb_dense_rowsum": ([_P, c_int64, c_int64, _P, _P], 1),
@@ -73,6 +76,7 @@ _PLAIN = {
     "gtb_version": ([], c_int),
     "gtb_col_mean_ws_doubles": ([c_int], c_int64),
     "gtb_scan_ws_elems": ([c_int64], c_int64),
+    "gtb_sym_merge_reg_rows": ([], c_int),
     "gtb_cluster_aggregate_ws_elems": ([c_int], c_int64),
     "gtb_tc_max_kp": ([], c_int),
     "gtb_tc_set_cluster": ([c_int], c_int),

@@ -5,7 +5,10 @@
 // Replaces TraditionalGraph.build_kernel / build_kernel_to_data (reference graphtools/graphs.py
 // :1546-1609, :1651-1677: scipy pdist/squareform/cdist + numpy partition/power/exp) and the dense
 // branches of symmetrize_kernel / apply_anisotropy / normalize (base.py:557-592, :645).
-// Distances are float64 direct differences of the float32 inputs (what pdist computes).
+// Distances are float64 direct differences of the inputs as given -- float32 rows or float64 rows (PCA output,
+// float64 user data), template T -- which is what scipy's pdist / cdist compute.  Metrics: euclidean, cosine,
+// cityblock.  Row sums are NOT accumulated here (a floating-point atomic per tile would make the degree vector
+// depend on the tile order): gtb_dense_rowsum makes one deterministic pass afterwards.
 #include "common.cuh"
 #include "gtb200.h"
 
@@ -24,8 +27,9 @@ __device__ __forceinline__ double sym_dense(int mode, double theta, double a, do
 }
 
 // out[i][j] for i in query rows (Xq), j in reference rows (Xr).
-__global__ void __launch_bounds__(256) dense_kernel(const float* __restrict__ Xq, int64_t nq,
-                                                    const float* __restrict__ Xr, int64_t nr, int d, int what,
+template <typename T>
+__global__ void __launch_bounds__(256) dense_kernel(const T* __restrict__ Xq, int64_t nq,
+                                                    const T* __restrict__ Xr, int64_t nr, int d, int what,
                                                     int metric, const double* __restrict__ bw_q, const double* __restrict__ bw_r,
                                                     double decay, double thresh, double rfac, int symm,
                                                     double theta, double* __restrict__ out,
@@ -64,6 +68,11 @@ __global__ void __launch_bounds__(256) dense_kernel(const float* __restrict__ Xq
 #pragma unroll
           for (int b = 0; b < 4; ++b) acc[a][b] = fma(qv[a], rv[b], acc[a][b]);
         }
+      } else if (metric == 2) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] += fabs(qv[a] - rv[b]);
       } else {
 #pragma unroll
         for (int a = 0; a < 4; ++a)
@@ -92,6 +101,8 @@ __global__ void __launch_bounds__(256) dense_kernel(const float* __restrict__ Xq
           double c = acc[a][b] / (sqrt(qn[a]) * sqrt(rn[b]));
           if (fabs(c) > 1.0) c = copysign(1.0, c);
           dist = 1.0 - c;
+        } else if (metric == 2) {
+          dist = acc[a][b];
         } else {
           dist = sqrt(acc[a][b]);
         }
@@ -120,12 +131,7 @@ __global__ void __launch_bounds__(256) dense_kernel(const float* __restrict__ Xq
         rsum += fabs(v);
       }
     }
-    if (rowsum) {
-      // reduce over the 16 threads sharing this row (same ty => same half-warp)
-#pragma unroll
-      for (int off = 8; off > 0; off >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, off);
-      if (tx == 0 && i < nq) atomicAdd(rowsum + i, rsum);
-    }
+    (void)rsum; (void)rowsum;
   }
 }
 
@@ -170,23 +176,30 @@ __global__ void dense_rowsum_kernel(const double* __restrict__ K, int64_t nq, in
 
 }  // namespace
 
-extern "C" int gtb_dense_kernel(const float* Xq, int64_t nq, const float* Xr, int64_t nr, int d, int what,
+extern "C" int gtb_dense_kernel(const void* Xq, int64_t nq, const void* Xr, int64_t nr, int d, int x_is_f64, int what,
                                 int metric, const double* bw_q, const double* bw_r, double decay, double thresh, int symm,
                                 double theta, double* out, double* rowsum, void* stream) {
   GTB_CHECK_ARG(nq > 0 && nr > 0 && d > 0, "empty input");
   GTB_CHECK_ARG(what >= 0 && what <= 2, "bad mode");
-  GTB_CHECK_ARG(metric == 0 || metric == 1, "metric must be 0 (euclidean) or 1 (cosine)");
+  GTB_CHECK_ARG(metric >= 0 && metric <= 2, "metric must be 0 (euclidean), 1 (cosine) or 2 (cityblock)");
   GTB_CHECK_ARG(what == 0 || bw_q != nullptr, "bandwidth required");
   GTB_CHECK_ARG(what != 2 || (bw_r != nullptr && nq == nr), "symmetric mode needs a square problem");
   cudaStream_t st = (cudaStream_t)stream;
-  if (rowsum) GTB_CUDA(cudaMemsetAsync(rowsum, 0, sizeof(double) * nq, st));
   dim3 grid((unsigned)gtb_cdiv(nr, DT), (unsigned)gtb_cdiv(nq, DT));
   // support radius factor; +inf when nothing is thresholded away (thresh <= 0) or in distance mode
   double rfac = INFINITY;
   if (what != DENSE_DIST && thresh > 0 && thresh < 1 && decay > 0) rfac = pow(-log(thresh), 1.0 / decay) * (1.0 + 1e-9);
-  dense_kernel<<<grid, 256, 0, st>>>(Xq, nq, Xr, nr, d, what, metric, bw_q, bw_r, decay, thresh, rfac, symm, theta, out,
-                                     rowsum);
+  if (x_is_f64)
+    dense_kernel<double><<<grid, 256, 0, st>>>((const double*)Xq, nq, (const double*)Xr, nr, d, what, metric, bw_q, bw_r,
+                                               decay, thresh, rfac, symm, theta, out, nullptr);
+  else
+    dense_kernel<float><<<grid, 256, 0, st>>>((const float*)Xq, nq, (const float*)Xr, nr, d, what, metric, bw_q, bw_r,
+                                              decay, thresh, rfac, symm, theta, out, nullptr);
   GTB_CHECK_LAUNCH();
+  if (rowsum) {
+    dense_rowsum_kernel<<<(unsigned)gtb_cdiv(nq * 32, 256), 256, 0, st>>>(out, nq, nr, rowsum);
+    GTB_CHECK_LAUNCH();
+  }
   return GTB_OK;
 }
 

@@ -25,7 +25,8 @@ struct RowParams {
   double thresh; double rfac;  // rfac = (-ln thresh)^(1/decay)
   const double* bw_fixed; int bw_mode;  // 0 adaptive (k-th neighbour), 1 scalar, 2 per-row
   double bw_scale; double bw_floor;     // bw_floor = eps (np.finfo(float).eps)
-  int metric;                           // 0 euclidean, 1 cosine (1 - x.y / (|x||y|), sklearn cosine_distances)
+  int metric;                           // 0 euclidean, 1 cosine (1 - x.y / (|x||y|), sklearn cosine_distances),
+                                        // 2 cityblock (sum |x - y|, sklearn manhattan_distances)
 };
 
 // exact squared distance between query row xq and reference row xr, cooperatively by one warp
@@ -64,8 +65,13 @@ __device__ __forceinline__ double warp_dist2(const T* __restrict__ xq, const T* 
 // Cosine metric.  The fast pass runs on the row-normalised copies, where |x^ - y^|^2 = 2 (1 - cos) = 2 d_cos: same
 // ordering, and the certification arithmetic below converts between the metric's own units (in which key[] holds the
 // SQUARED exact distance, so sqrt(key) is the distance for both metrics) and search-space squared distances.
-__device__ __forceinline__ double search2_of_key(double key, int metric) { return metric == 0 ? key : 2.0 * sqrt(key); }
-__device__ __forceinline__ double search2_of_radius(double r, int metric) { return metric == 0 ? r * r : 2.0 * r; }
+// Cityblock: the fast pass accumulates sum |x - y| itself, so the search-space value IS the distance.
+__device__ __forceinline__ double search2_of_key(double key, int metric) {
+  return metric == 0 ? key : (metric == 1 ? 2.0 * sqrt(key) : sqrt(key));
+}
+__device__ __forceinline__ double search2_of_radius(double r, int metric) {
+  return metric == 0 ? r * r : (metric == 1 ? 2.0 * r : r);
+}
 
 // squared cosine distance between two rows of the ORIGINAL data, float64, one warp
 template <typename T>
@@ -84,6 +90,21 @@ __device__ __forceinline__ double warp_cos2(const T* __restrict__ xq, const T* _
   double dc = 1.0 - dot / (sqrt(nx) * sqrt(ny));
   dc = fmin(fmax(dc, 0.0), 2.0);          // np.clip(S, 0, 2) in sklearn cosine_distances
   return dc * dc;
+}
+
+// squared cityblock distance between two rows of the ORIGINAL data, float64, one warp
+template <typename T>
+__device__ __forceinline__ double warp_l1sq(const T* __restrict__ xq, const T* __restrict__ xr, int d, int lane) {
+  double s = 0.0;
+  for (int k = lane; k < d; k += 32) s += fabs((double)xq[k] - (double)xr[k]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  return s * s;
+}
+
+template <typename T>
+__device__ __forceinline__ double warp_metric2(const T* xq, const T* xr, int d, int lane, int metric) {
+  return metric == 1 ? warp_cos2<T>(xq, xr, d, lane) : warp_l1sq<T>(xq, xr, d, lane);
 }
 
 __device__ __forceinline__ int next_pow2(int x) {
@@ -206,10 +227,10 @@ __global__ void __launch_bounds__(R1_WARPS * 32, 6) refine_topk_kernel(Refine1Pa
   const T* Xr = reinterpret_cast<const T*>(rp.Xr);
   int n_cand = 0;
   bool vec = false;
-  if (rp.metric == 1) {
+  if (rp.metric != 0) {
     for (int c0 = 0; c0 < S; ++c0) {
       const int j = p.cand_idx[row * p.cand_stride + c0];
-      const double v = (j >= 0) ? warp_cos2<T>(xq, Xr + (int64_t)j * rp.d, rp.d, lane) : DBL_MAX * 2.0;
+      const double v = (j >= 0) ? warp_metric2<T>(xq, Xr + (int64_t)j * rp.d, rp.d, lane, rp.metric) : DBL_MAX * 2.0;
       if (j >= 0) ++n_cand;
       if (lane == 0) { key[c0] = v; idx[c0] = (j >= 0) ? j : 0x7fffffff; }
     }
@@ -217,7 +238,7 @@ __global__ void __launch_bounds__(R1_WARPS * 32, 6) refine_topk_kernel(Refine1Pa
   if constexpr (sizeof(T) == 4) {
     vec = ((rp.d & 3) == 0) && (((reinterpret_cast<uintptr_t>(rp.Xq) | reinterpret_cast<uintptr_t>(rp.Xr)) & 15) == 0);
   }
-  if (rp.metric == 1) {
+  if (rp.metric != 0) {
     // done above
   } else if (p.staged && sizeof(T) == 4) {
     if constexpr (sizeof(T) == 4) {
@@ -365,7 +386,12 @@ __global__ void __launch_bounds__(R1_WARPS * 32, 6) refine_topk_kernel(Refine1Pa
   float tau = p.tau[row * p.ntau];
   for (int t = 1; t < p.ntau; ++t) tau = fminf(tau, p.tau[row * p.ntau + t]);  // lists of disjoint reference subsets
   const bool all_found = isinf(tau);  // list never filled: every reference is a candidate
-  const double E = p.eps_rel * ((double)p.qn2[row] + (double)p.maxrn2);
+  // euclidean / cosine: absolute bound relative to the squared norms of the centred rows; cityblock: the float32
+  // accumulation of |x - y| is accurate RELATIVE to the distance (eps_rel * tau), plus the rounding of float64
+  // inputs to the float32 search copy (2^-23 of the rows' L1 norms; qn2 is NULL for float32 inputs)
+  const double E = (rp.metric == 2)
+                       ? p.eps_rel * fabs((double)tau) + (p.qn2 ? ((double)p.qn2[row] + (double)p.maxrn2) * 0x1p-23 : 0.0)
+                       : p.eps_rel * ((double)p.qn2[row] + (double)p.maxrn2);
   const double rho2 = (double)tau - E;  // exact d2 of every non-candidate is >= rho2
   double bw = 0.0, r_search = 0.0, dk = 0.0;
   bool done, bw_cert = true;
@@ -397,6 +423,7 @@ __global__ void __launch_bounds__(R1_WARPS * 32, 6) refine_topk_kernel(Refine1Pa
     p.nzero[row] = nz;
     if (!done) {
       double l2 = search2_of_radius(r_search, rp.metric) * (1.0 + 1e-6) + E;
+      if (rp.metric == 2) l2 += 2.0 * p.eps_rel * r_search;     // relative error at the radius, not at tau
       p.lim2_out[row] = __double2float_ru(l2);
       p.n_keep[row] = 0;
     } else {
@@ -472,7 +499,7 @@ __global__ void __launch_bounds__(R2_THREADS) refine_ball_kernel(Refine2Params p
   const T* Xr = reinterpret_cast<const T*>(rp.Xr);
   for (int c = warp; c < L; c += R2_THREADS / 32) {
     int j = p.seg_idx[p0 + c];
-    double d2 = (rp.metric == 1) ? warp_cos2<T>(xq, Xr + (int64_t)j * rp.d, rp.d, lane)
+    double d2 = (rp.metric != 0) ? warp_metric2<T>(xq, Xr + (int64_t)j * rp.d, rp.d, lane, rp.metric)
                                  : warp_dist2<T>(xq, Xr + (int64_t)j * rp.d, rp.d, lane);
     if (lane == 0) { key[c] = d2; idx[c] = j; }
   }
@@ -593,7 +620,7 @@ extern "C" int gtb_refine_topk(const void* Xq, int64_t nq, const void* Xr, int d
   GTB_CHECK_ARG(nq > 0 && S > 0 && S <= R1_CAP, "S out of range");
   GTB_CHECK_ARG(knn >= 1 && knn <= S, "knn must be in [1, S]");
   GTB_CHECK_ARG(decay < 0 || (thresh > 0 && thresh <= 1), "thresh must be in (0, 1]");
-  GTB_CHECK_ARG(x_kind >= 0 && x_kind <= 3, "x_kind: bit 0 = float64 rows, bit 1 = cosine metric");
+  GTB_CHECK_ARG(x_kind >= 0 && x_kind <= 5, "x_kind: bit 0 = float64 rows, bits 1-2 = metric (0 euclidean, 1 cosine, 2 cityblock)");
   const int x_is_f64 = x_kind & 1;
   Refine1Params p;
   p.rp = make_row_params(Xq, Xr, d, knn, kmax, decay, thresh, bw_fixed, bw_mode, bw_scale, x_kind >> 1);
@@ -642,7 +669,7 @@ extern "C" int gtb_refine_ball(const void* Xq, const int32_t* todo_rows, const i
   GTB_CHECK_ARG(nt > 0, "no rows");
   GTB_CHECK_ARG(cap >= 2 && (cap & (cap - 1)) == 0 && cap <= 8192, "cap must be a power of two <= 8192");
   cudaStream_t st = (cudaStream_t)stream;
-  GTB_CHECK_ARG(x_kind >= 0 && x_kind <= 3, "x_kind: bit 0 = float64 rows, bit 1 = cosine metric");
+  GTB_CHECK_ARG(x_kind >= 0 && x_kind <= 5, "x_kind: bit 0 = float64 rows, bits 1-2 = metric (0 euclidean, 1 cosine, 2 cityblock)");
   const int x_is_f64 = x_kind & 1;
   Refine2Params p;
   p.rp = make_row_params(Xq, Xr, d, knn, kmax, decay, thresh, bw_fixed, bw_mode, bw_scale, x_kind >> 1);

@@ -43,7 +43,10 @@ struct SearchParams {
   int32_t* rowcnt;
 };
 
-template <int S, bool RADIUS>
+// L1 = true: cityblock metric.  The tile accumulates sum_k |x_k - y_k| directly (two FADDs per pair and feature
+// instead of one FFMA; there is no GEMM form of the L1 distance), the norms are not used, and padding columns are
+// masked by index (their zero rows would otherwise be at a finite distance).
+template <int S, bool RADIUS, bool L1>
 __global__ void __launch_bounds__(NTHREADS, (S <= 64 ? 2 : 1))
 search_simt_kernel(SearchParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -63,7 +66,7 @@ search_simt_kernel(SearchParams p) {
   // per-row state
   if (tid < TM) {
     int64_t q = q0 + tid;
-    float nx = (q < p.nq) ? p.qn2[q] : 0.f;
+    float nx = (q < p.nq && !L1) ? p.qn2[q] : 0.f;
     nx_s[tid] = nx;
     if (RADIUS) thr_s[tid] = (q < p.nq) ? (p.lim2[q] - nx) : -gtb_inf_f();
     else thr_s[tid] = (q < p.nq) ? gtb_inf_f() : -gtb_inf_f();
@@ -105,7 +108,7 @@ search_simt_kernel(SearchParams p) {
     const int64_t tile = c / nk;
     const int kc = (int)(c - tile * nk);
     const bool last = (kc == nk - 1);
-    if (last) ny = __ldg(reinterpret_cast<const float4*>(p.rn2 + tile * TN) + lane);
+    if (last && !L1) ny = __ldg(reinterpret_cast<const float4*>(p.rn2 + tile * TN) + lane);
     const float* a_base = As + st * KC * TM + warp * 16;
     const float* b_base = Bs + st * KC * TN + lane * 4;
 #pragma unroll
@@ -120,10 +123,17 @@ search_simt_kernel(SearchParams p) {
       float4 b = *reinterpret_cast<const float4*>(b_base + kk * TN);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        acc[i][0] = fmaf(a[i], b.x, acc[i][0]);
-        acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
-        acc[i][2] = fmaf(a[i], b.z, acc[i][2]);
-        acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+        if (L1) {
+          acc[i][0] += fabsf(a[i] - b.x);
+          acc[i][1] += fabsf(a[i] - b.y);
+          acc[i][2] += fabsf(a[i] - b.z);
+          acc[i][3] += fabsf(a[i] - b.w);
+        } else {
+          acc[i][0] = fmaf(a[i], b.x, acc[i][0]);
+          acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+          acc[i][2] = fmaf(a[i], b.z, acc[i][2]);
+          acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+        }
       }
     }
     if (!last) continue;
@@ -137,7 +147,11 @@ search_simt_kernel(SearchParams p) {
       float t = thr_s[r];
       float v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { v[j] = fmaf(-2.f, acc[i][j], nyv[j]); acc[i][j] = 0.f; }
+      for (int j = 0; j < 4; ++j) {
+        if (L1) v[j] = (colbase + j < p.nr) ? acc[i][j] : gtb_inf_f();
+        else v[j] = fmaf(-2.f, acc[i][j], nyv[j]);
+        acc[i][j] = 0.f;
+      }
       if (RADIUS) {
         int cnt = (v[0] <= t) + (v[1] <= t) + (v[2] <= t) + (v[3] <= t);
         unsigned any = __ballot_sync(0xffffffffu, cnt > 0);
@@ -223,10 +237,10 @@ search_simt_kernel(SearchParams p) {
   }
 }
 
-template <int S, bool RADIUS>
+template <int S, bool RADIUS, bool L1 = false>
 int launch(const SearchParams& p, cudaStream_t st) {
   size_t smem = sizeof(float) * (NST * KC * (TM + TN) + 2 * TM) + (RADIUS ? 0 : (size_t)TM * S * 8);
-  auto kern = search_simt_kernel<S, RADIUS>;
+  auto kern = search_simt_kernel<S, RADIUS, L1>;
   GTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)(p.nq_pad / TM), NTHREADS, smem, st>>>(p);
   GTB_CHECK_LAUNCH();
@@ -263,4 +277,36 @@ extern "C" int gtb_knn_radius_simt(const float* QT, const float* qn2, const floa
   p.nr_pad = nr_pad; p.d_pad = d_pad; p.lim2 = lim2; p.pairs = reinterpret_cast<int2*>(pairs);
   p.capacity = (unsigned long long)capacity; p.counter = counter; p.rowcnt = rowcnt;
   return launch<16, true>(p, (cudaStream_t)stream);
+}
+
+// cityblock (L1) variants: same operands (k-major rows, NOT centred -- |x - y| is translation invariant and the
+// uncentred float32 copy keeps the rounding error relative to the distance itself), approximate distance
+// sum_k |x_k - y_k| in float32; tau / lim hold distances, not squared distances.  Replaces sklearn's brute-force
+// manhattan search behind knn_tree for distance="cityblock" (graphs.py:763-768).
+extern "C" int gtb_knn_topk_simt_l1(const float* QT, int64_t nq, int64_t nq_pad, const float* RT, int64_t nr,
+                                    int64_t nr_pad, int d_pad, int S, int32_t* cand_idx, float* tau, void* stream) {
+  GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TM == 0 && nr_pad % TN == 0 && d_pad % KC == 0, "bad shape");
+  SearchParams p{};
+  p.QT = QT; p.nq = nq; p.nq_pad = nq_pad; p.RT = RT; p.nr = nr;
+  p.nr_pad = nr_pad; p.d_pad = d_pad; p.cand_idx = cand_idx; p.tau = tau;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (S) {
+    case 16: return launch<16, false, true>(p, st);
+    case 32: return launch<32, false, true>(p, st);
+    case 48: return launch<48, false, true>(p, st);
+    case 64: return launch<64, false, true>(p, st);
+    case 128: return launch<128, false, true>(p, st);
+    default: gtb_set_error("gtb_knn_topk: S must be one of 16,32,48,64,128 (got %d)", S); return GTB_ERR_ARG;
+  }
+}
+
+extern "C" int gtb_knn_radius_simt_l1(const float* QT, const float* lim, int64_t nq, int64_t nq_pad, const float* RT,
+                                      int64_t nr, int64_t nr_pad, int d_pad, int32_t* pairs, int64_t capacity,
+                                      unsigned long long* counter, int32_t* rowcnt, void* stream) {
+  GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TM == 0 && nr_pad % TN == 0 && d_pad % KC == 0, "bad shape");
+  SearchParams p{};
+  p.QT = QT; p.nq = nq; p.nq_pad = nq_pad; p.RT = RT; p.nr = nr;
+  p.nr_pad = nr_pad; p.d_pad = d_pad; p.lim2 = lim; p.pairs = reinterpret_cast<int2*>(pairs);
+  p.capacity = (unsigned long long)capacity; p.counter = counter; p.rowcnt = rowcnt;
+  return launch<16, true, true>(p, (cudaStream_t)stream);
 }

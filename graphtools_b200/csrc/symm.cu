@@ -5,18 +5,22 @@
 // matrix.py:16-29), sklearn normalize(K, "l1") (base.py:645), kernel_degree (base.py:648-666) and the diagonal
 // check of BaseGraph._build_kernel (base.py:553-554).
 //
-//   transpose_count   histogram of the column indices                        (thread per edge)
-//   scan              row pointers of R^T                                    (sparse.cu, single pass)
-//   transpose_scatter every edge (i, j, w) -> slot of row j of R^T           (8 lanes per row, atomic cursor)
-//   csr_sort_rows     rows of R^T ordered by column (= source row i)         (tiered segmented sort, in place)
-//   sym_merge<count>  |row i of R  UNION  row i of R^T| under the merge rule (warp per row)
+//   transpose_count   histogram of the column indices                          (thread per edge, one atomic each)
+//   scan              row pointers of R^T (sparse.cu, single pass), cast to 32-bit cursors
+//   transpose_scatter every edge (i, j, w) -> one 16-byte record {i, j, w} in row j of R^T: ONE atomic on the row's
+//                     cursor (which already holds the row's start) + ONE 16-byte store per edge
+//   rec_sort_rows     rows that are too long for the register path of the merge are ordered by column, in place
+//   sym_merge<count>  |row i of R  UNION  row i of R^T| under the merge rule     (warp per row)
 //   scan
 //   sym_merge<fill>   K row (column-sorted), P = K / rowsum, degree, diagonal flag, one sweep
 //
-// Both inputs of the merge are column-sorted with unique columns, so the result does not depend on the order
-// in which the atomics of the scatter landed: K, P and the degree vector are bit-reproducible, and identical
-// between the single-GPU build and the row-sharded multi-GPU build (same kernels, same per-row order).
-// All three merge rules are symmetric functions s(w, w'), hence K is bitwise symmetric.
+// The merge takes A = a row of R (column-sorted CSR) and T = the matching row of R^T as records in ARRIVAL order.
+// Rows with |A| + |T| <= 32 (every row of a kNN kernel on low-intrinsic-dimension data) live one element per lane:
+// mutual edges are found with one match.any on the column, output positions by counting -- no sort at all, and the
+// result does not depend on the order in which the atomics of the scatter landed (columns are unique within A and
+// within T).  Longer rows are sorted first and merged with two pointers.  K, P and the degree vector are therefore
+// bit-reproducible and identical between the single-GPU build and the row-sharded multi-GPU build (same kernels,
+// same per-row order).  All three merge rules are symmetric functions s(w, w'), hence K is bitwise symmetric.
 #include "common.cuh"
 #include "gtb200.h"
 
@@ -27,39 +31,46 @@ enum { SYM_PLUS = 0, SYM_MULT = 1, SYM_MNN = 2 };
 __device__ __forceinline__ double sym_combine(int mode, double theta, double w, double wr) {
   if (mode == SYM_PLUS) return (w + wr) / 2;
   if (mode == SYM_MULT) return w * wr;
+  // scipy: theta * K.minimum(K.T) + (1 - theta) * K.maximum(K.T) -- two rounded products, one rounded sum
   const double lo = fmin(w, wr), hi = fmax(w, wr);
-  return theta * lo + (1 - theta) * hi;
+  return __dadd_rn(__dmul_rn(theta, lo), __dmul_rn(1 - theta, hi));
 }
 
 constexpr int GRP = 8;  // lanes cooperating on one raw row (~9 edges)
 
 // ------------------------------------------------------------------------------ transpose
+struct __align__(16) EdgeRec { int32_t i, j; double w; };     // edge (i, j, w): entry (j, i) of the transposed matrix
+
+__device__ __forceinline__ void store_rec(EdgeRec* dst, int32_t i, int32_t j, double w) {
+  int4 v;
+  v.x = i; v.y = j;
+  v.z = __double2loint(w); v.w = __double2hiint(w);
+  *reinterpret_cast<int4*>(dst) = v;
+}
+
 __global__ void __launch_bounds__(256) transpose_count_kernel(const int32_t* __restrict__ idx, int64_t nnz,
                                                               int32_t col0, int32_t* __restrict__ cnt) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x)
     atomicAdd(cnt + (idx[e] - col0), 1);
 }
 
-// cnt[] holds the row lengths of R^T on entry and is counted down to zero: slot = ptr_t[j] + (--cnt[j])
+// cursor[j] = start of row j of the transposed matrix on entry (32-bit copy of the scanned row pointers); every edge
+// takes the next slot of its row with one atomic and writes its record with one 16-byte store
 __global__ void __launch_bounds__(256) transpose_scatter_kernel(
     const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
-    int64_t n_rows, int32_t row0, int32_t col0, const int64_t* __restrict__ ptr_t, int32_t* __restrict__ cnt,
-    int32_t* __restrict__ t_idx, double* __restrict__ t_val) {
+    int64_t n_rows, int32_t row0, int32_t col0, int32_t* __restrict__ cursor, EdgeRec* __restrict__ t_rec) {
   const int sub = threadIdx.x % GRP;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GRP;
   if (row >= n_rows) return;
   const int64_t e1 = indptr[row + 1];
   for (int64_t e = indptr[row] + sub; e < e1; e += GRP) {
-    const int32_t j = idx[e] - col0;
-    const int64_t o = ptr_t[j] + (atomicSub(cnt + j, 1) - 1);
-    t_idx[o] = (int32_t)row + row0;
-    t_val[o] = val[e];
+    const int32_t j = idx[e];
+    const int32_t o = atomicAdd(cursor + (j - col0), 1);
+    store_rec(t_rec + o, (int32_t)row + row0, j, val[e]);
   }
 }
 
 // the same two steps for a list of packed edge records {i, j, w} (what the all-to-all delivers)
-struct __align__(16) EdgeRec { int32_t i, j; double w; };
-
 __global__ void __launch_bounds__(256) records_count_kernel(const EdgeRec* __restrict__ rec, int64_t k, int32_t col0,
                                                             int32_t* __restrict__ cnt) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < k; e += (int64_t)gridDim.x * blockDim.x)
@@ -67,28 +78,48 @@ __global__ void __launch_bounds__(256) records_count_kernel(const EdgeRec* __res
 }
 
 __global__ void __launch_bounds__(256) records_scatter_kernel(const EdgeRec* __restrict__ rec, int64_t k, int32_t col0,
-                                                              const int64_t* __restrict__ ptr_t,
-                                                              int32_t* __restrict__ cnt, int32_t* __restrict__ t_idx,
-                                                              double* __restrict__ t_val) {
+                                                              int32_t* __restrict__ cursor,
+                                                              EdgeRec* __restrict__ t_rec) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < k; e += (int64_t)gridDim.x * blockDim.x) {
-    const EdgeRec r = rec[e];
-    const int32_t j = r.j - col0;
-    const int64_t o = ptr_t[j] + (atomicSub(cnt + j, 1) - 1);
-    t_idx[o] = r.i;
-    t_val[o] = r.w;
+    const int4 r = reinterpret_cast<const int4*>(rec)[e];
+    const int32_t o = atomicAdd(cursor + (r.y - col0), 1);
+    reinterpret_cast<int4*>(t_rec)[o] = r;
   }
 }
 
 // ------------------------------------------------------------------------------ segmented sort (in place)
-// Rows of a CSR ordered by column; columns are unique within a row.  Tiers: <= 32 entries: one per lane, rank by
-// counting (3 instructions per entry, no network); <= SORT_WARP_CAP: warp bitonic in shared memory; longer rows
-// are left to csr_sort_long_kernel (block per row: shared memory up to SORT_BLOCK_CAP, global memory beyond).
+// Rows of a CSR ordered by column; columns are unique within a row.  Storage policies: separate index / value arrays
+// (MNN block assembly) or 16-byte edge records keyed by .i (rows of a transposed matrix).  Tiers: <= 32 entries: one
+// per lane, rank by counting (3 instructions per entry, no network); <= SORT_WARP_CAP: warp bitonic in shared
+// memory; longer rows are left to csr_sort_long_kernel (block per row: shared memory up to SORT_BLOCK_CAP, global
+// memory beyond).  `pa` (optional): rows whose length plus the length of the matching row of `pa` stays <= min_total
+// are skipped -- the merge handles those unsorted.
 constexpr int SORT_WARPS = 4, SORT_WARP_CAP = 256, SORT_BLOCK_CAP = 4096, SORT_BLOCK_THREADS = 256;
 
-__global__ void __launch_bounds__(SORT_WARPS * 32) csr_sort_rows_kernel(const int64_t* __restrict__ ptr,
-                                                                        int32_t* __restrict__ idx,
-                                                                        double* __restrict__ val, int64_t n,
-                                                                        int32_t* __restrict__ has_long) {
+struct SoAStore {
+  int32_t* idx; double* val;
+  __device__ __forceinline__ int32_t key(int64_t p) const { return idx[p]; }
+  __device__ __forceinline__ double pay(int64_t p) const { return val[p]; }
+  __device__ __forceinline__ int32_t aux(int64_t) const { return 0; }
+  __device__ __forceinline__ void put(int64_t p, int32_t k, double v, int32_t) const { idx[p] = k; val[p] = v; }
+};
+struct RecStore {
+  EdgeRec* rec;
+  __device__ __forceinline__ int32_t key(int64_t p) const { return rec[p].i; }
+  __device__ __forceinline__ double pay(int64_t p) const { return rec[p].w; }
+  __device__ __forceinline__ int32_t aux(int64_t p0) const { return rec[p0].j; }      // constant within a row
+  __device__ __forceinline__ void put(int64_t p, int32_t k, double v, int32_t j) const { store_rec(rec + p, k, j, v); }
+};
+
+__device__ __forceinline__ bool sort_skips(const int64_t* __restrict__ pa, int64_t row, int64_t L, int min_total) {
+  const int64_t la = pa ? (pa[row + 1] - pa[row]) : 0;
+  return L <= 1 || la + L <= min_total;
+}
+
+template <typename Store>
+__global__ void __launch_bounds__(SORT_WARPS * 32) csr_sort_rows_kernel(const int64_t* __restrict__ ptr, Store st,
+                                                                        int64_t n, const int64_t* __restrict__ pa,
+                                                                        int min_total, int32_t* __restrict__ has_long) {
   __shared__ int32_t ks[SORT_WARPS][SORT_WARP_CAP];
   __shared__ double vs[SORT_WARPS][SORT_WARP_CAP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -96,36 +127,38 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) csr_sort_rows_kernel(const in
   if (row >= n) return;
   const int64_t p0 = ptr[row];
   const int64_t L = ptr[row + 1] - p0;
-  if (L <= 1) return;
+  if (sort_skips(pa, row, L, min_total)) return;
   if (L <= 32) {
     int32_t c = 0x7fffffff;
     double w = 0.0;
-    if (lane < L) { c = idx[p0 + lane]; w = val[p0 + lane]; }
+    const int32_t aux = st.aux(p0);
+    if (lane < L) { c = st.key(p0 + lane); w = st.pay(p0 + lane); }
     int rank = 0;
     for (int k = 0; k < (int)L; ++k) rank += (__shfl_sync(0xffffffffu, c, k) < c);
     __syncwarp();
-    if (lane < L) { idx[p0 + rank] = c; val[p0 + rank] = w; }
+    if (lane < L) st.put(p0 + rank, c, w, aux);
   } else if (L <= SORT_WARP_CAP) {
     int32_t* k = ks[warp];
     double* v = vs[warp];
+    const int32_t aux = st.aux(p0);
     int np2 = 64;
     while (np2 < L) np2 <<= 1;
     for (int t = lane; t < np2; t += 32) {
-      if (t < L) { k[t] = idx[p0 + t]; v[t] = val[p0 + t]; }
+      if (t < L) { k[t] = st.key(p0 + t); v[t] = st.pay(p0 + t); }
       else { k[t] = 0x7fffffff; v[t] = 0.0; }
     }
     __syncwarp();
     auto sync = [] { __syncwarp(); };
     GTB_BITONIC_SORT(k, v, np2, lane, 32, sync, int32_t, double);
-    for (int t = lane; t < L; t += 32) { idx[p0 + t] = k[t]; val[p0 + t] = v[t]; }
+    for (int t = lane; t < L; t += 32) st.put(p0 + t, k[t], v[t], aux);
   } else if (lane == 0) {
     *has_long = 1;
   }
 }
 
-__global__ void __launch_bounds__(SORT_BLOCK_THREADS) csr_sort_long_kernel(const int64_t* __restrict__ ptr,
-                                                                           int32_t* __restrict__ idx,
-                                                                           double* __restrict__ val, int64_t n,
+template <typename Store>
+__global__ void __launch_bounds__(SORT_BLOCK_THREADS) csr_sort_long_kernel(const int64_t* __restrict__ ptr, Store st,
+                                                                           int64_t n,
                                                                            const int32_t* __restrict__ has_long) {
   extern __shared__ __align__(16) unsigned char sort_smem[];
   double* v = reinterpret_cast<double*>(sort_smem);                    // [SORT_BLOCK_CAP]
@@ -148,16 +181,18 @@ __global__ void __launch_bounds__(SORT_BLOCK_THREADS) csr_sort_long_kernel(const
         const int64_t row = base + w * 32 + b;
         const int64_t p0 = ptr[row];
         const int64_t L = ptr[row + 1] - p0;
+        const int32_t aux = st.aux(p0);
+        __syncthreads();
         if (L <= SORT_BLOCK_CAP) {
           int np2 = 512;
           while (np2 < L) np2 <<= 1;
           for (int t = tid; t < np2; t += SORT_BLOCK_THREADS) {
-            if (t < L) { k[t] = idx[p0 + t]; v[t] = val[p0 + t]; }
+            if (t < L) { k[t] = st.key(p0 + t); v[t] = st.pay(p0 + t); }
             else { k[t] = 0x7fffffff; v[t] = 0.0; }
           }
           __syncthreads();
           GTB_BITONIC_SORT(k, v, np2, tid, SORT_BLOCK_THREADS, sync, int32_t, double);
-          for (int t = tid; t < L; t += SORT_BLOCK_THREADS) { idx[p0 + t] = k[t]; val[p0 + t] = v[t]; }
+          for (int t = tid; t < L; t += SORT_BLOCK_THREADS) st.put(p0 + t, k[t], v[t], aux);
           __syncthreads();
         } else {
           // hub rows beyond the shared-memory tile: bitonic network straight on global memory, in the form whose
@@ -165,17 +200,16 @@ __global__ void __launch_bounds__(SORT_BLOCK_THREADS) csr_sort_long_kernel(const
           // virtual +infinity padding past L then never has to move, so no scratch row is needed
           int64_t np2 = SORT_BLOCK_CAP;
           while (np2 < L) np2 <<= 1;
-          int32_t* gk = idx + p0;
-          double* gv = val + p0;
           for (int64_t kk = 2; kk <= np2; kk <<= 1) {
             for (int64_t j = kk >> 1; j > 0; j >>= 1) {
               for (int64_t t = tid; t < L; t += SORT_BLOCK_THREADS) {
                 const int64_t q = (j == (kk >> 1)) ? (t ^ (kk - 1)) : (t ^ j);
                 if (q > t && q < L) {
-                  const int32_t a = gk[t], b2 = gk[q];
+                  const int32_t a = st.key(p0 + t), b2 = st.key(p0 + q);
                   if (a > b2) {
-                    const double va = gv[t], vb = gv[q];
-                    gk[t] = b2; gk[q] = a; gv[t] = vb; gv[q] = va;
+                    const double va = st.pay(p0 + t), vb = st.pay(p0 + q);
+                    st.put(p0 + t, b2, vb, aux);
+                    st.put(p0 + q, a, va, aux);
                   }
                 }
               }
@@ -190,29 +224,37 @@ __global__ void __launch_bounds__(SORT_BLOCK_THREADS) csr_sort_long_kernel(const
   }
 }
 
-// ------------------------------------------------------------------------------ merge
-// Row r of A = raw kernel rows [pa, ia, va] (columns global), row r of T = rows of the transposed matrix
-// [pt, it, vt]; both column-sorted.  FILL = false: newlen[r] = number of non-zero results; FILL = true: K row,
-// P = K / sum|K|, degree, flags bit 1 when the row has no diagonal entry (global row id = row0 + r).
-constexpr int MRG_WARPS = 8;
-
-// number of entries of the sorted slice a[0, n) that are < c
-__device__ __forceinline__ int lower_bound_g(const int32_t* __restrict__ a, int n, int32_t c) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (a[mid] < c) lo = mid + 1; else hi = mid;
-  }
-  return lo;
+template <typename Store>
+int launch_sort(const int64_t* ptr, Store st, int64_t n, const int64_t* pa, int min_total, int32_t* has_long,
+                cudaStream_t stream) {
+  GTB_CUDA(cudaMemsetAsync(has_long, 0, sizeof(int32_t), stream));
+  csr_sort_rows_kernel<Store><<<(unsigned)gtb_cdiv(n, SORT_WARPS), SORT_WARPS * 32, 0, stream>>>(ptr, st, n, pa,
+                                                                                               min_total, has_long);
+  GTB_CHECK_LAUNCH();
+  const size_t smem = (size_t)SORT_BLOCK_CAP * 12;
+  GTB_CUDA(cudaFuncSetAttribute(csr_sort_long_kernel<Store>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = gtb_cdiv(n, SORT_BLOCK_THREADS);
+  csr_sort_long_kernel<Store><<<(unsigned)(blocks < 148 * 4 ? blocks : 148 * 4), SORT_BLOCK_THREADS, smem, stream>>>(
+      ptr, st, n, has_long);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
 }
+
+// ------------------------------------------------------------------------------ merge
+// Row r of A = raw kernel rows [pa, ia, va] (column-sorted, columns global), row r of T = records [pt, tr] of the
+// transposed matrix (entry column = .i, value = .w): in arrival order when |A| + |T| <= 32, column-sorted otherwise
+// (rec_sort_rows).  FILL = false: newlen[r] = number of non-zero results; FILL = true: K row, P = K / sum|K|, degree,
+// flags bit 1 when the row has no diagonal entry (global row id = row0 + r).
+constexpr int MRG_WARPS = 8;
+constexpr int MRG_REG = 32;          // longest row handled one element per lane
 
 template <bool FILL>
 __global__ void __launch_bounds__(MRG_WARPS * 32) sym_merge_kernel(
     const int64_t* __restrict__ pa, const int32_t* __restrict__ ia, const double* __restrict__ va,
-    const int64_t* __restrict__ pt, const int32_t* __restrict__ it, const double* __restrict__ vt, int64_t n_rows,
-    int32_t row0, int mode, double theta, int32_t* __restrict__ newlen, const int64_t* __restrict__ outptr,
-    int32_t* __restrict__ out_idx, double* __restrict__ out_val, double* __restrict__ p_val,
-    double* __restrict__ degree, int32_t* __restrict__ flags) {
+    const int64_t* __restrict__ pt, const EdgeRec* __restrict__ tr, int64_t n_rows, int32_t row0, int mode,
+    double theta, int32_t* __restrict__ newlen, const int64_t* __restrict__ outptr, int32_t* __restrict__ out_idx,
+    double* __restrict__ out_val, double* __restrict__ p_val, double* __restrict__ degree,
+    int32_t* __restrict__ flags) {
   __shared__ double sv[MRG_WARPS][32];
   __shared__ int32_t sc[MRG_WARPS][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -222,40 +264,24 @@ __global__ void __launch_bounds__(MRG_WARPS * 32) sym_merge_kernel(
   const int la = (int)(pa[row + 1] - a0), lt = (int)(pt[row + 1] - t0);
   const int L = la + lt;
   const int32_t grow = (int32_t)row + row0;
-  if (L <= 32) {
+  if (L <= MRG_REG) {
     // ---- the common case (a kNN kernel row and its transpose): one element per lane, A in lanes [0, la), T in
-    //      lanes [la, L); no sort, no loop -- lookups are binary searches over lanes, output order by popcounts
+    //      lanes [la, L) in arrival order.  Idle lanes carry distinct negative columns so they never match.
     const bool isA = lane < la, isT = (lane >= la) && (lane < L);
-    int32_t c = 0x7fffffff;
+    int32_t c = -1 - lane;
     double w = 0.0;
     if (isA) { c = ia[a0 + lane]; w = va[a0 + lane]; }
-    else if (isT) { c = it[t0 + lane - la]; w = vt[t0 + lane - la]; }
-    // position of this element's column in the OTHER list (binary search over lanes; both lists sorted)
-    int lo = isA ? la : 0, hi = isA ? L : la;
-#pragma unroll
-    for (int s = 0; s < 5; ++s) {
-      const int mid = (lo + hi) >> 1;
-      const int32_t cm = __shfl_sync(0xffffffffu, c, mid & 31);
-      const bool go = (lo < hi) && (cm < c);
-      const bool stay = (lo < hi) && !(cm < c);
-      lo = go ? mid + 1 : lo;
-      hi = stay ? mid : hi;
+    else if (isT) {
+      const int4 r = reinterpret_cast<const int4*>(tr)[t0 + lane - la];
+      c = r.x;
+      w = __hiloint2double(r.w, r.z);
     }
-    // one more step covers lists of 17..32 entries (2^5 = 32 needs ceil(log2(33)) = 6 probes)
-    {
-      const int mid = (lo + hi) >> 1;
-      const int32_t cm = __shfl_sync(0xffffffffu, c, mid & 31);
-      const bool go = (lo < hi) && (cm < c);
-      const bool stay = (lo < hi) && !(cm < c);
-      lo = go ? mid + 1 : lo;
-      hi = stay ? mid : hi;
-    }
-    const int pos = lo;                                  // absolute lane of the first entry >= c in the other list
-    const int32_t c_at = __shfl_sync(0xffffffffu, c, pos & 31);
-    const double w_at = __shfl_sync(0xffffffffu, w, pos & 31);
-    const bool in_other = isA ? (pos < L) : (pos < la);
-    const bool mutual = (isA || isT) && in_other && (c_at == c);
-    const double s = sym_combine(mode, theta, w, mutual ? w_at : 0.0);
+    // columns are unique within A and within T: a column held by two lanes is a mutual edge
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    const bool mutual = (peers & (peers - 1)) != 0;
+    const int partner = mutual ? (isA ? (31 - __clz(peers)) : (__ffs(peers) - 1)) : lane;   // A copy is the lower lane
+    const double w_other = __shfl_sync(0xffffffffu, w, partner);
+    const double s = sym_combine(mode, theta, w, mutual ? w_other : 0.0);
     const bool emit = (isA || isT) && (s != 0.0) && !(mutual && isT);   // a mutual pair is emitted by its A copy
     const unsigned em = __ballot_sync(0xffffffffu, emit);
     const int cnt = __popc(em);
@@ -263,14 +289,12 @@ __global__ void __launch_bounds__(MRG_WARPS * 32) sym_merge_kernel(
       if (lane == 0) newlen[row] = cnt;
       return;
     }
-    // rank among the emitted entries = emitted entries of my own list before me + emitted entries of the other
-    // list with a smaller column (those sit before `pos`)
-    const unsigned mA = (la >= 32) ? 0xffffffffu : ((1u << la) - 1u);
-    const unsigned below_me = (1u << lane) - 1u;
-    const unsigned below_pos = (pos >= 32) ? 0xffffffffu : ((1u << pos) - 1u);
-    const unsigned own = isA ? (em & mA & below_me) : (em & ~mA & below_me);
-    const unsigned oth = isA ? (em & ~mA & below_pos) : (em & mA & below_pos);
-    const int rank = __popc(own) + __popc(oth);
+    // output position = number of emitted entries with a smaller column
+    int rank = 0;
+    for (int k = 0; k < L; ++k) {
+      const int32_t ck = __shfl_sync(0xffffffffu, c, k);
+      rank += (int)((em >> k) & 1u) & (int)(ck < c);
+    }
     if (emit) { sv[warp][rank] = s; sc[warp][rank] = c; }
     __syncwarp();
     const bool on = lane < cnt;
@@ -292,53 +316,42 @@ __global__ void __launch_bounds__(MRG_WARPS * 32) sym_merge_kernel(
     }
     return;
   }
-  // ---- rows with more than 32 entries (hub rows; every row of an isotropic, high-intrinsic-dimension data set)
+  // ---- rows with more than 32 entries (hub rows; every row of an isotropic, high-intrinsic-dimension data set):
+  //      T was sorted by rec_sort_rows.  Sequential two-pointer merge by one lane (O(L), any length, fixed order);
+  //      the row sum runs in column order, which is sklearn's own summation order
+  //      (sparsefuncs_fast.pyx:_inplace_csr_row_normalize_l1)
   const int32_t* A = ia + a0;
-  const int32_t* T = it + t0;
-  if (!FILL) {
-    // count: every element looks its column up in the other (sorted) list
-    int cnt = 0;
-    for (int t = lane; t < la; t += 32) {
-      const int32_t c = A[t];
-      const int p = lower_bound_g(T, lt, c);
-      const bool mutual = (p < lt) && (T[p] == c);
-      cnt += (sym_combine(mode, theta, va[a0 + t], mutual ? vt[t0 + p] : 0.0) != 0.0);
-    }
-    for (int t = lane; t < lt; t += 32) {
-      const int32_t c = T[t];
-      const int p = lower_bound_g(A, la, c);
-      const bool mutual = (p < la) && (A[p] == c);
-      if (!mutual) cnt += (sym_combine(mode, theta, 0.0, vt[t0 + t]) != 0.0);
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-    if (lane == 0) newlen[row] = cnt;
-    return;
-  }
-  // fill: sequential two-pointer merge by one lane (O(L), any length, fixed order); the row sum runs in column
-  // order, which is sklearn's own summation order (sparsefuncs_fast.pyx:_inplace_csr_row_normalize_l1)
-  const int64_t o0 = outptr[row];
+  const EdgeRec* T = tr + t0;
+  const int64_t o0 = FILL ? outptr[row] : 0;
   int o = 0;
   double sum = 0.0;
   if (lane == 0) {
     bool has_diag = false;
     int a = 0, b = 0;
     while (a < la || b < lt) {
-      const int32_t ca = (a < la) ? A[a] : 0x7fffffff, cb = (b < lt) ? T[b] : 0x7fffffff;
+      const int32_t ca = (a < la) ? A[a] : 0x7fffffff, cb = (b < lt) ? T[b].i : 0x7fffffff;
       const int32_t c = ca < cb ? ca : cb;
-      const double w = (ca == c) ? va[a0 + a] : 0.0, wr = (cb == c) ? vt[t0 + b] : 0.0;
+      const double w = (ca == c) ? va[a0 + a] : 0.0, wr = (cb == c) ? T[b].w : 0.0;
       a += (ca == c);
       b += (cb == c);
       const double sv2 = sym_combine(mode, theta, w, wr);
       if (sv2 != 0.0) {
-        out_idx[o0 + o] = c; out_val[o0 + o] = sv2; ++o;
-        sum += fabs(sv2);
-        has_diag |= (c == grow);
+        if (FILL) {
+          out_idx[o0 + o] = c; out_val[o0 + o] = sv2;
+          sum += fabs(sv2);
+          has_diag |= (c == grow);
+        }
+        ++o;
       }
     }
-    if (degree) degree[row] = sum;
-    if (flags && !has_diag) atomicOr(flags, 2);
+    if (FILL) {
+      if (degree) degree[row] = sum;
+      if (flags && !has_diag) atomicOr(flags, 2);
+    } else {
+      newlen[row] = o;
+    }
   }
+  if (!FILL) return;
   o = __shfl_sync(0xffffffffu, o, 0);
   sum = __shfl_sync(0xffffffffu, sum, 0);
   __syncwarp();
@@ -401,11 +414,10 @@ extern "C" int gtb_transpose_count(const int32_t* idx, int64_t nnz, int32_t col0
 }
 
 extern "C" int gtb_transpose_scatter(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n_rows,
-                                     int32_t row0, int32_t col0, const int64_t* ptr_t, int32_t* cnt, int32_t* t_idx,
-                                     double* t_val, void* stream) {
+                                     int32_t row0, int32_t col0, int32_t* cursor, void* t_rec, void* stream) {
   GTB_CHECK_ARG(n_rows > 0, "empty matrix");
   transpose_scatter_kernel<<<(unsigned)gtb_cdiv(n_rows * GRP, 256), 256, 0, (cudaStream_t)stream>>>(
-      indptr, idx, val, n_rows, row0, col0, ptr_t, cnt, t_idx, t_val);
+      indptr, idx, val, n_rows, row0, col0, cursor, reinterpret_cast<EdgeRec*>(t_rec));
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }
@@ -424,12 +436,12 @@ extern "C" int gtb_records_count(const void* rec, int64_t k, int32_t col0, int32
   return GTB_OK;
 }
 
-extern "C" int gtb_records_scatter(const void* rec, int64_t k, int32_t col0, const int64_t* ptr_t, int32_t* cnt,
-                                   int32_t* t_idx, double* t_val, void* stream) {
+extern "C" int gtb_records_scatter(const void* rec, int64_t k, int32_t col0, int32_t* cursor, void* t_rec,
+                                   void* stream) {
   if (k > 0) {
     const int64_t blocks = gtb_cdiv(k, 256);
     records_scatter_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const EdgeRec*>(rec), k, col0, ptr_t, cnt, t_idx, t_val);
+        reinterpret_cast<const EdgeRec*>(rec), k, col0, cursor, reinterpret_cast<EdgeRec*>(t_rec));
     GTB_CHECK_LAUNCH();
   }
   return GTB_OK;
@@ -438,40 +450,38 @@ extern "C" int gtb_records_scatter(const void* rec, int64_t k, int32_t col0, con
 extern "C" int gtb_csr_sort_rows(const int64_t* ptr, int32_t* idx, double* val, int64_t n, int32_t* has_long,
                                  void* stream) {
   GTB_CHECK_ARG(n > 0, "empty matrix");
-  cudaStream_t st = (cudaStream_t)stream;
-  GTB_CUDA(cudaMemsetAsync(has_long, 0, sizeof(int32_t), st));
-  csr_sort_rows_kernel<<<(unsigned)gtb_cdiv(n, SORT_WARPS), SORT_WARPS * 32, 0, st>>>(ptr, idx, val, n, has_long);
-  GTB_CHECK_LAUNCH();
-  const size_t smem = (size_t)SORT_BLOCK_CAP * 12;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GTB_CUDA(cudaFuncSetAttribute(csr_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  const int64_t blocks = gtb_cdiv(n, SORT_BLOCK_THREADS);
-  csr_sort_long_kernel<<<(unsigned)(blocks < 148 * 4 ? blocks : 148 * 4), SORT_BLOCK_THREADS, smem, st>>>(
-      ptr, idx, val, n, has_long);
-  GTB_CHECK_LAUNCH();
-  return GTB_OK;
+  SoAStore st{idx, val};
+  return launch_sort<SoAStore>(ptr, st, n, nullptr, 0, has_long, (cudaStream_t)stream);
 }
 
+extern "C" int gtb_rec_sort_rows(const int64_t* ptr, void* rec, int64_t n, const int64_t* pa, int min_total,
+                                 int32_t* has_long, void* stream) {
+  GTB_CHECK_ARG(n > 0, "empty matrix");
+  RecStore st{reinterpret_cast<EdgeRec*>(rec)};
+  return launch_sort<RecStore>(ptr, st, n, pa, min_total, has_long, (cudaStream_t)stream);
+}
+
+extern "C" int gtb_sym_merge_reg_rows(void) { return MRG_REG; }
+
 extern "C" int gtb_sym_merge_count(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pt,
-                                   const int32_t* it, const double* vt, int64_t n_rows, int mode, double theta,
-                                   int32_t* newlen, void* stream) {
+                                   const void* t_rec, int64_t n_rows, int mode, double theta, int32_t* newlen,
+                                   void* stream) {
   GTB_CHECK_ARG(n_rows > 0 && mode >= 0 && mode <= 2, "bad arguments");
   sym_merge_kernel<false><<<(unsigned)gtb_cdiv(n_rows, MRG_WARPS), MRG_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      pa, ia, va, pt, it, vt, n_rows, 0, mode, theta, newlen, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+      pa, ia, va, pt, reinterpret_cast<const EdgeRec*>(t_rec), n_rows, 0, mode, theta, newlen, nullptr, nullptr,
+      nullptr, nullptr, nullptr, nullptr);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }
 
 extern "C" int gtb_sym_merge_fill(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pt,
-                                  const int32_t* it, const double* vt, int64_t n_rows, int32_t row0, int mode,
-                                  double theta, const int64_t* outptr, int32_t* out_idx, double* out_val,
-                                  double* p_val, double* degree, int32_t* flags, void* stream) {
+                                  const void* t_rec, int64_t n_rows, int32_t row0, int mode, double theta,
+                                  const int64_t* outptr, int32_t* out_idx, double* out_val, double* p_val,
+                                  double* degree, int32_t* flags, void* stream) {
   GTB_CHECK_ARG(n_rows > 0 && mode >= 0 && mode <= 2, "bad arguments");
   sym_merge_kernel<true><<<(unsigned)gtb_cdiv(n_rows, MRG_WARPS), MRG_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      pa, ia, va, pt, it, vt, n_rows, row0, mode, theta, nullptr, outptr, out_idx, out_val, p_val, degree, flags);
+      pa, ia, va, pt, reinterpret_cast<const EdgeRec*>(t_rec), n_rows, row0, mode, theta, nullptr, outptr, out_idx,
+      out_val, p_val, degree, flags);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }

@@ -6,27 +6,37 @@ from . import _engine as E
 from . import pipeline
 
 SYM = {"+": 0, "*": 1, "mnn": 2, None: 3}
-METRIC = {"euclidean": 0, "cosine": 1}
+METRIC = {"euclidean": 0, "cosine": 1, "cityblock": 2, "manhattan": 2, "l1": 2}
+
+
+def _same_dtype(Xq, Xr):
+    """Both operands in the precision of the data as given: float64 when either is (scipy's pdist / cdist work on
+    the float64 values the reference holds), else float32."""
+    is64 = Xq.dtype == torch.float64 or Xr.dtype == torch.float64
+    dt = torch.float64 if is64 else torch.float32
+    return Xq.to(dt).contiguous(), Xr.to(dt).contiguous(), int(is64)
 
 
 def dense_affinity(Xq, Xr, bw_q, bw_r, decay, thresh, symm=None, theta=None, want_rowsum=True, metric="euclidean"):
     """[nq, nr] float64 thresholded alpha-decay affinities; symmetrised in the same sweep when
     ``bw_r`` is given (square problems)."""
+    Xq, Xr, is64 = _same_dtype(Xq, Xr)
     nq, d = Xq.shape
     nr = Xr.shape[0]
     out = pipeline._empty((nq, nr), torch.float64)
     rowsum = pipeline._empty((nq,), torch.float64) if want_rowsum else None
     what = 2 if bw_r is not None else 1
-    E.call("gtb_dense_kernel", Xq, nq, Xr, nr, d, what, METRIC[metric], bw_q, bw_r, float(decay), float(thresh),
+    E.call("gtb_dense_kernel", Xq, nq, Xr, nr, d, is64, what, METRIC[metric], bw_q, bw_r, float(decay), float(thresh),
            SYM[symm], 0.0 if theta is None else float(theta), out, rowsum)
     return out, rowsum
 
 
 def dense_distances(Xq, Xr, metric="euclidean"):
+    Xq, Xr, is64 = _same_dtype(Xq, Xr)
     nq, d = Xq.shape
     nr = Xr.shape[0]
     out = pipeline._empty((nq, nr), torch.float64)
-    E.call("gtb_dense_kernel", Xq, nq, Xr, nr, d, 0, METRIC[metric], None, None, 0.0, 0.0, 3, 0.0, out, None)
+    E.call("gtb_dense_kernel", Xq, nq, Xr, nr, d, is64, 0, METRIC[metric], None, None, 0.0, 0.0, 3, 0.0, out, None)
     return out
 
 

@@ -43,9 +43,10 @@ class TraditionalGraph(DataGraph):
                     precomputed, data.shape))
             elif (data < 0).sum() > 0:
                 raise ValueError("Precomputed {} should be non-negative".format(precomputed))
-        if precomputed is None and distance not in ("euclidean", "cosine"):
+        if precomputed is None and distance not in ("euclidean", "cosine", "cityblock", "manhattan", "l1"):
             raise NotImplementedError(
-                "graphtools_b200 accelerates the euclidean and cosine metrics (got distance={!r})".format(distance))
+                "graphtools_b200 accelerates the euclidean, cosine and cityblock metrics (got distance={!r})".format(
+                    distance))
         self.knn = knn
         self.decay = decay
         self.bandwidth = bandwidth
@@ -115,13 +116,12 @@ class TraditionalGraph(DataGraph):
                     return self._build_precomputed()
             finally:
                 self.kernel_symm, self.anisotropy = saved
-        X = self._X()
+        X = self._X()                    # float32 or float64 as given: distances are evaluated on these rows
         op = pipeline.SearchOperand(X, metric=self._metric())
-        Xf = X.float()
-        bw = self._resolve_bandwidth(self.bandwidth, X.shape[0], lambda: dense.dense_distances(Xf, Xf, self._metric()), op, op,
+        bw = self._resolve_bandwidth(self.bandwidth, X.shape[0], lambda: dense.dense_distances(X, X, self._metric()), op, op,
                                      (self.knn or 0) + 1)
         bw = (bw * float(self.bandwidth_scale)).contiguous()
-        K, _ = dense.dense_affinity(Xf, Xf, bw, None, self.decay, self.thresh, want_rowsum=False, metric=self._metric())
+        K, _ = dense.dense_affinity(X, X, bw, None, self.decay, self.thresh, want_rowsum=False, metric=self._metric())
         return K
 
     def _sparse_route_ok(self):
@@ -156,16 +156,20 @@ class TraditionalGraph(DataGraph):
             return self._build_precomputed()
         if self._sparse_route_ok():
             with _logger.log_task("affinities"):
-                return self._build_kernel_via_sparse()
+                try:
+                    return self._build_kernel_via_sparse()
+                except pipeline.RowTooLong:
+                    # a kernel this wide (fixed bandwidth / small decay: thousands of neighbours inside the support
+                    # radius) is not sparse in any useful sense: evaluate every pair with the dense kernel below
+                    pass
         with _logger.log_task("affinities"):
             X = self._X()
             n = X.shape[0]
             op = pipeline.SearchOperand(X, metric=self._metric())
-            bw = self._resolve_bandwidth(self.bandwidth, n, lambda: dense.dense_distances(X.float(), X.float(), self._metric()), op, op,
+            bw = self._resolve_bandwidth(self.bandwidth, n, lambda: dense.dense_distances(X, X, self._metric()), op, op,
                                          (self.knn or 0) + 1)
             bw = (bw * float(self.bandwidth_scale)).contiguous()
             self._dev_bandwidth = bw
-            X = X.float()          # the dense fp64-accumulating kernel reads float32 rows
             if self.kernel_symm is None:
                 K, rowsum = dense.dense_affinity(X, X, bw, None, self.decay, self.thresh, metric=self._metric())
                 if float((K - K.T).max().item()) > 1e-5:
@@ -185,6 +189,27 @@ class TraditionalGraph(DataGraph):
         computation involved; element-wise host evaluation, results handed to the device containers."""
         data = self.data_nu
         dev = pipeline._dev()
+        if sparse.issparse(data) and self.precomputed in ("affinity", "adjacency"):
+            # sparse precomputed inputs stay sparse, as in the reference (graphs.py:1532-1544, :1597-1607): unit
+            # diagonal for adjacencies, threshold, then the shared symmetrise / normalise kernels; K and P come back
+            # as scipy CSR (no N x N densification on host or device)
+            K = sparse.csr_matrix(data, dtype=np.float64, copy=True)
+            if self.precomputed == "adjacency":
+                K = K.tolil()
+                K.setdiag(1)
+                K = K.tocsr()
+            K.data[K.data < self.thresh] = 0
+            K.eliminate_zeros()
+            Ks, Pv, degree, flags = pipeline.symmetrize_normalize(pipeline.csr_from_scipy(K), self.kernel_symm,
+                                                                  self.theta, float(self.anisotropy))
+            if self.kernel_symm is not None:
+                flags &= ~1
+            if flags & 1:
+                warnings.warn("K should be symmetric", RuntimeWarning)
+            if flags & 2:
+                warnings.warn("K should have a non-zero diagonal", RuntimeWarning)
+            self._dev_degree, self._dev_P = degree, Pv
+            return Ks
         if self.precomputed == "distance":
             pdx = data.toarray() if sparse.issparse(data) else np.asarray(data, dtype=np.float64)
             if self.bandwidth is None:
@@ -230,10 +255,9 @@ class TraditionalGraph(DataGraph):
             Yd = self._dense_f32(Y)
             ref = pipeline.SearchOperand(X, metric=self._metric())
             qry = pipeline.SearchOperand(Yd.to(X.dtype), mean=ref.mean, metric=self._metric())
-            Xf, Yf = X.float(), Yd.float()
-            bw = self._resolve_bandwidth(bandwidth, Yd.shape[0], lambda: dense.dense_distances(Yf, Xf, self._metric()), qry, ref, knn)
+            bw = self._resolve_bandwidth(bandwidth, Yd.shape[0], lambda: dense.dense_distances(Yd, X, self._metric()), qry, ref, knn)
             bw = (bw * float(bandwidth_scale)).contiguous()
-            K, _ = dense.dense_affinity(Yf, Xf, bw, None, self.decay, self.thresh, want_rowsum=False, metric=self._metric())
+            K, _ = dense.dense_affinity(Yd, X, bw, None, self.decay, self.thresh, want_rowsum=False, metric=self._metric())
         return K
 
     def build_kernel_to_data(self, Y, knn=None, bandwidth=None, bandwidth_scale=None):

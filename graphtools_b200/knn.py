@@ -45,9 +45,10 @@ class kNNGraph(DataGraph):
         if n_pca in [None, 0, False] and data.shape[1] > 500:
             warnings.warn("Building a kNNGraph on data of shape {} is "
                           "expensive. Consider setting n_pca.".format(data.shape), UserWarning)
-        if distance not in ("euclidean", "cosine"):
+        if distance not in ("euclidean", "cosine", "cityblock", "manhattan", "l1"):
             raise NotImplementedError(
-                "graphtools_b200 accelerates the euclidean and cosine metrics (got distance={!r})".format(distance))
+                "graphtools_b200 accelerates the euclidean, cosine and cityblock metrics (got distance={!r})".format(
+                    distance))
         self.knn = knn
         self.knn_max = knn_max
         self.search_multiplier = search_multiplier
@@ -194,12 +195,11 @@ class kNNGraph(DataGraph):
             cnt = pipeline._empty((m,), torch.int32)
             E.call("gtb_records_count", rec, k, lo, cnt, m)
             ptr_t = pipeline.exclusive_scan(cnt)
-            t_idx = pipeline._empty((k,), torch.int32)
-            t_val = pipeline._empty((k,), torch.float64)
-            E.call("gtb_records_scatter", rec, k, lo, ptr_t, cnt, t_idx, t_val)
-            pipeline.sort_rows(ptr_t, t_idx, t_val, m)
+            t_rec = pipeline._empty((k, 2), torch.int64)
+            E.call("gtb_records_scatter", rec, k, lo, pipeline.cursor32(ptr_t), t_rec)
+            pipeline.sort_records(ptr_t, t_rec, m, indptr_a, E.lib().gtb_sym_merge_reg_rows())
             outptr, k_idx, k_val, p_val, deg, newlen = pipeline.merge_with_transpose(
-                indptr_a, idx, val, ptr_t, t_idx, t_val, m, lo, mode, theta, want_p=True, flags=flags)
+                indptr_a, idx, val, ptr_t, t_rec, m, lo, mode, theta, want_p=True, flags=flags)
         else:
             newlen = torch.zeros((0,), dtype=torch.int32, device=dev)
             outptr = torch.zeros((1,), dtype=torch.int64, device=dev)

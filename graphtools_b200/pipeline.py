@@ -14,9 +14,15 @@ import torch
 from . import _engine as E
 
 SYM_MODES = {"+": 0, "*": 1, "mnn": 2, None: 3}
+METRIC_ALIASES = {"manhattan": "cityblock", "l1": "cityblock", "l2": "euclidean"}
+METRIC_CODE = {"euclidean": 0, "cosine": 1, "cityblock": 2}
 AUTO_TC = "tc16"         # tensor-core flavour picked by impl="auto": "tc" (3xTF32) or "tc16" (bf16x3)
 BALL_CAP = 8192          # longest radius-pass row handled by refine_ball (shared-memory sort)
 _STATS = {}
+
+
+class RowTooLong(NotImplementedError):
+    """A row has more neighbours inside the kernel radius than the radius-pass refine handles (BALL_CAP)."""
 
 
 def stats():
@@ -160,9 +166,18 @@ class SearchOperand:
         self.is64 = X.dtype == torch.float64
         self.n_pad = (n + 127) // 128 * 128
         self.d_pad = (d + 7) // 8 * 8
-        if metric not in ("euclidean", "cosine"):
+        metric = METRIC_ALIASES.get(metric, metric)
+        self.metric = metric
+        if metric not in ("euclidean", "cosine", "cityblock"):
             raise NotImplementedError("metric {!r} is not supported by the CUDA search".format(metric))
-        if self.is64 or metric == "cosine":
+        if metric == "cityblock":
+            # |x - y| is translation invariant and has no GEMM form: the search copy is the float32 data itself,
+            # NOT centred, so that the float32 accumulation of sum |x - y| stays accurate relative to the distance
+            # (float64 inputs are rounded once; that rounding enters the certification bound through the L1 norms)
+            self.Xs = X.to(torch.float32).contiguous() if self.is64 else X
+            self._kmean = None
+            mean = torch.zeros((d,), dtype=torch.float32, device=X.device) if mean is None else mean
+        elif self.is64 or metric == "cosine":
             rows = X.to(torch.float64)
             if metric == "cosine":
                 rows = rows / rows.norm(dim=1, keepdim=True)
@@ -220,7 +235,16 @@ class SearchOperand:
         return self.kp(0)
 
     def tc_ok(self, dtype=0):
+        if self.metric == "cityblock":
+            return False                                  # no GEMM form: CUDA-core L1 kernel only
         return self.kp(dtype) // (16 if dtype else 8) <= (8 if dtype else 13)
+
+    def l1_norms(self):
+        """(per-row L1 norms float32 [n], max) of the search copy -- bound on its rounding for float64 inputs."""
+        if getattr(self, "_l1", None) is None:
+            n1 = self.Xs.abs().sum(dim=1, dtype=torch.float64)
+            self._l1 = (n1.to(torch.float32).contiguous(), float(n1.max().item()))
+        return self._l1
 
     def tc(self, role, dtype=0):
         key = (role, dtype)
@@ -326,6 +350,12 @@ def eps_rel_tc16(d):
     return 2.0 * (2.0 ** -16 + 2.0 ** -18) + 2.0 * (d + 32) * 2.0 ** -24
 
 
+def eps_rel_l1(d):
+    """Cityblock pass: float32 subtraction and accumulation of d terms |x_k - y_k| -- relative error of the
+    DISTANCE at most (d + 1) * 2^-24 (all terms non-negative, no cancellation), doubled."""
+    return 2.0 * (d + 2) * 2.0 ** -24
+
+
 def eps_rel_simt(d):
     """Relative bound on |approx d^2 - exact d^2| / (|x~|^2 + |y~|^2) for the fp32 CUDA-core pass:
     (d + 11) * 2^-24 from a standard rounding analysis (dot product, norms, centring), doubled."""
@@ -347,12 +377,15 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
     nq, nr, d = qry.n, ref.n, ref.d
     if qry.is64 != ref.is64 or qry.metric != ref.metric:
         raise ValueError("query and reference operands must have the same dtype and metric")
-    x64 = int(ref.is64) | (2 if ref.metric == "cosine" else 0)      # x_kind of the refine entry points
+    x64 = int(ref.is64) | (METRIC_CODE[ref.metric] << 1)            # x_kind of the refine entry points
+    l1 = ref.metric == "cityblock"
     binary = decay is None
     knn = int(min(knn, nr))
     kmax = 0 if knn_max is None else int(knn_max)
     if kmax >= nr:
         kmax = 0
+    if l1:
+        impl = "simt"
     if impl is None:
         # GTB_SEARCH_IMPL is a preference: a flavour that cannot take this shape (feature count beyond the
         # resident query tile, knn beyond the 2 x 32 candidate lists) hands over to the next one
@@ -401,12 +434,17 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         if S is None:
             S = choose_S(knn, binary)
         stride = S
-        eps_rel = eps_rel_simt(d)
-        q_n2 = qry.n2
         tau = _empty((nq,), torch.float32)
         cand = _empty((nq, S), torch.int32)
-        E.call("gtb_knn_topk_simt", qry.XT, qry.n2, nq, qry.n_pad, ref.XT, ref.n2, nr, ref.n_pad, ref.d_pad, S,
-               cand, tau)
+        if l1:
+            eps_rel = eps_rel_l1(d)
+            q_n2 = qry.l1_norms()[0] if ref.is64 else None       # float32 inputs: the search copy is exact
+            E.call("gtb_knn_topk_simt_l1", qry.XT, nq, qry.n_pad, ref.XT, nr, ref.n_pad, ref.d_pad, S, cand, tau)
+        else:
+            eps_rel = eps_rel_simt(d)
+            q_n2 = qry.n2
+            E.call("gtb_knn_topk_simt", qry.XT, qry.n2, nq, qry.n_pad, ref.XT, ref.n2, nr, ref.n_pad, ref.d_pad, S,
+                   cand, tau)
     else:
         raise ValueError("unknown impl %r" % (impl,))
 
@@ -431,7 +469,8 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
     lim2 = _empty((nq,), torch.float32)
     status = _empty((nq,), torch.int32)
     nzero = _empty((nq,), torch.int32)
-    E.call("gtb_refine_topk", qry.X, nq, ref.X, d, x64, cand, S, stride, tau, ntau, q_n2, ref.maxnorm, eps_rel, knn, kmax, decay_f,
+    maxnorm = (ref.l1_norms()[1] if ref.is64 else 0.0) if l1 else ref.maxnorm
+    E.call("gtb_refine_topk", qry.X, nq, ref.X, d, x64, cand, S, stride, tau, ntau, q_n2, maxnorm, eps_rel, knn, kmax, decay_f,
            thresh_f, bw_fixed, bw_mode, float(bandwidth_scale), st_idx, st_val, n_keep, bw_out, lim2, status, nzero)
 
     todo_rows = _empty((nq,), torch.int32)
@@ -463,6 +502,9 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
             if impl in ("tc", "tc16"):
                 E.call("gtb_knn_radius_tc", s_hi, s_lo, s_n2, lim_t, nt, nt_pad, r_hi, r_lo, nr, ref.n_pad, Kp, tcd,
                        pairs, capacity, counter, rowcnt)
+            elif l1:
+                E.call("gtb_knn_radius_simt_l1", QT, lim_t, nt, nt_pad, ref.XT, nr, ref.n_pad, ref.d_pad, pairs,
+                       capacity, counter, rowcnt)
             else:
                 E.call("gtb_knn_radius_simt", QT, qn2, lim_t, nt, nt_pad, ref.XT, ref.n2, nr, ref.n_pad, ref.d_pad,
                        pairs, capacity, counter, rowcnt)
@@ -483,9 +525,10 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         while cap < longest:
             cap *= 2
         if cap > BALL_CAP:
-            raise NotImplementedError(
-                "a row has {} neighbours inside the kernel radius; rows longer than {} are not supported "
-                "(use graphtype='exact' for such dense kernels)".format(longest, BALL_CAP))
+            raise RowTooLong(
+                "a row has {} neighbours inside the kernel radius; the sparse kNN pipeline handles rows of up to {} "
+                "(a kernel this dense calls for graphtype='exact', which evaluates every pair)".format(
+                    longest, BALL_CAP))
         E.call("gtb_refine_ball", qry.X, todo_rows, status, nt, ref.X, d, x64, seg_ptr, seg_idx, seg_val, knn, kmax,
                decay_f, thresh_f, bw_fixed, bw_mode, float(bandwidth_scale), n_keep_t, n_keep, bw_out, nzero,
                overflow, cap)
@@ -508,32 +551,57 @@ def sort_rows(ptr, idx, val, n):
     E.call("gtb_csr_sort_rows", ptr, idx, val, n, _empty((1,), torch.int32))
 
 
-def transpose_csr(R):
-    """R^T as a DeviceCSR with column-sorted rows: histogram of the columns -> scan -> scatter -> per-row sort."""
+def cursor32(ptr):
+    """32-bit copy of the first n entries of a row-pointer array: the per-row scatter cursors."""
+    n = ptr.shape[0] - 1
+    cur = _empty((max(n, 1),), torch.int32)
+    if n:
+        E.call("gtb_cast_indptr", ptr, n, cur)
+    return cur
+
+
+def transpose_records(R, sort_min_total=None, pa=None):
+    """Rows of R^T as 16-byte edge records {int32 i, int32 j, float64 w} (csrc/symm.cu): histogram of the columns ->
+    scan -> scatter (one atomic + one 16-byte store per edge).  Rows come out in arrival order; rows whose length plus
+    the matching row of ``pa`` exceeds ``sort_min_total`` are then ordered by column (None: no sort, 0: every row).
+    Returns (ptr_t int64 [n_cols + 1], records [nnz, 2] int64)."""
     n_rows, n_cols = R.shape
     cnt = _empty((n_cols,), torch.int32)
     E.call("gtb_transpose_count", R.indices, R.nnz, 0, cnt, n_cols)
     ptr_t = exclusive_scan(cnt)
-    t_idx = _empty((R.nnz,), torch.int32)
-    t_val = _empty((R.nnz,), torch.float64)
+    rec = _empty((R.nnz, 2), torch.int64)
     if R.nnz:
-        E.call("gtb_transpose_scatter", R.indptr, R.indices, R.data, n_rows, 0, 0, ptr_t, cnt, t_idx, t_val)
-        sort_rows(ptr_t, t_idx, t_val, n_cols)
-    return DeviceCSR(ptr_t, t_idx, t_val, (n_cols, n_rows))
+        E.call("gtb_transpose_scatter", R.indptr, R.indices, R.data, n_rows, 0, 0, cursor32(ptr_t), rec)
+        if sort_min_total is not None:
+            sort_records(ptr_t, rec, n_cols, pa, sort_min_total)
+    return ptr_t, rec
 
 
-def merge_with_transpose(A_ptr, A_idx, A_val, T_ptr, T_idx, T_val, n_rows, row0, mode, theta, want_p=True,
-                         flags=None):
-    """sym(A, T) row by row (csrc/symm.cu sym_merge): returns (outptr, k_idx, k_val, p_val | None, degree, newlen)."""
+def sort_records(ptr_t, rec, n, pa=None, min_total=0):
+    if n and rec.shape[0]:
+        E.call("gtb_rec_sort_rows", ptr_t, rec, n, pa, int(min_total), _empty((1,), torch.int32))
+
+
+def transpose_csr(R):
+    """R^T as a DeviceCSR with column-sorted rows."""
+    ptr_t, rec = transpose_records(R, sort_min_total=0)
+    idx = rec.view(torch.int32).view(-1, 4)[:, 0].contiguous()
+    val = rec.view(torch.float64).view(-1, 2)[:, 1].contiguous()
+    return DeviceCSR(ptr_t, idx, val, (R.shape[1], R.shape[0]))
+
+
+def merge_with_transpose(A_ptr, A_idx, A_val, T_ptr, T_rec, n_rows, row0, mode, theta, want_p=True, flags=None):
+    """sym(A, T) row by row (csrc/symm.cu sym_merge): returns (outptr, k_idx, k_val, p_val | None, degree, newlen).
+    ``T_rec``: record rows of the transposed matrix; rows too long for the register path must be column-sorted."""
     newlen = _empty((n_rows,), torch.int32)
-    E.call("gtb_sym_merge_count", A_ptr, A_idx, A_val, T_ptr, T_idx, T_val, n_rows, mode, theta, newlen)
+    E.call("gtb_sym_merge_count", A_ptr, A_idx, A_val, T_ptr, T_rec, n_rows, mode, theta, newlen)
     outptr = exclusive_scan(newlen)
     nnz = int(outptr[-1].item())
     k_idx = _empty((nnz,), torch.int32)
     k_val = _empty((nnz,), torch.float64)
     p_val = _empty((nnz,), torch.float64) if want_p else None
     degree = _empty((n_rows,), torch.float64)
-    E.call("gtb_sym_merge_fill", A_ptr, A_idx, A_val, T_ptr, T_idx, T_val, n_rows, row0, mode, theta, outptr,
+    E.call("gtb_sym_merge_fill", A_ptr, A_idx, A_val, T_ptr, T_rec, n_rows, row0, mode, theta, outptr,
            k_idx, k_val, p_val, degree, flags)
     return outptr, k_idx, k_val, p_val, degree, newlen
 
@@ -559,9 +627,9 @@ def symmetrize_normalize(R, kernel_symm="+", theta=None, anisotropy=0.0, want_p=
         E.call("gtb_row_finalize", K.indptr, K.indices, K.data, n, P, degree, flags, int(square))
     else:
         th = 0.0 if theta is None else float(theta)
-        T = transpose_csr(R)
+        ptr_t, rec = transpose_records(R, sort_min_total=E.lib().gtb_sym_merge_reg_rows(), pa=R.indptr)
         outptr, k_idx, k_val, P, degree, _ = merge_with_transpose(
-            R.indptr, R.indices, R.data, T.indptr, T.indices, T.data, n, 0, mode, th,
+            R.indptr, R.indices, R.data, ptr_t, rec, n, 0, mode, th,
             want_p=want_p and anisotropy == 0, flags=flags)
         K = DeviceCSR(outptr, k_idx, k_val, R.shape)
     if anisotropy != 0:

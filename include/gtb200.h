@@ -55,6 +55,15 @@ int gtb_knn_radius_simt(const float* QT, const float* qn2, const float* lim2, in
                         const float* RT, const float* rn2, int64_t nr, int64_t nr_pad, int d_pad,
                         int32_t* pairs, int64_t capacity, unsigned long long* counter, int32_t* rowcnt,
                         void* stream);
+/* cityblock (L1) metric -- sklearn's brute-force manhattan search behind knn_tree for distance="cityblock"
+ * (graphs.py:763-768; the reference's landmark tests run it, test/test_landmark.py:195-322): the tile accumulates
+ * sum_k |x_k - y_k| in float32 on the CUDA cores (the L1 distance has no GEMM form), operands are the k-major rows
+ * WITHOUT centring, tau / lim hold distances (not squared) */
+int gtb_knn_topk_simt_l1(const float* QT, int64_t nq, int64_t nq_pad, const float* RT, int64_t nr, int64_t nr_pad,
+                         int d_pad, int S, int32_t* cand_idx, float* tau, void* stream);
+int gtb_knn_radius_simt_l1(const float* QT, const float* lim, int64_t nq, int64_t nq_pad, const float* RT, int64_t nr,
+                           int64_t nr_pad, int d_pad, int32_t* pairs, int64_t capacity, unsigned long long* counter,
+                           int32_t* rowcnt, void* stream);
 
 /* Tensor-core variant (tcgen05.mma, TMA-fed, TMEM accumulators, persistent 2-CTA clusters).  Operands are
  * row-major [n_pad][Kp] hi/lo pairs built by gtb_prepare_operand_tc: role 0 (query) = [x~, 1, 0..],
@@ -86,9 +95,10 @@ int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float* qn2, cons
 /* ---- K3 float64 re-evaluation, bandwidth, affinities, CSR emission: replaces graphs.py:886-911
  * and _build_csr_from_neighbors (graphs.py:450-559) ------------------------------------------ */
 /* Xq / Xr are the ORIGINAL rows used for the exact distances; x_kind bit 0: rows are float64 (e.g. PCA output)
- * instead of float32; bit 1: cosine metric -- exact distances 1 - x.y/(|x||y|) (sklearn cosine_distances, the metric
- * behind knn_tree for distance="cosine", graphs.py:763-768) while the fast pass ran on the row-normalised copies,
- * where |x^ - y^|^2 = 2 d_cos.  decay < 0 means binary kNN (decay=None); kmax <= 0 means knn_max=None;
+ * instead of float32; bits 1-2: metric -- 1 = cosine: exact distances 1 - x.y/(|x||y|) (sklearn cosine_distances, the
+ * metric behind knn_tree for distance="cosine", graphs.py:763-768) while the fast pass ran on the row-normalised
+ * copies, where |x^ - y^|^2 = 2 d_cos; 2 = cityblock: exact sum |x - y|, fast pass = gtb_knn_topk_simt_l1 (tau is a
+ * distance, the rounding bound is eps_rel * tau, qn2 / maxrn2 carry L1 norms for float64 inputs or NULL / 0).  decay < 0 means binary kNN (decay=None); kmax <= 0 means knn_max=None;
  * bw_mode 0: bandwidth = distance to the knn-th candidate (graphs.py:892), 1: scalar bw_fixed[0],
  * 2: per-row bw_fixed[nq].  cand_idx rows are cand_stride apart (first S entries used); tau holds ntau
  * thresholds per row (lists built over disjoint reference subsets), the row's bound is their minimum.  status: 1 done, 0 needs radius pass, 2 needs radius pass and its
@@ -118,33 +128,36 @@ int64_t gtb_scan_ws_elems(int64_t n);
  * ws: gtb_scan_ws_elems(n) int64 of scratch */
 int gtb_exclusive_scan(const int32_t* in, int64_t n, int64_t* out, int64_t* ws, void* stream);
 int gtb_cast_indptr(const int64_t* in, int64_t n1, int32_t* out, void* stream);
-/* Sort-based transpose of a CSR (K^T of base.py:561-571 without scipy's csr_tocsc):
- * cnt[n_cols] = histogram of (idx - col0); after gtb_exclusive_scan(cnt) -> ptr_t, scatter writes every edge
- * (row0 + r, j, w) into row j - col0 of the transposed matrix (cnt is consumed as the per-row cursor); the rows
- * come out in arrival order -> gtb_csr_sort_rows orders them by column, in place (has_long: one int of scratch) */
+/* Sort-based transpose of a CSR (K^T of base.py:561-571 without scipy's csr_tocsc), as 16-byte edge records
+ * {int32 i, int32 j, float64 w}: cnt[n_cols] = histogram of (idx - col0); gtb_exclusive_scan(cnt) -> ptr_t, whose
+ * 32-bit copy (gtb_cast_indptr) is the per-row cursor; scatter then places every edge (row0 + r, j, w) in row j - col0
+ * of t_rec with ONE atomic on the cursor and ONE 16-byte store.  Rows come out in arrival order. */
 int gtb_transpose_count(const int32_t* idx, int64_t nnz, int32_t col0, int32_t* cnt, int64_t n_cols, void* stream);
 int gtb_transpose_scatter(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n_rows, int32_t row0,
-                          int32_t col0, const int64_t* ptr_t, int32_t* cnt, int32_t* t_idx, double* t_val,
-                          void* stream);
-int gtb_csr_sort_rows(const int64_t* ptr, int32_t* idx, double* val, int64_t n, int32_t* has_long, void* stream);
-/* The same transpose for a list of k packed 16-byte edge records {int32 i, int32 j, float64 w} (what the
- * multi-GPU all-to-all delivers): row j - col0 of the result receives (i, w) */
+                          int32_t col0, int32_t* cursor, void* t_rec, void* stream);
+/* The same transpose for a list of k packed edge records (what the multi-GPU all-to-all delivers): row j - col0 of
+ * t_rec receives the record */
 int gtb_records_count(const void* rec, int64_t k, int32_t col0, int32_t* cnt, int64_t n_cols, void* stream);
-int gtb_records_scatter(const void* rec, int64_t k, int32_t col0, const int64_t* ptr_t, int32_t* cnt, int32_t* t_idx,
-                        double* t_val, void* stream);
-/* Merge of the raw kernel rows A = (pa, ia, va) with the rows T = (pt, it, vt) of the transposed matrix, both
- * column-sorted, under mode 0 '+' ((w + w')/2), 1 '*' (w w'), 2 'mnn' (theta min + (1 - theta) max):
- * count -> gtb_exclusive_scan -> fill.  fill emits the column-sorted K row, P = K / sum|K| (base.py:645), the degree
- * vector (base.py:648-666) and sets flags bit 1 when a row lacks its diagonal (base.py:553-554; global row id =
- * row0 + r, columns are global).  Used on the whole matrix (one GPU) and on a row shard (multi-GPU, after the
- * all-to-all) alike, so the two builds agree bit for bit. */
-int gtb_sym_merge_count(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pt,
-                        const int32_t* it, const double* vt, int64_t n_rows, int mode, double theta,
-                        int32_t* newlen, void* stream);
-int gtb_sym_merge_fill(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pt, const int32_t* it,
-                       const double* vt, int64_t n_rows, int32_t row0, int mode, double theta, const int64_t* outptr,
-                       int32_t* out_idx, double* out_val, double* p_val, double* degree, int32_t* flags,
-                       void* stream);
+int gtb_records_scatter(const void* rec, int64_t k, int32_t col0, int32_t* cursor, void* t_rec, void* stream);
+/* In-place segmented sort of CSR rows by column (columns unique within a row; has_long: one int of scratch):
+ * separate index / value arrays, or record rows keyed by .i.  For records, rows r with
+ * len(r) + (pa ? pa[r+1] - pa[r] : 0) <= min_total are skipped (the merge handles them unsorted). */
+int gtb_csr_sort_rows(const int64_t* ptr, int32_t* idx, double* val, int64_t n, int32_t* has_long, void* stream);
+int gtb_rec_sort_rows(const int64_t* ptr, void* rec, int64_t n, const int64_t* pa, int min_total, int32_t* has_long,
+                      void* stream);
+/* Merge of the raw kernel rows A = (pa, ia, va), column-sorted, with the record rows T = (pt, t_rec) of the transposed
+ * matrix under mode 0 '+' ((w + w')/2), 1 '*' (w w'), 2 'mnn' (theta min + (1 - theta) max): count ->
+ * gtb_exclusive_scan -> fill.  Rows with |A| + |T| <= gtb_sym_merge_reg_rows() may hold T in any order; longer rows need
+ * T column-sorted (gtb_rec_sort_rows(..., pa, gtb_sym_merge_reg_rows(), ...)).  fill emits the column-sorted K row,
+ * P = K / sum|K| (base.py:645), the degree vector (base.py:648-666) and sets flags bit 1 when a row lacks its diagonal
+ * (base.py:553-554; global row id = row0 + r, columns are global).  Used on the whole matrix (one GPU) and on a row
+ * shard (multi-GPU, after the all-to-all) alike, so the two builds agree bit for bit. */
+int gtb_sym_merge_reg_rows(void);
+int gtb_sym_merge_count(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pt, const void* t_rec,
+                        int64_t n_rows, int mode, double theta, int32_t* newlen, void* stream);
+int gtb_sym_merge_fill(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pt, const void* t_rec,
+                       int64_t n_rows, int32_t row0, int mode, double theta, const int64_t* outptr, int32_t* out_idx,
+                       double* out_val, double* p_val, double* degree, int32_t* flags, void* stream);
 /* kernel_symm=None: flags bit 0 set when max(K - K^T) > 1e-5 (base.py:551-552) */
 int gtb_asym_check(const int64_t* indptr, const int32_t* idx, const double* val, int64_t n, int32_t* flags,
                    void* stream);
@@ -200,11 +213,13 @@ int gtb_landmark_op(const int64_t* ptr, const int32_t* lab, const double* raw, c
 
 /* ---- K5 dense exact graph: replaces TraditionalGraph.build_kernel / build_kernel_to_data
  * (graphs.py:1546-1609, :1651-1677) and the dense branches of base.py:557-592, :645 ---------- */
-/* what 0: out = distances; 1: out = thresholded affinities exp(-(d/bw_q[i])^decay);
+/* Xq / Xr: float32 rows, or float64 rows when x_is_f64 (distances are float64 differences of the rows as given,
+ * what pdist / cdist compute).  what 0: out = distances; 1: out = thresholded affinities exp(-(d/bw_q[i])^decay);
  * 2: additionally symmetrised with the transposed entry (symm 0 '+', 1 '*', 2 'mnn', 3 none);
- * rowsum (optional) receives the row L1 sums.  metric 0: Euclidean distances; 1: cosine distances
- * 1 - x.y/(|x||y|) with |cos| clamped to 1 (scipy pdist / cdist "cosine", graphs.py:1552, :1653) */
-int gtb_dense_kernel(const float* Xq, int64_t nq, const float* Xr, int64_t nr, int d, int what, int metric,
+ * rowsum (optional) receives the row L1 sums (a separate deterministic pass).  metric 0: Euclidean distances;
+ * 1: cosine distances 1 - x.y/(|x||y|) with |cos| clamped to 1; 2: cityblock (scipy pdist / cdist, graphs.py:1552,
+ * :1653) */
+int gtb_dense_kernel(const void* Xq, int64_t nq, const void* Xr, int64_t nr, int d, int x_is_f64, int what, int metric,
                      const double* bw_q, const double* bw_r, double decay, double thresh, int symm, double theta,
                      double* out, double* rowsum, void* stream);
 int gtb_dense_row_scale(const double* in, const double* rowsum, int64_t nq, int64_t nr, double* out, void* stream);

@@ -81,6 +81,21 @@ def cases():
                                    Y=small[:97] + np.float32(0.02))
     c["small_exact_cosine_thresh0"] = dict(X=small[:250], params=dict(knn=3, decay=10, thresh=0, distance="cosine",
                                                                       kernel_symm="mnn", theta=0.3))
+    # cityblock metric (sklearn brute-force manhattan search / scipy pdist "cityblock"; the reference's own landmark
+    # tests run it, test/test_landmark.py:195-322)
+    c["mix_cityblock"] = dict(X=mix, X_ref="mix_knn", params=dict(knn=5, decay=40, distance="cityblock"), Y=Yq)
+    c["mix_cityblock_binary"] = dict(X=mix, X_ref="mix_knn", params=dict(knn=6, decay=None, distance="cityblock"))
+    c["iso_cityblock_refine"] = dict(X=iso, params=dict(knn=5, decay=20, distance="cityblock", thresh=1e-3))
+    c["mix_cityblock_landmark_random"] = dict(X=mix, X_from="mix_knn", params=dict(
+        knn=5, decay=40, distance="cityblock", n_landmark=100, random_landmarking=True, random_state=7))
+    c["small_exact_cityblock"] = dict(X=small, params=dict(knn=5, decay=40, graphtype="exact", distance="cityblock"),
+                                      Y=small[:97] + np.float32(0.02))
+    # float64 input that is NOT float32-exact and carries a large offset: distances must come from the float64 rows
+    # on every route (the dense route used to round its inputs to float32)
+    off = (small.astype(np.float64) * (1.0 + 1e-9) + 1000.0)
+    c["small_exact_f64_offset_thresh0"] = dict(X=off[:250], params=dict(knn=3, decay=10, thresh=0), keep64=True)
+    c["small_exact_f64_offset"] = dict(X=off, params=dict(knn=5, decay=40, graphtype="exact"), keep64=True,
+                                       Y=off[:97] + 0.02)
     return c
 
 
@@ -109,7 +124,7 @@ def main():
             out["sample_idx"] = np.asarray(params["sample_idx"])
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            G = gt.Graph(X32.astype(np.float64), n_jobs=-1, verbose=0, **params)
+            G = gt.Graph(X32.astype(np.float64), n_jobs=-1, verbose=0, **params)   # keep64 inputs: already float64
             if "X_from" not in case:
                 pack("K", G.kernel, out)
                 pack("P", G.diff_op, out)
@@ -121,7 +136,7 @@ def main():
                 pack("landmark_op", G.landmark_op, out)
                 pack("transitions", G.transitions, out)
             if "Y" in case:
-                Y32 = np.ascontiguousarray(case["Y"].astype(np.float32))
+                Y32 = np.ascontiguousarray(case["Y"] if case.get("keep64") else case["Y"].astype(np.float32))
                 out["Y"] = Y32
                 pack("Kyx", G.build_kernel_to_data(Y32.astype(np.float64)), out)
                 pack("ext", G.extend_to_data(Y32.astype(np.float64)), out)

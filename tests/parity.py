@@ -29,15 +29,20 @@ def _tie_exempt(rows, cols, X, knn_eff, Y=None, metric="euclidean"):
     ok = np.zeros(len(rows), dtype=bool)
     cache = {}
 
+    l1 = metric in ("cityblock", "manhattan", "l1")
+
+    def dist(A, b):
+        return np.abs(A - b).sum(-1) if l1 else np.sqrt(((A - b) ** 2).sum(-1))
+
     def kth(i, A):
         key = (i, id(A))
         if key not in cache:
-            d = np.sqrt(((X - A[i]) ** 2).sum(1))
+            d = dist(X, A[i])
             cache[key] = np.partition(d, knn_eff - 1)[knn_eff - 1]
         return cache[key]
 
     for n, (i, j) in enumerate(zip(rows, cols)):
-        dij = np.sqrt(((Q[i] - X[j]) ** 2).sum())
+        dij = dist(Q[i], X[j])
         dk = kth(i, Q)
         if abs(dij - dk) <= 1e-6 * max(dk, 1e-300):
             ok[n] = True

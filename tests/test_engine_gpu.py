@@ -296,13 +296,12 @@ def test_sharded_symmetrise_merge_matches_global(mode, theta):
         cnt = torch.empty(m, dtype=torch.int32, device="cuda")
         E.call("gtb_records_count", rec, k, lo, cnt, m)
         ptr_t = pipeline.exclusive_scan(cnt)
-        t_idx = torch.empty(k, dtype=torch.int32, device="cuda")
-        t_val = torch.empty(k, dtype=torch.float64, device="cuda")
-        E.call("gtb_records_scatter", rec, k, lo, ptr_t, cnt, t_idx, t_val)
-        pipeline.sort_rows(ptr_t, t_idx, t_val, m)
+        t_rec = torch.empty((k, 2), dtype=torch.int64, device="cuda")
+        E.call("gtb_records_scatter", rec, k, lo, pipeline.cursor32(ptr_t), t_rec)
         pa, ia, va = _csr_dev(Rh[lo:hi])
+        pipeline.sort_records(ptr_t, t_rec, m, pa, E.lib().gtb_sym_merge_reg_rows())
         flags = torch.zeros(1, dtype=torch.int32, device="cuda")
-        outptr, oi, ov, pv, dg, _ = pipeline.merge_with_transpose(pa, ia, va, ptr_t, t_idx, t_val, m, lo, smode,
+        outptr, oi, ov, pv, dg, _ = pipeline.merge_with_transpose(pa, ia, va, ptr_t, t_rec, m, lo, smode,
                                                                   0.0 if theta is None else theta, True, flags)
         Ks, Ps = Kh[lo:hi], Ph[lo:hi]
         assert np.array_equal(outptr.cpu().numpy(), Ks.indptr)
