@@ -152,9 +152,9 @@ def test_pca_reduction_on_host():
 
 
 def test_unsupported_metric_is_rejected_loudly():
-    with pytest.raises(NotImplementedError, match="euclidean and cosine"):
-        build(distance="manhattan")
-    with pytest.raises(NotImplementedError, match="euclidean and cosine"):
+    with pytest.raises(NotImplementedError, match="euclidean, cosine and cityblock"):
+        build(distance="minkowski")
+    with pytest.raises(NotImplementedError, match="euclidean, cosine and cityblock"):
         build(distance="chebyshev", graphtype="exact")
 
 
