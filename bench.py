@@ -305,7 +305,7 @@ def run_gpu_arm(a):
     impl = pipeline.default_impl()
     if impl == "auto":
         impl = pipeline.AUTO_TC if d + 1 <= 104 else "simt"
-    SEARCH = "gtb_knn_topk_tc" if impl in ("tc", "tc16") else "gtb_knn_topk_simt"
+    SEARCH = "gtb_knn_topk_tc" if impl in ("tc", "tc16", "tch") else "gtb_knn_topk_simt"
 
     def step():
         """device-resident hot path through the public API: X is already in HBM, nothing is copied back.
@@ -362,7 +362,14 @@ def run_gpu_arm(a):
     achieved = flop / (per_launch_ms / 1e3) / 1e12
     peaks, how = measured_peaks()
     peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-    if impl == "tc16":
+    if impl == "tch":
+        kp = (d + 1 + 15) // 16 * 16
+        kname = "search_tc_kernel<TOPK, CL=2, FP16x2, LS=16> (%s): tcgen05.mma kind::f16 on float16 hi/lo pairs, two " \
+                "products A_hi.B_hi + A_hi.B_lo, A in TMEM, TMA multicast, persistent, quickselect epilogue" % SEARCH
+        issued, ceiling = achieved * 2.0 * kp / d, d / (2.0 * kp)
+        note = "the tensor pipe issues 2x that (fp16x2 split: the reference operand keeps 22 bits, the query operand " \
+               "11; certified bound 2^-11 (|x|^2 + |y|^2)) on K padded to %d, so frac <= %.3f by construction" % (kp, ceiling)
+    elif impl == "tc16":
         kp = (d + 1 + 15) // 16 * 16
         kname = "search_tc_kernel<TOPK, CL=2, BF16, LS=16> (%s): tcgen05.mma kind::f16 on bf16 hi/lo pairs " \
                 "(bf16x3), A in TMEM, TMA multicast, persistent, quickselect epilogue" % SEARCH
@@ -472,7 +479,9 @@ def run_gpu_arm(a):
             "metric": METRIC, "value": value, "unit": "points/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16x3 tensor-core select (f32 accumulate) / f64 values", "data": "synthetic",
+            "dtype": "%s tensor-core select (f32 accumulate) / f64 values" % {"tch": "fp16x2", "tc16": "bf16x3",
+                                                                                "tc": "3xTF32"}.get(impl, "f32"),
+            "data": "synthetic",
             "config": bench_config(a),
             "run": {"sharding": "query rows over %d rank(s); reference set assembled by NCCL all-gather of the ranks' "
                                 "row blocks; K / P row-sharded in HBM" % world if world > 1 else

@@ -35,14 +35,14 @@ def knn_alpha_decay_kernel(X, Y, knn, decay, thresh, bandwidth_scale=1.0):
     def operand(A, role):
         m = A.shape[0]; hi, lo, n2, mx = e(npad(m), Kp), e(npad(m), Kp), e(npad(m)), e(1)
         _call("gtb_prepare_operand_tc", p(A), I64(m), I(d), p(mean), I(role), p(hi), p(lo), I64(npad(m)), I(Kp),
-              I(0), p(n2), p(mx))        # dtype 0 = tf32 hi/lo pairs in float32 (1 = bfloat16 pairs, Kp % 16 == 0)
+              I(0), F(1.0), p(n2), p(mx))        # dtype 0 = tf32 hi/lo pairs in float32 (1 = bfloat16 pairs, Kp % 16 == 0)
         return hi, lo, n2, mx
     q_hi, q_lo, q_n2, _ = operand(Yd, 0)
     r_hi, r_lo, _, r_max = operand(Xd, 1)
     cand = e(ny, 64, dt=torch.int32); tau = e(ny, 2)
     scratch = e(_L.gtb_tc_scratch_bytes(I64(npad(ny))), dt=torch.uint8)
     _call("gtb_knn_topk_tc", p(q_hi), p(q_lo), p(q_n2), I64(ny), I64(npad(ny)), p(r_hi), p(r_lo), I64(n),
-          I64(npad(n)), I(Kp), I(0), I(32), p(cand), p(scratch), p(tau))
+          I64(npad(n)), I(Kp), I(0), I(32), I(2), p(cand), p(scratch), p(tau), P(0))
     st_idx = e(ny, 64, dt=torch.int32); st_val = e(ny, 64, dt=torch.float64)
     n_keep, status, nzero = (e(ny, dt=torch.int32) for _ in range(3))
     bw = e(ny, dt=torch.float64); lim2 = e(ny)

@@ -29,10 +29,12 @@ _SIGS = {
     "gtb_knn_topk_simt": ([_P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P], 1),
     "gtb_knn_radius_simt": ([_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, _P, c_int64, _P, _P,
                              _P], 1),
-    "gtb_prepare_operand_tc": ([_P, c_int64, c_int, _P, c_int, _P, _P, c_int64, c_int, c_int, _P, _P, _P], 2),
-    "gtb_knn_topk_tc": ([_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P, _P, _P, _P], 1),
-    "gtb_knn_radius_tc": ([_P, _P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, _P,
-                           _P, _P], 1),
+    "gtb_row_norms": ([_P, c_int64, c_int, _P, c_int64, _P, _P, _P], 1),
+    "gtb_prepare_operand_tc": ([_P, c_int64, c_int, _P, c_int, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P], 2),
+    "gtb_knn_topk_tc": ([_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P,
+                         _P, _P], 1),
+    "gtb_knn_radius_tc": ([_P, _P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P, c_int64,
+                           _P, _P, _P, _P], 1),
     "gtb_refine_topk": ([_P, c_int64, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_float, c_double, c_int, c_int64, c_double,
                          c_double, _P, c_int, c_double, _P, _P, _P, _P, _P, _P, _P, _P], 1),
     "gtb_compact_todo": ([_P, c_int64, _P, _P, _P], 1),
@@ -79,8 +81,7 @@ _PLAIN = {
     "gtb_sym_merge_reg_rows": ([], c_int),
     "gtb_cluster_aggregate_ws_elems": ([c_int], c_int64),
     "gtb_tc_max_kp": ([], c_int),
-    "gtb_tc_set_cluster": ([c_int], c_int),
-    "gtb_tc_set_pacing": ([c_int], c_int),
+    "gtb_tc_fp16_maxnorm": ([], c_float),
     "gtb_tc_scratch_bytes": ([c_int64], c_int64),
 }
 

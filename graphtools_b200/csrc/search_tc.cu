@@ -4,11 +4,16 @@
 //   d~2(i,j) - |x_i|^2  =  |y_j|^2 - 2 x_i.y_j  =  sum_k A[i,k] * B[j,k]
 //       A (query role) = [ x~_1 .. x~_d , 1 , 0.. ]        B (ref role) = [ -2y~_1 .. -2y~_d , |y~|^2 , 0.. ]
 //
-// Every float32 operand value v is split v = hi + lo and the tile is accumulated as A_hi.B_hi + A_hi.B_lo + A_lo.B_hi
-// into a float32 TMEM accumulator, in one of two flavours: bf16x3 (hi = bf16(v), lo = bf16(v - hi), kind::f16,
-// 16 elements per 32-byte k-step; the default) or 3xTF32 (hi = tf32(v), lo = tf32(v - hi), kind::tf32, 8 per
-// k-step).  Either keeps >= 16 mantissa bits -- enough to SELECT candidates; every value that reaches the output
-// is re-evaluated in float64 by refine.cu.
+// Every float32 operand value v is split v = hi + lo and the tile is accumulated into a float32 TMEM accumulator, in one
+// of three flavours (template FMT):
+//   0  3xTF32  hi = tf32(v), lo = tf32(v - hi), kind::tf32, 8 elements per 32-byte k-step, A_hi.B_hi + A_hi.B_lo + A_lo.B_hi
+//   1  bf16x3  hi = bf16(v), lo = bf16(v - hi), kind::f16, 16 per k-step, the same three products (>= 16 mantissa bits)
+//   2  fp16x2  hi = fp16(s v), lo = fp16(s v - hi) with a power-of-two scale s that brings the data into fp16 range;
+//              TWO products A_hi.B_hi + A_hi.B_lo: the reference operand keeps 22 bits, the query operand 11, so the
+//              dropped term A_lo.B is bounded by 2^-11 sum|a||b| -- two thirds of the tensor work of the other flavours
+//              for a wider (but still certified) rounding bound.
+// All of them are only used to SELECT candidates; every value that reaches the output is re-evaluated in float64 by
+// refine.cu, and rows whose candidate list cannot be certified against the flavour's bound take the radius pass.
 //
 // CTA = 128 query rows (UMMA M=128, cta_group::1), persistent: cluster c sweeps the whole reference set once per
 // round for its next pair of query tiles.  The query tile (A_hi, A_lo) lives in TENSOR MEMORY for the whole sweep
@@ -32,6 +37,7 @@
 #include "gtb200.h"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -45,6 +51,11 @@ constexpr int TC_M = 128, TC_N = 128, TC_CAP = GTB_TC_CAP, TC_S = 32, TC_GROUPS 
 static_assert(TC_CAP % 32 == 0 && TC_CAP >= TC_S + 64 && TC_CAP <= 128, "candidate buffer: TC_S kept + two batches of 32");
 constexpr float TC_BIG = 1e29f;       // "no threshold yet"; padded reference rows carry |y|^2 = 1e30
 constexpr float TC_PAD_NORM = 1e30f;
+// fp16 operands: the scaled data keeps |y|^2 <= 2^13, so every real value |y|^2 - 2 x.y stays below 3 * 2^13 < TC_BIG_H,
+// and padded reference rows (|y|^2 = TC_PAD_NORM_H, the rest zero) never pass the initial threshold
+constexpr float TC_BIG_H = 50000.f;
+constexpr float TC_PAD_NORM_H = 60000.f;
+constexpr float TC_H_MAXNORM = 8192.f;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -275,10 +286,10 @@ __device__ __forceinline__ void tc_commit_mc_pred(uint32_t bar, uint16_t mask, u
       : "memory");
 }
 
-// BF16 = false: operands are tf32 hi/lo float32 pairs (3xTF32, kind::tf32, 8 elements per 32-byte k-step);
-// BF16 = true : operands are bfloat16 hi/lo pairs (bf16x3, kind::f16, 16 elements per k-step, twice the MMA rate;
-//               the split keeps 16 mantissa bits -- still only used to SELECT candidates).
-template <int MODE, int CL, bool BF16, int LS>  // MODE 0 = TOPK (two lists of LS per row), 1 = RADIUS
+// FMT 0: operands are tf32 hi/lo float32 pairs (3xTF32, kind::tf32, 8 elements per 32-byte k-step);
+// FMT 1: bfloat16 hi/lo pairs (bf16x3, kind::f16, 16 elements per k-step, twice the MMA rate);
+// FMT 2: float16 hi/lo pairs, two products (fp16x2, kind::f16).
+template <int MODE, int CL, int FMT, int LS>  // MODE 0 = TOPK (two lists of LS per row), 1 = RADIUS
 __global__ void __launch_bounds__(TC_THREADS, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBht,
                  const __grid_constant__ CUtensorMap mBl, const __grid_constant__ CUtensorMap mBlt,
@@ -288,6 +299,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* gbase = smem_raw + (base - raw);
 
+  constexpr bool BF16 = FMT != 0;                            // 2-byte operand elements (bf16 or fp16): kind::f16
+  constexpr int NPROD = (FMT == 2) ? 2 : 3;                  // (A_hi,B_hi), (A_hi,B_lo)[, (A_lo,B_hi)]
+  constexpr float BIG = (FMT == 2) ? TC_BIG_H : TC_BIG;
   constexpr int EPK = BF16 ? 16 : 8;                         // elements per 32-byte k-step
   const int nks = p.nks;                                     // 32-byte k-steps per operand row
   const int nfull = nks / 4, ntail = nks % 4;                // SWIZZLE_128B blocks (4 k-steps) + SWIZZLE_32B tail blocks
@@ -404,8 +418,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     // are predicated on the elected lane.  (Issuing from inside an `if (lane == 0)` region costs ~18
     // SASS instructions per MMA -- R2UR + an ELECT loop -- and left the tensor pipe 3/4 idle.)
     const bool leader = elect_one();
-    // instruction descriptor: D=f32, A=B=tf32 (2) or bf16 (1), K-major, N=TC_N, M=128
-    constexpr uint32_t fmt = BF16 ? 1u : 2u;
+    // instruction descriptor: D=f32, A=B=tf32 (2, kind::tf32) / bf16 (1) / f16 (0, both kind::f16), K-major, N=TC_N, M=128
+    constexpr uint32_t fmt = (FMT == 0) ? 2u : (FMT == 1 ? 1u : 0u);
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                            ((uint32_t)(TC_M >> 4) << 24);
     const uint64_t bd_main0 = make_desc(B0, 1024, 2);                          // stage 0, hi part, block 0
@@ -427,7 +441,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
       uint32_t accum = 0;
       const uint32_t lead = leader ? 1u : 0u;
 #pragma unroll 1
-      for (int prod = 0; prod < 3; ++prod) {   // (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi)
+      for (int prod = 0; prod < NPROD; ++prod) {   // (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi)
         uint32_t ac = tmem_base + (uint32_t)((prod == 2) ? a_lo_col : 0);
         const uint64_t boff = (uint64_t)(s * stage_off + ((prod == 1) ? part_off : 0u));
         uint64_t bd = bd_main0 + boff;
@@ -482,7 +496,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int ks = 0; ks < nks; ++ks) {
         tmem_st8(lane_addr + (uint32_t)(ks * 8), in_pad ? rh[2 * ks] : z4, in_pad ? rh[2 * ks + 1] : z4);
-        tmem_st8(lane_addr + (uint32_t)(a_lo_col + ks * 8), in_pad ? rl[2 * ks] : z4, in_pad ? rl[2 * ks + 1] : z4);
+        if (NPROD == 3)
+          tmem_st8(lane_addr + (uint32_t)(a_lo_col + ks * 8), in_pad ? rl[2 * ks] : z4, in_pad ? rl[2 * ks + 1] : z4);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
@@ -492,7 +507,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
 
     const float nx = valid ? p.qn2[gq] : 0.f;
     float thr;
-    if (MODE == 0) thr = valid ? TC_BIG : -gtb_inf_f();
+    if (MODE == 0) thr = valid ? BIG : -gtb_inf_f();
     else thr = valid ? (p.lim2[gq] - nx) : -gtb_inf_f();
     int cnt = 0;
     // this thread's candidate buffer: uniform base + per-thread offset (rows past nq never append)
@@ -625,7 +640,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
       if (valid) {
         int32_t* out = p.cand_idx + gq * (TC_GROUPS * LS) + grp * LS;
         for (int e = 0; e < LS; ++e) out[e] = (e < cnt) ? (int32_t)p.cand_buf[boff + e].y : -1;
-        p.tau[gq * TC_GROUPS + grp] = (cnt < LS || thr >= TC_BIG) ? gtb_inf_f() : thr + nx;
+        p.tau[gq * TC_GROUPS + grp] = (cnt < LS || thr >= BIG) ? gtb_inf_f() : thr + nx;
       }
     }
     }  // rounds
@@ -715,6 +730,30 @@ __global__ void tc_split16_kernel(const float* __restrict__ X, int64_t n, int d,
   lo[e] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+// fp16 pairs of the scaled data: hi = fp16(s v), lo = fp16(s v - hi); the norm column carries s^2 |y|^2
+__global__ void tc_split16h_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ mean,
+                                   int role, const float* __restrict__ norm2, int64_t n_pad, int Kp, float scale,
+                                   __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_pad * Kp) return;
+  const int64_t r = e / Kp;
+  const int k = (int)(e - r * Kp);
+  float v = 0.f;
+  if (r < n) {
+    if (k < d) {
+      v = (X[r * d + k] - (mean ? mean[k] : 0.f)) * scale;
+      if (role == 1) v *= -2.f;
+    } else if (k == d) {
+      v = (role == 1) ? norm2[r] * scale * scale : 1.f;
+    }
+  } else if (role == 1 && k == d) {
+    v = TC_PAD_NORM_H;
+  }
+  const __half h = __float2half_rn(v);
+  hi[e] = h;
+  lo[e] = __float2half_rn(v - __half2float(h));
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -733,35 +772,35 @@ EncodeTiledFn get_encode() {
 }
 
 // 2-D map over a row-major [rows][Kp] float32 / bfloat16 array; box = {box_k elements, box_rows}
-int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int Kp, int box_k, int box_rows, bool sw128, bool bf16) {
+int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int Kp, int box_k, int box_rows, bool sw128, int fmt) {
+  const bool bf16 = fmt != 0;
   EncodeTiledFn enc = get_encode();
   if (!enc) { gtb_set_error("cuTensorMapEncodeTiled entry point not available"); return GTB_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)Kp * (bf16 ? 2 : 4)};
   cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+  CUresult r = enc(m, fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : (fmt == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 2, (void*)ptr, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { gtb_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return GTB_ERR_CUDA; }
   return GTB_OK;
 }
 
-int g_tc_pacing = 1;
-
-template <int MODE, int CL, bool BF16, int LS>
+template <int MODE, int CL, int FMT, int LS>
 int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, TcParams& p,
                  cudaStream_t st) {
   CUtensorMap mBh, mBht, mBl, mBlt;
   int rc;
+  constexpr bool BF16 = FMT != 0;
   constexpr int EPK = BF16 ? 16 : 8;
   p.nks = Kp / EPK;
-  if ((rc = make_map(&mBh, r_hi, p.nr_pad, Kp, 4 * EPK, TC_N / CL, true, BF16))) return rc;
-  if ((rc = make_map(&mBht, r_hi, p.nr_pad, Kp, EPK, TC_N / CL, false, BF16))) return rc;
-  if ((rc = make_map(&mBl, r_lo, p.nr_pad, Kp, 4 * EPK, TC_N / CL, true, BF16))) return rc;
-  if ((rc = make_map(&mBlt, r_lo, p.nr_pad, Kp, EPK, TC_N / CL, false, BF16))) return rc;
+  if ((rc = make_map(&mBh, r_hi, p.nr_pad, Kp, 4 * EPK, TC_N / CL, true, FMT))) return rc;
+  if ((rc = make_map(&mBht, r_hi, p.nr_pad, Kp, EPK, TC_N / CL, false, FMT))) return rc;
+  if ((rc = make_map(&mBl, r_lo, p.nr_pad, Kp, 4 * EPK, TC_N / CL, true, FMT))) return rc;
+  if ((rc = make_map(&mBlt, r_lo, p.nr_pad, Kp, EPK, TC_N / CL, false, FMT))) return rc;
   size_t smem = 1024 + (size_t)2 * (BF16 ? 3 : 2) * TC_N * p.nks * 32 + 256 + 1024;
-  auto kern = search_tc_kernel<MODE, CL, BF16, LS>;
+  auto kern = search_tc_kernel<MODE, CL, FMT, LS>;
   GTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, nsm = 0;
   GTB_CUDA(cudaGetDevice(&dev));
@@ -781,18 +820,11 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
     n_clusters = n_cluster_tiles * splits;
   }
   const unsigned nblk = (unsigned)(n_clusters * CL);
-  // pacing counter: a small ring of device words, one fresh (zeroed) slot per launch
-  static unsigned int* ring[64] = {nullptr};
-  static int ring_pos[64] = {0};
-  p.sync_ctr = nullptr;
-  if (dev < 64 && g_tc_pacing && nblk > (unsigned)CL && splits == 1) {
-    if (!ring[dev]) {
-      if (cudaMalloc(&ring[dev], 32 * 64) != cudaSuccess) { ring[dev] = nullptr; (void)cudaGetLastError(); }
-    }
-    if (ring[dev]) {
-      p.sync_ctr = ring[dev] + 16 * (ring_pos[dev]++ % 32);
-      GTB_CUDA(cudaMemsetAsync(p.sync_ctr, 0, sizeof(unsigned int), st));
-    }
+  // pacing counter: one caller-owned device word, zeroed per launch (no state is kept in the library)
+  if (p.sync_ctr != nullptr && nblk > (unsigned)CL && splits == 1) {
+    GTB_CUDA(cudaMemsetAsync(p.sync_ctr, 0, sizeof(unsigned int), st));
+  } else {
+    p.sync_ctr = nullptr;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nblk);
@@ -811,30 +843,31 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
   return GTB_OK;
 }
 
-int g_tc_cluster = 2;
+template <int MODE, int FMT>
+int launch_tc_fmt(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, int list, int cluster,
+                  TcParams& p, cudaStream_t st) {
+  constexpr int LS_SHORT = (MODE == 0) ? 16 : 32;
+  const bool short_list = (MODE == 0) && list == 16;
+  switch (cluster) {
+    case 1: return short_list ? launch_tc_cl<MODE, 1, FMT, LS_SHORT>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
+                              : launch_tc_cl<MODE, 1, FMT, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+    case 2: return short_list ? launch_tc_cl<MODE, 2, FMT, LS_SHORT>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
+                              : launch_tc_cl<MODE, 2, FMT, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+    case 4:
+      if (FMT == 0)
+        return short_list ? launch_tc_cl<MODE, 4, 0, LS_SHORT>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
+                          : launch_tc_cl<MODE, 4, 0, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+      // fall through: the 2-byte flavours support clusters of 1 or 2
+    default: gtb_set_error("cluster size must be 1 or 2 (or 4 for the tf32 flavour)"); return GTB_ERR_ARG;
+  }
+}
 
 template <int MODE>
-int launch_tc(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, bool bf16, int list,
-              TcParams& p, cudaStream_t st) {
-  const bool short_list = (MODE == 0) && list == 16;
-  if (bf16) {
-    switch (g_tc_cluster) {
-      case 1: return short_list ? launch_tc_cl<MODE, 1, true, (MODE == 0 ? 16 : 32)>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
-                                : launch_tc_cl<MODE, 1, true, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
-      case 2: return short_list ? launch_tc_cl<MODE, 2, true, (MODE == 0 ? 16 : 32)>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
-                                : launch_tc_cl<MODE, 2, true, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
-      default: gtb_set_error("cluster size must be 1 or 2 for the bf16 variant"); return GTB_ERR_ARG;
-    }
-  }
-  switch (g_tc_cluster) {
-    case 1: return short_list ? launch_tc_cl<MODE, 1, false, (MODE == 0 ? 16 : 32)>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
-                              : launch_tc_cl<MODE, 1, false, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
-    case 2: return short_list ? launch_tc_cl<MODE, 2, false, (MODE == 0 ? 16 : 32)>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
-                              : launch_tc_cl<MODE, 2, false, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
-    case 4: return short_list ? launch_tc_cl<MODE, 4, false, (MODE == 0 ? 16 : 32)>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
-                              : launch_tc_cl<MODE, 4, false, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
-    default: gtb_set_error("cluster size must be 1, 2 or 4"); return GTB_ERR_ARG;
-  }
+int launch_tc(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, int dtype, int list,
+              int cluster, TcParams& p, cudaStream_t st) {
+  if (dtype == 1) return launch_tc_fmt<MODE, 1>(q_hi, q_lo, r_hi, r_lo, Kp, list, cluster, p, st);
+  if (dtype == 2) return launch_tc_fmt<MODE, 2>(q_hi, q_lo, r_hi, r_lo, Kp, list, cluster, p, st);
+  return launch_tc_fmt<MODE, 0>(q_hi, q_lo, r_hi, r_lo, Kp, list, cluster, p, st);
 }
 
 }  // namespace
@@ -842,25 +875,31 @@ int launch_tc(const void* q_hi, const void* q_lo, const void* r_hi, const void* 
 // largest operand row: 13 k-steps of 32 bytes = 104 tf32 or 208 bf16 elements (TMEM: 2 x 104 columns for A)
 extern "C" int gtb_tc_max_kp(void) { return 104; }
 
-// cluster size used by the tensor-core search (1, 2 or 4 CTAs sharing each reference tile via TMA multicast)
-// grid-wide pacing of the TMA producers (1 = on, default; 0 = off)
-extern "C" int gtb_tc_set_pacing(int on) { g_tc_pacing = on ? 1 : 0; return GTB_OK; }
-
-extern "C" int gtb_tc_set_cluster(int cl) {
-  GTB_CHECK_ARG(cl == 1 || cl == 2 || cl == 4, "cluster size must be 1, 2 or 4");
-  g_tc_cluster = cl;
+// squared norms of the centred rows (rounded up) and their maximum: what the fp16 flavour needs BEFORE the split, to
+// pick the power-of-two scale that brings the data into fp16 range
+extern "C" int gtb_row_norms(const float* X, int64_t n, int d, const float* mean, int64_t n_pad, float* norm2,
+                             float* maxnorm, void* stream) {
+  GTB_CHECK_ARG(n > 0 && d > 0 && n_pad >= n, "bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (maxnorm) GTB_CUDA(cudaMemsetAsync(maxnorm, 0, sizeof(float), st));
+  tc_norms_kernel<<<(unsigned)gtb_cdiv(n_pad * 32, 256), 256, 0, st>>>(X, n, d, mean, n_pad, norm2, maxnorm);
+  GTB_CHECK_LAUNCH();
   return GTB_OK;
 }
 
+// largest scaled squared norm the fp16 flavour accepts: scale^2 * max|row|^2 must stay <= this
+extern "C" float gtb_tc_fp16_maxnorm(void) { return TC_H_MAXNORM; }
+
 extern "C" int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const float* mean, int role, void* hi,
-                                      void* lo, int64_t n_pad, int Kp, int dtype, float* norm2, float* maxnorm,
-                                      void* stream) {
+                                      void* lo, int64_t n_pad, int Kp, int dtype, float scale, float* norm2,
+                                      float* maxnorm, void* stream) {
   GTB_CHECK_ARG(n > 0 && d > 0 && n_pad >= n && n_pad % 128 == 0, "bad shape");
-  GTB_CHECK_ARG(dtype == 0 || dtype == 1, "dtype must be 0 (tf32 pairs in float32) or 1 (bfloat16 pairs)");
+  GTB_CHECK_ARG(dtype >= 0 && dtype <= 2, "dtype must be 0 (tf32 pairs in float32), 1 (bfloat16 pairs) or 2 (float16 pairs)");
   const int epk = dtype ? 16 : 8;
   GTB_CHECK_ARG(Kp % epk == 0 && Kp >= d + 1 && Kp / epk <= (dtype ? 8 : 13),
-                "Kp must be a multiple of 8 (tf32, <= 104) / 16 (bf16, <= 128) and >= d+1");
+                "Kp must be a multiple of 8 (tf32, <= 104) / 16 (bf16 / fp16, <= 128) and >= d+1");
   GTB_CHECK_ARG(role == 0 || role == 1, "role must be 0 (query) or 1 (reference)");
+  GTB_CHECK_ARG(dtype != 2 || scale > 0.f, "the fp16 flavour needs a positive scale");
   cudaStream_t st = (cudaStream_t)stream;
   if (maxnorm) GTB_CUDA(cudaMemsetAsync(maxnorm, 0, sizeof(float), st));
   tc_norms_kernel<<<(unsigned)gtb_cdiv(n_pad * 32, 256), 256, 0, st>>>(X, n, d, mean, n_pad, norm2, maxnorm);
@@ -868,9 +907,12 @@ extern "C" int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const fl
   if (dtype == 0)
     tc_split_kernel<<<(unsigned)gtb_cdiv(n_pad * Kp, 256), 256, 0, st>>>(X, n, d, mean, role, norm2, n_pad, Kp,
                                                                         (float*)hi, (float*)lo);
-  else
+  else if (dtype == 1)
     tc_split16_kernel<<<(unsigned)gtb_cdiv(n_pad * Kp, 256), 256, 0, st>>>(X, n, d, mean, role, norm2, n_pad, Kp,
                                                                           (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  else
+    tc_split16h_kernel<<<(unsigned)gtb_cdiv(n_pad * Kp, 256), 256, 0, st>>>(X, n, d, mean, role, norm2, n_pad, Kp, scale,
+                                                                           (__half*)hi, (__half*)lo);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }
@@ -879,7 +921,7 @@ extern "C" int64_t gtb_tc_scratch_bytes(int64_t nq_pad) { return nq_pad * TC_GRO
 
 static int tc_check(int64_t nq, int64_t nr, int64_t nq_pad, int64_t nr_pad, int Kp, int dtype) {
   GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TC_M == 0 && nr_pad % TC_N == 0, "bad shape (pads must be x128)");
-  GTB_CHECK_ARG(dtype == 0 || dtype == 1, "dtype must be 0 (tf32) or 1 (bf16)");
+  GTB_CHECK_ARG(dtype >= 0 && dtype <= 2, "dtype must be 0 (tf32), 1 (bf16) or 2 (fp16, two products)");
   const int epk = dtype ? 16 : 8;
   GTB_CHECK_ARG(Kp % epk == 0 && Kp >= epk && Kp / epk <= (dtype ? 8 : 13), "Kp out of range");
   GTB_CHECK_ARG(nr_pad < (1ll << 31) && nq_pad < (1ll << 31), "too many rows for 32-bit TMA coordinates");
@@ -888,25 +930,26 @@ static int tc_check(int64_t nq, int64_t nr, int64_t nq_pad, int64_t nr_pad, int 
 
 extern "C" int gtb_knn_topk_tc(const void* q_hi, const void* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
                                const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp, int dtype,
-                               int list, int32_t* cand_idx, void* scratch, float* tau, void* stream) {
+                               int list, int cluster, int32_t* cand_idx, void* scratch, float* tau,
+                               unsigned int* pace, void* stream) {
   int rc = tc_check(nq, nr, nq_pad, nr_pad, Kp, dtype);
   if (rc) return rc;
   GTB_CHECK_ARG(list == 16 || list == 32, "list size must be 16 or 32");
   TcParams p{};
   p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.qn2 = qn2;
-  p.cand_idx = cand_idx; p.cand_buf = reinterpret_cast<uint2*>(scratch); p.tau = tau;
-  return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, Kp, dtype == 1, list, p, (cudaStream_t)stream);
+  p.cand_idx = cand_idx; p.cand_buf = reinterpret_cast<uint2*>(scratch); p.tau = tau; p.sync_ctr = pace;
+  return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, Kp, dtype, list, cluster, p, (cudaStream_t)stream);
 }
 
 extern "C" int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float* qn2, const float* lim2,
                                  int64_t nq, int64_t nq_pad, const void* r_hi, const void* r_lo, int64_t nr,
-                                 int64_t nr_pad, int Kp, int dtype, int32_t* pairs, int64_t capacity,
-                                 unsigned long long* counter, int32_t* rowcnt, void* stream) {
+                                 int64_t nr_pad, int Kp, int dtype, int cluster, int32_t* pairs, int64_t capacity,
+                                 unsigned long long* counter, int32_t* rowcnt, unsigned int* pace, void* stream) {
   int rc = tc_check(nq, nr, nq_pad, nr_pad, Kp, dtype);
   if (rc) return rc;
   TcParams p{};
   p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.qn2 = qn2; p.lim2 = lim2;
   p.pairs = reinterpret_cast<int2*>(pairs); p.capacity = (unsigned long long)capacity; p.counter = counter;
-  p.rowcnt = rowcnt;
-  return launch_tc<1>(q_hi, q_lo, r_hi, r_lo, Kp, dtype == 1, 32, p, (cudaStream_t)stream);
+  p.rowcnt = rowcnt; p.sync_ctr = pace;
+  return launch_tc<1>(q_hi, q_lo, r_hi, r_lo, Kp, dtype, 32, cluster, p, (cudaStream_t)stream);
 }

@@ -246,21 +246,33 @@ class SearchOperand:
             self._l1 = (n1.to(torch.float32).contiguous(), float(n1.max().item()))
         return self._l1
 
-    def tc(self, role, dtype=0):
-        key = (role, dtype)
+    def tc(self, role, dtype=0, scale=1.0):
+        """(hi, lo, norm2) of one role; dtype 0 = tf32 pairs in float32, 1 = bfloat16 pairs, 2 = float16 pairs of the
+        data scaled by ``scale`` (norm2 stays unscaled)."""
+        key = (role, dtype, float(scale))
         if key not in self._tc:
             Kp = self.kp(dtype)
-            st = torch.bfloat16 if dtype else torch.float32
+            st = (torch.float32, torch.bfloat16, torch.float16)[dtype]
             hi = _empty((self.n_pad, Kp), st)
             lo = _empty((self.n_pad, Kp), st)
             n2 = _empty((self.n_pad,), torch.float32)
             mx = _empty((1,), torch.float32)
             E.call("gtb_prepare_operand_tc", self.Xs, self.n, self.d, self._kmean, role, hi, lo, self.n_pad, Kp,
-                   dtype, n2, mx)
+                   dtype, float(scale), n2, mx)
             self._tc[key] = (hi, lo, n2)
             if self._maxnorm is None:
                 self._maxnorm = mx
         return self._tc[key]
+
+    def norm_max(self):
+        """max squared norm of the centred rows WITHOUT building an operand (the fp16 flavour needs it to choose its
+        scale before the split); one pass over X and one host read."""
+        if self._maxnorm_host is None and self._maxnorm is None:
+            n2 = _empty((self.n_pad,), torch.float32)
+            mx = _empty((1,), torch.float32)
+            E.call("gtb_row_norms", self.Xs, self.n, self.d, self._kmean, self.n_pad, n2, mx)
+            self._maxnorm = mx
+        return self.maxnorm
 
     @property
     def maxnorm(self):
@@ -331,8 +343,9 @@ def tc_cluster():
 
 
 def default_impl():
-    """GTB_SEARCH_IMPL = tc (3xTF32 tensor cores) | tc16 (bf16x3 tensor cores) | simt (fp32 CUDA cores) |
-    auto (default: tensor cores whenever the operand fits)."""
+    """GTB_SEARCH_IMPL = tc (3xTF32 tensor cores) | tc16 (bf16x3 tensor cores) | tch (fp16x2 tensor cores: two
+    products, wider certified bound) | simt (fp32 CUDA cores) | auto (default: tensor cores whenever the operand
+    fits)."""
     import os
     return os.environ.get("GTB_SEARCH_IMPL", "auto")
 
@@ -354,6 +367,25 @@ def eps_rel_l1(d):
     """Cityblock pass: float32 subtraction and accumulation of d terms |x_k - y_k| -- relative error of the
     DISTANCE at most (d + 1) * 2^-24 (all terms non-negative, no cancellation), doubled."""
     return 2.0 * (d + 2) * 2.0 ** -24
+
+
+def eps_rel_tch(d):
+    """fp16x2 (A_hi B_hi + A_hi B_lo on float16 pairs): the dropped query low part is <= 2^-11 |a| per element, so
+    the dropped product is <= 2^-11 sum |a||b| <= 2^-11 |x~| |2 y~| <= 2^-11 (|x~|^2 + |y~|^2); the reference operand
+    keeps 22 bits (2^-22, twice for the two parts), float32 accumulation as for the other flavours, 1e-6 covers fp16
+    subnormals of the low parts at the chosen scale."""
+    return 2.0 ** -11 + 2.0 ** -20 + 2.0 * (d + 32) * 2.0 ** -24 + 1e-6
+
+
+def fp16_scale(maxnorm):
+    """Power of two s with s^2 * maxnorm <= gtb_tc_fp16_maxnorm(): scaled data fits float16 with headroom."""
+    limit = float(E.lib().gtb_tc_fp16_maxnorm())
+    if not (maxnorm > 0):
+        return 1.0
+    return 2.0 ** math.floor(0.5 * math.log2(limit / maxnorm))
+
+
+TC_DTYPE = {"tc": 0, "tc16": 1, "tch": 2}
 
 
 def eps_rel_simt(d):
@@ -390,20 +422,22 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         # GTB_SEARCH_IMPL is a preference: a flavour that cannot take this shape (feature count beyond the
         # resident query tile, knn beyond the 2 x 32 candidate lists) hands over to the next one
         want = default_impl()
-        order = {"auto": (AUTO_TC, "tc16" if AUTO_TC == "tc" else "tc", "simt"), "tc": ("tc", "tc16", "simt"),
-                 "tc16": ("tc16", "tc", "simt"), "simt": ("simt",)}.get(want)
+        order = {"auto": (AUTO_TC,) + tuple(x for x in ("tc16", "tc") if x != AUTO_TC) + ("simt",),
+                 "tc": ("tc", "tc16", "simt"), "tc16": ("tc16", "tc", "simt"), "tch": ("tch", "tc16", "tc", "simt"),
+                 "simt": ("simt",)}.get(want)
         if order is None:
-            raise ValueError("GTB_SEARCH_IMPL must be auto, tc, tc16 or simt (got %r)" % (want,))
+            raise ValueError("GTB_SEARCH_IMPL must be auto, tc, tc16, tch or simt (got %r)" % (want,))
         impl = "simt"
         for cand_impl in order:
             if cand_impl == "simt" or (knn + 8 <= 32 and S in (None, 32, 64)
-                                       and ref.tc_ok(1 if cand_impl == "tc16" else 0)):
+                                       and ref.tc_ok(TC_DTYPE[cand_impl])):
                 impl = cand_impl
                 break
     dev = _dev()
     ntau = 1
-    tcd = 1 if impl == "tc16" else 0
-    if impl in ("tc", "tc16"):
+    tcd = TC_DTYPE.get(impl, 0)
+    tc_scale = 1.0
+    if impl in TC_DTYPE:
         if not ref.tc_ok(tcd):
             raise ValueError("tensor-core search: d = {} does not fit the resident query tile".format(d))
         import os
@@ -415,20 +449,27 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         if ls not in (16, 32) or knn > ls:
             raise ValueError("GTB_TC_LIST must be 16 or 32 and >= knn")
         S, stride, ntau = 2 * ls, 2 * ls, 2
-        E.lib().gtb_tc_set_pacing(int(os.environ.get("GTB_TC_PACING", "1")))
-        if E.lib().gtb_tc_set_cluster(min(tc_cluster(), 2) if tcd else tc_cluster()) != 0:
+        cluster = min(tc_cluster(), 2) if tcd else tc_cluster()
+        if cluster not in (1, 2, 4):
             raise ValueError("GTB_TC_CLUSTER must be 1, 2 or 4")
+        # grid-wide pacing of the TMA producers: one caller-owned device word per launch (no library state)
+        pace = _empty((1,), torch.int32) if int(os.environ.get("GTB_TC_PACING", "1")) else None
         if knn > 32:
             raise NotImplementedError("knn={} exceeds the tensor-core candidate lists (2 x 32)".format(knn))
-        eps_rel = eps_rel_tc16(d) if tcd else eps_rel_tc(d)
-        q_hi, q_lo, q_n2 = qry.tc(0, tcd)
-        r_hi, r_lo, _ = ref.tc(1, tcd)
+        eps_rel = (eps_rel_tc, eps_rel_tc16, eps_rel_tch)[tcd](d)
+        if tcd == 2:
+            tc_scale = fp16_scale(max(qry.norm_max(), ref.norm_max()))
+        q_hi, q_lo, q_n2 = qry.tc(0, tcd, tc_scale)
+        r_hi, r_lo, _ = ref.tc(1, tcd, tc_scale)
         Kp = ref.kp(tcd)
         cand = _empty((nq, stride), torch.int32)
         tau = _empty((nq, ntau), torch.float32)
         scratch = _empty((E.lib().gtb_tc_scratch_bytes(qry.n_pad),), torch.uint8)
-        E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, nq, qry.n_pad, r_hi, r_lo, nr, ref.n_pad, Kp, tcd, ls, cand,
-               scratch, tau)
+        s2 = tc_scale * tc_scale
+        E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2 * s2 if tcd == 2 else q_n2, nq, qry.n_pad, r_hi, r_lo, nr,
+               ref.n_pad, Kp, tcd, ls, cluster, cand, scratch, tau, pace)
+        if tcd == 2:
+            tau = tau / s2                                   # scaled squared distances -> data units (inf stays inf)
         del scratch
     elif impl == "simt":
         if S is None:
@@ -485,11 +526,14 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         nt_pad = (nt + 127) // 128 * 128
         lim_t = torch.zeros((nt_pad,), dtype=torch.float32, device=dev)
         lim_t[:nt] = lim2[todo_rows.long()]
-        if impl in ("tc", "tc16"):
+        if impl in TC_DTYPE:
             # the radius rows form their own (small) query operand; build it from the gathered rows
             sub = SearchOperand(qry.X[todo_rows.long()].contiguous(), mean=ref.mean, metric=ref.metric)
-            s_hi, s_lo, s_n2 = sub.tc(0, tcd)
-            r_hi, r_lo, _ = ref.tc(1, tcd)
+            s_hi, s_lo, s_n2 = sub.tc(0, tcd, tc_scale)
+            r_hi, r_lo, _ = ref.tc(1, tcd, tc_scale)
+            if tcd == 2:
+                s_n2 = s_n2 * (tc_scale * tc_scale)
+                lim_t = lim_t * (tc_scale * tc_scale)
         else:
             QT = _empty((ref.d_pad, nt_pad), torch.float32)
             qn2 = _empty((nt_pad,), torch.float32)
@@ -499,9 +543,9 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
             pairs = _empty((capacity, 2), torch.int32)
             counter = _zeros((1,), torch.int64)
             rowcnt = _zeros((nt_pad,), torch.int32)
-            if impl in ("tc", "tc16"):
+            if impl in TC_DTYPE:
                 E.call("gtb_knn_radius_tc", s_hi, s_lo, s_n2, lim_t, nt, nt_pad, r_hi, r_lo, nr, ref.n_pad, Kp, tcd,
-                       pairs, capacity, counter, rowcnt)
+                       cluster, pairs, capacity, counter, rowcnt, pace)
             elif l1:
                 E.call("gtb_knn_radius_simt_l1", QT, lim_t, nt, nt_pad, ref.XT, nr, ref.n_pad, ref.d_pad, pairs,
                        capacity, counter, rowcnt)

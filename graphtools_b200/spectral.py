@@ -15,11 +15,15 @@ of magnitude more than the whole kernel build on the GPU.  This module runs the 
   assignment step -- nearest centre of every batch sample, and the final labelling of all N samples -- is the fused
   distance / top-1 kernel (exact float64 argmin).
 
-The random streams are torch's, not numpy's: clusters are NOT bit-identical to the host path (they cannot be --
-k-means labels flip under any change of summation order).  The host path stays the pin for parity and the default
-up to landmark.SPECTRAL_AUTO_N samples; this path is selected with ``GTB_SPECTRAL=device`` (and by ``auto`` above
-that size) and is graded by what it must achieve: known spectra to machine precision, the captured energy of the
-SVD and the k-means inertia relative to sklearn's on the same input (tests/test_spectral_gpu.py).
+Random streams (``GTB_SPECTRAL_RNG``): ``numpy`` (default) draws every random number on the HOST from the same
+``numpy.random.RandomState(seed)`` streams, in the same order, as scikit-learn does -- the Gaussian test matrix of
+``randomized_svd`` ([N, n_svd + 10]: 3.7 s of single-thread MT19937 at 1M samples, the price of starting from the
+reference's own matrix), the validation / init subsets, the k-means++ draws, every mini-batch and every
+reassignment of ``MiniBatchKMeans``.  The run then follows the reference's trajectory up to floating-point
+summation order: V agrees with sklearn's to rounding and the clusters agree except for samples that sit on a
+boundary (tests/test_spectral_gpu.py reports the agreement).  ``torch`` uses device generators instead (no host
+draw; same algorithms, unrelated clusters).  The host path (``GTB_SPECTRAL=host``) stays the bit-exact pin; this
+path is selected with ``GTB_SPECTRAL=device`` and by ``auto`` above landmark.SPECTRAL_AUTO_N samples.
 """
 import math
 
@@ -28,6 +32,58 @@ import torch
 
 from . import _engine as E
 from . import pipeline
+
+
+def rng_mode():
+    import os
+    mode = os.environ.get("GTB_SPECTRAL_RNG", "numpy")
+    if mode not in ("numpy", "torch"):
+        raise ValueError("GTB_SPECTRAL_RNG must be numpy or torch (got %r)" % (mode,))
+    return mode
+
+
+def _check_random_state(seed):
+    from sklearn.utils import check_random_state
+    return check_random_state(seed)
+
+
+class _Draws:
+    """The random draws of the two algorithms behind one interface: numpy RandomState on the host (scikit-learn's
+    streams and call order) or torch device generators."""
+
+    def __init__(self, random_state, mode, salt=0):
+        self.mode = mode
+        self.dev = pipeline._dev()
+        if mode == "numpy":
+            self.rs = _check_random_state(random_state)
+        else:
+            self.gen = torch.Generator(device=self.dev)
+            self.gen.manual_seed(_seed_of(random_state) + salt)
+
+    def normal(self, n, k):
+        if self.mode == "numpy":
+            return torch.from_numpy(self.rs.normal(size=(n, k))).to(self.dev)
+        return torch.randn((n, k), dtype=torch.float64, device=self.dev, generator=self.gen)
+
+    def randint(self, high, size):
+        if self.mode == "numpy":
+            return torch.from_numpy(self.rs.randint(0, high, size)).to(self.dev)
+        return torch.randint(0, high, (size,), device=self.dev, generator=self.gen)
+
+    def first_center(self, n):
+        if self.mode == "numpy":          # random_state.choice(n, p=sample_weight / sample_weight.sum())
+            return int(self.rs.choice(n, p=np.full(n, 1.0 / n)))
+        return int(torch.randint(0, n, (1,), device=self.dev, generator=self.gen).item())
+
+    def uniform(self, size):
+        if self.mode == "numpy":
+            return torch.from_numpy(self.rs.uniform(size=size)).to(self.dev)
+        return torch.rand((size,), dtype=torch.float64, device=self.dev, generator=self.gen)
+
+    def choice_no_replace(self, n, size):
+        if self.mode == "numpy":
+            return torch.from_numpy(self.rs.choice(n, replace=False, size=size)).to(self.dev)
+        return torch.randperm(n, device=self.dev, generator=self.gen)[:size]
 
 
 def _seed_of(random_state):
@@ -75,9 +131,7 @@ def randomized_svd_sym(K, A, n_components, random_state=None, n_oversamples=10, 
     k = int(min(n_components + n_oversamples, n))
     if n_iter == "auto":
         n_iter = 7 if n_components < 0.1 * n else 4
-    gen = torch.Generator(device=pipeline._dev())
-    gen.manual_seed(_seed_of(random_state))
-    Q = torch.randn((n, k), dtype=torch.float64, device=pipeline._dev(), generator=gen)
+    Q = _Draws(random_state, rng_mode()).normal(n, k)     # sklearn: random_state.normal(size=(A.shape[1], k))
     for _ in range(int(n_iter)):
         Q = _cholesky_qr(pipeline.spmm(K, Q, A), passes=1)      # A Q
         Q = _cholesky_qr(pipeline.spmm(K, Q, A), passes=1)      # A^T Q (A symmetric)
@@ -109,19 +163,20 @@ def assign_nearest(X, centers):
     return labels, d2
 
 
-def _kmeans_plusplus(X, n_clusters, gen):
-    """k-means++ seeding with sklearn's greedy local trials (2 + log k candidates per step)."""
+def _kmeans_plusplus(X, n_clusters, draws):
+    """k-means++ seeding with sklearn's greedy local trials (2 + log k candidates per step;
+    sklearn.cluster._kmeans._kmeans_plusplus, same draws in the same order)."""
     n = X.shape[0]
     dev = X.device
     n_trials = 2 + int(math.log(n_clusters))
     centers = torch.empty((n_clusters, X.shape[1]), dtype=X.dtype, device=dev)
-    first = int(torch.randint(0, n, (1,), device=dev, generator=gen).item())
+    first = draws.first_center(n)
     centers[0] = X[first]
     closest = ((X - X[first]) ** 2).sum(dim=1)
     xn = (X * X).sum(dim=1)
     for c in range(1, n_clusters):
         pot = closest.sum()
-        r = torch.rand((n_trials,), dtype=torch.float64, device=dev, generator=gen) * pot
+        r = draws.uniform(n_trials) * pot
         cand = torch.searchsorted(torch.cumsum(closest, 0), r).clamp_(max=n - 1)
         Xc = X[cand]                                                         # [t, d]
         d2 = (xn[None, :] + (Xc * Xc).sum(dim=1)[:, None] - 2.0 * (Xc @ X.T)).clamp_(min=0)
@@ -137,12 +192,12 @@ def minibatch_kmeans(X, n_clusters, init_size=None, batch_size=10000, max_iter=1
     """Labels [N] (int64 device tensor) and centres of a mini-batch k-means run with sklearn's schedule."""
     n, d = X.shape
     dev = X.device
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(_seed_of(random_state) + 1)
+    draws = _Draws(random_state, rng_mode(), salt=1)     # sklearn: check_random_state(self.random_state), a fresh stream
     batch_size = int(min(batch_size, n))
     init_size = int(min(n, max(3 * batch_size if init_size is None else init_size, n_clusters)))
-    init_idx = torch.randint(0, n, (init_size,), device=dev, generator=gen)
-    centers = _kmeans_plusplus(X[init_idx], n_clusters, gen)
+    draws.randint(n, init_size)                          # validation_indices: drawn first, only scores the n_init runs
+    init_idx = draws.randint(n, init_size) if init_size < n else torch.arange(n, device=dev)
+    centers = _kmeans_plusplus(X[init_idx], n_clusters, draws)
     counts = torch.zeros((n_clusters,), dtype=torch.float64, device=dev)
     n_steps = (max_iter * n) // batch_size
     ewa = ewa_min = None
@@ -150,7 +205,7 @@ def minibatch_kmeans(X, n_clusters, init_size=None, batch_size=10000, max_iter=1
     since_reassign = 0
     alpha = min(batch_size * 2.0 / (n + 1), 1.0)
     for step in range(n_steps):
-        idx = torch.randint(0, n, (batch_size,), device=dev, generator=gen)
+        idx = draws.randint(n, batch_size)
         Xb = X[idx].contiguous()
         labels, d2 = assign_nearest(Xb, centers)
         batch_inertia = float(d2.sum().item()) / batch_size
@@ -181,7 +236,7 @@ def minibatch_kmeans(X, n_clusters, init_size=None, batch_size=10000, max_iter=1
                 starved[keep] = True
                 ns = int(starved.sum().item())
             if ns:
-                pick = torch.randperm(batch_size, device=dev, generator=gen)[:ns]
+                pick = draws.choice_no_replace(batch_size, ns)
                 centers[starved] = Xb[pick]
                 counts[starved] = counts[~starved].min() if bool((~starved).any().item()) else 0.0
         # early stopping on the smoothed batch inertia (the first step only measures the initialisation)

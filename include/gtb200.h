@@ -70,27 +70,33 @@ int gtb_knn_radius_simt_l1(const float* QT, const float* lim, int64_t nq, int64_
  * role 1 (reference) = [-2y~, |y~|^2, 0..].
  *   dtype 0: 3xTF32 -- float32 storage, hi = tf32(v), lo = tf32(v - hi), kind::tf32, Kp = roundup(d+1, 8) <= 104
  *   dtype 1: bf16x3 -- bfloat16 storage, hi = bf16(v), lo = bf16(v - hi), kind::f16,  Kp multiple of 16, <= 128
- *            (3 smem stages, 3 TMEM accumulators)
+ *            (3 smem stages, 3 TMEM accumulators); products A_hi.B_hi + A_hi.B_lo + A_lo.B_hi like dtype 0
+ *   dtype 2: fp16x2 -- float16 storage of the data scaled by the power of two `scale` (scale^2 max|row|^2 <=
+ *            gtb_tc_fp16_maxnorm(); gtb_row_norms gives the norms beforehand), TWO products A_hi.B_hi + A_hi.B_lo:
+ *            2/3 of the tensor work, rounding bound 2^-11 (|x~|^2 + |y~|^2) on the (scaled) squared distance.  tau and
+ *            the radius limits are in scaled units (scale^2 x squared distance); the caller converts.
  * topk: cand_idx[nq][2 * list] = two lists of `list` = 32 or 16 entries (disjoint halves of the reference tiles, -1 = empty; shorter
  * lists halve the selection work -- rows whose kernel support they do not cover fail certification in gtb_refine_topk and are
  * completed by the radius pass, so the result does not depend on `list`) with their
- * thresholds tau[nq][2]; scratch = gtb_tc_scratch_bytes(nq_pad) bytes.  radius: contract of gtb_knn_radius_simt. */
+ * thresholds tau[nq][2]; scratch = gtb_tc_scratch_bytes(nq_pad) bytes.  radius: contract of gtb_knn_radius_simt.
+ * cluster: 1, 2 (or 4, tf32 only) CTAs share each reference tile through TMA multicast.  pace: one caller-owned device
+ * word for the grid-wide pacing of the TMA producers (so that one DRAM read of a reference tile serves all SMs), or
+ * NULL for no pacing -- the library keeps no state between calls. */
 int gtb_tc_max_kp(void);
-/* thread-block cluster size of the search kernel: 1, 2 (default) or 4 CTAs share each reference tile
- * through TMA multicast */
-int gtb_tc_set_cluster(int cl);
-/* grid-wide pacing of the TMA producers so that one DRAM read of a reference tile serves all SMs (default on) */
-int gtb_tc_set_pacing(int on);
+float gtb_tc_fp16_maxnorm(void);
+int gtb_row_norms(const float* X, int64_t n, int d, const float* mean, int64_t n_pad, float* norm2, float* maxnorm,
+                  void* stream);
 int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const float* mean, int role, void* hi, void* lo,
-                           int64_t n_pad, int Kp, int dtype, float* norm2, float* maxnorm, void* stream);
+                           int64_t n_pad, int Kp, int dtype, float scale, float* norm2, float* maxnorm, void* stream);
 int gtb_knn_topk_tc(const void* q_hi, const void* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
                     const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp, int dtype,
-                    int list, int32_t* cand_idx, void* scratch, float* tau, void* stream);
+                    int list, int cluster, int32_t* cand_idx, void* scratch, float* tau, unsigned int* pace,
+                    void* stream);
 int64_t gtb_tc_scratch_bytes(int64_t nq_pad);
 int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float* qn2, const float* lim2, int64_t nq,
                       int64_t nq_pad, const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp,
-                      int dtype, int32_t* pairs, int64_t capacity, unsigned long long* counter, int32_t* rowcnt,
-                      void* stream);
+                      int dtype, int cluster, int32_t* pairs, int64_t capacity, unsigned long long* counter,
+                      int32_t* rowcnt, unsigned int* pace, void* stream);
 
 /* ---- K3 float64 re-evaluation, bandwidth, affinities, CSR emission: replaces graphs.py:886-911
  * and _build_csr_from_neighbors (graphs.py:450-559) ------------------------------------------ */

@@ -18,11 +18,13 @@ ap.add_argument("--tag", default="")
 a = ap.parse_args()
 X, _ = synth.gaussian_mixture(a.n, a.d, n_clusters=50, intrinsic_dim=10, seed=3)
 ref = pipeline.SearchOperand(torch.from_numpy(X).cuda())
-q_hi, q_lo, q_n2 = ref.tc(0, a.dtype)
-r_hi, r_lo, _ = ref.tc(1, a.dtype)
+scale = pipeline.fp16_scale(ref.norm_max()) if a.dtype == 2 else 1.0
+q_hi, q_lo, q_n2 = ref.tc(0, a.dtype, scale)
+r_hi, r_lo, _ = ref.tc(1, a.dtype, scale)
+q_n2 = q_n2 * (scale * scale)
 Kp = ref.kp(a.dtype)
-E.lib().gtb_tc_set_pacing(int(os.environ.get("GTB_TC_PACING", "1")))
-E.lib().gtb_tc_set_cluster(int(os.environ.get("GTB_TC_CLUSTER", "2")))
+pace = torch.zeros(1, dtype=torch.int32, device="cuda") if int(os.environ.get("GTB_TC_PACING", "1")) else None
+cluster = int(os.environ.get("GTB_TC_CLUSTER", "2"))
 ls = int(os.environ.get("GTB_TC_LIST", "32"))
 cand = torch.empty((a.n, 2 * ls), dtype=torch.int32, device="cuda")
 tau = torch.empty((a.n, 2), dtype=torch.float32, device="cuda")
@@ -31,8 +33,8 @@ times = []
 for rep in range(a.reps + 1):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, a.n, ref.n_pad, r_hi, r_lo, a.n, ref.n_pad, Kp, a.dtype, ls, cand, scratch,
-           tau)
+    E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, a.n, ref.n_pad, r_hi, r_lo, a.n, ref.n_pad, Kp, a.dtype, ls, cluster, cand,
+           scratch, tau, pace)
     e1.record()
     torch.cuda.synchronize()
     times.append(e0.elapsed_time(e1))

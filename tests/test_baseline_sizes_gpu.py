@@ -81,16 +81,18 @@ def test_tc_certification_bound_1m(headline):
     n, d = X.shape
     Xd = pipeline.to_device_f32(X)
     ref = pipeline.SearchOperand(Xd)
-    for tcd, eps_fn in ((1, pipeline.eps_rel_tc16), (0, pipeline.eps_rel_tc)):
+    for tcd, eps_fn in ((1, pipeline.eps_rel_tc16), (2, pipeline.eps_rel_tch), (0, pipeline.eps_rel_tc)):
         ls = 16
-        q_hi, q_lo, q_n2 = ref.tc(0, tcd)
-        r_hi, r_lo, _ = ref.tc(1, tcd)
+        scale = pipeline.fp16_scale(ref.norm_max()) if tcd == 2 else 1.0
+        q_hi, q_lo, q_n2 = ref.tc(0, tcd, scale)
+        r_hi, r_lo, _ = ref.tc(1, tcd, scale)
         cand = pipeline._empty((n, 2 * ls), torch.int32)
         tau = pipeline._empty((n, 2), torch.float32)
         scratch = pipeline._empty((E.lib().gtb_tc_scratch_bytes(ref.n_pad),), torch.uint8)
-        E.lib().gtb_tc_set_cluster(2)
-        E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, n, ref.n_pad, r_hi, r_lo, n, ref.n_pad, ref.kp(tcd), tcd, ls,
-               cand, scratch, tau)
+        pace = pipeline._empty((1,), torch.int32)
+        E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2 * (scale * scale), n, ref.n_pad, r_hi, r_lo, n, ref.n_pad,
+               ref.kp(tcd), tcd, ls, 2, cand, scratch, tau, pace)
+        tau = tau / (scale * scale)
         del scratch
         rows = torch.linspace(0, n - 1, 192, device=Xd.device).long()
         X64d = Xd.double()

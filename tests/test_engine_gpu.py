@@ -99,15 +99,17 @@ def test_radius_pairs_complete():
 def _tc_topk(X, Y=None, dtype=0, ls=32):
     ref = pipeline.SearchOperand(_dev(X))
     qry = ref if Y is None else pipeline.SearchOperand(_dev(Y), mean=ref.mean)
-    q_hi, q_lo, q_n2 = qry.tc(0, dtype)
-    r_hi, r_lo, _ = ref.tc(1, dtype)
+    scale = pipeline.fp16_scale(max(qry.norm_max(), ref.norm_max())) if dtype == 2 else 1.0
+    q_hi, q_lo, q_n2 = qry.tc(0, dtype, scale)
+    r_hi, r_lo, _ = ref.tc(1, dtype, scale)
     cand = torch.full((qry.n, 2 * ls), -7, dtype=torch.int32, device="cuda")
     scratch = torch.zeros((E.lib().gtb_tc_scratch_bytes(qry.n_pad),), dtype=torch.uint8, device="cuda")
     tau = torch.empty((qry.n, 2), dtype=torch.float32, device="cuda")
-    E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, qry.n, qry.n_pad, r_hi, r_lo, ref.n, ref.n_pad, ref.kp(dtype),
-           dtype, ls, cand, scratch, tau)
+    pace = torch.zeros(1, dtype=torch.int32, device="cuda")
+    E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2 * (scale * scale), qry.n, qry.n_pad, r_hi, r_lo, ref.n, ref.n_pad,
+           ref.kp(dtype), dtype, ls, 2, cand, scratch, tau, pace)
     torch.cuda.synchronize()
-    return cand.cpu().numpy(), tau.cpu().numpy().min(axis=1), qry, ref
+    return cand.cpu().numpy(), (tau / (scale * scale)).cpu().numpy().min(axis=1), qry, ref
 
 
 def test_tc_operand_split():
@@ -128,7 +130,7 @@ def test_tc_operand_split():
 
 
 @pytest.mark.parametrize("ls", [32, 16])
-@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("dtype", [0, 1, 2])
 @pytest.mark.parametrize("n,d", [(1797, 64), (3000, 100), (700, 20), (2500, 10), (300, 5), (40, 3), (1000, 31),
                                  (1000, 55), (777, 103)])
 def test_tc_topk_candidates(n, d, dtype, ls):
@@ -139,7 +141,7 @@ def test_tc_topk_candidates(n, d, dtype, ls):
     order = np.argsort(D2, axis=1, kind="stable")
     Xc = X64 - X64.mean(0)
     nrm = (Xc ** 2).sum(1)
-    eps = pipeline.eps_rel_tc16(d) if dtype else pipeline.eps_rel_tc(d)
+    eps = (pipeline.eps_rel_tc, pipeline.eps_rel_tc16, pipeline.eps_rel_tch)[dtype](d)
     # two lists of ls: references in even / odd 128-row tiles
     tile_par = (np.arange(n) // 128) % 2
     n_even, n_odd = int((tile_par == 0).sum()), int((tile_par == 1).sum())
@@ -174,7 +176,7 @@ def test_tc_topk_out_of_sample():
         assert set(order[i, :24]).issubset(set(cand[i]))
 
 
-@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("dtype", [0, 1, 2])
 def test_tc_radius_pairs_complete(dtype):
     n, d = 2000, 30
     X, _ = synth.gaussian_mixture(n, d, n_clusters=3, intrinsic_dim=6, seed=4)
@@ -184,23 +186,24 @@ def test_tc_radius_pairs_complete(dtype):
     r2 = np.partition(D2, 40, axis=1)[:, 40]
     limp = torch.zeros(op.n_pad, dtype=torch.float32, device="cuda")
     Xc = X64 - X64.mean(0)
-    slack = (pipeline.eps_rel_tc16(d) if dtype else pipeline.eps_rel_tc(d)) * 2 * (Xc ** 2).sum(1).max()
+    slack = (pipeline.eps_rel_tc, pipeline.eps_rel_tc16, pipeline.eps_rel_tch)[dtype](d) * 2 * (Xc ** 2).sum(1).max()
     limp[:n] = _dev((r2 * 1.0001 + slack).astype(np.float32))
     cap = 1 << 20
     pairs = torch.empty((cap, 2), dtype=torch.int32, device="cuda")
     counter = torch.zeros(1, dtype=torch.int64, device="cuda")
     rowcnt = torch.zeros(op.n_pad, dtype=torch.int32, device="cuda")
-    q_hi, q_lo, q_n2 = op.tc(0, dtype)
-    r_hi, r_lo, _ = op.tc(1, dtype)
-    E.call("gtb_knn_radius_tc", q_hi, q_lo, q_n2, limp, n, op.n_pad, r_hi, r_lo, n, op.n_pad, op.kp(dtype), dtype,
-           pairs, cap, counter, rowcnt)
+    scale = pipeline.fp16_scale(op.norm_max()) if dtype == 2 else 1.0
+    q_hi, q_lo, q_n2 = op.tc(0, dtype, scale)
+    r_hi, r_lo, _ = op.tc(1, dtype, scale)
+    E.call("gtb_knn_radius_tc", q_hi, q_lo, q_n2 * (scale * scale), limp * (scale * scale), n, op.n_pad, r_hi, r_lo, n,
+           op.n_pad, op.kp(dtype), dtype, 2, pairs, cap, counter, rowcnt, None)
     m = int(counter.item())
     pr = pairs[:m].cpu().numpy()
     got = set(map(tuple, pr))
     assert len(got) == m
     want = set(zip(*np.nonzero(D2 <= r2[:, None])))
     assert want.issubset(got)
-    assert len(got - want) < (0.5 if dtype else 0.05) * len(want) + 50
+    assert len(got - want) < (0.05, 0.5, 3.0)[dtype] * len(want) + 50
     assert np.array_equal(np.bincount(pr[:, 0], minlength=n), rowcnt[:n].cpu().numpy())
 
 

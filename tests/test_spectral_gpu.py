@@ -127,3 +127,42 @@ def test_device_spectral_landmark_graph(monkeypatch):
     _, comp = synth.gaussian_mixture(6000, 30, n_clusters=6, intrinsic_dim=8, seed=22)
     purity = sum(np.bincount(comp[clusters == c]).max() for c in np.unique(clusters)) / 6000.0
     assert purity > 0.95, purity
+
+
+def test_device_spectral_follows_the_reference_streams(monkeypatch):
+    """GTB_SPECTRAL_RNG=numpy (default): the device path starts from scikit-learn's own Gaussian test matrix and
+    consumes the same RandomState draws in the same order, so (a) the singular values / subspace agree with
+    sklearn.utils.extmath.randomized_svd for the same seed to rounding, and (b) the clusters agree with the
+    reference's host path (graphs.py:1216-1230) except for boundary samples.  The agreement is reported."""
+    from sklearn.utils.extmath import randomized_svd
+    monkeypatch.setenv("GTB_SPECTRAL_RNG", "numpy")
+    X, _ = synth.gaussian_mixture(20_000, 50, n_clusters=10, intrinsic_dim=8, seed=23)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = gt.Graph(X, knn=5, decay=40, verbose=0)
+    G._ensure_built()
+    n_svd, L, seed = 60, 300, 42
+    s, Vt = spectral.randomized_svd_vt(G._dev_kernel, G._dev_degree, n_svd, random_state=seed)
+    s, Vt = s.cpu().numpy(), Vt.cpu().numpy()
+    A = G.diff_aff
+    _, s_sk, Vt_sk = randomized_svd(A, n_components=n_svd, random_state=seed)
+    assert np.abs(s - s_sk).max() < 1e-8, np.abs(s - s_sk).max()
+    # same subspace: principal angles between the two row spaces
+    cosines = np.linalg.svd(Vt @ Vt_sk.T, compute_uv=False)
+    assert cosines.min() > 1 - 1e-8, 1 - cosines.min()
+    # vectors of well separated singular values agree individually (sign convention included)
+    gap = np.minimum(np.abs(np.diff(s_sk, prepend=s_sk[0] + 1)), np.abs(np.diff(s_sk, append=0)))
+    well = gap > 1e-3
+    if well.any():
+        assert np.abs(Vt[well] - Vt_sk[well]).max() < 1e-6
+    # clusters: device k-means on the device features vs the reference's host path on the reference's kernel
+    monkeypatch.setenv("GTB_SPECTRAL", "device")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Gd = gt.Graph(X, knn=5, decay=40, n_landmark=L, n_svd=n_svd, random_state=seed, verbose=0)
+        c_dev = Gd.clusters
+        K_ref, _ = go.knn_graph(X.astype(np.float64), knn=5, decay=40)
+        c_ref = go.spectral_clusters(K_ref, L, n_svd, seed)
+    agree = float(np.mean(c_dev == c_ref))
+    print("spectral clusters, device vs reference (same seed): %.4f identical labels" % agree)
+    assert agree > 0.5, agree
