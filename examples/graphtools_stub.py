@@ -42,7 +42,7 @@ def knn_alpha_decay_kernel(X, Y, knn, decay, thresh, bandwidth_scale=1.0):
     cand = e(ny, 64, dt=torch.int32); tau = e(ny, 2)
     scratch = e(_L.gtb_tc_scratch_bytes(I64(npad(ny))), dt=torch.uint8)
     _call("gtb_knn_topk_tc", p(q_hi), p(q_lo), p(q_n2), I64(ny), I64(npad(ny)), p(r_hi), p(r_lo), I64(n),
-          I64(npad(n)), I(Kp), I(0), I(32), I(2), p(cand), p(scratch), p(tau), P(0))
+          I64(npad(n)), I(Kp), I(0), I(32), I(2), I(1), p(cand), p(scratch), p(tau), P(0))
     st_idx = e(ny, 64, dt=torch.int32); st_val = e(ny, 64, dt=torch.float64)
     n_keep, status, nzero = (e(ny, dt=torch.int32) for _ in range(3))
     bw = e(ny, dt=torch.float64); lim2 = e(ny)

@@ -31,8 +31,8 @@ _SIGS = {
                              _P], 1),
     "gtb_row_norms": ([_P, c_int64, c_int, _P, c_int64, _P, _P, _P], 1),
     "gtb_prepare_operand_tc": ([_P, c_int64, c_int, _P, c_int, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P], 2),
-    "gtb_knn_topk_tc": ([_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P,
-                         _P, _P], 1),
+    "gtb_knn_topk_tc": ([_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, _P,
+                         _P, _P, _P, _P], 1),
     "gtb_knn_radius_tc": ([_P, _P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P, c_int64,
                            _P, _P, _P, _P], 1),
     "gtb_refine_topk": ([_P, c_int64, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_float, c_double, c_int, c_int64, c_double,
@@ -50,7 +50,7 @@ _SIGS = {
     "gtb_rec_sort_rows": ([_P, _P, c_int64, _P, c_int, _P, _P], 2),
     "gtb_records_count": ([_P, c_int64, c_int, _P, c_int64, _P], 1),
     "gtb_records_scatter": ([_P, c_int64, c_int, _P, _P, _P], 1),
-    "gtb_sym_merge_count": ([_P, _P, _P, _P, _P, c_int64, c_int, c_double, _P, _P], 1),
+    "gtb_sym_merge_count": ([_P, _P, _P, _P, _P, c_int64, c_int, c_double, _P, _P, _P], 2),
     "gtb_sym_merge_fill": ([_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_double, _P, _P, _P, _P, _P, _P, _P], 1),
     "gtb_asym_check": ([_P, _P, _P, c_int64, _P, _P], 1),
     "gtb_row_finalize": ([_P, _P, _P, c_int64, _P, _P, _P, c_int, _P], 1),

@@ -289,7 +289,13 @@ __device__ __forceinline__ void tc_commit_mc_pred(uint32_t bar, uint16_t mask, u
 // FMT 0: operands are tf32 hi/lo float32 pairs (3xTF32, kind::tf32, 8 elements per 32-byte k-step);
 // FMT 1: bfloat16 hi/lo pairs (bf16x3, kind::f16, 16 elements per k-step, twice the MMA rate);
 // FMT 2: float16 hi/lo pairs, two products (fp16x2, kind::f16).
-template <int MODE, int CL, int FMT, int LS>  // MODE 0 = TOPK (two lists of LS per row), 1 = RADIUS
+// QT: query tiles per CTA.  QT = 1: the two epilogue groups alternate over the reference tiles of ONE query tile (two
+// candidate lists of LS per row, over disjoint halves of the reference set).  QT = 2 (fp16x2 only: its query operand
+// needs a single 64-column TMEM slice per tile): every reference stage is multiplied against TWO resident query tiles,
+// epilogue group g owning query tile g and ONE list of 2 LS entries per row -- each byte streamed from L2 feeds twice
+// the tensor work.  (The L2 -> SM path, ~6300 B/clk chip-wide, is what bounds a single-tile sweep once the MMA work
+// drops to two products: 57 KB per stage and SM = 1340 clk against 896 clk of MMAs.)
+template <int MODE, int CL, int FMT, int LS, int QT>  // MODE 0 = TOPK, 1 = RADIUS
 __global__ void __launch_bounds__(TC_THREADS, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBht,
                  const __grid_constant__ CUtensorMap mBl, const __grid_constant__ CUtensorMap mBlt,
@@ -303,6 +309,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   constexpr int NPROD = (FMT == 2) ? 2 : 3;                  // (A_hi,B_hi), (A_hi,B_lo)[, (A_lo,B_hi)]
   constexpr float BIG = (FMT == 2) ? TC_BIG_H : TC_BIG;
   constexpr int EPK = BF16 ? 16 : 8;                         // elements per 32-byte k-step
+  static_assert(QT == 1 || (QT == 2 && FMT == 2 && MODE == 0), "two query tiles per CTA: fp16x2 top-k only");
+  constexpr int LSO = (QT == 2) ? 2 * LS : LS;               // entries of one output list
   const int nks = p.nks;                                     // 32-byte k-steps per operand row
   const int nfull = nks / 4, ntail = nks % 4;                // SWIZZLE_128B blocks (4 k-steps) + SWIZZLE_32B tail blocks
   const int a_lo_col = nks * 8;                              // TMEM column of A_lo (A_hi at 0)
@@ -337,14 +345,17 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   const int64_t tile0 = (cluster_id / p.n_qclusters) * p.tiles_per_split;
   const int64_t tiles_left = p.nr_pad / TC_N - tile0;
   const int64_t ntiles = tiles_left < p.tiles_per_split ? tiles_left : p.tiles_per_split;
-  auto q0_of = [&](int64_t round) { return ((qcluster + round * n_clusters) * CL + (blockIdx.x % CL)) * TC_M; };
+  // first query row of (round, query tile qt of this CTA)
+  auto q0_of = [&](int64_t round, int qt) {
+    return (((qcluster + round * n_clusters) * CL + (blockIdx.x % CL)) * QT + qt) * TC_M;
+  };
   auto btile = [&](int64_t round, int64_t t) { return tile0 + ((round & 1) ? (ntiles - 1 - t) : t); };
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
   constexpr int ROWS = TC_N / CL;                            // rows of each B block this CTA loads
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_a, 4);
+    mbar_init(bar_a, 4 * QT);
     mbar_init(round_done, 1);
     for (int s = 0; s < NS; ++s) {
       mbar_init(full_b + 8 * s, 1);
@@ -432,17 +443,20 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     for (int64_t tile = 0; tile < ntiles; ++tile, ++it) {
       const int s = (int)(it % NS);            // shared-memory stage
       const uint32_t ph = (uint32_t)((it / NS) & 1);
-      const int ac_i = (int)(it % NA);         // TMEM accumulator
-      const uint32_t aph = (uint32_t)((it / NA) & 1);
-      mbar_wait(tm_empty + 8 * ac_i, aph ^ 1);
       mbar_wait(full_b + 8 * s, ph);
+      const uint32_t lead = leader ? 1u : 0u;
+#pragma unroll 1
+      for (int qt = 0; qt < QT; ++qt) {
+      const int64_t ait = it * QT + qt;        // running accumulator index
+      const int ac_i = (int)(ait % NA);        // TMEM accumulator
+      const uint32_t aph = (uint32_t)((ait / NA) & 1);
+      mbar_wait(tm_empty + 8 * ac_i, aph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(ACC0 + ac_i * TC_N);
       uint32_t accum = 0;
-      const uint32_t lead = leader ? 1u : 0u;
 #pragma unroll 1
       for (int prod = 0; prod < NPROD; ++prod) {   // (A_hi,B_hi), (A_hi,B_lo), (A_lo,B_hi)
-        uint32_t ac = tmem_base + (uint32_t)((prod == 2) ? a_lo_col : 0);
+        uint32_t ac = tmem_base + (uint32_t)((prod == 2) ? a_lo_col : 0) + (uint32_t)(qt * 64);
         const uint64_t boff = (uint64_t)(s * stage_off + ((prod == 1) ? part_off : 0u));
         uint64_t bd = bd_main0 + boff;
 #pragma unroll 1
@@ -464,10 +478,11 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
           ac += 8;
         }
       }
+      tc_commit_pred(tm_full + 8 * ac_i, lead);   // accumulator ready for the epilogue
+      }
       // smem stage free once these MMAs retire -- signalled to every CTA that multicasts into it
       if (CL > 1) tc_commit_mc_pred(empty_b + 8 * s, cmask, lead);
       else tc_commit_pred(empty_b + 8 * s, lead);
-      tc_commit_pred(tm_full + 8 * ac_i, lead);   // accumulator ready for the epilogue
     }
     tc_commit_pred(round_done, leader ? 1u : 0u);   // every MMA that reads this round's A has retired
     }
@@ -482,12 +497,17 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     float* xpose = reinterpret_cast<float*>(gbase + (bar0 - base) + 256) + (warp - 2) * 32;   // 128-byte slot per warp
     const int row = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    // QT == 2: group g owns query tile g of this CTA (its A slice at TMEM columns [64 g, 64 g + 8 nks)), sees every
+    // reference tile and keeps ONE candidate list of 2 LS entries per row.
+    const int my_qt = (QT == 2) ? grp : 0;
+    const int lgrp = (QT == 2) ? 0 : grp;            // list index inside a row's candidate storage
+    const uint32_t a_col0 = (uint32_t)(my_qt * 64);
     for (int64_t round = 0; round < nrounds; ++round) {
-    const int64_t q0 = q0_of(round);
+    const int64_t q0 = q0_of(round, my_qt);
     const int64_t gq = q0 + row;
     const bool valid = gq < p.nq;
 
-    if (grp == 0) {
+    if (grp == 0 || QT == 2) {
       if (round > 0) { mbar_wait(round_done, (uint32_t)((round - 1) & 1)); tc_fence_after(); }
       // ---- stage the query tile into TMEM: thread == row, one column per K element
       const bool in_pad = gq < p.nq_pad;             // cluster padding CTAs carry all-zero query rows
@@ -495,7 +515,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
       const float4* rl = reinterpret_cast<const float4*>(q_lo + (in_pad ? gq : 0) * (int64_t)(nks * 32));
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int ks = 0; ks < nks; ++ks) {
-        tmem_st8(lane_addr + (uint32_t)(ks * 8), in_pad ? rh[2 * ks] : z4, in_pad ? rh[2 * ks + 1] : z4);
+        tmem_st8(lane_addr + a_col0 + (uint32_t)(ks * 8), in_pad ? rh[2 * ks] : z4, in_pad ? rh[2 * ks + 1] : z4);
         if (NPROD == 3)
           tmem_st8(lane_addr + (uint32_t)(a_lo_col + ks * 8), in_pad ? rl[2 * ks] : z4, in_pad ? rl[2 * ks + 1] : z4);
       }
@@ -511,17 +531,19 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     else thr = valid ? (p.lim2[gq] - nx) : -gtb_inf_f();
     int cnt = 0;
     // this thread's candidate buffer: uniform base + per-thread offset (rows past nq never append)
-    const int64_t boff = valid ? (gq * TC_GROUPS + grp) * TC_CAP : 0;
+    const int64_t boff = valid ? (gq * TC_GROUPS + lgrp) * TC_CAP : 0;
     uint2* wbuf = p.cand_buf + (q0 + quad * 32) * TC_GROUPS * TC_CAP;   // warp-uniform: first row of this quadrant
     uint2* mybuf = p.cand_buf + boff;                                     // this row's buffer (never written when !valid)
 
-    // this group's tiles: running iteration index it = round * ntiles + t with it % 2 == grp
+    // this group's tiles.  QT == 1: running iteration index it = round * ntiles + t with it % 2 == grp; QT == 2:
+    // every tile, accumulator index 2 it + grp
     const int64_t it0 = round * ntiles;
-    for (int64_t t = (grp + (it0 & 1)) & 1; t < ntiles; t += TC_GROUPS) {
+    for (int64_t t = (QT == 2) ? 0 : ((grp + (it0 & 1)) & 1); t < ntiles; t += (QT == 2 ? 1 : TC_GROUPS)) {
       const int64_t it = it0 + t;
       const int64_t tile = btile(round, t);
-      const int s = (int)(it % NA);                    // accumulator of this iteration
-      const uint32_t ph = (uint32_t)((it / NA) & 1);
+      const int64_t ait = (QT == 2) ? (it * 2 + grp) : it;
+      const int s = (int)(ait % NA);                   // accumulator of this iteration
+      const uint32_t ph = (uint32_t)((ait / NA) & 1);
       mbar_wait(tm_full + 8 * s, ph);
       tc_fence_after();
       // drain the whole accumulator into registers, hand it back to the MMA warp, THEN select: the
@@ -594,7 +616,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
           const int rank = __popc(pm & ((1u << lane) - 1u));
           if (MODE == 0) {
             const int cL = __shfl_sync(0xffffffffu, cnt, L);
-            if (pass) wbuf[(L * TC_GROUPS + grp) * TC_CAP + cL + rank] = make_uint2(__float_as_uint(x), (uint32_t)(col0 + lane));
+            if (pass) wbuf[(L * TC_GROUPS + lgrp) * TC_CAP + cL + rank] = make_uint2(__float_as_uint(x), (uint32_t)(col0 + lane));
             if (lane == L) cnt += npass;
           } else {
             unsigned long long basepos = 0;
@@ -616,31 +638,35 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
             need &= need - 1;
             const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
             __syncwarp();
-            const float nt = compact_row<LS>(wbuf + (owner * TC_GROUPS + grp) * TC_CAP, ocnt, lane);
+            const float nt = compact_row<LSO>(wbuf + (owner * TC_GROUPS + lgrp) * TC_CAP, ocnt, lane);
             __syncwarp();
-            if (lane == owner) { thr = nt; cnt = LS; }
+            if (lane == owner) { thr = nt; cnt = LSO; }
           }
         }
       }
     }
 
     if (MODE == 0) {
-      // final compaction of every buffer still holding more than TC_S candidates
-      unsigned need = __ballot_sync(0xffffffffu, cnt > LS);
+      // final compaction of every buffer still holding more than a list's worth of candidates
+      unsigned need = __ballot_sync(0xffffffffu, cnt > LSO);
       while (need) {
         const int owner = __ffs(need) - 1;
         need &= need - 1;
         const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
         __syncwarp();
-        const float nt = compact_row<LS>(wbuf + (owner * TC_GROUPS + grp) * TC_CAP, ocnt, lane);
+        const float nt = compact_row<LSO>(wbuf + (owner * TC_GROUPS + lgrp) * TC_CAP, ocnt, lane);
         __syncwarp();
-        if (lane == owner) { thr = nt; cnt = LS; }
+        if (lane == owner) { thr = nt; cnt = LSO; }
       }
       __syncwarp();
       if (valid) {
-        int32_t* out = p.cand_idx + gq * (TC_GROUPS * LS) + grp * LS;
-        for (int e = 0; e < LS; ++e) out[e] = (e < cnt) ? (int32_t)p.cand_buf[boff + e].y : -1;
-        p.tau[gq * TC_GROUPS + grp] = (cnt < LS || thr >= BIG) ? gtb_inf_f() : thr + nx;
+        // QT == 1: two lists of LS per row (one per group) with their own thresholds; QT == 2: one list of 2 LS,
+        // the second threshold slot repeats the first (the refine takes the minimum)
+        int32_t* out = p.cand_idx + gq * (TC_GROUPS * LS) + lgrp * LS;
+        for (int e = 0; e < LSO; ++e) out[e] = (e < cnt) ? (int32_t)p.cand_buf[boff + e].y : -1;
+        const float tv = (cnt < LSO || thr >= BIG) ? gtb_inf_f() : thr + nx;
+        p.tau[gq * TC_GROUPS + lgrp] = tv;
+        if (QT == 2) p.tau[gq * TC_GROUPS + 1] = tv;
       }
     }
     }  // rounds
@@ -787,7 +813,7 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int Kp, int box_k, i
   return GTB_OK;
 }
 
-template <int MODE, int CL, int FMT, int LS>
+template <int MODE, int CL, int FMT, int LS, int QT = 1>
 int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, TcParams& p,
                  cudaStream_t st) {
   CUtensorMap mBh, mBht, mBl, mBlt;
@@ -800,12 +826,12 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
   if ((rc = make_map(&mBl, r_lo, p.nr_pad, Kp, 4 * EPK, TC_N / CL, true, FMT))) return rc;
   if ((rc = make_map(&mBlt, r_lo, p.nr_pad, Kp, EPK, TC_N / CL, false, FMT))) return rc;
   size_t smem = 1024 + (size_t)2 * (BF16 ? 3 : 2) * TC_N * p.nks * 32 + 256 + 1024;
-  auto kern = search_tc_kernel<MODE, CL, FMT, LS>;
+  auto kern = search_tc_kernel<MODE, CL, FMT, LS, QT>;
   GTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, nsm = 0;
   GTB_CUDA(cudaGetDevice(&dev));
   GTB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t n_cluster_tiles = gtb_cdiv(p.nq_pad / TC_M, CL);
+  const int64_t n_cluster_tiles = gtb_cdiv(p.nq_pad / TC_M, CL * QT);
   int64_t n_clusters = n_cluster_tiles < (nsm / CL) ? n_cluster_tiles : (nsm / CL);
   p.nrounds = gtb_cdiv(n_cluster_tiles, n_clusters);
   const int64_t total_tiles = p.nr_pad / TC_N;
@@ -845,9 +871,21 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
 
 template <int MODE, int FMT>
 int launch_tc_fmt(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, int list, int cluster,
-                  TcParams& p, cudaStream_t st) {
+                  int qtiles, TcParams& p, cudaStream_t st) {
   constexpr int LS_SHORT = (MODE == 0) ? 16 : 32;
   const bool short_list = (MODE == 0) && list == 16;
+  if (qtiles == 2) {
+    if constexpr (FMT == 2 && MODE == 0) {
+      if (!short_list) { gtb_set_error("two query tiles per CTA need list = 16 (one list of 32 per row)"); return GTB_ERR_ARG; }
+      if (cluster == 1) return launch_tc_cl<0, 1, 2, 16, 2>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+      if (cluster == 2) return launch_tc_cl<0, 2, 2, 16, 2>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+      gtb_set_error("cluster size must be 1 or 2");
+      return GTB_ERR_ARG;
+    } else {
+      gtb_set_error("two query tiles per CTA: fp16x2 top-k only");
+      return GTB_ERR_ARG;
+    }
+  }
   switch (cluster) {
     case 1: return short_list ? launch_tc_cl<MODE, 1, FMT, LS_SHORT>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
                               : launch_tc_cl<MODE, 1, FMT, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
@@ -864,10 +902,10 @@ int launch_tc_fmt(const void* q_hi, const void* q_lo, const void* r_hi, const vo
 
 template <int MODE>
 int launch_tc(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, int dtype, int list,
-              int cluster, TcParams& p, cudaStream_t st) {
-  if (dtype == 1) return launch_tc_fmt<MODE, 1>(q_hi, q_lo, r_hi, r_lo, Kp, list, cluster, p, st);
-  if (dtype == 2) return launch_tc_fmt<MODE, 2>(q_hi, q_lo, r_hi, r_lo, Kp, list, cluster, p, st);
-  return launch_tc_fmt<MODE, 0>(q_hi, q_lo, r_hi, r_lo, Kp, list, cluster, p, st);
+              int cluster, int qtiles, TcParams& p, cudaStream_t st) {
+  if (dtype == 1) return launch_tc_fmt<MODE, 1>(q_hi, q_lo, r_hi, r_lo, Kp, list, cluster, qtiles, p, st);
+  if (dtype == 2) return launch_tc_fmt<MODE, 2>(q_hi, q_lo, r_hi, r_lo, Kp, list, cluster, qtiles, p, st);
+  return launch_tc_fmt<MODE, 0>(q_hi, q_lo, r_hi, r_lo, Kp, list, cluster, qtiles, p, st);
 }
 
 }  // namespace
@@ -930,15 +968,16 @@ static int tc_check(int64_t nq, int64_t nr, int64_t nq_pad, int64_t nr_pad, int 
 
 extern "C" int gtb_knn_topk_tc(const void* q_hi, const void* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
                                const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp, int dtype,
-                               int list, int cluster, int32_t* cand_idx, void* scratch, float* tau,
+                               int list, int cluster, int qtiles, int32_t* cand_idx, void* scratch, float* tau,
                                unsigned int* pace, void* stream) {
   int rc = tc_check(nq, nr, nq_pad, nr_pad, Kp, dtype);
   if (rc) return rc;
   GTB_CHECK_ARG(list == 16 || list == 32, "list size must be 16 or 32");
+  GTB_CHECK_ARG(qtiles == 1 || qtiles == 2, "query tiles per CTA: 1 or 2");
   TcParams p{};
   p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.qn2 = qn2;
   p.cand_idx = cand_idx; p.cand_buf = reinterpret_cast<uint2*>(scratch); p.tau = tau; p.sync_ctr = pace;
-  return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, Kp, dtype, list, cluster, p, (cudaStream_t)stream);
+  return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, Kp, dtype, list, cluster, qtiles, p, (cudaStream_t)stream);
 }
 
 extern "C" int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float* qn2, const float* lim2,
@@ -951,5 +990,5 @@ extern "C" int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float
   p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.qn2 = qn2; p.lim2 = lim2;
   p.pairs = reinterpret_cast<int2*>(pairs); p.capacity = (unsigned long long)capacity; p.counter = counter;
   p.rowcnt = rowcnt; p.sync_ctr = pace;
-  return launch_tc<1>(q_hi, q_lo, r_hi, r_lo, Kp, dtype, 32, cluster, p, (cudaStream_t)stream);
+  return launch_tc<1>(q_hi, q_lo, r_hi, r_lo, Kp, dtype, 32, cluster, 1, p, (cudaStream_t)stream);
 }

@@ -252,9 +252,9 @@ template <bool FILL>
 __global__ void __launch_bounds__(MRG_WARPS * 32) sym_merge_kernel(
     const int64_t* __restrict__ pa, const int32_t* __restrict__ ia, const double* __restrict__ va,
     const int64_t* __restrict__ pt, const EdgeRec* __restrict__ tr, int64_t n_rows, int32_t row0, int mode,
-    double theta, int32_t* __restrict__ newlen, const int64_t* __restrict__ outptr, int32_t* __restrict__ out_idx,
-    double* __restrict__ out_val, double* __restrict__ p_val, double* __restrict__ degree,
-    int32_t* __restrict__ flags) {
+    double theta, int32_t* __restrict__ newlen, int32_t* __restrict__ worklist, int32_t* __restrict__ wl_count,
+    const int64_t* __restrict__ outptr, int32_t* __restrict__ out_idx, double* __restrict__ out_val,
+    double* __restrict__ p_val, double* __restrict__ degree, int32_t* __restrict__ flags) {
   __shared__ double sv[MRG_WARPS][32];
   __shared__ int32_t sc[MRG_WARPS][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -276,10 +276,14 @@ __global__ void __launch_bounds__(MRG_WARPS * 32) sym_merge_kernel(
       c = r.x;
       w = __hiloint2double(r.w, r.z);
     }
-    // columns are unique within A and within T: a column held by two lanes is a mutual edge
-    const unsigned peers = __match_any_sync(0xffffffffu, c);
-    const bool mutual = (peers & (peers - 1)) != 0;
-    const int partner = mutual ? (isA ? (31 - __clz(peers)) : (__ffs(peers) - 1)) : lane;   // A copy is the lower lane
+    // columns are unique within A and within T: a column held by two lanes is a mutual edge.  (A broadcast loop --
+    // match.any serialises on the number of distinct values and left the count pass latency-bound.)
+    int partner = lane;
+    for (int k = 0; k < L; ++k) {
+      const int32_t ck = __shfl_sync(0xffffffffu, c, k);
+      partner = (ck == c && k != lane) ? k : partner;
+    }
+    const bool mutual = partner != lane;
     const double w_other = __shfl_sync(0xffffffffu, w, partner);
     const double s = sym_combine(mode, theta, w, mutual ? w_other : 0.0);
     const bool emit = (isA || isT) && (s != 0.0) && !(mutual && isT);   // a mutual pair is emitted by its A copy
@@ -316,13 +320,42 @@ __global__ void __launch_bounds__(MRG_WARPS * 32) sym_merge_kernel(
     }
     return;
   }
-  // ---- rows with more than 32 entries (hub rows; every row of an isotropic, high-intrinsic-dimension data set):
-  //      T was sorted by rec_sort_rows.  Sequential two-pointer merge by one lane (O(L), any length, fixed order);
-  //      the row sum runs in column order, which is sklearn's own summation order
-  //      (sparsefuncs_fast.pyx:_inplace_csr_row_normalize_l1)
+  // ---- rows with more than 32 entries (hub rows; every row of an isotropic, high-intrinsic-dimension data set)
   const int32_t* A = ia + a0;
   const EdgeRec* T = tr + t0;
-  const int64_t o0 = FILL ? outptr[row] : 0;
+  if (!FILL) {
+    // count without sorted T: every T entry looks its column up in A (sorted).
+    //   #emitted = sum_a [s(w_a, 0) != 0] + sum_t (found ? [s(w_a, w_t) != 0] - [s(w_a, 0) != 0] : [s(0, w_t) != 0])
+    // The row is queued for the sort that the fill pass needs.
+    int cnt = 0;
+    for (int t = lane; t < la; t += 32) cnt += (sym_combine(mode, theta, va[a0 + t], 0.0) != 0.0);
+    for (int t = lane; t < lt; t += 32) {
+      const int32_t c = T[t].i;
+      const double wt = T[t].w;
+      int lo = 0, hi = la;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (A[mid] < c) lo = mid + 1; else hi = mid;
+      }
+      if (lo < la && A[lo] == c) {
+        const double wa = va[a0 + lo];
+        cnt += (int)(sym_combine(mode, theta, wa, wt) != 0.0) - (int)(sym_combine(mode, theta, wa, 0.0) != 0.0);
+      } else {
+        cnt += (sym_combine(mode, theta, 0.0, wt) != 0.0);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    if (lane == 0) {
+      newlen[row] = cnt;
+      if (worklist) worklist[atomicAdd(wl_count, 1)] = (int32_t)row;
+    }
+    return;
+  }
+  // fill: T was sorted by rec_sort_worklist.  Sequential two-pointer merge by one lane (O(L), any length, fixed
+  // order); the row sum runs in column order, which is sklearn's own summation order
+  // (sparsefuncs_fast.pyx:_inplace_csr_row_normalize_l1)
+  const int64_t o0 = outptr[row];
   int o = 0;
   double sum = 0.0;
   if (lane == 0) {
@@ -336,27 +369,73 @@ __global__ void __launch_bounds__(MRG_WARPS * 32) sym_merge_kernel(
       b += (cb == c);
       const double sv2 = sym_combine(mode, theta, w, wr);
       if (sv2 != 0.0) {
-        if (FILL) {
-          out_idx[o0 + o] = c; out_val[o0 + o] = sv2;
-          sum += fabs(sv2);
-          has_diag |= (c == grow);
-        }
-        ++o;
+        out_idx[o0 + o] = c; out_val[o0 + o] = sv2; ++o;
+        sum += fabs(sv2);
+        has_diag |= (c == grow);
       }
     }
-    if (FILL) {
-      if (degree) degree[row] = sum;
-      if (flags && !has_diag) atomicOr(flags, 2);
-    } else {
-      newlen[row] = o;
-    }
+    if (degree) degree[row] = sum;
+    if (flags && !has_diag) atomicOr(flags, 2);
   }
-  if (!FILL) return;
   o = __shfl_sync(0xffffffffu, o, 0);
   sum = __shfl_sync(0xffffffffu, sum, 0);
   __syncwarp();
   if (p_val)
     for (int e = lane; e < o; e += 32) { const double v = out_val[o0 + e]; p_val[o0 + e] = (sum != 0.0) ? v / sum : v; }
+}
+
+// Sort of the queued (long) record rows: one block per queue entry, shared-memory bitonic up to SORT_BLOCK_CAP entries,
+// the uniform-direction global-memory network beyond.
+__global__ void __launch_bounds__(SORT_BLOCK_THREADS) rec_sort_worklist_kernel(const int64_t* __restrict__ ptr,
+                                                                               EdgeRec* __restrict__ rec,
+                                                                               const int32_t* __restrict__ worklist,
+                                                                               const int32_t* __restrict__ wl_count) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  double* v = reinterpret_cast<double*>(sort_smem);                    // [SORT_BLOCK_CAP]
+  int32_t* k = reinterpret_cast<int32_t*>(v + SORT_BLOCK_CAP);         // [SORT_BLOCK_CAP]
+  const int tid = threadIdx.x;
+  const int nwork = *wl_count;
+  auto sync = [] { __syncthreads(); };
+  RecStore st{rec};
+  for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const int64_t row = worklist[wi];
+    const int64_t p0 = ptr[row];
+    const int64_t L = ptr[row + 1] - p0;
+    if (L <= 1) continue;
+    const int32_t aux = st.aux(p0);
+    __syncthreads();
+    if (L <= SORT_BLOCK_CAP) {
+      int np2 = 2;
+      while (np2 < L) np2 <<= 1;
+      for (int t = tid; t < np2; t += SORT_BLOCK_THREADS) {
+        if (t < L) { k[t] = st.key(p0 + t); v[t] = st.pay(p0 + t); }
+        else { k[t] = 0x7fffffff; v[t] = 0.0; }
+      }
+      __syncthreads();
+      GTB_BITONIC_SORT(k, v, np2, tid, SORT_BLOCK_THREADS, sync, int32_t, double);
+      for (int t = tid; t < L; t += SORT_BLOCK_THREADS) st.put(p0 + t, k[t], v[t], aux);
+    } else {
+      int64_t np2 = SORT_BLOCK_CAP;
+      while (np2 < L) np2 <<= 1;
+      for (int64_t kk = 2; kk <= np2; kk <<= 1) {
+        for (int64_t j = kk >> 1; j > 0; j >>= 1) {
+          for (int64_t t = tid; t < L; t += SORT_BLOCK_THREADS) {
+            const int64_t q = (j == (kk >> 1)) ? (t ^ (kk - 1)) : (t ^ j);
+            if (q > t && q < L) {
+              const int32_t a = st.key(p0 + t), b2 = st.key(p0 + q);
+              if (a > b2) {
+                const double va2 = st.pay(p0 + t), vb2 = st.pay(p0 + q);
+                st.put(p0 + t, b2, vb2, aux);
+                st.put(p0 + q, a, va2, aux);
+              }
+            }
+          }
+          __threadfence_block();
+          __syncthreads();
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------ edge routing (multi-GPU)
@@ -464,12 +543,23 @@ extern "C" int gtb_rec_sort_rows(const int64_t* ptr, void* rec, int64_t n, const
 extern "C" int gtb_sym_merge_reg_rows(void) { return MRG_REG; }
 
 extern "C" int gtb_sym_merge_count(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pt,
-                                   const void* t_rec, int64_t n_rows, int mode, double theta, int32_t* newlen,
-                                   void* stream) {
+                                   void* t_rec, int64_t n_rows, int mode, double theta, int32_t* newlen,
+                                   int32_t* worklist, void* stream) {
   GTB_CHECK_ARG(n_rows > 0 && mode >= 0 && mode <= 2, "bad arguments");
-  sym_merge_kernel<false><<<(unsigned)gtb_cdiv(n_rows, MRG_WARPS), MRG_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      pa, ia, va, pt, reinterpret_cast<const EdgeRec*>(t_rec), n_rows, 0, mode, theta, newlen, nullptr, nullptr,
-      nullptr, nullptr, nullptr, nullptr);
+  GTB_CHECK_ARG(worklist != nullptr, "worklist: n_rows + 1 ints of scratch");
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* wl_count = worklist + n_rows;
+  GTB_CUDA(cudaMemsetAsync(wl_count, 0, sizeof(int32_t), st));
+  sym_merge_kernel<false><<<(unsigned)gtb_cdiv(n_rows, MRG_WARPS), MRG_WARPS * 32, 0, st>>>(
+      pa, ia, va, pt, reinterpret_cast<const EdgeRec*>(t_rec), n_rows, 0, mode, theta, newlen, worklist, wl_count,
+      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  GTB_CHECK_LAUNCH();
+  // rows too long for the register path of the fill pass: order their transposed entries by column now
+  const size_t smem = (size_t)SORT_BLOCK_CAP * 12;
+  GTB_CUDA(cudaFuncSetAttribute(rec_sort_worklist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = n_rows < 148 * 4 ? n_rows : 148 * 4;
+  rec_sort_worklist_kernel<<<(unsigned)blocks, SORT_BLOCK_THREADS, smem, st>>>(
+      pt, reinterpret_cast<EdgeRec*>(t_rec), worklist, wl_count);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }
@@ -480,8 +570,8 @@ extern "C" int gtb_sym_merge_fill(const int64_t* pa, const int32_t* ia, const do
                                   double* degree, int32_t* flags, void* stream) {
   GTB_CHECK_ARG(n_rows > 0 && mode >= 0 && mode <= 2, "bad arguments");
   sym_merge_kernel<true><<<(unsigned)gtb_cdiv(n_rows, MRG_WARPS), MRG_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      pa, ia, va, pt, reinterpret_cast<const EdgeRec*>(t_rec), n_rows, row0, mode, theta, nullptr, outptr, out_idx,
-      out_val, p_val, degree, flags);
+      pa, ia, va, pt, reinterpret_cast<const EdgeRec*>(t_rec), n_rows, row0, mode, theta, nullptr, nullptr, nullptr,
+      outptr, out_idx, out_val, p_val, degree, flags);
   GTB_CHECK_LAUNCH();
   return GTB_OK;
 }

@@ -197,7 +197,6 @@ class kNNGraph(DataGraph):
             ptr_t = pipeline.exclusive_scan(cnt)
             t_rec = pipeline._empty((k, 2), torch.int64)
             E.call("gtb_records_scatter", rec, k, lo, pipeline.cursor32(ptr_t), t_rec)
-            pipeline.sort_records(ptr_t, t_rec, m, indptr_a, E.lib().gtb_sym_merge_reg_rows())
             outptr, k_idx, k_val, p_val, deg, newlen = pipeline.merge_with_transpose(
                 indptr_a, idx, val, ptr_t, t_rec, m, lo, mode, theta, want_p=True, flags=flags)
         else:

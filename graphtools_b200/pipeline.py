@@ -16,7 +16,7 @@ from . import _engine as E
 SYM_MODES = {"+": 0, "*": 1, "mnn": 2, None: 3}
 METRIC_ALIASES = {"manhattan": "cityblock", "l1": "cityblock", "l2": "euclidean"}
 METRIC_CODE = {"euclidean": 0, "cosine": 1, "cityblock": 2}
-AUTO_TC = "tc16"         # tensor-core flavour picked by impl="auto": "tc" (3xTF32) or "tc16" (bf16x3)
+AUTO_TC = "tch"          # tensor-core flavour picked by impl="auto": "tch" (fp16x2), "tc16" (bf16x3) or "tc" (3xTF32)
 BALL_CAP = 8192          # longest radius-pass row handled by refine_ball (shared-memory sort)
 _STATS = {}
 
@@ -445,8 +445,12 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         # selection work of the sweep; they are used when the neighbourhood asked for is small (knn + 8 <= 16) --
         # rows whose kernel support is wider fail certification and are finished by the radius pass.
         want = max(knn, kmax)                                   # knn_max neighbours must fit the lists as well
-        ls = int(os.environ.get("GTB_TC_LIST", "16" if want + 8 <= 16 else "32"))
-        if ls not in (16, 32) or knn > ls:
+        # (fp16x2 runs two query tiles per CTA and keeps ONE list of 32 per row, which covers want + 8 <= 32)
+        two_tiles = tcd == 2 and int(os.environ.get("GTB_TC_QTILES", "2")) == 2
+        short_ok = want + 8 <= (32 if two_tiles else 16)
+        ls = int(os.environ.get("GTB_TC_LIST", "16" if short_ok else "32"))
+        qtiles = 2 if (two_tiles and ls == 16) else 1
+        if ls not in (16, 32) or knn > ls * qtiles:
             raise ValueError("GTB_TC_LIST must be 16 or 32 and >= knn")
         S, stride, ntau = 2 * ls, 2 * ls, 2
         cluster = min(tc_cluster(), 2) if tcd else tc_cluster()
@@ -466,8 +470,9 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         tau = _empty((nq, ntau), torch.float32)
         scratch = _empty((E.lib().gtb_tc_scratch_bytes(qry.n_pad),), torch.uint8)
         s2 = tc_scale * tc_scale
+        # qtiles == 2: two query tiles per CTA share every reference stage (half the L2 traffic per MMA)
         E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2 * s2 if tcd == 2 else q_n2, nq, qry.n_pad, r_hi, r_lo, nr,
-               ref.n_pad, Kp, tcd, ls, cluster, cand, scratch, tau, pace)
+               ref.n_pad, Kp, tcd, ls, cluster, qtiles, cand, scratch, tau, pace)
         if tcd == 2:
             tau = tau / s2                                   # scaled squared distances -> data units (inf stays inf)
         del scratch
@@ -636,9 +641,10 @@ def transpose_csr(R):
 
 def merge_with_transpose(A_ptr, A_idx, A_val, T_ptr, T_rec, n_rows, row0, mode, theta, want_p=True, flags=None):
     """sym(A, T) row by row (csrc/symm.cu sym_merge): returns (outptr, k_idx, k_val, p_val | None, degree, newlen).
-    ``T_rec``: record rows of the transposed matrix; rows too long for the register path must be column-sorted."""
+    ``T_rec``: record rows of the transposed matrix in any order (long rows are sorted in place by the count call)."""
     newlen = _empty((n_rows,), torch.int32)
-    E.call("gtb_sym_merge_count", A_ptr, A_idx, A_val, T_ptr, T_rec, n_rows, mode, theta, newlen)
+    worklist = _empty((n_rows + 1,), torch.int32)        # rows too long for the register path, sorted inside the call
+    E.call("gtb_sym_merge_count", A_ptr, A_idx, A_val, T_ptr, T_rec, n_rows, mode, theta, newlen, worklist)
     outptr = exclusive_scan(newlen)
     nnz = int(outptr[-1].item())
     k_idx = _empty((nnz,), torch.int32)
@@ -671,7 +677,7 @@ def symmetrize_normalize(R, kernel_symm="+", theta=None, anisotropy=0.0, want_p=
         E.call("gtb_row_finalize", K.indptr, K.indices, K.data, n, P, degree, flags, int(square))
     else:
         th = 0.0 if theta is None else float(theta)
-        ptr_t, rec = transpose_records(R, sort_min_total=E.lib().gtb_sym_merge_reg_rows(), pa=R.indptr)
+        ptr_t, rec = transpose_records(R)                # arrival order: the merge sorts the (few) long rows itself
         outptr, k_idx, k_val, P, degree, _ = merge_with_transpose(
             R.indptr, R.indices, R.data, ptr_t, rec, n, 0, mode, th,
             want_p=want_p and anisotropy == 0, flags=flags)

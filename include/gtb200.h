@@ -79,6 +79,9 @@ int gtb_knn_radius_simt_l1(const float* QT, const float* lim, int64_t nq, int64_
  * lists halve the selection work -- rows whose kernel support they do not cover fail certification in gtb_refine_topk and are
  * completed by the radius pass, so the result does not depend on `list`) with their
  * thresholds tau[nq][2]; scratch = gtb_tc_scratch_bytes(nq_pad) bytes.  radius: contract of gtb_knn_radius_simt.
+ * qtiles: query tiles per CTA.  1: the layout above.  2 (dtype 2, list 16 only): every reference stage is multiplied
+ * against two resident query tiles -- half the L2 -> SM bytes per unit of tensor work -- and each row keeps ONE list of
+ * 2 * list entries (same cand_idx / tau layout; both tau slots carry the list's threshold).
  * cluster: 1, 2 (or 4, tf32 only) CTAs share each reference tile through TMA multicast.  pace: one caller-owned device
  * word for the grid-wide pacing of the TMA producers (so that one DRAM read of a reference tile serves all SMs), or
  * NULL for no pacing -- the library keeps no state between calls. */
@@ -90,8 +93,8 @@ int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const float* mean, 
                            int64_t n_pad, int Kp, int dtype, float scale, float* norm2, float* maxnorm, void* stream);
 int gtb_knn_topk_tc(const void* q_hi, const void* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
                     const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp, int dtype,
-                    int list, int cluster, int32_t* cand_idx, void* scratch, float* tau, unsigned int* pace,
-                    void* stream);
+                    int list, int cluster, int qtiles, int32_t* cand_idx, void* scratch, float* tau,
+                    unsigned int* pace, void* stream);
 int64_t gtb_tc_scratch_bytes(int64_t nq_pad);
 int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float* qn2, const float* lim2, int64_t nq,
                       int64_t nq_pad, const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp,
@@ -152,15 +155,16 @@ int gtb_csr_sort_rows(const int64_t* ptr, int32_t* idx, double* val, int64_t n, 
 int gtb_rec_sort_rows(const int64_t* ptr, void* rec, int64_t n, const int64_t* pa, int min_total, int32_t* has_long,
                       void* stream);
 /* Merge of the raw kernel rows A = (pa, ia, va), column-sorted, with the record rows T = (pt, t_rec) of the transposed
- * matrix under mode 0 '+' ((w + w')/2), 1 '*' (w w'), 2 'mnn' (theta min + (1 - theta) max): count ->
- * gtb_exclusive_scan -> fill.  Rows with |A| + |T| <= gtb_sym_merge_reg_rows() may hold T in any order; longer rows need
- * T column-sorted (gtb_rec_sort_rows(..., pa, gtb_sym_merge_reg_rows(), ...)).  fill emits the column-sorted K row,
+ * matrix -- in ARRIVAL order -- under mode 0 '+' ((w + w')/2), 1 '*' (w w'), 2 'mnn' (theta min + (1 - theta) max):
+ * count -> gtb_exclusive_scan -> fill.  Rows with |A| + |T| <= gtb_sym_merge_reg_rows() are merged unsorted, one entry
+ * per lane; count queues the longer ones (worklist: n_rows + 1 ints of scratch) and orders their T entries by column in
+ * place before it returns, which is what fill's two-pointer merge of those rows reads.  fill emits the column-sorted K row,
  * P = K / sum|K| (base.py:645), the degree vector (base.py:648-666) and sets flags bit 1 when a row lacks its diagonal
  * (base.py:553-554; global row id = row0 + r, columns are global).  Used on the whole matrix (one GPU) and on a row
  * shard (multi-GPU, after the all-to-all) alike, so the two builds agree bit for bit. */
 int gtb_sym_merge_reg_rows(void);
-int gtb_sym_merge_count(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pt, const void* t_rec,
-                        int64_t n_rows, int mode, double theta, int32_t* newlen, void* stream);
+int gtb_sym_merge_count(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pt, void* t_rec,
+                        int64_t n_rows, int mode, double theta, int32_t* newlen, int32_t* worklist, void* stream);
 int gtb_sym_merge_fill(const int64_t* pa, const int32_t* ia, const double* va, const int64_t* pt, const void* t_rec,
                        int64_t n_rows, int32_t row0, int mode, double theta, const int64_t* outptr, int32_t* out_idx,
                        double* out_val, double* p_val, double* degree, int32_t* flags, void* stream);

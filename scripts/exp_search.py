@@ -26,6 +26,7 @@ Kp = ref.kp(a.dtype)
 pace = torch.zeros(1, dtype=torch.int32, device="cuda") if int(os.environ.get("GTB_TC_PACING", "1")) else None
 cluster = int(os.environ.get("GTB_TC_CLUSTER", "2"))
 ls = int(os.environ.get("GTB_TC_LIST", "32"))
+qtiles = int(os.environ.get("GTB_TC_QTILES", "1"))
 cand = torch.empty((a.n, 2 * ls), dtype=torch.int32, device="cuda")
 tau = torch.empty((a.n, 2), dtype=torch.float32, device="cuda")
 scratch = torch.empty((E.lib().gtb_tc_scratch_bytes(ref.n_pad),), dtype=torch.uint8, device="cuda")
@@ -33,12 +34,12 @@ times = []
 for rep in range(a.reps + 1):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, a.n, ref.n_pad, r_hi, r_lo, a.n, ref.n_pad, Kp, a.dtype, ls, cluster, cand,
+    E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, a.n, ref.n_pad, r_hi, r_lo, a.n, ref.n_pad, Kp, a.dtype, ls, cluster, qtiles, cand,
            scratch, tau, pace)
     e1.record()
     torch.cuda.synchronize()
     times.append(e0.elapsed_time(e1))
 best = min(times[1:])
-print("EXP %s list=%d lib=%s n=%d d=%d Kp=%d dtype=%d: %s ms (best %.1f) -> %.1f TFLOP/s algorithmic; cand checksum %d" % (
-    a.tag, ls, os.path.basename(E.LIB_PATH), a.n, a.d, Kp, a.dtype, ["%.1f" % t for t in times], best,
+print("EXP %s qtiles=%d list=%d lib=%s n=%d d=%d Kp=%d dtype=%d: %s ms (best %.1f) -> %.1f TFLOP/s algorithmic; cand checksum %d" % (
+    a.tag, qtiles, ls, os.path.basename(E.LIB_PATH), a.n, a.d, Kp, a.dtype, ["%.1f" % t for t in times], best,
     2.0 * a.n * a.n * a.d / best / 1e9, int(cand.clamp(min=0).to(torch.int64).sum().item())), flush=True)

@@ -81,7 +81,8 @@ def test_tc_certification_bound_1m(headline):
     n, d = X.shape
     Xd = pipeline.to_device_f32(X)
     ref = pipeline.SearchOperand(Xd)
-    for tcd, eps_fn in ((1, pipeline.eps_rel_tc16), (2, pipeline.eps_rel_tch), (0, pipeline.eps_rel_tc)):
+    for tcd, eps_fn, qtiles in ((1, pipeline.eps_rel_tc16, 1), (2, pipeline.eps_rel_tch, 2), (2, pipeline.eps_rel_tch, 1),
+                                (0, pipeline.eps_rel_tc, 1)):
         ls = 16
         scale = pipeline.fp16_scale(ref.norm_max()) if tcd == 2 else 1.0
         q_hi, q_lo, q_n2 = ref.tc(0, tcd, scale)
@@ -91,7 +92,7 @@ def test_tc_certification_bound_1m(headline):
         scratch = pipeline._empty((E.lib().gtb_tc_scratch_bytes(ref.n_pad),), torch.uint8)
         pace = pipeline._empty((1,), torch.int32)
         E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2 * (scale * scale), n, ref.n_pad, r_hi, r_lo, n, ref.n_pad,
-               ref.kp(tcd), tcd, ls, 2, cand, scratch, tau, pace)
+               ref.kp(tcd), tcd, ls, 2, qtiles, cand, scratch, tau, pace)
         tau = tau / (scale * scale)
         del scratch
         rows = torch.linspace(0, n - 1, 192, device=Xd.device).long()
@@ -114,7 +115,7 @@ def test_tc_certification_bound_1m(headline):
             margin = float((d2[~is_cand] - (t - Ebound)).min().item())
             worst = max(worst, -margin / Ebound)
             assert margin >= 0.0, "row %d: a non-candidate lies %.3e inside tau - E (E = %.3e)" % (i, -margin, Ebound)
-        print("dtype %d: worst used fraction of the bound %.3f" % (tcd, worst))
+        print("dtype %d qtiles %d: worst used fraction of the bound %.3f" % (tcd, qtiles, worst))
         del cand, tau, X64d, n2
 
 

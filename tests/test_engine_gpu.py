@@ -96,7 +96,7 @@ def test_radius_pairs_complete():
 
 
 # ------------------------------------------------------------------ tensor-core (tcgen05) search
-def _tc_topk(X, Y=None, dtype=0, ls=32):
+def _tc_topk(X, Y=None, dtype=0, ls=32, qtiles=1):
     ref = pipeline.SearchOperand(_dev(X))
     qry = ref if Y is None else pipeline.SearchOperand(_dev(Y), mean=ref.mean)
     scale = pipeline.fp16_scale(max(qry.norm_max(), ref.norm_max())) if dtype == 2 else 1.0
@@ -107,7 +107,7 @@ def _tc_topk(X, Y=None, dtype=0, ls=32):
     tau = torch.empty((qry.n, 2), dtype=torch.float32, device="cuda")
     pace = torch.zeros(1, dtype=torch.int32, device="cuda")
     E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2 * (scale * scale), qry.n, qry.n_pad, r_hi, r_lo, ref.n, ref.n_pad,
-           ref.kp(dtype), dtype, ls, 2, cand, scratch, tau, pace)
+           ref.kp(dtype), dtype, ls, 2, qtiles, cand, scratch, tau, pace)
     torch.cuda.synchronize()
     return cand.cpu().numpy(), (tau / (scale * scale)).cpu().numpy().min(axis=1), qry, ref
 
@@ -162,6 +162,36 @@ def test_tc_topk_candidates(n, d, dtype, ls):
             assert np.isfinite(tau[i])
             assert D2[i, non].min() >= tau[i] - bound
         if n_even <= ls and n_odd <= ls:
+            assert np.isinf(tau[i])
+
+
+@pytest.mark.parametrize("n,d", [(1797, 64), (3000, 100), (300, 5), (40, 3), (1000, 31), (777, 103), (5000, 100)])
+def test_tc_topk_two_query_tiles(n, d):
+    """fp16x2 with two query tiles per CTA: ONE list of 32 per row over the whole reference set."""
+    X, _ = synth.gaussian_mixture(n, d, n_clusters=5, intrinsic_dim=min(8, d), seed=3)
+    ls = 16
+    cand, tau, qry, ref = _tc_topk(X, dtype=2, ls=ls, qtiles=2)
+    X64 = X.astype(np.float64)
+    D2 = ((X64[:, None, :] - X64[None, :, :]) ** 2).sum(-1)
+    order = np.argsort(D2, axis=1, kind="stable")
+    Xc = X64 - X64.mean(0)
+    nrm = (Xc ** 2).sum(1)
+    eps = pipeline.eps_rel_tch(d)
+    for i in range(0, n, max(1, n // 400)):
+        assert (cand[i] != -7).all(), "output slot never written"
+        c = cand[i][cand[i] >= 0]
+        assert (c < n).all(), "padded reference leaked into the candidates"
+        assert len(np.unique(c)) == len(c), "duplicate candidate"
+        assert len(c) == min(2 * ls, n), (i, len(c))
+        bound = eps * (nrm[i] + nrm.max())
+        sure = [j for j in order[i, :min(2 * ls - 8, n)]
+                if D2[i, j] + 2 * bound < D2[i, order[i, min(2 * ls - 1, n - 1)]]]
+        assert set(sure).issubset(set(c)), "row %d misses a true neighbour" % i
+        non = np.setdiff1d(np.arange(n), c)
+        if len(non):
+            assert np.isfinite(tau[i])
+            assert D2[i, non].min() >= tau[i] - bound
+        else:
             assert np.isinf(tau[i])
 
 
@@ -302,7 +332,6 @@ def test_sharded_symmetrise_merge_matches_global(mode, theta):
         t_rec = torch.empty((k, 2), dtype=torch.int64, device="cuda")
         E.call("gtb_records_scatter", rec, k, lo, pipeline.cursor32(ptr_t), t_rec)
         pa, ia, va = _csr_dev(Rh[lo:hi])
-        pipeline.sort_records(ptr_t, t_rec, m, pa, E.lib().gtb_sym_merge_reg_rows())
         flags = torch.zeros(1, dtype=torch.int32, device="cuda")
         outptr, oi, ov, pv, dg, _ = pipeline.merge_with_transpose(pa, ia, va, ptr_t, t_rec, m, lo, smode,
                                                                   0.0 if theta is None else theta, True, flags)
