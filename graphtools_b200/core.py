@@ -314,7 +314,21 @@ class BaseGraph(Base, metaclass=abc.ABCMeta):
         return self._finish_dense_kernel(raw)
 
     def _finish_dense_kernel(self, raw):
-        raise NotImplementedError
+        """Dense raw kernel (CUDA tensor [N, N]) -> symmetrise, anisotropy, sanity checks, degree, P
+        (base.py:534-592, :645 on an ndarray kernel)."""
+        import torch
+        from . import dense
+        K = dense.symmetrize_dense(raw, self.kernel_symm, self.theta).contiguous()
+        if self.anisotropy != 0:
+            dense.anisotropy_dense(K, self.anisotropy)
+        if float((K - K.T).max().item()) > 1e-5:
+            warnings.warn("K should be symmetric", RuntimeWarning)
+        if bool((torch.diagonal(K) == 0).any().item()):
+            warnings.warn("K should have a non-zero diagonal", RuntimeWarning)
+        self._dev_degree = dense.rowsum_dense(K)
+        self._dev_P = dense.row_normalize_dense(K, self._dev_degree)
+        self._dev_kernel = K
+        return K
 
     def _ensure_built(self):
         d = self.__dict__

@@ -87,10 +87,10 @@ class MNNGraph(DataGraph):
                 g = Graph(self.data_nu[idx], n_pca=None, knn=self.knn, decay=self.decay, bandwidth=self.bandwidth,
                           distance=self.distance, thresh=self.thresh, verbose=self.verbose,
                           random_state=self.random_state, n_jobs=self.n_jobs, kernel_symm="+", initialize=True)
-                if not isinstance(getattr(g, "_dev_kernel", None), pipeline.DeviceCSR):
-                    raise NotImplementedError("MNNGraph with dense (thresh=0) sub-graphs is not supported")
                 self.subgraphs.append(g)
                 members.append(torch.from_numpy(idx.astype(np.int32)).to(dev))
+        if not isinstance(self.subgraphs[0]._dev_kernel, pipeline.DeviceCSR):
+            return self._build_kernel_dense(members)
         with _logger.log_task("MNN kernel"):
             rowlen = torch.zeros((n,), dtype=torch.int32, device=dev)
             blocks = []
@@ -116,6 +116,24 @@ class MNNGraph(DataGraph):
                        float(self.beta), outptr, cursor, tmp_idx, tmp_val)
             pipeline.sort_rows(outptr, tmp_idx, tmp_val, n)      # blocks land in batch order -> column order
         return pipeline.DeviceCSR(outptr, tmp_idx, tmp_val, (n, n))
+
+    def _build_kernel_dense(self, members):
+        """thresh == 0 with a decay: the factory hands back exact (dense) sub-graphs (api.py:207-209) and the
+        reference assembles a dense ndarray (graphs.py:1901-1902).  Same blocks, same scaling, dense on the device."""
+        n = self.data_nu.shape[0]
+        with _logger.log_task("MNN kernel"):
+            K = torch.zeros((n, n), dtype=torch.float64, device=pipeline._dev())
+            for i, gi in enumerate(self.subgraphs):
+                ri = members[i].long()
+                K[ri[:, None], ri[None, :]] = gi._dev_kernel
+                within = gi._dev_degree
+                for j, gj in enumerate(self.subgraphs):
+                    if i == j:
+                        continue
+                    Kij = gj._kernel_to_data_device(gi.data_nu, knn=self.knn)
+                    scale = torch.clamp(within / Kij.sum(dim=1), max=1.0) * float(self.beta)   # graphs.py:1921-1925
+                    K[ri[:, None], members[j].long()[None, :]] = Kij * scale[:, None]
+        return K
 
     def _kernel_to_data_device(self, Y, theta=None):
         raise NotImplementedError

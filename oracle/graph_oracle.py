@@ -284,7 +284,7 @@ def mnn_kernel(X, sample_idx, knn=5, decay=None, bandwidth=None, thresh=1e-4, be
     X = np.asarray(X, dtype=np.float64)
     sample_idx = np.asarray(sample_idx)
     if decay is not None and thresh <= 0:
-        raise NotImplementedError("thresh=0 MNN sub-graphs are exact graphs in the reference")
+        return _mnn_kernel_dense(X, sample_idx, knn, decay, bandwidth, beta, distance)
     samples = np.unique(sample_idx)
     members = [np.flatnonzero(sample_idx == s) for s in samples]
     subs, within = [], []
@@ -312,6 +312,32 @@ def mnn_kernel(X, sample_idx, knn=5, decay=None, bandwidth=None, thresh=1e-4, be
     K = sparse.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
                           shape=(n, n)).tocsr()
     K.eliminate_zeros()
+    return K
+
+
+def _mnn_kernel_dense(X, sample_idx, knn, decay, bandwidth, beta, distance):
+    """``MNNGraph.build_kernel`` with ``thresh == 0``: the factory picks exact sub-graphs (api.py:207-209), the kernel
+    is the dense ndarray of graphs.py:1901-1935."""
+    samples = np.unique(sample_idx)
+    members = [np.flatnonzero(sample_idx == s) for s in samples]
+    n = X.shape[0]
+    K = np.zeros((n, n))
+    within = []
+    for idx in members:
+        Kbb = symmetrize(exact_kernel(X[idx], knn=knn, decay=decay, bandwidth=bandwidth, distance=distance, thresh=0),
+                         "+")
+        within.append(Kbb)
+    for i, idx_i in enumerate(members):
+        K[np.ix_(idx_i, idx_i)] = within[i]
+        within_norm = np.array(np.sum(within[i], 1)).flatten()
+        for j, idx_j in enumerate(members):
+            if i == j:
+                continue
+            Kij = exact_kernel_to_data(X[idx_j], X[idx_i], knn=knn, decay=decay, bandwidth=bandwidth,
+                                       distance=distance, thresh=0)
+            between_norm = np.array(np.sum(Kij, 1)).flatten()
+            scale = np.minimum(1, within_norm / between_norm) * beta
+            K[np.ix_(idx_i, idx_j)] = Kij * scale[:, None]
     return K
 
 

@@ -81,6 +81,9 @@ def cases():
                                    Y=small[:97] + np.float32(0.02))
     c["small_exact_cosine_thresh0"] = dict(X=small[:250], params=dict(knn=3, decay=10, thresh=0, distance="cosine",
                                                                       kernel_symm="mnn", theta=0.3))
+    # thresh = 0 with a decay: exact (dense) sub-graphs, dense MNN kernel (api.py:207-209, graphs.py:1901-1902)
+    c["mnn_thresh0"] = dict(X=mnnX[:480], params=dict(knn=4, decay=12, thresh=0, sample_idx=mnn_idx[:480],
+                                                      kernel_symm="mnn", theta=0.6, beta=0.8))
     # cityblock metric (sklearn brute-force manhattan search / scipy pdist "cityblock"; the reference's own landmark
     # tests run it, test/test_landmark.py:195-322)
     c["mix_cityblock"] = dict(X=mix, X_ref="mix_knn", params=dict(knn=5, decay=40, distance="cityblock"), Y=Yq)

@@ -3,7 +3,7 @@ NCCL all-gather of the reference set, kernel-bucketed edge exchange, per-shard m
 must give K, P and the degree vector bit-identical to the single-GPU build of the same data on every rank.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        scripts/check_multi.py [--n 200000]
+        scripts/check_multi.py [--size 200000]
 """
 import argparse
 import json
@@ -24,7 +24,7 @@ warnings.simplefilter("ignore")
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=200_000)
+    ap.add_argument("--size", dest="n", type=int, default=200_000)
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))

@@ -163,6 +163,14 @@ def test_mnn_golden(name):
     binary = p.get("decay", 40) is None
     thresh = None if binary else p.get("thresh", 1e-4)
     K, K_ref = G.kernel, case.mat("K")
+    if isinstance(K_ref, np.ndarray):
+        # thresh == 0: exact sub-graphs, dense kernel (api.py:207-209, graphs.py:1901-1902)
+        assert isinstance(K, np.ndarray) and K.dtype == np.float64
+        compare_dense(K, K_ref, what=name + ".K")
+        compare_dense(G.diff_op, case.mat("P"), what=name + ".P")
+        assert np.allclose(G.kernel_degree, case.z["degree"], rtol=1e-5)
+        compare_dense(G.build_kernel().cpu().numpy(), case.mat("R"), what=name + ".R")
+        return
     tied = sorted(_mnn_tie_points(case.X, p["sample_idx"], p["knn"])) if binary else []
     assert len(tied) <= 0.01 * K.shape[0], "too many tie-affected points for a meaningful check"
     if tied:
@@ -256,6 +264,30 @@ def test_pickle_roundtrip(tmp_path):
     with open(tmp_path / "g.pkl", "rb") as f:
         G2 = pickle.load(f)
     assert (G2.kernel != G.kernel).nnz == 0 and (G2.diff_op != G.diff_op).nnz == 0
+
+
+def test_pickled_landmark_graph_keeps_working(tmp_path):
+    """A graph pickled BEFORE its landmark operator was read (device handles are dropped, base.py:887-902 contract) must
+    rebuild its device state on demand: landmark_op, extend_to_data, interpolate and diffuse on the loaded copy."""
+    import pickle
+    case = Case("mix_landmark_random")
+    G = _build(case)
+    G.kernel
+    blob = pickle.dumps(G)
+    G2 = pickle.loads(blob)
+    assert not any(k.startswith("_dev_") for k in G2.__dict__)
+    op = G2.landmark_op
+    compare_dense(op, case.mat("landmark_op"), what="landmark_op after unpickling")
+    compare_sparse(G2.transitions, case.mat("transitions"), what="transitions after unpickling")
+    Y = case.z["Y"]
+    compare_sparse(G2.extend_to_data(Y), case.mat("ext"), thresh=1e-4, what="ext after unpickling")
+    x = np.random.default_rng(0).normal(size=(G2.kernel.shape[0], 2))
+    assert np.allclose(G2.diffuse(x, t=2), G.diff_op.dot(G.diff_op.dot(x)), rtol=1e-12, atol=1e-14)
+    sig = np.random.default_rng(1).normal(size=(op.shape[0], 2))
+    assert np.allclose(G2.interpolate(sig), G2.transitions.dot(sig), rtol=1e-12, atol=1e-14)
+    # a graph pickled after everything was read round-trips bit for bit
+    G3 = pickle.loads(pickle.dumps(G2))
+    assert np.array_equal(G3.landmark_op, op) and (G3.kernel != G2.kernel).nnz == 0
 
 
 def test_duplicate_points_warn_and_match(impl):
