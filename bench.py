@@ -400,6 +400,37 @@ def run_gpu_arm(a):
                                "--set full capture in profiles/ (1-GPU workload)" % (how, note),
                 "flops_per_launch": flop}
 
+    # ---- sparse stages against the HBM roofline (SURVEY 8d byte model: float64 values, int32 indices / row pointers),
+    # from the same CUDA-event timings; this rank's share of the rows
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    m_rows = hi - lo
+    nnz_r = float(stats.get("nnz_raw") or 0)
+    nnz_s_loc = float(Kv.shape[0])
+    S_cand = float(stats.get("S") or 32)
+
+    def _ms(*names):
+        return sum(tm[k][1] for k in names if k in tm) / a.steps
+
+    k4_names = ("gtb_transpose_count", "gtb_transpose_scatter", "gtb_sym_merge_count", "gtb_sym_merge_fill",
+                "gtb_rec_sort_rows", "gtb_records_count", "gtb_records_scatter", "gtb_route_count", "gtb_route_fill",
+                "gtb_cast_indptr")
+    sparse_stages = {}
+    for name, ms_, nbytes, what in (
+            ("K3 refine (float64 re-evaluation, bandwidth, certification, affinities)", _ms("gtb_refine_topk"),
+             m_rows * S_cand * (4.0 + 4.0 * d) + 12.0 * nnz_r + 4.0 * (m_rows + 1),
+             "Nq S (4 + 4 d) candidate gather + 12 nnz_r + 4 (Nq + 1) written"),
+            ("CSR emission (csr_gather + scans)", _ms("gtb_csr_gather", "gtb_exclusive_scan"),
+             12.0 * nnz_r + 4.0 * (m_rows + 1) + 12.0 * nnz_r, "staging read + 12 nnz_r + 4 (Nq + 1) written"),
+            ("K4 symmetrise + normalise (transpose, merge, P, degree)", _ms(*k4_names),
+             12.0 * nnz_r + 4.0 * (m_rows + 1) + 12.0 * nnz_s_loc + 4.0 * (m_rows + 1) + 16.0 * nnz_s_loc,
+             "[12 nnz_r + 4 (N + 1)] read + [12 nnz_s + 4 (N + 1)] written + 8 nnz_s read + 8 nnz_s written (P)")):
+        if ms_ > 0:
+            gbs = nbytes / (ms_ / 1e3) / 1e9
+            sparse_stages[name] = {"ms": ms_, "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm,
+                                   "byte_model": what}
+    roofline["sparse_stages"] = sparse_stages
+    roofline["hbm_peak_gbs"] = hbm
+
     # ---- end-to-end through the public API with host buffers (rank-sharded builds are not exposed
     # through Graph(); e2e is measured on rank 0's single-GPU API call when world == 1)
     e2e = None

@@ -9,6 +9,7 @@ import numpy as np
 from scipy import sparse
 
 RTOL = 1e-5
+SUBNORMAL_ATOL = 2 * 4.9406564584124654e-324
 
 
 def _coo_keys(M):
@@ -108,7 +109,9 @@ def compare_dense(gpu, ref, rtol=RTOL, thresh=None, what="matrix"):
     gpu = np.asarray(gpu); ref = np.asarray(ref)
     assert gpu.shape == ref.shape
     err = np.abs(gpu - ref)
-    ok = err <= rtol * np.abs(ref)
+    # float64 subnormals (|v| < 2.2e-308, reached by exp(-(d/bw)^decay) with thresh = 0) carry fewer than 53 bits -- the
+    # smallest one a single bit -- so a relative tolerance cannot apply there: two subnormal ulps absolute
+    ok = err <= rtol * np.abs(ref) + SUBNORMAL_ATOL
     if thresh:
         # entries zeroed by the threshold on one side only
         edge = (np.abs(np.maximum(gpu, ref) - thresh) / thresh < 1e-4) & ((gpu == 0) | (ref == 0))
