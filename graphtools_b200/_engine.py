@@ -72,6 +72,8 @@ _SIGS = {
     "gtb_dense_rowsum": ([_P, c_int64, c_int64, _P, _P], 1),
     "gtb_spmm_csr": ([_P, _P, _P, c_int64, _P, c_int64, c_int, _P, c_int64, _P], 1),
     "gtb_row_scale": ([_P, _P, c_int64, c_int, c_int, _P, _P], 1),
+    "gtb_slice_f64": ([_P, c_int64, c_int64, c_int64, c_int, c_int, c_int64, c_int64, _P, _P, _P], 2),
+    "gtb_gemm_i8": ([_P, _P, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_int64, c_int, _P], 1),
 }
 _PLAIN = {
     "gtb_last_error": ([], ctypes.c_char_p),
@@ -83,6 +85,7 @@ _PLAIN = {
     "gtb_tc_max_kp": ([], c_int),
     "gtb_tc_fp16_maxnorm": ([], c_float),
     "gtb_tc_scratch_bytes": ([c_int64], c_int64),
+    "gtb_gemm_max_k": ([], c_int),
 }
 
 

@@ -19,6 +19,7 @@ import warnings
 import numpy as np
 from scipy import sparse
 
+from . import _engine as E
 from . import pipeline
 from .logging_util import logger as _logger
 
@@ -528,8 +529,15 @@ class BaseGraph(Base, metaclass=abc.ABCMeta):
             for _ in range(int(t)):
                 x = pipeline.spmm(K, x, self._dev_P)
         else:
-            for _ in range(int(t)):
-                x = torch.matmul(self._dev_P, x)
+            from . import dense
+            if self._dev_P.shape[1] <= E.lib().gtb_gemm_max_k():
+                # dense graph: float64-faithful products on the int8 tensor cores; P is sliced once for all t steps
+                Pd = dense.slice_operand(self._dev_P.contiguous(), False)
+                for _ in range(int(t)):
+                    x = dense.gemm_digits(Pd, dense.slice_operand(x, True), self._dev_P.shape[0], x.shape[1])
+            else:
+                for _ in range(int(t)):
+                    x = torch.matmul(self._dev_P, x)
         if return_device:
             return x[:, 0] if one_d else x
         x = x.cpu().numpy()

@@ -109,3 +109,82 @@ def dense_landmark_extend(Kyx, labels, L):
     agg = Kyx @ _one_hot(labels, L)
     rs = agg.abs().sum(1, keepdim=True)
     return torch.where(rs != 0, agg / rs, agg).cpu().numpy()
+
+
+# ---------------------------------------------------------------------- float64-faithful products on the int8 tensor cores
+GEMM_SLICES = 7          # digit planes per operand: 54 significant bits below the row / column maximum
+
+
+def _pad128(n):
+    return (int(n) + 127) // 128 * 128
+
+
+def slice_operand(X, transposed=False, slices=GEMM_SLICES):
+    """Digit planes of a float64 device matrix for gtb_gemm_i8: the rows of X (left operand) or, with
+    ``transposed``, its columns (right operand).  Returns (int8 [slices, R_pad, K_pad], scale [R])."""
+    assert X.dtype == torch.float64 and X.dim() == 2 and X.stride(1) == 1
+    if transposed:
+        K, R = X.shape
+    else:
+        R, K = X.shape
+    R_pad, K_pad = _pad128(R), _pad128(K)
+    dig = pipeline._empty((slices, R_pad, K_pad), torch.int8)
+    scale = pipeline._empty((R,), torch.float64)
+    E.call("gtb_slice_f64", X, R, K, X.stride(0), int(bool(transposed)), slices, R_pad, K_pad, dig, scale)
+    return dig, scale
+
+
+def gemm_digits(a, b, M, N, row_bytes=None):
+    """C [M, N] float64 = A . B from the digit planes ``a = slice_operand(A)`` and ``b = slice_operand(B, True)``."""
+    import os
+    (ad, sa), (bd, sb) = a, b
+    S, M_pad, K_pad = ad.shape
+    assert bd.shape[0] == S and bd.shape[2] == K_pad
+    if K_pad > E.lib().gtb_gemm_max_k():
+        raise ValueError("inner dimension {} exceeds the exact int32 accumulation range ({})".format(
+            K_pad, E.lib().gtb_gemm_max_k()))
+    rb = int(os.environ.get("GTB_GEMM_ROW_BYTES", "64")) if row_bytes is None else int(row_bytes)
+    C = pipeline._empty((M, N), torch.float64)
+    E.call("gtb_gemm_i8", ad, bd, S, M, N, K_pad, M_pad, bd.shape[1], sa, sb, C, N, rb)
+    return C
+
+
+def gemm_f64(A, B, slices=GEMM_SLICES, row_bytes=None):
+    """A @ B for float64 device matrices: exact int32 accumulation of base-256 digit products on the tensor cores
+    (csrc/gemm.cu), combined in float64 -- error below that of a float64 dot product of the same length."""
+    A = A.contiguous() if A.stride(1) != 1 else A
+    B = B.contiguous() if B.stride(1) != 1 else B
+    assert A.shape[1] == B.shape[0], (tuple(A.shape), tuple(B.shape))
+    return gemm_digits(slice_operand(A, False, slices), slice_operand(B, True, slices), A.shape[0], B.shape[1],
+                       row_bytes)
+
+
+def matrix_power(M, t, slices=GEMM_SLICES):
+    """M^t for a square float64 device matrix with numpy's multiplication schedule (np.linalg.matrix_power: binary
+    decomposition of t, squarings of z, products result @ z) -- what the callers of ``G.landmark_op`` /
+    a dense ``G.diff_op`` run on the host.  Every product is gemm_f64; z^2 slices z once per operand role."""
+    t = int(t)
+    if M.dim() != 2 or M.shape[0] != M.shape[1]:
+        raise ValueError("matrix_power needs a square matrix")
+    if t < 0:
+        raise ValueError("negative powers are not supported on the device")
+    n = M.shape[0]
+    if t == 0:
+        return torch.eye(n, dtype=torch.float64, device=M.device)
+    M = M.to(torch.float64).contiguous()
+    if t == 1:
+        return M.clone()
+    if t == 2:
+        return gemm_f64(M, M, slices)
+    if t == 3:
+        return gemm_f64(gemm_f64(M, M, slices), M, slices)
+    z = result = None
+    while t > 0:
+        if z is None:
+            z = M
+        else:
+            z = gemm_f64(z, z, slices)
+        t, bit = divmod(t, 2)
+        if bit:
+            result = z if result is None else gemm_f64(result, z, slices)
+    return result

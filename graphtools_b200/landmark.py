@@ -185,12 +185,25 @@ class LandmarkGraph(DataGraph):
                 Kt = K if self.kernel_symm is not None else pipeline.transpose_csr(K)
                 pnm, pnm_norm, colsum = aggregate_by_cluster(Kt, labels, L, want_colsum=True)
                 op = landmark_operator(pnm, pnm_norm, colsum, K.shape[0], L)
+                self._dev_landmark_op = op
                 self._landmark_op = op.cpu().numpy()
                 self._transitions = pnm.to_scipy(pnm_norm)
                 self._dev_transitions = (pnm, pnm_norm)
             else:
                 from .dense import dense_landmark
                 self._landmark_op, self._transitions = dense_landmark(K, labels, L)
+
+    def landmark_op_power(self, t, return_device=False):
+        """``landmark_op ** t`` (matrix power): the diffusion chain the callers of ``G.landmark_op`` run as
+        ``np.linalg.matrix_power(G.landmark_op, t)`` on the operator of graphs.py:1240-1243, here as float64-faithful
+        products on the int8 tensor cores (dense.matrix_power, csrc/gemm.cu) without the operator leaving HBM."""
+        from .dense import matrix_power
+        self.landmark_op  # builds the operator if needed
+        op = getattr(self, "_dev_landmark_op", None)
+        if op is None:
+            op = self._dev_landmark_op = pipeline.to_device(np.ascontiguousarray(self._landmark_op, dtype=np.float64))
+        out = matrix_power(op, t)
+        return out if return_device else out.cpu().numpy()
 
     def _extend_to_data_device(self, data, **kwargs):
         """(DeviceCSR [n_y, L], normalised values): out-of-sample kernel aggregated by landmark, in HBM."""

@@ -248,6 +248,23 @@ int gtb_spmm_csr(const int64_t* indptr, const int32_t* idx, const double* val, i
 int gtb_row_scale(const double* in, const double* s, int64_t n, int f, int power_neg_half, double* out,
                   void* stream);
 
+/* ---- float64-faithful dense product on the INT8 tensor cores (section 8f row 3: the landmark diffusion chain
+ * landmark_op^t the callers run through np.linalg.matrix_power on the operator of graphs.py:1240-1243) ------- */
+/* Digit planes of a float64 operand.  Logical operand rows r < R of length K: row r of X[R][ld] (transposed = 0)
+ * or column r of X[K][ld] (transposed = 1).  scale[r] = power of two with |row r| / scale[r] < 1/4; digits is
+ * int8 [slices][R_pad][K_pad], zero padded, v / scale = sum_s digits[s] 2^(-8 (s + 1)) (balanced base-256 digits,
+ * exact up to the truncation at 2^(-8 slices)).  R_pad, K_pad multiples of 128; 2 <= slices <= 7 */
+int gtb_slice_f64(const double* X, int64_t R, int64_t K, int64_t ld, int transposed, int slices, int64_t R_pad,
+                  int64_t K_pad, int8_t* digits, double* scale, void* stream);
+/* C[M][ldc] (first N columns) = A . B from the digit planes of A's rows and B's columns (gtb_slice_f64): every digit
+ * pair product of order s + t < slices is accumulated EXACTLY in int32 by tcgen05.mma kind::i8 and combined in
+ * float64, C_ij = sa_i sb_j sum_o 2^(-8 (o + 2)) ACC_o.  K_pad <= gtb_gemm_max_k(); row_bytes = 32, 64 or 128
+ * selects the shared-memory row length (swizzle) of one k-block and with it the pipeline depth (4, 2, 1 stages) */
+int gtb_gemm_max_k(void);
+int gtb_gemm_i8(const int8_t* a_digits, const int8_t* b_digits, int slices, int64_t M, int64_t N, int64_t K_pad,
+                int64_t M_pad, int64_t N_pad, const double* sa, const double* sb, double* C, int64_t ldc,
+                int row_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
