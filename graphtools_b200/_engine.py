@@ -33,6 +33,8 @@ _SIGS = {
     "gtb_prepare_operand_tc": ([_P, c_int64, c_int, _P, c_int, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P], 2),
     "gtb_knn_topk_tc": ([_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, _P,
                          _P, _P, _P, _P], 1),
+    "gtb_knn_topk_tc_seeded": ([_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int,
+                                _P, c_int, _P, _P, _P, _P, _P], 1),
     "gtb_knn_radius_tc": ([_P, _P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P, c_int64,
                            _P, _P, _P, _P], 1),
     "gtb_refine_topk": ([_P, c_int64, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_float, c_double, c_int, c_int64, c_double,
@@ -152,6 +154,7 @@ def call(name, *args):
     """Invoke a compute entry point on the current torch stream; tensors are passed as pointers."""
     global launch_count, kernel_launches
     L = lib()
+    key, name = name, name.split("#")[0]         # "entry#tag": same entry point, timed under its own key
     argtypes, nk = _SIGS[name]
     conv = []
     for a, t in zip(args, argtypes):
@@ -164,7 +167,7 @@ def call(name, *args):
     rc = getattr(L, name)(*conv, stream_ptr())
     if timing is not None:
         ev1.record()
-        timing.setdefault(name, []).append((ev0, ev1))
+        timing.setdefault(key, []).append((ev0, ev1))
     if rc != 0:
         raise EngineError("%s failed (%d): %s" % (name, rc, L.gtb_last_error().decode()))
     launch_count += 1

@@ -12,6 +12,10 @@
 //              TWO products A_hi.B_hi + A_hi.B_lo: the reference operand keeps 22 bits, the query operand 11, so the
 //              dropped term A_lo.B is bounded by 2^-11 sum|a||b| -- two thirds of the tensor work of the other flavours
 //              for a wider (but still certified) rounding bound.
+//   3  fp16x1  the same float16 hi arrays, ONE product A_hi.B_hi (the low part of |y|^2 rides in a spare K column, so
+//              only the rounding of the coordinates remains: 2^-10 (|x|^2 + |y|^2)) -- half the tensor work again.
+//              Top-k only, two query tiles per CTA, one list of 64 per row; the per-row threshold can be SEEDED from
+//              a sweep over every tile_stride-th reference tile, which removes most of the threshold-update hits.
 // All of them are only used to SELECT candidates; every value that reaches the output is re-evaluated in float64 by
 // refine.cu, and rows whose candidate list cannot be certified against the flavour's bound take the radius pass.
 //
@@ -66,6 +70,8 @@ struct TcParams {
   int64_t nrounds;
   int64_t n_qclusters, tiles_per_split;                    // RADIUS with few query tiles: the reference range is split over CTAs
   unsigned int* sync_ctr;                                  // grid-wide pacing counter (zeroed per launch)
+  int64_t tile_stride;                                     // TOPK: sweep every tile_stride-th reference tile (1 = all)
+  const float* seed_tau;                                   // TOPK: optional per-row initial threshold, layout of `tau`
   const float* qn2;
   int32_t* cand_idx; uint2* cand_buf; float* tau;          // TOPK: out [nq][2*TC_S], scratch [nq_pad][2][TC_CAP], tau [nq][2]
   const float* lim2; int2* pairs; unsigned long long capacity; unsigned long long* counter; int32_t* rowcnt;
@@ -88,9 +94,9 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
 // pivot per step -- 64-bit compares, ballots and popcounts only, no data movement and no divergent branches
 // (the register bitonic sort this replaces compiled to ~100 shuffle stages of branchy compare-swaps, ~10k cycles
 // per call).  The survivors are written back in ballot-prefix order.
-template <int LS>
+template <int LS, int CAP>
 __device__ __noinline__ float compact_row(uint2* buf, int cnt, int lane) {
-  constexpr int NSLOT = TC_CAP / 32;
+  constexpr int NSLOT = CAP / 32;
   constexpr unsigned long long NONE = ~0ull;
   uint2 t[NSLOT];
   unsigned long long key[NSLOT];
@@ -105,7 +111,7 @@ __device__ __noinline__ float compact_row(uint2* buf, int cnt, int lane) {
     }
   }
   unsigned long long lo = 0ull, hi = NONE, T = NONE;    // the LS-th smallest key lies strictly inside (lo, hi)
-  for (int iter = 0; iter < TC_CAP + 1; ++iter) {
+  for (int iter = 0; iter < CAP + 1; ++iter) {
     // pivot = an element still inside the interval; slot and end of the lane scan rotate with the step so that no
     // arrival order of the buffer is systematically bad
     unsigned m[NSLOT];
@@ -212,11 +218,17 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   unsigned char* gbase = smem_raw + (base - raw);
 
   constexpr bool BF16 = FMT != 0;                            // 2-byte operand elements (bf16 or fp16): kind::f16
-  constexpr int NPROD = (FMT == 2) ? 2 : 3;                  // (A_hi,B_hi), (A_hi,B_lo)[, (A_lo,B_hi)]
-  constexpr float BIG = (FMT == 2) ? TC_BIG_H : TC_BIG;
+  constexpr int NPROD = (FMT == 3) ? 1 : (FMT == 2) ? 2 : 3;  // (A_hi,B_hi)[, (A_hi,B_lo)[, (A_lo,B_hi)]]
+  constexpr int NPART = (FMT == 3) ? 1 : 2;                  // operand arrays streamed per stage (hi[, lo])
+  constexpr float BIG = (FMT >= 2) ? TC_BIG_H : TC_BIG;
   constexpr int EPK = BF16 ? 16 : 8;                         // elements per 32-byte k-step
-  static_assert(QT == 1 || (QT == 2 && FMT == 2 && MODE == 0), "two query tiles per CTA: fp16x2 top-k only");
+  static_assert(QT == 1 || (QT == 2 && FMT >= 2 && MODE == 0), "two query tiles per CTA: fp16 top-k only");
+  static_assert(FMT != 3 || QT == 2, "the one-product flavour runs two query tiles per CTA");
   constexpr int LSO = (QT == 2) ? 2 * LS : LS;               // entries of one output list
+  // candidate buffer of one list: a row owns TC_GROUPS * TC_CAP slots of scratch; the single long list of QT == 2 may
+  // use all of them (fewer compactions between the seeded threshold and the final selection)
+  constexpr int CAP = (LSO > 32) ? TC_GROUPS * TC_CAP : TC_CAP;
+  static_assert(CAP >= LSO + 64, "room for a list and two batches of 32");
   const int nks = p.nks;                                     // 32-byte k-steps per operand row
   const int nfull = nks / 4, ntail = nks % 4;                // SWIZZLE_128B blocks (4 k-steps) + SWIZZLE_32B tail blocks
   const int a_lo_col = nks * 8;                              // TMEM column of A_lo (A_hi at 0)
@@ -225,13 +237,13 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   const char* q_lo = reinterpret_cast<const char*>(q_lo_v);
   // shared-memory ring of NS reference stages (3 fit for bf16 operands, 2 for tf32); the two TMEM
   // accumulators form an independent 2-deep ring
-  constexpr int NS = BF16 ? 3 : 2;
+  constexpr int NS = BF16 ? (NPART == 1 ? 4 : 3) : 2;
   // TMEM accumulator ring: bf16 query tiles need only 2 x 64 columns, leaving room for three 128-column
   // accumulators (the MMA warp can run two tiles ahead of a busy epilogue group); tf32 has room for two.
   constexpr int NA = BF16 ? 3 : 2;
   constexpr int ACC0 = BF16 ? 128 : 256;
-  const uint32_t B0 = base;                                  // stage s, part q at B0 + (2*s+q)*sizeB
-  const uint32_t bar0 = B0 + 2 * NS * sizeB;
+  const uint32_t B0 = base;                                  // stage s, part q at B0 + (NPART*s+q)*sizeB
+  const uint32_t bar0 = B0 + NPART * NS * sizeB;
   const uint32_t bar_a = bar0, full_b = bar0 + 8, empty_b = bar0 + 40, tm_full = bar0 + 72, tm_empty = bar0 + 104;
   const uint32_t round_done = bar0 + 136;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (bar0 - base) + 144);
@@ -249,13 +261,14 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   const int64_t nrounds = p.nrounds;
   const int64_t qcluster = cluster_id % p.n_qclusters;
   const int64_t tile0 = (cluster_id / p.n_qclusters) * p.tiles_per_split;
-  const int64_t tiles_left = p.nr_pad / TC_N - tile0;
+  const int64_t tstride = (MODE == 0) ? p.tile_stride : 1;
+  const int64_t tiles_left = (p.nr_pad / TC_N + tstride - 1) / tstride - tile0;
   const int64_t ntiles = tiles_left < p.tiles_per_split ? tiles_left : p.tiles_per_split;
   // first query row of (round, query tile qt of this CTA)
   auto q0_of = [&](int64_t round, int qt) {
     return (((qcluster + round * n_clusters) * CL + (blockIdx.x % CL)) * QT + qt) * TC_M;
   };
-  auto btile = [&](int64_t round, int64_t t) { return tile0 + ((round & 1) ? (ntiles - 1 - t) : t); };
+  auto btile = [&](int64_t round, int64_t t) { return (tile0 + ((round & 1) ? (ntiles - 1 - t) : t)) * tstride; };
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
   constexpr int ROWS = TC_N / CL;                            // rows of each B block this CTA loads
@@ -308,12 +321,12 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
             }
           }
           mbar_wait(empty_b + 8 * s, ph ^ 1);      // every CTA of the cluster has consumed this stage
-          mbar_arrive_expect_tx(full_b + 8 * s, 2 * sizeB);
+          mbar_arrive_expect_tx(full_b + 8 * s, NPART * sizeB);
           const int row0 = (int)(btile(round, t) * TC_N) + (int)crank * ROWS;
-          for (int part = 0; part < 2; ++part) {
+          for (int part = 0; part < NPART; ++part) {
             const CUtensorMap* mm = part ? &mBl : &mBh;
             const CUtensorMap* mt = part ? &mBlt : &mBht;
-            const uint32_t dst = B0 + (2 * s + part) * sizeB;
+            const uint32_t dst = B0 + (NPART * s + part) * sizeB;
             for (int b = 0; b < nfull; ++b) {
               const uint32_t d = dst + b * (TC_N * 128) + crank * (ROWS * 128);
               if (CL > 1) tma_load_2d_mc(d, mm, full_b + 8 * s, b * 4 * EPK, row0, cmask);
@@ -341,7 +354,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
                            ((uint32_t)(TC_M >> 4) << 24);
     const uint64_t bd_main0 = make_desc(B0, 1024, 2);                          // stage 0, hi part, block 0
     const uint64_t bd_tail0 = make_desc(B0 + nfull * (TC_N * 128), 256, 6);    // stage 0, hi part, first tail block
-    const uint32_t part_off = sizeB >> 4, stage_off = (2 * sizeB) >> 4;         // in descriptor address units (16 B)
+    const uint32_t part_off = sizeB >> 4, stage_off = (NPART * sizeB) >> 4;     // in descriptor address units (16 B)
     int64_t it = 0;
     for (int64_t round = 0; round < nrounds; ++round) {
     mbar_wait(bar_a, (uint32_t)(round & 1));   // this round's A rows stored to TMEM by the epilogue warps
@@ -433,11 +446,19 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
 
     const float nx = valid ? p.qn2[gq] : 0.f;
     float thr;
-    if (MODE == 0) thr = valid ? BIG : -gtb_inf_f();
-    else thr = valid ? (p.lim2[gq] - nx) : -gtb_inf_f();
+    if (MODE == 0) {
+      thr = valid ? BIG : -gtb_inf_f();
+      if (valid && p.seed_tau != nullptr) {
+        // seeded threshold: every reference point under it is appended, the buffer compacts as usual when it fills
+        const float t0 = p.seed_tau[gq * TC_GROUPS] - nx;
+        if (t0 < BIG) thr = t0;
+      }
+    } else {
+      thr = valid ? (p.lim2[gq] - nx) : -gtb_inf_f();
+    }
     int cnt = 0;
     // this thread's candidate buffer: uniform base + per-thread offset (rows past nq never append)
-    const int64_t boff = valid ? (gq * TC_GROUPS + lgrp) * TC_CAP : 0;
+    const int64_t boff = valid ? (gq * TC_GROUPS + lgrp) * TC_CAP : 0;     // (CAP > TC_CAP only with lgrp == 0)
     uint2* wbuf = p.cand_buf + (q0 + quad * 32) * TC_GROUPS * TC_CAP;   // warp-uniform: first row of this quadrant
     uint2* mybuf = p.cand_buf + boff;                                     // this row's buffer (never written when !valid)
 
@@ -538,13 +559,13 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         }
         if (MODE == 0) {
           // keep >= 32 free slots for the next batch
-          unsigned need = __ballot_sync(0xffffffffu, cnt > TC_CAP - 32);
+          unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - 32);
           while (need) {
             const int owner = __ffs(need) - 1;
             need &= need - 1;
             const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
             __syncwarp();
-            const float nt = compact_row<LSO>(wbuf + (owner * TC_GROUPS + lgrp) * TC_CAP, ocnt, lane);
+            const float nt = compact_row<LSO, CAP>(wbuf + (owner * TC_GROUPS + lgrp) * TC_CAP, ocnt, lane);
             __syncwarp();
             if (lane == owner) { thr = nt; cnt = LSO; }
           }
@@ -560,7 +581,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         need &= need - 1;
         const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
         __syncwarp();
-        const float nt = compact_row<LSO>(wbuf + (owner * TC_GROUPS + lgrp) * TC_CAP, ocnt, lane);
+        const float nt = compact_row<LSO, CAP>(wbuf + (owner * TC_GROUPS + lgrp) * TC_CAP, ocnt, lane);
         __syncwarp();
         if (lane == owner) { thr = nt; cnt = LSO; }
       }
@@ -570,7 +591,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         // the second threshold slot repeats the first (the refine takes the minimum)
         int32_t* out = p.cand_idx + gq * (TC_GROUPS * LS) + lgrp * LS;
         for (int e = 0; e < LSO; ++e) out[e] = (e < cnt) ? (int32_t)p.cand_buf[boff + e].y : -1;
-        const float tv = (cnt < LSO || thr >= BIG) ? gtb_inf_f() : thr + nx;
+        // a list that never filled keeps its initial threshold: +inf unseeded, the seed otherwise (every point under
+        // the seed IS in the list)
+        const float tv = (thr >= BIG) ? gtb_inf_f() : thr + nx;
         p.tau[gq * TC_GROUPS + lgrp] = tv;
         if (QT == 2) p.tau[gq * TC_GROUPS + 1] = tv;
       }
@@ -677,13 +700,22 @@ __global__ void tc_split16h_kernel(const float* __restrict__ X, int64_t n, int d
       if (role == 1) v *= -2.f;
     } else if (k == d) {
       v = (role == 1) ? norm2[r] * scale * scale : 1.f;
+    } else if (k == d + 1) {
+      // spare column: the low part of |y|^2 rides in the hi array (query side: 1), so the one-product flavour sees
+      // |y|^2 to 22 bits as well; the lo array carries nothing for the norm
+      if (role == 1) {
+        const float nv = norm2[r] * scale * scale;
+        v = nv - __half2float(__float2half_rn(nv));
+      } else {
+        v = 1.f;
+      }
     }
   } else if (role == 1 && k == d) {
     v = TC_PAD_NORM_H;
   }
   const __half h = __float2half_rn(v);
   hi[e] = h;
-  lo[e] = __float2half_rn(v - __half2float(h));
+  lo[e] = (k >= d) ? __float2half_rn(0.f) : __float2half_rn(v - __half2float(h));
 }
 
 // ---------------------------------------------------------------- host side
@@ -715,7 +747,9 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
   if ((rc = make_map(&mBht, r_hi, p.nr_pad, Kp, EPK, TC_N / CL, false, FMT))) return rc;
   if ((rc = make_map(&mBl, r_lo, p.nr_pad, Kp, 4 * EPK, TC_N / CL, true, FMT))) return rc;
   if ((rc = make_map(&mBlt, r_lo, p.nr_pad, Kp, EPK, TC_N / CL, false, FMT))) return rc;
-  size_t smem = 1024 + (size_t)2 * (BF16 ? 3 : 2) * TC_N * p.nks * 32 + 256 + 1024;
+  constexpr int NPART = (FMT == 3) ? 1 : 2;
+  constexpr int NS = BF16 ? (NPART == 1 ? 4 : 3) : 2;
+  size_t smem = 1024 + (size_t)NPART * NS * TC_N * p.nks * 32 + 256 + 1024;
   auto kern = search_tc_kernel<MODE, CL, FMT, LS, QT>;
   GTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, nsm = 0;
@@ -724,7 +758,8 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
   const int64_t n_cluster_tiles = gtb_cdiv(p.nq_pad / TC_M, CL * QT);
   int64_t n_clusters = n_cluster_tiles < (nsm / CL) ? n_cluster_tiles : (nsm / CL);
   p.nrounds = gtb_cdiv(n_cluster_tiles, n_clusters);
-  const int64_t total_tiles = p.nr_pad / TC_N;
+  if (p.tile_stride < 1 || MODE != 0) p.tile_stride = 1;
+  const int64_t total_tiles = gtb_cdiv(p.nr_pad / TC_N, p.tile_stride);
   p.n_qclusters = n_clusters;
   p.tiles_per_split = total_tiles;
   int64_t splits = 1;
@@ -764,6 +799,24 @@ int launch_tc_fmt(const void* q_hi, const void* q_lo, const void* r_hi, const vo
                   int qtiles, TcParams& p, cudaStream_t st) {
   constexpr int LS_SHORT = (MODE == 0) ? 16 : 32;
   const bool short_list = (MODE == 0) && list == 16;
+  if constexpr (FMT == 3) {
+    // one product: top-k only, two query tiles per CTA; list = 32 -> one list of 64 per row, list = 4 -> the 8
+    // smallest of a strided sample (threshold seeds)
+    if constexpr (MODE == 0) {
+      if (qtiles != 2 || (list != 32 && list != 4) || (cluster != 1 && cluster != 2)) {
+        gtb_set_error("the one-product flavour needs qtiles = 2, list = 32 or 4, cluster = 1 or 2");
+        return GTB_ERR_ARG;
+      }
+      if (list == 32)
+        return cluster == 1 ? launch_tc_cl<0, 1, 3, 32, 2>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
+                            : launch_tc_cl<0, 2, 3, 32, 2>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+      return cluster == 1 ? launch_tc_cl<0, 1, 3, 4, 2>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
+                          : launch_tc_cl<0, 2, 3, 4, 2>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+    } else {
+      gtb_set_error("the one-product flavour has no radius mode (use dtype 2 on the same operands)");
+      return GTB_ERR_ARG;
+    }
+  } else {
   if (qtiles == 2) {
     if constexpr (FMT == 2 && MODE == 0) {
       if (!short_list) { gtb_set_error("two query tiles per CTA need list = 16 (one list of 32 per row)"); return GTB_ERR_ARG; }
@@ -788,6 +841,7 @@ int launch_tc_fmt(const void* q_hi, const void* q_lo, const void* r_hi, const vo
       // fall through: the 2-byte flavours support clusters of 1 or 2
     default: gtb_set_error("cluster size must be 1 or 2 (or 4 for the tf32 flavour)"); return GTB_ERR_ARG;
   }
+  }
 }
 
 template <int MODE>
@@ -795,6 +849,7 @@ int launch_tc(const void* q_hi, const void* q_lo, const void* r_hi, const void* 
               int cluster, int qtiles, TcParams& p, cudaStream_t st) {
   if (dtype == 1) return launch_tc_fmt<MODE, 1>(q_hi, q_lo, r_hi, r_lo, Kp, list, cluster, qtiles, p, st);
   if (dtype == 2) return launch_tc_fmt<MODE, 2>(q_hi, q_lo, r_hi, r_lo, Kp, list, cluster, qtiles, p, st);
+  if (dtype == 3) return launch_tc_fmt<MODE, 3>(q_hi, q_lo, r_hi, r_lo, Kp, list, cluster, qtiles, p, st);
   return launch_tc_fmt<MODE, 0>(q_hi, q_lo, r_hi, r_lo, Kp, list, cluster, qtiles, p, st);
 }
 
@@ -824,8 +879,8 @@ extern "C" int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const fl
   GTB_CHECK_ARG(n > 0 && d > 0 && n_pad >= n && n_pad % 128 == 0, "bad shape");
   GTB_CHECK_ARG(dtype >= 0 && dtype <= 2, "dtype must be 0 (tf32 pairs in float32), 1 (bfloat16 pairs) or 2 (float16 pairs)");
   const int epk = dtype ? 16 : 8;
-  GTB_CHECK_ARG(Kp % epk == 0 && Kp >= d + 1 && Kp / epk <= (dtype ? 8 : 13),
-                "Kp must be a multiple of 8 (tf32, <= 104) / 16 (bf16 / fp16, <= 128) and >= d+1");
+  GTB_CHECK_ARG(Kp % epk == 0 && Kp >= d + 1 + (dtype == 2) && Kp / epk <= (dtype ? 8 : 13),
+                "Kp must be a multiple of 8 (tf32, <= 104) / 16 (bf16 / fp16, <= 128) and >= d+1 (fp16: d+2)");
   GTB_CHECK_ARG(role == 0 || role == 1, "role must be 0 (query) or 1 (reference)");
   GTB_CHECK_ARG(dtype != 2 || scale > 0.f, "the fp16 flavour needs a positive scale");
   cudaStream_t st = (cudaStream_t)stream;
@@ -849,25 +904,35 @@ extern "C" int64_t gtb_tc_scratch_bytes(int64_t nq_pad) { return nq_pad * TC_GRO
 
 static int tc_check(int64_t nq, int64_t nr, int64_t nq_pad, int64_t nr_pad, int Kp, int dtype) {
   GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TC_M == 0 && nr_pad % TC_N == 0, "bad shape (pads must be x128)");
-  GTB_CHECK_ARG(dtype >= 0 && dtype <= 2, "dtype must be 0 (tf32), 1 (bf16) or 2 (fp16, two products)");
+  GTB_CHECK_ARG(dtype >= 0 && dtype <= 3, "dtype must be 0 (tf32), 1 (bf16), 2 (fp16, two products) or 3 (fp16, one)");
   const int epk = dtype ? 16 : 8;
   GTB_CHECK_ARG(Kp % epk == 0 && Kp >= epk && Kp / epk <= (dtype ? 8 : 13), "Kp out of range");
   GTB_CHECK_ARG(nr_pad < (1ll << 31) && nq_pad < (1ll << 31), "too many rows for 32-bit TMA coordinates");
   return GTB_OK;
 }
 
+extern "C" int gtb_knn_topk_tc_seeded(const void* q_hi, const void* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
+                                      const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp, int dtype,
+                                      int list, int cluster, int qtiles, const float* seed_tau, int tile_stride,
+                                      int32_t* cand_idx, void* scratch, float* tau, unsigned int* pace, void* stream) {
+  int rc = tc_check(nq, nr, nq_pad, nr_pad, Kp, dtype);
+  if (rc) return rc;
+  GTB_CHECK_ARG(list == 16 || list == 32 || (dtype == 3 && list == 4), "list size must be 16 or 32 (or 4 with dtype 3)");
+  GTB_CHECK_ARG(qtiles == 1 || qtiles == 2, "query tiles per CTA: 1 or 2");
+  GTB_CHECK_ARG(tile_stride >= 1, "tile_stride must be >= 1");
+  TcParams p{};
+  p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.qn2 = qn2;
+  p.cand_idx = cand_idx; p.cand_buf = reinterpret_cast<uint2*>(scratch); p.tau = tau; p.sync_ctr = pace;
+  p.seed_tau = seed_tau; p.tile_stride = tile_stride;
+  return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, Kp, dtype, list, cluster, qtiles, p, (cudaStream_t)stream);
+}
+
 extern "C" int gtb_knn_topk_tc(const void* q_hi, const void* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
                                const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp, int dtype,
                                int list, int cluster, int qtiles, int32_t* cand_idx, void* scratch, float* tau,
                                unsigned int* pace, void* stream) {
-  int rc = tc_check(nq, nr, nq_pad, nr_pad, Kp, dtype);
-  if (rc) return rc;
-  GTB_CHECK_ARG(list == 16 || list == 32, "list size must be 16 or 32");
-  GTB_CHECK_ARG(qtiles == 1 || qtiles == 2, "query tiles per CTA: 1 or 2");
-  TcParams p{};
-  p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.qn2 = qn2;
-  p.cand_idx = cand_idx; p.cand_buf = reinterpret_cast<uint2*>(scratch); p.tau = tau; p.sync_ctr = pace;
-  return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, Kp, dtype, list, cluster, qtiles, p, (cudaStream_t)stream);
+  return gtb_knn_topk_tc_seeded(q_hi, q_lo, qn2, nq, nq_pad, r_hi, r_lo, nr, nr_pad, Kp, dtype, list, cluster, qtiles,
+                                nullptr, 1, cand_idx, scratch, tau, pace, stream);
 }
 
 extern "C" int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float* qn2, const float* lim2,
@@ -879,6 +944,6 @@ extern "C" int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float
   TcParams p{};
   p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.qn2 = qn2; p.lim2 = lim2;
   p.pairs = reinterpret_cast<int2*>(pairs); p.capacity = (unsigned long long)capacity; p.counter = counter;
-  p.rowcnt = rowcnt; p.sync_ctr = pace;
+  p.rowcnt = rowcnt; p.sync_ctr = pace; p.tile_stride = 1;
   return launch_tc<1>(q_hi, q_lo, r_hi, r_lo, Kp, dtype, 32, cluster, 1, p, (cudaStream_t)stream);
 }

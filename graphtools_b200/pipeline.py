@@ -228,7 +228,8 @@ class SearchOperand:
         import os
         step = 16 if dtype else 8
         step = int(os.environ.get("GTB_KP_STEP", step))      # experiments: 64 (bf16) / 32 (tf32) = whole 128-byte blocks
-        return (self.d + 1 + step - 1) // step * step
+        # float16 operands keep one more column: the low part of |y|^2 (shared by the two- and one-product flavours)
+        return (self.d + 1 + (1 if dtype >= 2 else 0) + step - 1) // step * step
 
     @property
     def Kp(self):
@@ -249,6 +250,7 @@ class SearchOperand:
     def tc(self, role, dtype=0, scale=1.0):
         """(hi, lo, norm2) of one role; dtype 0 = tf32 pairs in float32, 1 = bfloat16 pairs, 2 = float16 pairs of the
         data scaled by ``scale`` (norm2 stays unscaled)."""
+        dtype = min(dtype, 2)                             # the one-product flavour reads the fp16x2 hi arrays
         key = (role, dtype, float(scale))
         if key not in self._tc:
             Kp = self.kp(dtype)
@@ -344,8 +346,8 @@ def tc_cluster():
 
 def default_impl():
     """GTB_SEARCH_IMPL = tc (3xTF32 tensor cores) | tc16 (bf16x3 tensor cores) | tch (fp16x2 tensor cores: two
-    products, wider certified bound) | simt (fp32 CUDA cores) | auto (default: tensor cores whenever the operand
-    fits)."""
+    products, wider certified bound) | tch1 (fp16, ONE product, seeded thresholds, lists of 64) | simt (fp32 CUDA
+    cores) | auto (default: tensor cores whenever the operand fits)."""
     import os
     return os.environ.get("GTB_SEARCH_IMPL", "auto")
 
@@ -385,7 +387,14 @@ def fp16_scale(maxnorm):
     return 2.0 ** math.floor(0.5 * math.log2(limit / maxnorm))
 
 
-TC_DTYPE = {"tc": 0, "tc16": 1, "tch": 2}
+TC_DTYPE = {"tc": 0, "tc16": 1, "tch": 2, "tch1": 3}
+
+
+def eps_rel_tch1(d):
+    """fp16x1 (A_hi B_hi only, float16): both operands are rounded to 11 bits, |delta(2 x.y)| <= 2 (2 u + u^2)
+    sum |x_k||y_k| <= 2^-10 (1 + 2^-12) (|x~|^2 + |y~|^2) with u = 2^-11; |y|^2 keeps 22 bits (hi + spare-column low
+    part); float32 accumulation and fp16 subnormals as for fp16x2."""
+    return 2.0 ** -10 + 2.0 ** -20 + 2.0 * (d + 32) * 2.0 ** -24 + 1e-6
 
 
 def eps_rel_simt(d):
@@ -422,14 +431,15 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         # GTB_SEARCH_IMPL is a preference: a flavour that cannot take this shape (feature count beyond the
         # resident query tile, knn beyond the 2 x 32 candidate lists) hands over to the next one
         want = default_impl()
-        order = {"auto": (AUTO_TC,) + tuple(x for x in ("tc16", "tc") if x != AUTO_TC) + ("simt",),
+        order = {"auto": (AUTO_TC,) + tuple(x for x in ("tch", "tc16", "tc") if x != AUTO_TC) + ("simt",),
                  "tc": ("tc", "tc16", "simt"), "tc16": ("tc16", "tc", "simt"), "tch": ("tch", "tc16", "tc", "simt"),
-                 "simt": ("simt",)}.get(want)
+                 "tch1": ("tch1", "tch", "tc16", "tc", "simt"), "simt": ("simt",)}.get(want)
         if order is None:
-            raise ValueError("GTB_SEARCH_IMPL must be auto, tc, tc16, tch or simt (got %r)" % (want,))
+            raise ValueError("GTB_SEARCH_IMPL must be auto, tc, tc16, tch, tch1 or simt (got %r)" % (want,))
         impl = "simt"
         for cand_impl in order:
-            if cand_impl == "simt" or (knn + 8 <= 32 and S in (None, 32, 64)
+            # neighbours asked for must fit the candidate lists: 2 x 32 entries, one list of 64 for tch1
+            if cand_impl == "simt" or (knn + 8 <= (64 if cand_impl == "tch1" else 32) and S in (None, 32, 64)
                                        and ref.tc_ok(TC_DTYPE[cand_impl])):
                 impl = cand_impl
                 break
@@ -450,6 +460,8 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         short_ok = want + 8 <= (32 if two_tiles else 16)
         ls = int(os.environ.get("GTB_TC_LIST", "16" if short_ok else "32"))
         qtiles = 2 if (two_tiles and ls == 16) else 1
+        if tcd == 3:
+            ls, qtiles = 32, 2                                  # one product: one list of 64 per row, always two tiles
         if ls not in (16, 32) or knn > ls * qtiles:
             raise ValueError("GTB_TC_LIST must be 16 or 32 and >= knn")
         S, stride, ntau = 2 * ls, 2 * ls, 2
@@ -458,10 +470,10 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
             raise ValueError("GTB_TC_CLUSTER must be 1, 2 or 4")
         # grid-wide pacing of the TMA producers: one caller-owned device word per launch (no library state)
         pace = _empty((1,), torch.int32) if int(os.environ.get("GTB_TC_PACING", "1")) else None
-        if knn > 32:
+        if knn > (64 if tcd == 3 else 32):
             raise NotImplementedError("knn={} exceeds the tensor-core candidate lists (2 x 32)".format(knn))
-        eps_rel = (eps_rel_tc, eps_rel_tc16, eps_rel_tch)[tcd](d)
-        if tcd == 2:
+        eps_rel = (eps_rel_tc, eps_rel_tc16, eps_rel_tch, eps_rel_tch1)[tcd](d)
+        if tcd >= 2:
             tc_scale = fp16_scale(max(qry.norm_max(), ref.norm_max()))
         q_hi, q_lo, q_n2 = qry.tc(0, tcd, tc_scale)
         r_hi, r_lo, _ = ref.tc(1, tcd, tc_scale)
@@ -471,9 +483,26 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         scratch = _empty((E.lib().gtb_tc_scratch_bytes(qry.n_pad),), torch.uint8)
         s2 = tc_scale * tc_scale
         # qtiles == 2: two query tiles per CTA share every reference stage (half the L2 traffic per MMA)
-        E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2 * s2 if tcd == 2 else q_n2, nq, qry.n_pad, r_hi, r_lo, nr,
-               ref.n_pad, Kp, tcd, ls, cluster, qtiles, cand, scratch, tau, pace)
-        if tcd == 2:
+        qn2_s = q_n2 * s2 if tcd >= 2 else q_n2
+        seed = None
+        stride_s = int(os.environ.get("GTB_TC_SEED_STRIDE", "16"))
+        if tcd == 3 and stride_s > 1 and ref.n_pad // 128 >= 32 * stride_s:
+            # threshold seeds: the 8 smallest of every stride-th reference tile (6 % of a sweep); the 8th smallest of
+            # the sample sits near the (8 stride)-th smallest overall, so the full sweep starts with a threshold that
+            # admits ~8 stride points per row instead of climbing down from +inf (64 ln(N / 64) updates)
+            seed = _empty((nq, ntau), torch.float32)
+            cand_s = _empty((nq, 8), torch.int32)
+            E.call("gtb_knn_topk_tc_seeded#seed", q_hi, q_lo, qn2_s, nq, qry.n_pad, r_hi, r_lo, nr, ref.n_pad, Kp, 3, 4,
+                   cluster, 2, None, stride_s, cand_s, scratch, seed, pace)
+            del cand_s
+        if tcd == 3:
+            E.call("gtb_knn_topk_tc_seeded", q_hi, q_lo, qn2_s, nq, qry.n_pad, r_hi, r_lo, nr, ref.n_pad, Kp, tcd, ls,
+                   cluster, qtiles, seed, 1, cand, scratch, tau, pace)
+        else:
+            E.call("gtb_knn_topk_tc", q_hi, q_lo, qn2_s, nq, qry.n_pad, r_hi, r_lo, nr, ref.n_pad, Kp, tcd, ls,
+                   cluster, qtiles, cand, scratch, tau, pace)
+        del seed
+        if tcd >= 2:
             tau = tau / s2                                   # scaled squared distances -> data units (inf stays inf)
         del scratch
     elif impl == "simt":
@@ -536,7 +565,7 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
             sub = SearchOperand(qry.X[todo_rows.long()].contiguous(), mean=ref.mean, metric=ref.metric)
             s_hi, s_lo, s_n2 = sub.tc(0, tcd, tc_scale)
             r_hi, r_lo, _ = ref.tc(1, tcd, tc_scale)
-            if tcd == 2:
+            if tcd >= 2:
                 s_n2 = s_n2 * (tc_scale * tc_scale)
                 lim_t = lim_t * (tc_scale * tc_scale)
         else:
@@ -549,8 +578,9 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
             counter = _zeros((1,), torch.int64)
             rowcnt = _zeros((nt_pad,), torch.int32)
             if impl in TC_DTYPE:
-                E.call("gtb_knn_radius_tc", s_hi, s_lo, s_n2, lim_t, nt, nt_pad, r_hi, r_lo, nr, ref.n_pad, Kp, tcd,
-                       cluster, pairs, capacity, counter, rowcnt, pace)
+                # (the one-product flavour hands its uncertified rows to the two-product sweep on the same operands)
+                E.call("gtb_knn_radius_tc", s_hi, s_lo, s_n2, lim_t, nt, nt_pad, r_hi, r_lo, nr, ref.n_pad, Kp,
+                       min(tcd, 2), cluster, pairs, capacity, counter, rowcnt, pace)
             elif l1:
                 E.call("gtb_knn_radius_simt_l1", QT, lim_t, nt, nt_pad, ref.XT, nr, ref.n_pad, ref.d_pad, pairs,
                        capacity, counter, rowcnt)

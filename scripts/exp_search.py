@@ -18,7 +18,7 @@ ap.add_argument("--tag", default="")
 a = ap.parse_args()
 X, _ = synth.gaussian_mixture(a.n, a.d, n_clusters=50, intrinsic_dim=10, seed=3)
 ref = pipeline.SearchOperand(torch.from_numpy(X).cuda())
-scale = pipeline.fp16_scale(ref.norm_max()) if a.dtype == 2 else 1.0
+scale = pipeline.fp16_scale(ref.norm_max()) if a.dtype >= 2 else 1.0
 q_hi, q_lo, q_n2 = ref.tc(0, a.dtype, scale)
 r_hi, r_lo, _ = ref.tc(1, a.dtype, scale)
 q_n2 = q_n2 * (scale * scale)
@@ -31,15 +31,30 @@ cand = torch.empty((a.n, 2 * ls), dtype=torch.int32, device="cuda")
 tau = torch.empty((a.n, 2), dtype=torch.float32, device="cuda")
 scratch = torch.empty((E.lib().gtb_tc_scratch_bytes(ref.n_pad),), dtype=torch.uint8, device="cuda")
 times = []
+stride = int(os.environ.get("GTB_TC_SEED_STRIDE", "16"))
+seed_ms = []
 for rep in range(a.reps + 1):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
-    E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2, a.n, ref.n_pad, r_hi, r_lo, a.n, ref.n_pad, Kp, a.dtype, ls, cluster, qtiles, cand,
-           scratch, tau, pace)
+    seed = None
+    if a.dtype == 3 and stride > 1:
+        seed = torch.empty((a.n, 2), dtype=torch.float32, device="cuda")
+        cand_s = torch.empty((a.n, 8), dtype=torch.int32, device="cuda")
+        E.call("gtb_knn_topk_tc_seeded", q_hi, q_lo, q_n2, a.n, ref.n_pad, r_hi, r_lo, a.n, ref.n_pad, Kp, 3, 4, cluster, 2,
+               None, stride, cand_s, scratch, seed, pace)
     e1.record()
+    E.call("gtb_knn_topk_tc_seeded", q_hi, q_lo, q_n2, a.n, ref.n_pad, r_hi, r_lo, a.n, ref.n_pad, Kp, a.dtype, ls, cluster,
+           qtiles, seed, 1, cand, scratch, tau, pace)
+    e2.record()
     torch.cuda.synchronize()
-    times.append(e0.elapsed_time(e1))
+    times.append(e1.elapsed_time(e2))
+    seed_ms.append(e0.elapsed_time(e1))
 best = min(times[1:])
+if a.dtype == 3:
+    full = (cand >= 0).sum(1)
+    print("EXP seed stride %d: seed pass %.1f ms; lists full %.3f, mean candidates %.1f, tau finite %.4f" % (
+        stride, min(seed_ms[1:]), float((full == cand.shape[1]).float().mean()), float(full.float().mean()),
+        float(torch.isfinite(tau[:, 0]).float().mean())), flush=True)
 print("EXP %s qtiles=%d list=%d lib=%s n=%d d=%d Kp=%d dtype=%d: %s ms (best %.1f) -> %.1f TFLOP/s algorithmic; cand checksum %d" % (
     a.tag, qtiles, ls, os.path.basename(E.LIB_PATH), a.n, a.d, Kp, a.dtype, ["%.1f" % t for t in times], best,
     2.0 * a.n * a.n * a.d / best / 1e9, int(cand.clamp(min=0).to(torch.int64).sum().item())), flush=True)

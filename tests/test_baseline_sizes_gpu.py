@@ -81,18 +81,25 @@ def test_tc_certification_bound_1m(headline):
     n, d = X.shape
     Xd = pipeline.to_device_f32(X)
     ref = pipeline.SearchOperand(Xd)
-    for tcd, eps_fn, qtiles in ((1, pipeline.eps_rel_tc16, 1), (2, pipeline.eps_rel_tch, 2), (2, pipeline.eps_rel_tch, 1),
-                                (0, pipeline.eps_rel_tc, 1)):
-        ls = 16
-        scale = pipeline.fp16_scale(ref.norm_max()) if tcd == 2 else 1.0
+    for tcd, eps_fn, qtiles in ((3, pipeline.eps_rel_tch1, 2), (1, pipeline.eps_rel_tc16, 1), (2, pipeline.eps_rel_tch, 2),
+                                (2, pipeline.eps_rel_tch, 1), (0, pipeline.eps_rel_tc, 1)):
+        ls = 32 if tcd == 3 else 16
+        scale = pipeline.fp16_scale(ref.norm_max()) if tcd >= 2 else 1.0
         q_hi, q_lo, q_n2 = ref.tc(0, tcd, scale)
         r_hi, r_lo, _ = ref.tc(1, tcd, scale)
         cand = pipeline._empty((n, 2 * ls), torch.int32)
         tau = pipeline._empty((n, 2), torch.float32)
         scratch = pipeline._empty((E.lib().gtb_tc_scratch_bytes(ref.n_pad),), torch.uint8)
         pace = pipeline._empty((1,), torch.int32)
-        E.call("gtb_knn_topk_tc", q_hi, q_lo, q_n2 * (scale * scale), n, ref.n_pad, r_hi, r_lo, n, ref.n_pad,
-               ref.kp(tcd), tcd, ls, 2, qtiles, cand, scratch, tau, pace)
+        seed = None
+        if tcd == 3:
+            # the one-product flavour as the pipeline runs it: thresholds seeded from every 16th reference tile
+            seed = pipeline._empty((n, 2), torch.float32)
+            cand_s = pipeline._empty((n, 8), torch.int32)
+            E.call("gtb_knn_topk_tc_seeded", q_hi, q_lo, q_n2 * (scale * scale), n, ref.n_pad, r_hi, r_lo, n, ref.n_pad,
+                   ref.kp(tcd), 3, 4, 2, 2, None, 16, cand_s, scratch, seed, pace)
+        E.call("gtb_knn_topk_tc_seeded", q_hi, q_lo, q_n2 * (scale * scale), n, ref.n_pad, r_hi, r_lo, n, ref.n_pad,
+               ref.kp(tcd), tcd, ls, 2, qtiles, seed, 1, cand, scratch, tau, pace)
         tau = tau / (scale * scale)
         del scratch
         rows = torch.linspace(0, n - 1, 192, device=Xd.device).long()

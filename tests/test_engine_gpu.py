@@ -195,6 +195,73 @@ def test_tc_topk_two_query_tiles(n, d):
             assert np.isinf(tau[i])
 
 
+def _tc_topk_one_product(X, stride):
+    """fp16x1 sweep (dtype 3): optional seed pass over every stride-th tile, then the full sweep, one list of 64."""
+    ref = pipeline.SearchOperand(_dev(X))
+    scale = pipeline.fp16_scale(ref.norm_max())
+    q_hi, q_lo, q_n2 = ref.tc(0, 3, scale)
+    r_hi, r_lo, _ = ref.tc(1, 3, scale)
+    n = ref.n
+    scratch = torch.zeros((E.lib().gtb_tc_scratch_bytes(ref.n_pad),), dtype=torch.uint8, device="cuda")
+    pace = torch.zeros(1, dtype=torch.int32, device="cuda")
+    seed = None
+    if stride > 1:
+        seed = torch.empty((n, 2), dtype=torch.float32, device="cuda")
+        cand_s = torch.empty((n, 8), dtype=torch.int32, device="cuda")
+        E.call("gtb_knn_topk_tc_seeded", q_hi, q_lo, q_n2 * (scale * scale), n, ref.n_pad, r_hi, r_lo, n, ref.n_pad,
+               ref.kp(3), 3, 4, 2, 2, None, stride, cand_s, scratch, seed, pace)
+    cand = torch.full((n, 64), -7, dtype=torch.int32, device="cuda")
+    tau = torch.empty((n, 2), dtype=torch.float32, device="cuda")
+    E.call("gtb_knn_topk_tc_seeded", q_hi, q_lo, q_n2 * (scale * scale), n, ref.n_pad, r_hi, r_lo, n, ref.n_pad,
+           ref.kp(3), 3, 32, 2, 2, seed, 1, cand, scratch, tau, pace)
+    torch.cuda.synchronize()
+    seed_h = None if seed is None else (seed / (scale * scale)).cpu().numpy()[:, 0]
+    return cand.cpu().numpy(), (tau / (scale * scale)).cpu().numpy(), seed_h
+
+
+@pytest.mark.parametrize("stride", [1, 2, 5])
+@pytest.mark.parametrize("n,d", [(1797, 64), (3000, 100), (300, 5), (40, 3), (1000, 31), (777, 103), (6000, 100),
+                                 (2500, 110)])
+def test_tc_topk_one_product_seeded(n, d, stride):
+    """fp16x1 (one product, dtype 3), cold and with thresholds seeded from a strided sample: every reference point
+    that is not a candidate lies at an exact squared distance >= tau - E (the certification contract), the list is
+    complete when it is not full, and both tau slots agree."""
+    X, _ = synth.gaussian_mixture(n, d, n_clusters=5, intrinsic_dim=min(8, d), seed=3)
+    cand, tau2, seed = _tc_topk_one_product(X, stride)
+    assert np.array_equal(tau2[:, 0], tau2[:, 1])
+    tau = tau2[:, 0]
+    X64 = X.astype(np.float64)
+    D2 = ((X64[:, None, :] - X64[None, :, :]) ** 2).sum(-1)
+    Xc = X64 - X64.mean(0)
+    nrm = (Xc ** 2).sum(1)
+    eps = pipeline.eps_rel_tch1(d)
+    n_full = 0
+    for i in range(0, n, max(1, n // 400)):
+        assert (cand[i] != -7).all(), "output slot never written"
+        c = cand[i][cand[i] >= 0]
+        assert (c < n).all(), "padded reference leaked into the candidates"
+        assert len(np.unique(c)) == len(c), "duplicate candidate"
+        bound = eps * (nrm[i] + nrm.max())
+        non = np.setdiff1d(np.arange(n), c)
+        if len(non):
+            assert np.isfinite(tau[i]), i
+            assert D2[i, non].min() >= tau[i] - bound, i
+        if stride == 1:
+            assert len(c) == min(64, n)
+            if n <= 64:
+                assert np.isinf(tau[i])
+        else:
+            # seeded: a list that did not fill reports the seed and holds everything (approximately) under it
+            if len(c) < min(64, n):
+                assert tau[i] == seed[i] or (np.isinf(tau[i]) and np.isinf(seed[i]))
+                assert set(np.flatnonzero(D2[i] < tau[i] - bound)).issubset(set(c))
+            else:
+                n_full += 1
+                assert tau[i] <= seed[i]
+        # the nearest neighbours well inside the threshold are present
+        assert set(np.flatnonzero(D2[i] < tau[i] - bound)).issubset(set(c))
+
+
 def test_tc_topk_out_of_sample():
     X, _ = synth.gaussian_mixture(5000, 100, n_clusters=6, intrinsic_dim=10, seed=5)
     Y, _ = synth.gaussian_mixture(333, 100, n_clusters=6, intrinsic_dim=10, seed=5)

@@ -22,7 +22,7 @@ def _build(case, **extra):
         return gt.Graph(case.X, n_jobs=-1, verbose=0, **dict(case.params, **extra))
 
 
-@pytest.fixture(params=["tc", "tc16", "tch", "simt"])
+@pytest.fixture(params=["tc", "tc16", "tch", "tch1", "simt"])
 def impl(request, monkeypatch):
     monkeypatch.setenv("GTB_SEARCH_IMPL", request.param)
     return request.param
@@ -312,14 +312,14 @@ def test_bit_identical_across_search_implementations():
     import os
     X, _ = synth.gaussian_mixture(30_000, 64, n_clusters=10, intrinsic_dim=8, seed=5)
     out = {}
-    for impl in ("tc", "tc16", "tch", "simt"):
+    for impl in ("tc", "tc16", "tch", "tch1", "simt"):
         os.environ["GTB_SEARCH_IMPL"] = impl
         try:
             G = gt.Graph(X, knn=5, decay=40, verbose=0)
             out[impl] = (G.kernel, G.diff_op)
         finally:
             os.environ.pop("GTB_SEARCH_IMPL", None)
-    for impl in ("tc16", "tch", "simt"):
+    for impl in ("tc16", "tch", "tch1", "simt"):
         assert (out[impl][0] != out["tc"][0]).nnz == 0
         assert (out[impl][1] != out["tc"][1]).nnz == 0
 
