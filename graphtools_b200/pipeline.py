@@ -16,7 +16,7 @@ from . import _engine as E
 SYM_MODES = {"+": 0, "*": 1, "mnn": 2, None: 3}
 METRIC_ALIASES = {"manhattan": "cityblock", "l1": "cityblock", "l2": "euclidean"}
 METRIC_CODE = {"euclidean": 0, "cosine": 1, "cityblock": 2}
-AUTO_TC = "tch"          # tensor-core flavour picked by impl="auto": "tch" (fp16x2), "tc16" (bf16x3) or "tc" (3xTF32)
+AUTO_TC = "tch1"         # tensor-core flavour picked by impl="auto": "tch1" (fp16, one product, seeded), "tch" (fp16x2), "tc16" (bf16x3) or "tc" (3xTF32)
 BALL_CAP = 8192          # longest radius-pass row handled by refine_ball (shared-memory sort)
 _STATS = {}
 
