@@ -229,6 +229,10 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   // use all of them (fewer compactions between the seeded threshold and the final selection)
   constexpr int CAP = (LSO > 32) ? TC_GROUPS * TC_CAP : TC_CAP;
   static_assert(CAP >= LSO + 64, "room for a list and two batches of 32");
+  // burst append (per-lane predicated stores when >= GTB_TC_HYBRID rows of a batch hit): pays off while thresholds
+  // are still falling from +inf; the one-product sweep over all tiles starts from seeded thresholds, where bursts do
+  // not occur and the extra code only costs instruction-cache misses (188.7 vs 204.3 ms at 1M) -- compiled out there
+  constexpr bool HYB = !(FMT == 3 && LS == 32);
   const int nks = p.nks;                                     // 32-byte k-steps per operand row
   const int nfull = nks / 4, ntail = nks % 4;                // SWIZZLE_128B blocks (4 k-steps) + SWIZZLE_32B tail blocks
   const int a_lo_col = nks * 8;                              // TMEM column of A_lo (A_hi at 0)
@@ -510,7 +514,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
           // Burst regime (round start: most rows hit in every batch): every lane appends its own hits to its own
           // row buffer with predicated stores behind one warp-uniform branch -- a fixed ~130 issue slots instead
           // of ~350 cycles per hot row.  With few hot rows the cooperative path below is cheaper.
-          if (__popc(hot) >= GTB_TC_HYBRID) {
+          if (HYB && __popc(hot) >= GTB_TC_HYBRID) {
             uint2* wp = mybuf + cnt;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {

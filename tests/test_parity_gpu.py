@@ -396,14 +396,16 @@ def test_exact_landmark_and_mnn_landmark_graphs():
     compare_sparse(G2.transitions, pnm2, what="mnn transitions")
 
 
-def test_large_knn_uses_cuda_core_search():
-    """knn beyond the tensor-core candidate lists (2 x 32) falls back to the CUDA-core kernel (S = 128)."""
+@pytest.mark.parametrize("knn,impl_used", [(40, "tch1"), (70, "simt")])
+def test_large_knn(knn, impl_used):
+    """knn up to 55 fits the one-product flavour's candidate list of 64 (tensor cores); beyond that the build falls
+    back to the CUDA-core kernel (S = 128)."""
     from oracle import graph_oracle as go
     X, _ = synth.gaussian_mixture(3000, 30, n_clusters=3, intrinsic_dim=6, seed=8)
-    K_ref, _ = go.knn_graph(X.astype(np.float64), knn=40, decay=None)
-    G = gt.Graph(X, knn=40, decay=None, verbose=0)
-    assert pipeline.stats()["impl"] == "simt"
-    compare_sparse(G.kernel, K_ref, what="knn=40 binary", tie=dict(X=X, knn=41))
+    K_ref, _ = go.knn_graph(X.astype(np.float64), knn=knn, decay=None)
+    G = gt.Graph(X, knn=knn, decay=None, verbose=0)
+    assert pipeline.stats()["impl"] == impl_used
+    compare_sparse(G.kernel, K_ref, what="knn=%d binary" % knn, tie=dict(X=X, knn=knn + 1))
 
 
 def test_float64_inputs_are_evaluated_in_float64(impl):
