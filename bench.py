@@ -449,7 +449,8 @@ def run_gpu_arm(a):
         def api_call():
             G = gt.Graph(Xh, knn=KNN, decay=DECAY, thresh=THRESH, verbose=0)
             return G.kernel, G.diff_op
-        api_call()
+        for _ in range(2):              # warm-up with the loop's own object lifetimes (result memory is pooled)
+            Kh, Ph = api_call()
         barrier()
         t0 = time.perf_counter()
         reps = max(1, min(a.steps, 5))
@@ -470,8 +471,9 @@ def run_gpu_arm(a):
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3,
                "api": "graphtools_b200.Graph(X_host_pinned, knn=5, decay=40).kernel / .diff_op (scipy CSR, K and P "
                       "sharing one structure) called on every rank; with N > 1 each rank uploads its row block of X "
-                      "(NCCL all-gather assembles the reference set) and writes its rows of the result into one "
-                      "shared-memory segment that all ranks view"}
+                      "(NCCL all-gather assembles the reference set) and DMAs its rows of the result into one "
+                      "page-locked shared-memory segment that all ranks view; result memory is recycled between "
+                      "builds (graphtools_b200/hostpool.py)"}
         parity_e2e = {"nnz": int(Kh.nnz), "checksum_K": float(Kh.data.sum()), "checksum_P": float(Ph.data.sum()),
                       "symmetric": bool(abs(Kh[:2000, :2000] - Kh[:2000, :2000].T).max() == 0.0)}
     else:

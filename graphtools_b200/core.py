@@ -394,6 +394,39 @@ class BaseGraph(Base, metaclass=abc.ABCMeta):
         nnz_all = gd.allgather_counts(sh["indices"].shape[0], sh["indices"].device)
         nnz = int(sum(nnz_all))
         off = int(sum(nnz_all[:rank]))
+        from . import hostpool
+        specs = [("indptr", n + 1, np.int32), ("indices", nnz, np.int32), ("K", nnz, np.float64),
+                 ("P", nnz, np.float64), ("degree", n, np.float64)]
+        lay, total = hostpool.layout(specs)
+        base = hostpool.take_shared(total)
+        if base is not None:
+            # one recycled page-locked shared segment: every rank DMAs its own shard straight into its slice
+            arr = hostpool.carve(base, lay)
+            m = hi - lo
+            if m > 0:
+                ip32 = pipeline._empty((m + 1,), torch.int32)
+                E.call("gtb_cast_indptr", sh["indptr"], m + 1, ip32)
+                ip32 += off
+                hostpool.d2h_async(ip32[:m], arr["indptr"][lo:hi])
+                hostpool.d2h_async(sh["indices"], arr["indices"][off:off + nnz_all[rank]])
+                hostpool.d2h_async(sh["data"], arr["K"][off:off + nnz_all[rank]])
+                hostpool.d2h_async(sh["P"], arr["P"][off:off + nnz_all[rank]])
+                hostpool.d2h_async(sh["degree"], arr["degree"][lo:hi])
+            if rank == 0:
+                arr["indptr"][bounds[-1][1]:] = nnz
+            torch.cuda.current_stream().synchronize()
+            gd.dist.barrier()                                  # every shard has landed
+            if rank != 0:
+                for a in arr.values():
+                    a.flags.writeable = False
+            K = sparse.csr_matrix((arr["K"], arr["indices"], arr["indptr"]), shape=(n, n), copy=False)
+            P = sparse.csr_matrix((arr["P"], arr["indices"], arr["indptr"]), shape=(n, n), copy=False)
+            for M in (K, P):
+                M.has_sorted_indices = True
+                M.has_canonical_format = True
+            self._kernel, self._diff_op = K, P
+            self._kernel_degree = arr["degree"].reshape(-1, 1)
+            return
         if not gd.SharedResult.available(24 * nnz + 4 * (n + 1)):
             # no room in /dev/shm: assemble on the device, copy the whole matrix on every rank
             self._kernel = self._dev_kernel.to_scipy()

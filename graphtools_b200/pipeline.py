@@ -285,6 +285,27 @@ class SearchOperand:
         return self._maxnorm_host
 
 
+_NP_OF = {torch.int32: np.int32, torch.int64: np.int64, torch.float64: np.float64, torch.float32: np.float32}
+
+
+def _d2h_pooled(named):
+    """[(name, device tensor)] -> {name: numpy array} carved out of ONE recycled page-locked block (hostpool.py) and
+    filled by DMA -- no staging copy, no first-touch page faults after the first build.  None when the pool is off,
+    full, or the arrays are small (the plain path is as good)."""
+    from . import hostpool
+    if not all(t.is_cuda for _, t in named) or sum(t.numel() * t.element_size() for _, t in named) < (8 << 20):
+        return None
+    lay, total = hostpool.layout([(nm, t.numel(), _NP_OF[t.dtype]) for nm, t in named])
+    base = hostpool.take_local(total)
+    if base is None:
+        return None
+    out = hostpool.carve(base, lay)
+    for nm, t in named:
+        hostpool.d2h_async(t, out[nm])
+    torch.cuda.current_stream().synchronize()
+    return out
+
+
 class DeviceCSR:
     """CSR in HBM: int64 indptr [n+1], int32 indices, float64 data."""
 
@@ -302,17 +323,23 @@ class DeviceCSR:
             n1 = self.indptr.shape[0]
             ip32 = _empty((n1,), torch.int32)
             E.call("gtb_cast_indptr", self.indptr, n1, ip32)
-            idx_h, ip_h = d2h_pinned(self.indices), d2h_pinned(ip32)
-            torch.cuda.current_stream().synchronize()
-            self._host_struct = (idx_h.numpy(), ip_h.numpy())
+            got = _d2h_pooled([("indices", self.indices), ("indptr", ip32)])
+            if got is not None:
+                self._host_struct = (got["indices"], got["indptr"])
+            else:
+                idx_h, ip_h = d2h_pinned(self.indices), d2h_pinned(ip32)
+                torch.cuda.current_stream().synchronize()
+                self._host_struct = (idx_h.numpy(), ip_h.numpy())
         return self._host_struct
 
     def to_scipy(self, data=None):
         from scipy import sparse
-        vals = d2h_pinned(self.data if data is None else data)
+        src = self.data if data is None else data
+        got = _d2h_pooled([("vals", src)])
+        vals = got["vals"] if got is not None else d2h_pinned(src).numpy()
         indices, indptr = self._host_structure()
         torch.cuda.current_stream().synchronize()
-        M = sparse.csr_matrix((vals.numpy(), indices, indptr), shape=self.shape)
+        M = sparse.csr_matrix((vals, indices, indptr), shape=self.shape)
         M.has_sorted_indices = True
         M.has_canonical_format = True
         return M

@@ -1,5 +1,6 @@
 """Parity of the CUDA path against the golden vectors of the unmodified reference and against the
 CPU oracle on seeded inputs (run on the B200 box through the public Graph API -> C ABI)."""
+import os
 import warnings
 
 import numpy as np
@@ -449,3 +450,35 @@ def test_edge_shapes(n, d, knn, impl):
         Gb = gt.Graph(X, knn=min(knn, 5), decay=None, verbose=0)
         Kb, _ = go.knn_graph(X.astype(np.float64), knn=min(knn, 5), decay=None)
     compare_sparse(Gb.kernel, Kb, what="binary", tie=dict(X=X, knn=min(knn, 5) + 1))
+
+
+def test_host_result_pool_recycles_without_aliasing():
+    """K / P live in recycled page-locked blocks (hostpool.py): a graph that is still referenced keeps its memory,
+    a dropped one hands its block to the next build, and the values are the same either way."""
+    import gc
+    from graphtools_b200 import hostpool
+    X, _ = synth.gaussian_mixture(120_000, 40, n_clusters=8, intrinsic_dim=8, seed=12)
+    X2 = X[::-1].copy()
+    G1 = gt.Graph(X, knn=5, decay=40, verbose=0)
+    K1, P1 = G1.kernel, G1.diff_op
+    assert any(not b.free for b in hostpool._local), "the result did not come from the pool"
+    k1_copy, p1_copy = K1.data.copy(), P1.data.copy()
+    G2 = gt.Graph(X2, knn=5, decay=40, verbose=0)               # K1 is alive: must not be overwritten
+    K2 = G2.kernel
+    assert np.array_equal(K1.data, k1_copy) and np.array_equal(P1.data, p1_copy)
+    assert not np.shares_memory(K1.data, K2.data)
+    n_blocks = len(hostpool._local)
+    k2_copy = K2.data.copy()
+    del G2, K2
+    gc.collect()
+    G3 = gt.Graph(X2, knn=5, decay=40, verbose=0)               # reuses G2's blocks
+    K3 = G3.kernel
+    assert len(hostpool._local) == n_blocks
+    assert np.array_equal(K3.data, k2_copy)
+    assert np.array_equal(K1.data, k1_copy)
+    os.environ["GTB_HOST_POOL"] = "0"
+    try:
+        K4 = gt.Graph(X2, knn=5, decay=40, verbose=0).kernel
+    finally:
+        os.environ.pop("GTB_HOST_POOL")
+    assert np.array_equal(K4.data, k2_copy) and np.array_equal(K4.indices, K3.indices)
