@@ -398,10 +398,10 @@ class BaseGraph(Base, metaclass=abc.ABCMeta):
         specs = [("indptr", n + 1, np.int32), ("indices", nnz, np.int32), ("K", nnz, np.float64),
                  ("P", nnz, np.float64), ("degree", n, np.float64)]
         lay, total = hostpool.layout(specs)
-        base = hostpool.take_shared(total)
-        if base is not None:
+        blk = hostpool.take_shared(total)
+        if blk is not None:
             # one recycled page-locked shared segment: every rank DMAs its own shard straight into its slice
-            arr = hostpool.carve(base, lay)
+            arr = blk.carve(lay)
             m = hi - lo
             if m > 0:
                 ip32 = pipeline._empty((m + 1,), torch.int32)

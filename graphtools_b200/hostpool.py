@@ -44,23 +44,30 @@ def layout(specs):
 
 
 class _Block:
-    """One page-locked block.  ``mem`` owns the memory (pinned torch tensor, or mmap of a shared segment)."""
+    """One page-locked block.  ``tensor`` / ``mm`` owns the memory (pinned torch tensor, or mmap of a shared segment)."""
 
     def __init__(self, nbytes, tensor=None, mm=None, registered=False):
         self.nbytes = nbytes
         self.tensor, self.mm, self.registered = tensor, mm, registered
         self.free = True
 
-    def base(self):
-        """A fresh uint8 ndarray over the whole block (every hand-out gets its own base object, whose death -- and that
-        of all views derived from it -- marks the block free again)."""
-        if self.tensor is not None:
-            arr = self.tensor.numpy()
-        else:
-            arr = np.frombuffer(self.mm, dtype=np.uint8, count=self.nbytes)
+    def carve(self, lay, writeable=True):
+        """{name: typed ndarray} according to ``lay``; the block is busy until every one of them (and every view
+        derived from them) has been garbage-collected.  Each array is its own ``np.frombuffer`` over the block, NOT a
+        view of one big uint8 array: scipy's constructors copy any array that is a view of a much larger ndarray
+        (``_prune_array``), which would silently move the result out of the pool."""
+        buf = memoryview(self.tensor.numpy()) if self.tensor is not None else self.mm
+        holder = {"live": len(lay)}
         self.free = False
-        weakref.finalize(arr, _release, weakref.ref(self))
-        return arr
+        out = {}
+        for name, (off, count, dt) in lay.items():
+            a = np.frombuffer(buf, dtype=dt, count=count, offset=off)
+            weakref.finalize(a, _release, weakref.ref(self), holder)
+            out[name] = a
+        if not writeable:
+            for a in out.values():
+                a.flags.writeable = False
+        return out
 
     def close(self):
         if self.mm is not None and self.registered:
@@ -72,21 +79,11 @@ class _Block:
         self.tensor = self.mm = None
 
 
-def _release(ref):
+def _release(ref, holder):
+    holder["live"] -= 1
     blk = ref()
-    if blk is not None:
+    if blk is not None and holder["live"] == 0:
         blk.free = True
-
-
-def carve(base, lay, writeable=True):
-    """{name: typed ndarray view} of a block according to ``lay``."""
-    out = {}
-    for name, (off, count, dt) in lay.items():
-        a = base[off: off + count * dt.itemsize].view(dt)
-        if not writeable:
-            a.flags.writeable = False
-        out[name] = a
-    return out
 
 
 # ----------------------------------------------------------------------------------- one process
@@ -94,12 +91,13 @@ _local = []
 
 
 def take_local(nbytes):
-    """uint8 base array of a free page-locked block of at least ``nbytes`` (None when the pool is off or full)."""
+    """A free page-locked block of at least ``nbytes`` (None when the pool is off or full); ``block.carve(layout)``
+    hands out the arrays."""
     if not enabled():
         return None
     for blk in _local:
         if blk.free and nbytes <= blk.nbytes <= 2 * nbytes + (1 << 20):
-            return blk.base()
+            return blk
     held = sum(b.nbytes for b in _local)
     size = (nbytes + nbytes // 8 + (1 << 20) - 1) >> 20 << 20          # headroom: the next build's nnz differs a little
     # drop free blocks that no longer fit the requests being made
@@ -116,7 +114,7 @@ def take_local(nbytes):
         return None
     blk = _Block(size, tensor=t)
     _local.append(blk)
-    return blk.base()
+    return blk
 
 
 def d2h_async(dev_tensor, host_array):
@@ -136,8 +134,8 @@ _seq = [0]
 
 
 def take_shared(nbytes, group=None):
-    """Collective.  uint8 base array over a page-locked shared segment of at least ``nbytes`` that every rank of the
-    group maps (None on every rank when the pool is off, /dev/shm is too small or registration fails anywhere)."""
+    """Collective.  A page-locked shared segment of at least ``nbytes`` that every rank of the group maps (None on
+    every rank when the pool is off, /dev/shm is too small or registration fails anywhere)."""
     import torch.distributed as dist
     if not enabled():
         return None
@@ -151,7 +149,7 @@ def take_shared(nbytes, group=None):
         flags = flags.tolist()
         for blk, ok in zip(_shared, flags):
             if ok:
-                return blk.base()
+                return blk
         # retire blocks that are free everywhere but have the wrong size
         free_all = torch.tensor([int(b.free) for b in _shared], dtype=torch.int32, device=dev)
         dist.all_reduce(free_all, op=dist.ReduceOp.MIN, group=group)
@@ -206,4 +204,4 @@ def take_shared(nbytes, group=None):
         blk.close()
         return None
     _shared.append(blk)
-    return blk.base()
+    return blk

@@ -296,10 +296,10 @@ def _d2h_pooled(named):
     if not all(t.is_cuda for _, t in named) or sum(t.numel() * t.element_size() for _, t in named) < (8 << 20):
         return None
     lay, total = hostpool.layout([(nm, t.numel(), _NP_OF[t.dtype]) for nm, t in named])
-    base = hostpool.take_local(total)
-    if base is None:
+    blk = hostpool.take_local(total)
+    if blk is None:
         return None
-    out = hostpool.carve(base, lay)
+    out = blk.carve(lay)
     for nm, t in named:
         hostpool.d2h_async(t, out[nm])
     torch.cuda.current_stream().synchronize()
