@@ -35,6 +35,7 @@ _SIGS = {
                          _P, _P, _P, _P], 1),
     "gtb_knn_topk_tc_seeded": ([_P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int,
                                 _P, c_int, _P, _P, _P, _P, _P], 1),
+    "gtb_knn_seed_tc": ([_P, _P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, _P, _P, _P], 1),
     "gtb_knn_radius_tc": ([_P, _P, _P, _P, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P, c_int64,
                            _P, _P, _P, _P], 1),
     "gtb_refine_topk": ([_P, c_int64, _P, c_int, c_int, _P, c_int, c_int, _P, c_int, _P, c_float, c_double, c_int, c_int64, c_double,
@@ -88,6 +89,7 @@ _PLAIN = {
     "gtb_tc_fp16_maxnorm": ([], c_float),
     "gtb_tc_scratch_bytes": ([c_int64], c_int64),
     "gtb_gemm_max_k": ([], c_int),
+    "gtb_knn_seed_k": ([], c_int),
 }
 
 

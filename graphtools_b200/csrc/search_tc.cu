@@ -61,6 +61,7 @@ constexpr float TC_PAD_NORM = 1e30f;
 constexpr float TC_BIG_H = 50000.f;
 constexpr float TC_PAD_NORM_H = 60000.f;
 constexpr float TC_H_MAXNORM = 8192.f;
+constexpr int TC_SEED_K = 8;          // SEED mode: order statistic of the sampled tile minima that becomes the threshold
 
 using namespace gtbptx;
 
@@ -207,7 +208,7 @@ __device__ __forceinline__ void tc_commit_mc_pred(uint32_t bar, uint16_t mask, u
 // epilogue group g owning query tile g and ONE list of 2 LS entries per row -- each byte streamed from L2 feeds twice
 // the tensor work.  (The L2 -> SM path, ~6300 B/clk chip-wide, is what bounds a single-tile sweep once the MMA work
 // drops to two products: 57 KB per stage and SM = 1340 clk against 896 clk of MMAs.)
-template <int MODE, int CL, int FMT, int LS, int QT>  // MODE 0 = TOPK, 1 = RADIUS
+template <int MODE, int CL, int FMT, int LS, int QT>  // MODE 0 = TOPK, 1 = RADIUS, 2 = SEED
 __global__ void __launch_bounds__(TC_THREADS, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBht,
                  const __grid_constant__ CUtensorMap mBl, const __grid_constant__ CUtensorMap mBlt,
@@ -222,7 +223,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   constexpr int NPART = (FMT == 3) ? 1 : 2;                  // operand arrays streamed per stage (hi[, lo])
   constexpr float BIG = (FMT >= 2) ? TC_BIG_H : TC_BIG;
   constexpr int EPK = BF16 ? 16 : 8;                         // elements per 32-byte k-step
-  static_assert(QT == 1 || (QT == 2 && FMT >= 2 && MODE == 0), "two query tiles per CTA: fp16 top-k only");
+  static_assert(QT == 1 || (QT == 2 && FMT >= 2 && MODE != 1), "two query tiles per CTA: fp16 top-k / seed only");
+  static_assert(MODE != 2 || (FMT == 3 && QT == 2), "seed sweeps use the one-product flavour");
   static_assert(FMT != 3 || QT == 2, "the one-product flavour runs two query tiles per CTA");
   constexpr int LSO = (QT == 2) ? 2 * LS : LS;               // entries of one output list
   // candidate buffer of one list: a row owns TC_GROUPS * TC_CAP slots of scratch; the single long list of QT == 2 may
@@ -265,7 +267,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   const int64_t nrounds = p.nrounds;
   const int64_t qcluster = cluster_id % p.n_qclusters;
   const int64_t tile0 = (cluster_id / p.n_qclusters) * p.tiles_per_split;
-  const int64_t tstride = (MODE == 0) ? p.tile_stride : 1;
+  const int64_t tstride = (MODE != 1) ? p.tile_stride : 1;
   const int64_t tiles_left = (p.nr_pad / TC_N + tstride - 1) / tstride - tile0;
   const int64_t ntiles = tiles_left < p.tiles_per_split ? tiles_left : p.tiles_per_split;
   // first query row of (round, query tile qt of this CTA)
@@ -457,9 +459,18 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         const float t0 = p.seed_tau[gq * TC_GROUPS] - nx;
         if (t0 < BIG) thr = t0;
       }
-    } else {
+    } else if (MODE == 1) {
       thr = valid ? (p.lim2[gq] - nx) : -gtb_inf_f();
+    } else {
+      thr = 0.f;
     }
+    // SEED mode: the TC_SEED_K smallest TILE MINIMA of the row, ascending, in registers.  Distinct tiles hold distinct
+    // points, so the k-th smallest tile minimum bounds the k-th smallest value from above (and equals it unless two of
+    // the k smallest share a tile) -- a threshold estimate that needs no candidate buffer, no hit servicing and no
+    // divergent code: one min tree and one 8-deep insertion network per tile.
+    float best[TC_SEED_K];
+#pragma unroll
+    for (int i = 0; i < TC_SEED_K; ++i) best[i] = BIG;
     int cnt = 0;
     // this thread's candidate buffer: uniform base + per-thread offset (rows past nq never append)
     const int64_t boff = valid ? (gq * TC_GROUPS + lgrp) * TC_CAP : 0;     // (CAP > TC_CAP only with lgrp == 0)
@@ -493,6 +504,25 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
 #ifdef GTB_EXP_NOSELECT
       continue;                                   // experiment build: the sweep without any selection work
 #endif
+      if (MODE == 2) {
+        float m0 = __uint_as_float(r0[0]), m1 = __uint_as_float(r1[0]), m2 = __uint_as_float(r2[0]),
+              m3 = __uint_as_float(r3[0]);
+#pragma unroll
+        for (int j = 1; j < 32; ++j) {
+          m0 = fminf(m0, __uint_as_float(r0[j]));
+          m1 = fminf(m1, __uint_as_float(r1[j]));
+          m2 = fminf(m2, __uint_as_float(r2[j]));
+          m3 = fminf(m3, __uint_as_float(r3[j]));
+        }
+        float v = fminf(fminf(m0, m1), fminf(m2, m3));
+#pragma unroll
+        for (int i = 0; i < TC_SEED_K; ++i) {      // sorted insertion: best[] stays ascending, v carries the evicted value
+          const float lo = fminf(best[i], v);
+          v = fmaxf(best[i], v);
+          best[i] = lo;
+        }
+        continue;
+      }
 #pragma unroll
       for (int part = 0; part < TC_N / 32; ++part) {
         float v[32];
@@ -577,6 +607,13 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
       }
     }
 
+    if (MODE == 2) {
+      if (valid) {
+        const float tv = (best[TC_SEED_K - 1] >= BIG) ? gtb_inf_f() : best[TC_SEED_K - 1] + nx;
+        p.tau[gq * TC_GROUPS] = tv;
+        p.tau[gq * TC_GROUPS + 1] = tv;
+      }
+    }
     if (MODE == 0) {
       // final compaction of every buffer still holding more than a list's worth of candidates
       unsigned need = __ballot_sync(0xffffffffu, cnt > LSO);
@@ -762,7 +799,7 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
   const int64_t n_cluster_tiles = gtb_cdiv(p.nq_pad / TC_M, CL * QT);
   int64_t n_clusters = n_cluster_tiles < (nsm / CL) ? n_cluster_tiles : (nsm / CL);
   p.nrounds = gtb_cdiv(n_cluster_tiles, n_clusters);
-  if (p.tile_stride < 1 || MODE != 0) p.tile_stride = 1;
+  if (p.tile_stride < 1 || MODE == 1) p.tile_stride = 1;
   const int64_t total_tiles = gtb_cdiv(p.nr_pad / TC_N, p.tile_stride);
   p.n_qclusters = n_clusters;
   p.tiles_per_split = total_tiles;
@@ -804,22 +841,22 @@ int launch_tc_fmt(const void* q_hi, const void* q_lo, const void* r_hi, const vo
   constexpr int LS_SHORT = (MODE == 0) ? 16 : 32;
   const bool short_list = (MODE == 0) && list == 16;
   if constexpr (FMT == 3) {
-    // one product: top-k only, two query tiles per CTA; list = 32 -> one list of 64 per row, list = 4 -> the 8
-    // smallest of a strided sample (threshold seeds)
-    if constexpr (MODE == 0) {
-      if (qtiles != 2 || (list != 32 && list != 4) || (cluster != 1 && cluster != 2)) {
-        gtb_set_error("the one-product flavour needs qtiles = 2, list = 32 or 4, cluster = 1 or 2");
+    // one product: two query tiles per CTA; top-k keeps one list of 64 per row (list = 32), the seed sweep none
+    if constexpr (MODE != 1) {
+      if (qtiles != 2 || list != 32 || (cluster != 1 && cluster != 2)) {
+        gtb_set_error("the one-product flavour needs qtiles = 2, list = 32, cluster = 1 or 2");
         return GTB_ERR_ARG;
       }
-      if (list == 32)
-        return cluster == 1 ? launch_tc_cl<0, 1, 3, 32, 2>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
-                            : launch_tc_cl<0, 2, 3, 32, 2>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
-      return cluster == 1 ? launch_tc_cl<0, 1, 3, 4, 2>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
-                          : launch_tc_cl<0, 2, 3, 4, 2>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+      return cluster == 1 ? launch_tc_cl<MODE, 1, 3, 32, 2>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
+                          : launch_tc_cl<MODE, 2, 3, 32, 2>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
     } else {
       gtb_set_error("the one-product flavour has no radius mode (use dtype 2 on the same operands)");
       return GTB_ERR_ARG;
     }
+  } else {
+  if constexpr (MODE == 2) {
+    gtb_set_error("seed sweeps use the one-product flavour (dtype 3)");
+    return GTB_ERR_ARG;
   } else {
   if (qtiles == 2) {
     if constexpr (FMT == 2 && MODE == 0) {
@@ -844,6 +881,7 @@ int launch_tc_fmt(const void* q_hi, const void* q_lo, const void* r_hi, const vo
                           : launch_tc_cl<MODE, 4, 0, 32>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
       // fall through: the 2-byte flavours support clusters of 1 or 2
     default: gtb_set_error("cluster size must be 1 or 2 (or 4 for the tf32 flavour)"); return GTB_ERR_ARG;
+  }
   }
   }
 }
@@ -921,7 +959,7 @@ extern "C" int gtb_knn_topk_tc_seeded(const void* q_hi, const void* q_lo, const 
                                       int32_t* cand_idx, void* scratch, float* tau, unsigned int* pace, void* stream) {
   int rc = tc_check(nq, nr, nq_pad, nr_pad, Kp, dtype);
   if (rc) return rc;
-  GTB_CHECK_ARG(list == 16 || list == 32 || (dtype == 3 && list == 4), "list size must be 16 or 32 (or 4 with dtype 3)");
+  GTB_CHECK_ARG(list == 16 || list == 32, "list size must be 16 or 32");
   GTB_CHECK_ARG(qtiles == 1 || qtiles == 2, "query tiles per CTA: 1 or 2");
   GTB_CHECK_ARG(tile_stride >= 1, "tile_stride must be >= 1");
   TcParams p{};
@@ -930,6 +968,22 @@ extern "C" int gtb_knn_topk_tc_seeded(const void* q_hi, const void* q_lo, const 
   p.seed_tau = seed_tau; p.tile_stride = tile_stride;
   return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, Kp, dtype, list, cluster, qtiles, p, (cudaStream_t)stream);
 }
+
+// Threshold seeds for gtb_knn_topk_tc_seeded: tau[nq][2] (both slots) = the TC_SEED_K-th smallest TILE MINIMUM of the
+// approximate squared distances over every tile_stride-th 128-row reference tile (+inf with fewer sampled tiles)
+extern "C" int gtb_knn_seed_tc(const void* q_hi, const float* qn2, int64_t nq, int64_t nq_pad, const void* r_hi,
+                               int64_t nr, int64_t nr_pad, int Kp, int cluster, int tile_stride, float* tau,
+                               unsigned int* pace, void* stream) {
+  int rc = tc_check(nq, nr, nq_pad, nr_pad, Kp, 3);
+  if (rc) return rc;
+  GTB_CHECK_ARG(tile_stride >= 1, "tile_stride must be >= 1");
+  TcParams p{};
+  p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.qn2 = qn2;
+  p.tau = tau; p.sync_ctr = pace; p.tile_stride = tile_stride;
+  return launch_tc<2>(q_hi, q_hi, r_hi, r_hi, Kp, 3, 32, cluster, 2, p, (cudaStream_t)stream);
+}
+
+extern "C" int gtb_knn_seed_k(void) { return TC_SEED_K; }
 
 extern "C" int gtb_knn_topk_tc(const void* q_hi, const void* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
                                const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp, int dtype,

@@ -365,6 +365,18 @@ def choose_S(knn_eff, binary):
         "knn={} needs a candidate list longer than 128; not supported by the fused top-k yet".format(knn_eff))
 
 
+def seed_stride():
+    """GTB_TC_SEED_STRIDE: the seed sweep of the one-product flavour visits every stride-th reference tile (1 = off)."""
+    import os
+    return int(os.environ.get("GTB_TC_SEED_STRIDE", "16"))
+
+
+def seedable(ref):
+    """A strided sample needs enough tiles to carry the order statistic: 32 sampled tiles at least."""
+    st = seed_stride()
+    return st > 1 and ref.n_pad // 128 >= 32 * st
+
+
 def tc_cluster():
     """GTB_TC_CLUSTER = 1 | 2 | 4: CTAs per cluster sharing each reference tile by TMA multicast."""
     import os
@@ -465,6 +477,11 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
             raise ValueError("GTB_SEARCH_IMPL must be auto, tc, tc16, tch, tch1 or simt (got %r)" % (want,))
         impl = "simt"
         for cand_impl in order:
+            # auto: the one-product flavour pays off only with seeded thresholds, i.e. when the reference set is
+            # large enough for a strided sample (cold, its list of 64 costs more than the second product saves:
+            # C3 at 50k x 50 6.7 ms against 2.5 ms) -- unless the longer list is what the request needs
+            if (cand_impl == "tch1" and want == "auto" and not seedable(ref) and knn + 8 <= 32):
+                continue
             # neighbours asked for must fit the candidate lists: 2 x 32 entries, one list of 64 for tch1
             if cand_impl == "simt" or (knn + 8 <= (64 if cand_impl == "tch1" else 32) and S in (None, 32, 64)
                                        and ref.tc_ok(TC_DTYPE[cand_impl])):
@@ -512,16 +529,14 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         # qtiles == 2: two query tiles per CTA share every reference stage (half the L2 traffic per MMA)
         qn2_s = q_n2 * s2 if tcd >= 2 else q_n2
         seed = None
-        stride_s = int(os.environ.get("GTB_TC_SEED_STRIDE", "16"))
-        if tcd == 3 and stride_s > 1 and ref.n_pad // 128 >= 32 * stride_s:
-            # threshold seeds: the 8 smallest of every stride-th reference tile (6 % of a sweep); the 8th smallest of
-            # the sample sits near the (8 stride)-th smallest overall, so the full sweep starts with a threshold that
-            # admits ~8 stride points per row instead of climbing down from +inf (64 ln(N / 64) updates)
+        stride_s = seed_stride()
+        if tcd == 3 and seedable(ref):
+            # threshold seeds: the 8th smallest tile minimum over every stride-th reference tile (6 % of the tensor work
+            # of a sweep, no selection work); it sits near the (8 stride)-th smallest distance overall, so the full
+            # sweep starts with a threshold that admits ~8 stride points per row instead of climbing down from +inf
+            # (64 ln(N / 64) threshold updates)
             seed = _empty((nq, ntau), torch.float32)
-            cand_s = _empty((nq, 8), torch.int32)
-            E.call("gtb_knn_topk_tc_seeded#seed", q_hi, q_lo, qn2_s, nq, qry.n_pad, r_hi, r_lo, nr, ref.n_pad, Kp, 3, 4,
-                   cluster, 2, None, stride_s, cand_s, scratch, seed, pace)
-            del cand_s
+            E.call("gtb_knn_seed_tc", q_hi, qn2_s, nq, qry.n_pad, r_hi, nr, ref.n_pad, Kp, cluster, stride_s, seed, pace)
         if tcd == 3:
             E.call("gtb_knn_topk_tc_seeded", q_hi, q_lo, qn2_s, nq, qry.n_pad, r_hi, r_lo, nr, ref.n_pad, Kp, tcd, ls,
                    cluster, qtiles, seed, 1, cand, scratch, tau, pace)

@@ -96,16 +96,22 @@ int gtb_knn_topk_tc(const void* q_hi, const void* q_lo, const float* qn2, int64_
                     int list, int cluster, int qtiles, int32_t* cand_idx, void* scratch, float* tau,
                     unsigned int* pace, void* stream);
 /* The same sweep with (a) dtype = 3: float16 operands of dtype 2 (hi arrays only), ONE product A_hi.B_hi -- rounding
- * bound 2^-10 (|x|^2 + |y|^2); qtiles = 2 only; list = 32 (one list of 64 per row, cand_idx [nq][64]) or list = 4 (the 8
- * smallest, cand_idx [nq][8]); (b) tile_stride > 1: only every tile_stride-th 128-row reference tile is visited (a
- * sample of the reference set); (c) seed_tau != NULL (layout of tau, slot 0 read): the row's threshold starts at the
- * seed instead of +inf, every reference point under it is kept (compacting to the list length when the buffer fills)
- * and a list that never filled reports the seed as its tau -- a seed taken from a strided sample removes most of the
- * list * ln(N / list) threshold updates of a cold start.  seed_tau = NULL, tile_stride = 1 is gtb_knn_topk_tc. */
+ * bound 2^-10 (|x|^2 + |y|^2); qtiles = 2 and list = 32 only (one list of 64 per row, cand_idx [nq][64]); (b)
+ * tile_stride > 1: only every tile_stride-th 128-row reference tile is visited; (c) seed_tau != NULL (layout of tau,
+ * slot 0 read): the row's threshold starts at the seed instead of +inf, every reference point under it is kept
+ * (compacting to the list length when the buffer fills) and a list that never filled reports the seed as its tau -- a
+ * seed from gtb_knn_seed_tc removes most of the list * ln(N / list) threshold updates of a cold start.
+ * seed_tau = NULL, tile_stride = 1 is gtb_knn_topk_tc. */
 int gtb_knn_topk_tc_seeded(const void* q_hi, const void* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
                            const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp, int dtype,
                            int list, int cluster, int qtiles, const float* seed_tau, int tile_stride,
                            int32_t* cand_idx, void* scratch, float* tau, unsigned int* pace, void* stream);
+/* Threshold seeds (one-product float16 sweep over every tile_stride-th reference tile, no candidate lists): tau[nq][2]
+ * (both slots) = the gtb_knn_seed_k()-th smallest TILE MINIMUM of the approximate squared distances, an upper bound of
+ * the k-th smallest sampled value kept in registers by a branch-free insertion network -- no hit servicing at all */
+int gtb_knn_seed_k(void);
+int gtb_knn_seed_tc(const void* q_hi, const float* qn2, int64_t nq, int64_t nq_pad, const void* r_hi, int64_t nr,
+                    int64_t nr_pad, int Kp, int cluster, int tile_stride, float* tau, unsigned int* pace, void* stream);
 int64_t gtb_tc_scratch_bytes(int64_t nq_pad);
 int gtb_knn_radius_tc(const void* q_hi, const void* q_lo, const float* qn2, const float* lim2, int64_t nq,
                       int64_t nq_pad, const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp,

@@ -77,7 +77,7 @@ if __name__ == "__main__":
         st["host wall: build"] = 1e3 * t_build
         st["host wall: build + K/P assembled on the host (all ranks)"] = 1e3 * t_all
         st["host assembly of K / P (shared memory, D2H per rank)"] = 1e3 * (t_all - t_build)
-        for k in ("gtb_knn_topk_tc_seeded", "gtb_knn_topk_tc_seeded#seed", "gtb_knn_topk_tc", "gtb_refine_topk",
+        for k in ("gtb_knn_topk_tc_seeded", "gtb_knn_seed_tc", "gtb_knn_topk_tc", "gtb_refine_topk",
                   "gtb_records_count", "gtb_records_scatter", "gtb_rec_sort_rows", "gtb_sym_merge_count",
                   "gtb_sym_merge_fill", "gtb_route_count", "gtb_route_fill", "gtb_prepare_operand_tc"):
             if k in tm:

@@ -39,9 +39,7 @@ for rep in range(a.reps + 1):
     seed = None
     if a.dtype == 3 and stride > 1:
         seed = torch.empty((a.n, 2), dtype=torch.float32, device="cuda")
-        cand_s = torch.empty((a.n, 8), dtype=torch.int32, device="cuda")
-        E.call("gtb_knn_topk_tc_seeded", q_hi, q_lo, q_n2, a.n, ref.n_pad, r_hi, r_lo, a.n, ref.n_pad, Kp, 3, 4, cluster, 2,
-               None, stride, cand_s, scratch, seed, pace)
+        E.call("gtb_knn_seed_tc", q_hi, q_n2, a.n, ref.n_pad, r_hi, a.n, ref.n_pad, Kp, cluster, stride, seed, pace)
     e1.record()
     E.call("gtb_knn_topk_tc_seeded", q_hi, q_lo, q_n2, a.n, ref.n_pad, r_hi, r_lo, a.n, ref.n_pad, Kp, a.dtype, ls, cluster,
            qtiles, seed, 1, cand, scratch, tau, pace)

@@ -95,9 +95,8 @@ def test_tc_certification_bound_1m(headline):
         if tcd == 3:
             # the one-product flavour as the pipeline runs it: thresholds seeded from every 16th reference tile
             seed = pipeline._empty((n, 2), torch.float32)
-            cand_s = pipeline._empty((n, 8), torch.int32)
-            E.call("gtb_knn_topk_tc_seeded", q_hi, q_lo, q_n2 * (scale * scale), n, ref.n_pad, r_hi, r_lo, n, ref.n_pad,
-                   ref.kp(tcd), 3, 4, 2, 2, None, 16, cand_s, scratch, seed, pace)
+            E.call("gtb_knn_seed_tc", q_hi, q_n2 * (scale * scale), n, ref.n_pad, r_hi, n, ref.n_pad, ref.kp(tcd), 2, 16,
+                   seed, pace)
         E.call("gtb_knn_topk_tc_seeded", q_hi, q_lo, q_n2 * (scale * scale), n, ref.n_pad, r_hi, r_lo, n, ref.n_pad,
                ref.kp(tcd), tcd, ls, 2, qtiles, seed, 1, cand, scratch, tau, pace)
         tau = tau / (scale * scale)

@@ -207,9 +207,8 @@ def _tc_topk_one_product(X, stride):
     seed = None
     if stride > 1:
         seed = torch.empty((n, 2), dtype=torch.float32, device="cuda")
-        cand_s = torch.empty((n, 8), dtype=torch.int32, device="cuda")
-        E.call("gtb_knn_topk_tc_seeded", q_hi, q_lo, q_n2 * (scale * scale), n, ref.n_pad, r_hi, r_lo, n, ref.n_pad,
-               ref.kp(3), 3, 4, 2, 2, None, stride, cand_s, scratch, seed, pace)
+        E.call("gtb_knn_seed_tc", q_hi, q_n2 * (scale * scale), n, ref.n_pad, r_hi, n, ref.n_pad, ref.kp(3), 2, stride,
+               seed, pace)
     cand = torch.full((n, 64), -7, dtype=torch.int32, device="cuda")
     tau = torch.empty((n, 2), dtype=torch.float32, device="cuda")
     E.call("gtb_knn_topk_tc_seeded", q_hi, q_lo, q_n2 * (scale * scale), n, ref.n_pad, r_hi, r_lo, n, ref.n_pad,
