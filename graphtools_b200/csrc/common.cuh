@@ -43,8 +43,24 @@ static inline int64_t gtb_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __device__ __forceinline__ float gtb_inf_f() { return __int_as_float(0x7f800000); }
 
 // alpha-decay affinity exp(-(d/bw)^decay); NaN -> 1 (reference graphs.py:503-507)
+// Integer decays up to 64 (the default is 40) are evaluated by binary exponentiation: at most 6 squarings and 5
+// products instead of the ~150 instructions of the general double-precision pow -- within 6 ulp of it, i.e. a relative
+// difference below 1e-14 in the affinity at the threshold (where (d/bw)^decay = 9.2), far inside the 1e-5 tolerance.
+__device__ __forceinline__ double gtb_pow_decay(double x, double decay) {
+  const int n = (int)decay;
+  if ((double)n == decay && n >= 1 && n <= 64) {
+    double r = (n & 1) ? x : 1.0, b = x;
+#pragma unroll
+    for (int bit = 1; bit < 7; ++bit) {
+      b *= b;
+      if ((n >> bit) & 1) r *= b;
+    }
+    return r;
+  }
+  return pow(x, decay);
+}
 __device__ __forceinline__ double gtb_affinity(double dist, double bw, double decay) {
-  double w = exp(-pow(dist / bw, decay));
+  double w = exp(-gtb_pow_decay(dist / bw, decay));
   return (w != w) ? 1.0 : w;
 }
 
