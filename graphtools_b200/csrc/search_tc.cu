@@ -61,6 +61,7 @@ constexpr float TC_PAD_NORM = 1e30f;
 constexpr float TC_BIG_H = 50000.f;
 constexpr float TC_PAD_NORM_H = 60000.f;
 constexpr float TC_H_MAXNORM = 8192.f;
+constexpr int64_t TC_SPLIT_ROWS_MAX = 40 * 4 * 128;   // rows of a split round: at most half of the (<= 80) clusters x 4 tiles
 constexpr int TC_SEED_K = 8;          // SEED mode: order statistic of the sampled tile minima that becomes the threshold
 
 using namespace gtbptx;
@@ -73,6 +74,11 @@ struct TcParams {
   unsigned int* sync_ctr;                                  // grid-wide pacing counter (zeroed per launch)
   int64_t tile_stride;                                     // TOPK: sweep every tile_stride-th reference tile (1 = all)
   const float* seed_tau;                                   // TOPK: optional per-row initial threshold, layout of `tau`
+  // TOPK, one-product flavour: the LAST round, when it has work for at most half of the clusters, is split -- split_units
+  // cluster-units of query tiles x split_k pieces of split_tpp reference tiles; piece lists land in piece_buf /
+  // piece_meta and are merged by merge_pieces_kernel.  split_round = -1: no split.
+  int64_t split_round, split_units, split_k, split_tpp, split_row0;
+  uint2* piece_buf; uint2* piece_meta;
   const float* qn2;
   int32_t* cand_idx; uint2* cand_buf; float* tau;          // TOPK: out [nq][2*TC_S], scratch [nq_pad][2][TC_CAP], tau [nq][2]
   const float* lim2; int2* pairs; unsigned long long capacity; unsigned long long* counter; int32_t* rowcnt;
@@ -270,11 +276,28 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   const int64_t tstride = (MODE != 1) ? p.tile_stride : 1;
   const int64_t tiles_left = (p.nr_pad / TC_N + tstride - 1) / tstride - tile0;
   const int64_t ntiles = tiles_left < p.tiles_per_split ? tiles_left : p.tiles_per_split;
-  // first query row of (round, query tile qt of this CTA)
-  auto q0_of = [&](int64_t round, int qt) {
-    return (((qcluster + round * n_clusters) * CL + (blockIdx.x % CL)) * QT + qt) * TC_M;
+  // geometry of one round for this cluster: cluster-unit of query tiles, first reference tile, tile count, piece
+  // (-1 = the whole range); a cluster without a piece in the split round is done
+  constexpr bool SPLIT = (MODE == 0 && FMT == 3);
+  struct RoundGeom { int64_t unit, t0, nt; int piece; bool active; };
+  auto geom = [&](int64_t round) {
+    RoundGeom g;
+    g.unit = qcluster + round * n_clusters; g.t0 = tile0; g.nt = ntiles; g.piece = -1; g.active = true;
+    if (SPLIT && round == p.split_round) {
+      g.piece = (int)(cluster_id / p.split_units);
+      g.unit = round * n_clusters + cluster_id % p.split_units;
+      g.t0 = (int64_t)g.piece * p.split_tpp;
+      const int64_t left = ntiles - g.t0;
+      g.nt = left < p.split_tpp ? left : p.split_tpp;
+      g.active = g.piece < p.split_k && g.nt > 0;
+    }
+    return g;
   };
-  auto btile = [&](int64_t round, int64_t t) { return (tile0 + ((round & 1) ? (ntiles - 1 - t) : t)) * tstride; };
+  // first query row of (cluster-unit, query tile qt of this CTA)
+  auto q0_of = [&](int64_t unit, int qt) { return ((unit * CL + (blockIdx.x % CL)) * QT + qt) * TC_M; };
+  auto btile = [&](int64_t round, const RoundGeom& g, int64_t t) {
+    return (g.t0 + ((round & 1) ? (g.nt - 1 - t) : t)) * tstride;
+  };
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
   constexpr int ROWS = TC_N / CL;                            // rows of each B block this CTA loads
@@ -309,10 +332,12 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     if (lane == 0) {
       int64_t it = 0;                              // running stage counter across rounds
       for (int64_t round = 0; round < nrounds; ++round) {
-        for (int64_t t = 0; t < ntiles; ++t, ++it) {
+        const RoundGeom g = geom(round);
+        if (!g.active) break;
+        for (int64_t t = 0; t < g.nt; ++t, ++it) {
           const int s = (int)(it % NS);
           const uint32_t ph = (uint32_t)((it / NS) & 1);
-          if (p.sync_ctr != nullptr && (it % TC_SYNC_EVERY) == 0) {
+          if (p.sync_ctr != nullptr && (it % TC_SYNC_EVERY) == 0 && g.piece < 0) {
             // Pace the reference stream grid-wide: all producers enter tile `it` together, so one DRAM read
             // of a reference tile serves every SM out of L2 (without this the 74 clusters drift apart by more
             // than the 126 MB L2 window and each streams the operand from DRAM on its own: 2.1 TB instead of
@@ -328,7 +353,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
           }
           mbar_wait(empty_b + 8 * s, ph ^ 1);      // every CTA of the cluster has consumed this stage
           mbar_arrive_expect_tx(full_b + 8 * s, NPART * sizeB);
-          const int row0 = (int)(btile(round, t) * TC_N) + (int)crank * ROWS;
+          const int row0 = (int)(btile(round, g, t) * TC_N) + (int)crank * ROWS;
           for (int part = 0; part < NPART; ++part) {
             const CUtensorMap* mm = part ? &mBl : &mBh;
             const CUtensorMap* mt = part ? &mBlt : &mBht;
@@ -363,9 +388,11 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     const uint32_t part_off = sizeB >> 4, stage_off = (NPART * sizeB) >> 4;     // in descriptor address units (16 B)
     int64_t it = 0;
     for (int64_t round = 0; round < nrounds; ++round) {
+    const RoundGeom g = geom(round);
+    if (!g.active) break;
     mbar_wait(bar_a, (uint32_t)(round & 1));   // this round's A rows stored to TMEM by the epilogue warps
     tc_fence_after();
-    for (int64_t tile = 0; tile < ntiles; ++tile, ++it) {
+    for (int64_t tile = 0; tile < g.nt; ++tile, ++it) {
       const int s = (int)(it % NS);            // shared-memory stage
       const uint32_t ph = (uint32_t)((it / NS) & 1);
       mbar_wait(full_b + 8 * s, ph);
@@ -428,7 +455,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     const int lgrp = (QT == 2) ? 0 : grp;            // list index inside a row's candidate storage
     const uint32_t a_col0 = (uint32_t)(my_qt * 64);
     for (int64_t round = 0; round < nrounds; ++round) {
-    const int64_t q0 = q0_of(round, my_qt);
+    const RoundGeom g = geom(round);
+    if (!g.active) break;
+    const int64_t q0 = q0_of(g.unit, my_qt);
     const int64_t gq = q0 + row;
     const bool valid = gq < p.nq;
 
@@ -472,17 +501,22 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < TC_SEED_K; ++i) best[i] = BIG;
     int cnt = 0;
-    // this thread's candidate buffer: uniform base + per-thread offset (rows past nq never append)
-    const int64_t boff = valid ? (gq * TC_GROUPS + lgrp) * TC_CAP : 0;     // (CAP > TC_CAP only with lgrp == 0)
-    uint2* wbuf = p.cand_buf + (q0 + quad * 32) * TC_GROUPS * TC_CAP;   // warp-uniform: first row of this quadrant
-    uint2* mybuf = p.cand_buf + boff;                                     // this row's buffer (never written when !valid)
+    // candidate buffers: warp-uniform base (first row of this quadrant, this list) + rstride slots per row; rows past
+    // nq never append.  (CAP > TC_CAP only with lgrp == 0.)  A piece of a split round writes to its own buffers.
+    int64_t rstride = TC_GROUPS * TC_CAP;
+    uint2* wbuf = p.cand_buf + (q0 + quad * 32) * rstride + lgrp * TC_CAP;
+    if (SPLIT && g.piece >= 0) {
+      rstride = p.split_k * CAP;
+      wbuf = p.piece_buf + ((q0 + quad * 32 - p.split_row0) * p.split_k + g.piece) * CAP;
+    }
+    uint2* mybuf = wbuf + (valid ? lane * rstride : 0);                   // this row's buffer (never written when !valid)
 
     // this group's tiles.  QT == 1: running iteration index it = round * ntiles + t with it % 2 == grp; QT == 2:
     // every tile, accumulator index 2 it + grp
-    const int64_t it0 = round * ntiles;
-    for (int64_t t = (QT == 2) ? 0 : ((grp + (it0 & 1)) & 1); t < ntiles; t += (QT == 2 ? 1 : TC_GROUPS)) {
+    const int64_t it0 = round * ntiles;               // (every round before a split round is a full one)
+    for (int64_t t = (QT == 2) ? 0 : ((grp + (it0 & 1)) & 1); t < g.nt; t += (QT == 2 ? 1 : TC_GROUPS)) {
       const int64_t it = it0 + t;
-      const int64_t tile = btile(round, t);
+      const int64_t tile = btile(round, g, t);
       const int64_t ait = (QT == 2) ? (it * 2 + grp) : it;
       const int s = (int)(ait % NA);                   // accumulator of this iteration
       const uint32_t ph = (uint32_t)((ait / NA) & 1);
@@ -577,7 +611,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
           const int rank = __popc(pm & ((1u << lane) - 1u));
           if (MODE == 0) {
             const int cL = __shfl_sync(0xffffffffu, cnt, L);
-            if (pass) wbuf[(L * TC_GROUPS + lgrp) * TC_CAP + cL + rank] = make_uint2(__float_as_uint(x), (uint32_t)(col0 + lane));
+            if (pass) wbuf[L * rstride + cL + rank] = make_uint2(__float_as_uint(x), (uint32_t)(col0 + lane));
             if (lane == L) cnt += npass;
           } else {
             unsigned long long basepos = 0;
@@ -599,7 +633,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
             need &= need - 1;
             const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
             __syncwarp();
-            const float nt = compact_row<LSO, CAP>(wbuf + (owner * TC_GROUPS + lgrp) * TC_CAP, ocnt, lane);
+            const float nt = compact_row<LSO, CAP>(wbuf + owner * rstride, ocnt, lane);
             __syncwarp();
             if (lane == owner) { thr = nt; cnt = LSO; }
           }
@@ -622,21 +656,26 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         need &= need - 1;
         const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
         __syncwarp();
-        const float nt = compact_row<LSO, CAP>(wbuf + (owner * TC_GROUPS + lgrp) * TC_CAP, ocnt, lane);
+        const float nt = compact_row<LSO, CAP>(wbuf + owner * rstride, ocnt, lane);
         __syncwarp();
         if (lane == owner) { thr = nt; cnt = LSO; }
       }
       __syncwarp();
       if (valid) {
-        // QT == 1: two lists of LS per row (one per group) with their own thresholds; QT == 2: one list of 2 LS,
-        // the second threshold slot repeats the first (the refine takes the minimum)
-        int32_t* out = p.cand_idx + gq * (TC_GROUPS * LS) + lgrp * LS;
-        for (int e = 0; e < LSO; ++e) out[e] = (e < cnt) ? (int32_t)p.cand_buf[boff + e].y : -1;
         // a list that never filled keeps its initial threshold: +inf unseeded, the seed otherwise (every point under
         // the seed IS in the list)
         const float tv = (thr >= BIG) ? gtb_inf_f() : thr + nx;
-        p.tau[gq * TC_GROUPS + lgrp] = tv;
-        if (QT == 2) p.tau[gq * TC_GROUPS + 1] = tv;
+        if (SPLIT && g.piece >= 0) {
+          // piece of a split round: count and threshold of this piece's list; merge_pieces_kernel builds the row
+          p.piece_meta[(gq - p.split_row0) * p.split_k + g.piece] = make_uint2((uint32_t)cnt, __float_as_uint(tv));
+        } else {
+          // QT == 1: two lists of LS per row (one per group) with their own thresholds; QT == 2: one list of 2 LS,
+          // the second threshold slot repeats the first (the refine takes the minimum)
+          int32_t* out = p.cand_idx + gq * (TC_GROUPS * LS) + lgrp * LS;
+          for (int e = 0; e < LSO; ++e) out[e] = (e < cnt) ? (int32_t)mybuf[e].y : -1;
+          p.tau[gq * TC_GROUPS + lgrp] = tv;
+          if (QT == 2) p.tau[gq * TC_GROUPS + 1] = tv;
+        }
       }
     }
     }  // rounds
@@ -649,6 +688,45 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
   if (CL > 1) cluster_sync_all();               // no CTA exits while a peer may still signal its barriers
+}
+
+// ---------------------------------------------------------------- merge of a split round
+// One warp per row of the split round: the row's split_k piece lists (<= LS entries each after the piece's final
+// compaction) are concatenated in shared memory; if the union exceeds LS entries the LS smallest are selected with the
+// same quickselect as in the sweep.  Every point that is not in the result lies above its piece's threshold or above
+// the LS-th smallest of the union, so tau = min(piece thresholds, LS-th smallest of the union).
+constexpr int TC_SPLIT_MAX = 4, TC_MERGE_WARPS = 4;
+
+template <int LS>
+__global__ void __launch_bounds__(TC_MERGE_WARPS * 32) merge_pieces_kernel(TcParams p, int64_t rows_split) {
+  constexpr int CAP = TC_GROUPS * TC_CAP, MCAP = TC_SPLIT_MAX * LS;
+  __shared__ uint2 stage_s[TC_MERGE_WARPS][MCAP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * TC_MERGE_WARPS + warp;
+  const int64_t gq = p.split_row0 + r;
+  if (r >= rows_split || gq >= p.nq) return;                 // whole warp
+  uint2* stage = stage_s[warp];
+  const float nx = p.qn2[gq];
+  float tau = gtb_inf_f();
+  int total = 0;
+  for (int pc = 0; pc < (int)p.split_k; ++pc) {
+    const uint2 meta = p.piece_meta[r * p.split_k + pc];
+    const int c = (int)meta.x < LS ? (int)meta.x : LS;
+    tau = fminf(tau, __uint_as_float(meta.y));
+    const uint2* src = p.piece_buf + (r * p.split_k + pc) * CAP;
+    for (int e = lane; e < c; e += 32) stage[total + e] = src[e];
+    total += c;
+  }
+  __syncwarp();
+  if (total > LS) {
+    const float t = compact_row<LS, MCAP>(stage, total, lane);
+    tau = fminf(tau, t + nx);
+    total = LS;
+    __syncwarp();
+  }
+  int32_t* out = p.cand_idx + gq * (TC_GROUPS * (LS / 2));
+  for (int e = lane; e < LS; e += 32) out[e] = (e < total) ? (int32_t)stage[e].y : -1;
+  if (lane == 0) { p.tau[gq * TC_GROUPS] = tau; p.tau[gq * TC_GROUPS + 1] = tau; }
 }
 
 // ---------------------------------------------------------------- operand preparation (row-major hi/lo)
@@ -811,6 +889,27 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
     splits = gtb_cdiv(total_tiles, p.tiles_per_split);
     n_clusters = n_cluster_tiles * splits;
   }
+  // one-product top-k: a last round with work for at most half of the clusters is split over the reference range
+  int64_t rows_split = 0;
+  uint2* piece_space = p.piece_buf;
+  p.split_round = -1;
+  if constexpr (MODE == 0 && FMT == 3) {
+    const int64_t full = n_cluster_tiles / n_clusters, rem = n_cluster_tiles % n_clusters;
+    if (piece_space != nullptr && full >= 1 && rem > 0 && rem * 2 <= n_clusters && total_tiles >= 64) {
+      int64_t k = n_clusters / rem;
+      if (k > TC_SPLIT_MAX) k = TC_SPLIT_MAX;
+      const int64_t tpp = gtb_cdiv(total_tiles, k);
+      k = gtb_cdiv(total_tiles, tpp);
+      rows_split = rem * CL * QT * TC_M;
+      if (k >= 2 && rows_split <= TC_SPLIT_ROWS_MAX) {
+        p.split_round = full; p.split_units = rem; p.split_k = k; p.split_tpp = tpp;
+        p.split_row0 = full * n_clusters * CL * QT * TC_M;
+        p.piece_meta = piece_space + rows_split * k * (TC_GROUPS * TC_CAP);
+      } else {
+        rows_split = 0;
+      }
+    }
+  }
   const unsigned nblk = (unsigned)(n_clusters * CL);
   // pacing counter: one caller-owned device word, zeroed per launch (no state is kept in the library)
   if (p.sync_ctr != nullptr && nblk > (unsigned)CL && splits == 1) {
@@ -832,6 +931,13 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
   cfg.numAttrs = 1;
   GTB_CUDA(cudaLaunchKernelEx(&cfg, kern, mBh, mBht, mBl, mBlt, q_hi, q_lo, p));
   GTB_CHECK_LAUNCH();
+  if constexpr (MODE == 0 && FMT == 3) {
+    if (p.split_round >= 0) {
+      merge_pieces_kernel<2 * LS><<<(unsigned)gtb_cdiv(rows_split, TC_MERGE_WARPS), TC_MERGE_WARPS * 32, 0, st>>>(
+          p, rows_split);
+      GTB_CHECK_LAUNCH();
+    }
+  }
   return GTB_OK;
 }
 
@@ -942,7 +1048,10 @@ extern "C" int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const fl
   return GTB_OK;
 }
 
-extern "C" int64_t gtb_tc_scratch_bytes(int64_t nq_pad) { return nq_pad * TC_GROUPS * TC_CAP * (int64_t)sizeof(uint2); }
+// candidate buffers of every row + the piece buffers and piece records of a split last round
+extern "C" int64_t gtb_tc_scratch_bytes(int64_t nq_pad) {
+  return (nq_pad * TC_GROUPS * TC_CAP + TC_SPLIT_ROWS_MAX * TC_SPLIT_MAX * (TC_GROUPS * TC_CAP + 1)) * (int64_t)sizeof(uint2);
+}
 
 static int tc_check(int64_t nq, int64_t nr, int64_t nq_pad, int64_t nr_pad, int Kp, int dtype) {
   GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TC_M == 0 && nr_pad % TC_N == 0, "bad shape (pads must be x128)");
@@ -966,6 +1075,7 @@ extern "C" int gtb_knn_topk_tc_seeded(const void* q_hi, const void* q_lo, const 
   p.nq = nq; p.nq_pad = nq_pad; p.nr = nr; p.nr_pad = nr_pad; p.qn2 = qn2;
   p.cand_idx = cand_idx; p.cand_buf = reinterpret_cast<uint2*>(scratch); p.tau = tau; p.sync_ctr = pace;
   p.seed_tau = seed_tau; p.tile_stride = tile_stride;
+  p.piece_buf = p.cand_buf + nq_pad * TC_GROUPS * TC_CAP;   // second part of the scratch (gtb_tc_scratch_bytes)
   return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, Kp, dtype, list, cluster, qtiles, p, (cudaStream_t)stream);
 }
 

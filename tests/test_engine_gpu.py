@@ -261,6 +261,37 @@ def test_tc_topk_one_product_seeded(n, d, stride):
         assert set(np.flatnonzero(D2[i] < tau[i] - bound)).issubset(set(c))
 
 
+@pytest.mark.parametrize("stride", [1, 16])
+def test_tc_one_product_split_last_round(stride):
+    """More query cluster-units than clusters with a short last round (50k queries: 98 units for 74 clusters -> 24 units
+    left, split three ways over the reference range and merged by merge_pieces_kernel): the certification contract
+    holds for rows of the full rounds and of the split round alike, against exact float64 distances."""
+    n, d = 50_000, 32
+    X, _ = synth.gaussian_mixture(n, d, n_clusters=8, intrinsic_dim=8, seed=21)
+    cand, tau2, seed = _tc_topk_one_product(X, stride)
+    assert np.array_equal(tau2[:, 0], tau2[:, 1])
+    tau = tau2[:, 0]
+    Xd = _dev(X).double()
+    Xc = Xd - Xd.mean(0)
+    nrm = (Xc * Xc).sum(1)
+    eps = pipeline.eps_rel_tch1(d)
+    rows = np.unique(np.concatenate([np.arange(0, n, 257), np.arange(37_888, n, 61), [n - 1]]))
+    assert (cand != -7).all(), "output slot never written"
+    for i in rows.tolist():
+        c = cand[i][cand[i] >= 0]
+        assert len(np.unique(c)) == len(c) and (c < n).all()
+        d2 = ((Xd - Xd[i]) ** 2).sum(1)
+        is_c = torch.zeros(n, dtype=torch.bool, device="cuda")
+        is_c[torch.from_numpy(c).cuda().long()] = True
+        bound = eps * float(nrm[i] + nrm.max())
+        assert np.isfinite(tau[i])
+        assert float(d2[~is_c].min()) >= tau[i] - bound, i
+        inside = torch.nonzero(d2 < tau[i] - bound).flatten()
+        assert bool(is_c[inside].all()), i
+        if stride == 1:
+            assert len(c) == 64
+
+
 def test_tc_topk_out_of_sample():
     X, _ = synth.gaussian_mixture(5000, 100, n_clusters=6, intrinsic_dim=10, seed=5)
     Y, _ = synth.gaussian_mixture(333, 100, n_clusters=6, intrinsic_dim=10, seed=5)
