@@ -43,6 +43,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -61,7 +62,7 @@ constexpr float TC_PAD_NORM = 1e30f;
 constexpr float TC_BIG_H = 50000.f;
 constexpr float TC_PAD_NORM_H = 60000.f;
 constexpr float TC_H_MAXNORM = 8192.f;
-constexpr int64_t TC_SPLIT_ROWS_MAX = 40 * 4 * 128;   // rows of a split round: at most half of the (<= 80) clusters x 4 tiles
+constexpr int64_t TC_SPLIT_ROWS_MAX = 40 * 4 * 128;   // rows of a piece launch: at most half of the (<= 80) clusters x 4 tiles
 constexpr int TC_SEED_K = 8;          // SEED mode: order statistic of the sampled tile minima that becomes the threshold
 
 using namespace gtbptx;
@@ -74,10 +75,11 @@ struct TcParams {
   unsigned int* sync_ctr;                                  // grid-wide pacing counter (zeroed per launch)
   int64_t tile_stride;                                     // TOPK: sweep every tile_stride-th reference tile (1 = all)
   const float* seed_tau;                                   // TOPK: optional per-row initial threshold, layout of `tau`
-  // TOPK, one-product flavour: the LAST round, when it has work for at most half of the clusters, is split -- split_units
-  // cluster-units of query tiles x split_k pieces of split_tpp reference tiles; piece lists land in piece_buf /
-  // piece_meta and are merged by merge_pieces_kernel.  split_round = -1: no split.
-  int64_t split_round, split_units, split_k, split_tpp, split_row0;
+  // TOPK, one-product flavour: a last round with work for at most half of the clusters runs as a SECOND launch of
+  // split_k pieces of the reference range per cluster-unit (the static n_qclusters / tiles_per_split mapping of the
+  // RADIUS launches); the piece lists land in piece_buf / piece_meta (piece-major, split_rows rows from split_row0)
+  // and merge_pieces_kernel builds the rows.  split_k = 0: ordinary launch.  q_unit0: first cluster-unit of the launch.
+  int64_t q_unit0, split_k, split_row0, split_rows;
   uint2* piece_buf; uint2* piece_meta;
   const float* qn2;
   int32_t* cand_idx; uint2* cand_buf; float* tau;          // TOPK: out [nq][2*TC_S], scratch [nq_pad][2][TC_CAP], tau [nq][2]
@@ -214,7 +216,9 @@ __device__ __forceinline__ void tc_commit_mc_pred(uint32_t bar, uint16_t mask, u
 // epilogue group g owning query tile g and ONE list of 2 LS entries per row -- each byte streamed from L2 feeds twice
 // the tensor work.  (The L2 -> SM path, ~6300 B/clk chip-wide, is what bounds a single-tile sweep once the MMA work
 // drops to two products: 57 KB per stage and SM = 1340 clk against 896 clk of MMAs.)
-template <int MODE, int CL, int FMT, int LS, int QT>  // MODE 0 = TOPK, 1 = RADIUS, 2 = SEED
+// PIECE: the second launch of a split top-k sweep (own instantiation: the ordinary sweep sits exactly at the register
+// budget ptxas grants this kernel, and one more live value in its epilogue costs 13 % of the sweep)
+template <int MODE, int CL, int FMT, int LS, int QT, bool PIECE = false>  // MODE 0 = TOPK, 1 = RADIUS, 2 = SEED
 __global__ void __launch_bounds__(TC_THREADS, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBht,
                  const __grid_constant__ CUtensorMap mBl, const __grid_constant__ CUtensorMap mBlt,
@@ -276,28 +280,12 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   const int64_t tstride = (MODE != 1) ? p.tile_stride : 1;
   const int64_t tiles_left = (p.nr_pad / TC_N + tstride - 1) / tstride - tile0;
   const int64_t ntiles = tiles_left < p.tiles_per_split ? tiles_left : p.tiles_per_split;
-  // geometry of one round for this cluster: cluster-unit of query tiles, first reference tile, tile count, piece
-  // (-1 = the whole range); a cluster without a piece in the split round is done
-  constexpr bool SPLIT = (MODE == 0 && FMT == 3);
-  struct RoundGeom { int64_t unit, t0, nt; int piece; bool active; };
-  auto geom = [&](int64_t round) {
-    RoundGeom g;
-    g.unit = qcluster + round * n_clusters; g.t0 = tile0; g.nt = ntiles; g.piece = -1; g.active = true;
-    if (SPLIT && round == p.split_round) {
-      g.piece = (int)(cluster_id / p.split_units);
-      g.unit = round * n_clusters + cluster_id % p.split_units;
-      g.t0 = (int64_t)g.piece * p.split_tpp;
-      const int64_t left = ntiles - g.t0;
-      g.nt = left < p.split_tpp ? left : p.split_tpp;
-      g.active = g.piece < p.split_k && g.nt > 0;
-    }
-    return g;
+  // first query row of (round, query tile qt of this CTA)
+  auto q0_of = [&](int64_t round, int qt) {
+    return ((((PIECE ? p.q_unit0 : 0) + qcluster + round * n_clusters) * CL + (blockIdx.x % CL)) * QT + qt) * TC_M;
   };
-  // first query row of (cluster-unit, query tile qt of this CTA)
-  auto q0_of = [&](int64_t unit, int qt) { return ((unit * CL + (blockIdx.x % CL)) * QT + qt) * TC_M; };
-  auto btile = [&](int64_t round, const RoundGeom& g, int64_t t) {
-    return (g.t0 + ((round & 1) ? (g.nt - 1 - t) : t)) * tstride;
-  };
+  static_assert(!PIECE || (MODE == 0 && FMT == 3), "piece launches belong to the one-product top-k sweep");
+  auto btile = [&](int64_t round, int64_t t) { return (tile0 + ((round & 1) ? (ntiles - 1 - t) : t)) * tstride; };
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
   constexpr int ROWS = TC_N / CL;                            // rows of each B block this CTA loads
@@ -332,12 +320,10 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     if (lane == 0) {
       int64_t it = 0;                              // running stage counter across rounds
       for (int64_t round = 0; round < nrounds; ++round) {
-        const RoundGeom g = geom(round);
-        if (!g.active) break;
-        for (int64_t t = 0; t < g.nt; ++t, ++it) {
+        for (int64_t t = 0; t < ntiles; ++t, ++it) {
           const int s = (int)(it % NS);
           const uint32_t ph = (uint32_t)((it / NS) & 1);
-          if (p.sync_ctr != nullptr && (it % TC_SYNC_EVERY) == 0 && g.piece < 0) {
+          if (p.sync_ctr != nullptr && (it % TC_SYNC_EVERY) == 0) {
             // Pace the reference stream grid-wide: all producers enter tile `it` together, so one DRAM read
             // of a reference tile serves every SM out of L2 (without this the 74 clusters drift apart by more
             // than the 126 MB L2 window and each streams the operand from DRAM on its own: 2.1 TB instead of
@@ -353,7 +339,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
           }
           mbar_wait(empty_b + 8 * s, ph ^ 1);      // every CTA of the cluster has consumed this stage
           mbar_arrive_expect_tx(full_b + 8 * s, NPART * sizeB);
-          const int row0 = (int)(btile(round, g, t) * TC_N) + (int)crank * ROWS;
+          const int row0 = (int)(btile(round, t) * TC_N) + (int)crank * ROWS;
           for (int part = 0; part < NPART; ++part) {
             const CUtensorMap* mm = part ? &mBl : &mBh;
             const CUtensorMap* mt = part ? &mBlt : &mBht;
@@ -388,11 +374,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     const uint32_t part_off = sizeB >> 4, stage_off = (NPART * sizeB) >> 4;     // in descriptor address units (16 B)
     int64_t it = 0;
     for (int64_t round = 0; round < nrounds; ++round) {
-    const RoundGeom g = geom(round);
-    if (!g.active) break;
     mbar_wait(bar_a, (uint32_t)(round & 1));   // this round's A rows stored to TMEM by the epilogue warps
     tc_fence_after();
-    for (int64_t tile = 0; tile < g.nt; ++tile, ++it) {
+    for (int64_t tile = 0; tile < ntiles; ++tile, ++it) {
       const int s = (int)(it % NS);            // shared-memory stage
       const uint32_t ph = (uint32_t)((it / NS) & 1);
       mbar_wait(full_b + 8 * s, ph);
@@ -455,9 +439,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
     const int lgrp = (QT == 2) ? 0 : grp;            // list index inside a row's candidate storage
     const uint32_t a_col0 = (uint32_t)(my_qt * 64);
     for (int64_t round = 0; round < nrounds; ++round) {
-    const RoundGeom g = geom(round);
-    if (!g.active) break;
-    const int64_t q0 = q0_of(g.unit, my_qt);
+    const int64_t q0 = q0_of(round, my_qt);
     const int64_t gq = q0 + row;
     const bool valid = gq < p.nq;
 
@@ -501,22 +483,23 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < TC_SEED_K; ++i) best[i] = BIG;
     int cnt = 0;
-    // candidate buffers: warp-uniform base (first row of this quadrant, this list) + rstride slots per row; rows past
-    // nq never append.  (CAP > TC_CAP only with lgrp == 0.)  A piece of a split round writes to its own buffers.
-    int64_t rstride = TC_GROUPS * TC_CAP;
-    uint2* wbuf = p.cand_buf + (q0 + quad * 32) * rstride + lgrp * TC_CAP;
-    if (SPLIT && g.piece >= 0) {
-      rstride = p.split_k * CAP;
-      wbuf = p.piece_buf + ((q0 + quad * 32 - p.split_row0) * p.split_k + g.piece) * CAP;
+    // this thread's candidate buffer: uniform base + per-thread offset (rows past nq never append)
+    const int64_t boff = valid ? (gq * TC_GROUPS + lgrp) * TC_CAP : 0;     // (CAP > TC_CAP only with lgrp == 0)
+    uint2* wbuf = p.cand_buf + (q0 + quad * 32) * TC_GROUPS * TC_CAP;   // warp-uniform: first row of this quadrant
+    uint2* mybuf = p.cand_buf + boff;                                     // this row's buffer (never written when !valid)
+    if (PIECE) {
+      // piece launch: this cluster's piece of the reference range has its own buffers (piece-major, same row stride)
+      uint2* pb = p.piece_buf + ((cluster_id / p.n_qclusters) * p.split_rows - p.split_row0) * (TC_GROUPS * TC_CAP);
+      wbuf = pb + (q0 + quad * 32) * TC_GROUPS * TC_CAP;
+      mybuf = pb + boff;
     }
-    uint2* mybuf = wbuf + (valid ? lane * rstride : 0);                   // this row's buffer (never written when !valid)
 
     // this group's tiles.  QT == 1: running iteration index it = round * ntiles + t with it % 2 == grp; QT == 2:
     // every tile, accumulator index 2 it + grp
-    const int64_t it0 = round * ntiles;               // (every round before a split round is a full one)
-    for (int64_t t = (QT == 2) ? 0 : ((grp + (it0 & 1)) & 1); t < g.nt; t += (QT == 2 ? 1 : TC_GROUPS)) {
+    const int64_t it0 = round * ntiles;
+    for (int64_t t = (QT == 2) ? 0 : ((grp + (it0 & 1)) & 1); t < ntiles; t += (QT == 2 ? 1 : TC_GROUPS)) {
       const int64_t it = it0 + t;
-      const int64_t tile = btile(round, g, t);
+      const int64_t tile = btile(round, t);
       const int64_t ait = (QT == 2) ? (it * 2 + grp) : it;
       const int s = (int)(ait % NA);                   // accumulator of this iteration
       const uint32_t ph = (uint32_t)((ait / NA) & 1);
@@ -611,7 +594,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
           const int rank = __popc(pm & ((1u << lane) - 1u));
           if (MODE == 0) {
             const int cL = __shfl_sync(0xffffffffu, cnt, L);
-            if (pass) wbuf[L * rstride + cL + rank] = make_uint2(__float_as_uint(x), (uint32_t)(col0 + lane));
+            if (pass) wbuf[(L * TC_GROUPS + lgrp) * TC_CAP + cL + rank] = make_uint2(__float_as_uint(x), (uint32_t)(col0 + lane));
             if (lane == L) cnt += npass;
           } else {
             unsigned long long basepos = 0;
@@ -633,7 +616,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
             need &= need - 1;
             const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
             __syncwarp();
-            const float nt = compact_row<LSO, CAP>(wbuf + owner * rstride, ocnt, lane);
+            const float nt = compact_row<LSO, CAP>(wbuf + (owner * TC_GROUPS + lgrp) * TC_CAP, ocnt, lane);
             __syncwarp();
             if (lane == owner) { thr = nt; cnt = LSO; }
           }
@@ -656,23 +639,24 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         need &= need - 1;
         const int ocnt = __shfl_sync(0xffffffffu, cnt, owner);
         __syncwarp();
-        const float nt = compact_row<LSO, CAP>(wbuf + owner * rstride, ocnt, lane);
+        const float nt = compact_row<LSO, CAP>(wbuf + (owner * TC_GROUPS + lgrp) * TC_CAP, ocnt, lane);
         __syncwarp();
         if (lane == owner) { thr = nt; cnt = LSO; }
       }
       __syncwarp();
       if (valid) {
+        // QT == 1: two lists of LS per row (one per group) with their own thresholds; QT == 2: one list of 2 LS,
+        // the second threshold slot repeats the first (the refine takes the minimum)
         // a list that never filled keeps its initial threshold: +inf unseeded, the seed otherwise (every point under
         // the seed IS in the list)
         const float tv = (thr >= BIG) ? gtb_inf_f() : thr + nx;
-        if (SPLIT && g.piece >= 0) {
-          // piece of a split round: count and threshold of this piece's list; merge_pieces_kernel builds the row
-          p.piece_meta[(gq - p.split_row0) * p.split_k + g.piece] = make_uint2((uint32_t)cnt, __float_as_uint(tv));
+        if (PIECE) {
+          // piece launch: count and threshold of this piece's list; merge_pieces_kernel builds the row
+          p.piece_meta[(cluster_id / p.n_qclusters) * p.split_rows + (gq - p.split_row0)] =
+              make_uint2((uint32_t)cnt, __float_as_uint(tv));
         } else {
-          // QT == 1: two lists of LS per row (one per group) with their own thresholds; QT == 2: one list of 2 LS,
-          // the second threshold slot repeats the first (the refine takes the minimum)
           int32_t* out = p.cand_idx + gq * (TC_GROUPS * LS) + lgrp * LS;
-          for (int e = 0; e < LSO; ++e) out[e] = (e < cnt) ? (int32_t)mybuf[e].y : -1;
+          for (int e = 0; e < LSO; ++e) out[e] = (e < cnt) ? (int32_t)p.cand_buf[boff + e].y : -1;
           p.tau[gq * TC_GROUPS + lgrp] = tv;
           if (QT == 2) p.tau[gq * TC_GROUPS + 1] = tv;
         }
@@ -690,30 +674,30 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   if (CL > 1) cluster_sync_all();               // no CTA exits while a peer may still signal its barriers
 }
 
-// ---------------------------------------------------------------- merge of a split round
-// One warp per row of the split round: the row's split_k piece lists (<= LS entries each after the piece's final
+// ---------------------------------------------------------------- merge of a split last round
+// One warp per row of the piece launch: the row's split_k piece lists (<= LS entries each after the piece's final
 // compaction) are concatenated in shared memory; if the union exceeds LS entries the LS smallest are selected with the
 // same quickselect as in the sweep.  Every point that is not in the result lies above its piece's threshold or above
 // the LS-th smallest of the union, so tau = min(piece thresholds, LS-th smallest of the union).
 constexpr int TC_SPLIT_MAX = 4, TC_MERGE_WARPS = 4;
 
 template <int LS>
-__global__ void __launch_bounds__(TC_MERGE_WARPS * 32) merge_pieces_kernel(TcParams p, int64_t rows_split) {
+__global__ void __launch_bounds__(TC_MERGE_WARPS * 32) merge_pieces_kernel(TcParams p) {
   constexpr int CAP = TC_GROUPS * TC_CAP, MCAP = TC_SPLIT_MAX * LS;
   __shared__ uint2 stage_s[TC_MERGE_WARPS][MCAP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t r = (int64_t)blockIdx.x * TC_MERGE_WARPS + warp;
   const int64_t gq = p.split_row0 + r;
-  if (r >= rows_split || gq >= p.nq) return;                 // whole warp
+  if (r >= p.split_rows || gq >= p.nq) return;               // whole warp
   uint2* stage = stage_s[warp];
   const float nx = p.qn2[gq];
   float tau = gtb_inf_f();
   int total = 0;
   for (int pc = 0; pc < (int)p.split_k; ++pc) {
-    const uint2 meta = p.piece_meta[r * p.split_k + pc];
+    const uint2 meta = p.piece_meta[pc * p.split_rows + r];
     const int c = (int)meta.x < LS ? (int)meta.x : LS;
     tau = fminf(tau, __uint_as_float(meta.y));
-    const uint2* src = p.piece_buf + (r * p.split_k + pc) * CAP;
+    const uint2* src = p.piece_buf + (pc * p.split_rows + r) * CAP;
     for (int e = lane; e < c; e += 32) stage[total + e] = src[e];
     total += c;
   }
@@ -724,7 +708,7 @@ __global__ void __launch_bounds__(TC_MERGE_WARPS * 32) merge_pieces_kernel(TcPar
     total = LS;
     __syncwarp();
   }
-  int32_t* out = p.cand_idx + gq * (TC_GROUPS * (LS / 2));
+  int32_t* out = p.cand_idx + gq * LS;
   for (int e = lane; e < LS; e += 32) out[e] = (e < total) ? (int32_t)stage[e].y : -1;
   if (lane == 0) { p.tau[gq * TC_GROUPS] = tau; p.tau[gq * TC_GROUPS + 1] = tau; }
 }
@@ -889,24 +873,21 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
     splits = gtb_cdiv(total_tiles, p.tiles_per_split);
     n_clusters = n_cluster_tiles * splits;
   }
-  // one-product top-k: a last round with work for at most half of the clusters is split over the reference range
-  int64_t rows_split = 0;
+  // one-product top-k: a last round with work for at most half of the clusters becomes a second launch in which
+  // every remaining cluster-unit is swept by split_k clusters, each over a piece of the reference range
+  int64_t rem_units = 0, piece_k = 0, piece_tpp = 0;
   uint2* piece_space = p.piece_buf;
-  p.split_round = -1;
+  p.q_unit0 = 0; p.split_k = 0;
   if constexpr (MODE == 0 && FMT == 3) {
     const int64_t full = n_cluster_tiles / n_clusters, rem = n_cluster_tiles % n_clusters;
     if (piece_space != nullptr && full >= 1 && rem > 0 && rem * 2 <= n_clusters && total_tiles >= 64) {
       int64_t k = n_clusters / rem;
       if (k > TC_SPLIT_MAX) k = TC_SPLIT_MAX;
-      const int64_t tpp = gtb_cdiv(total_tiles, k);
-      k = gtb_cdiv(total_tiles, tpp);
-      rows_split = rem * CL * QT * TC_M;
-      if (k >= 2 && rows_split <= TC_SPLIT_ROWS_MAX) {
-        p.split_round = full; p.split_units = rem; p.split_k = k; p.split_tpp = tpp;
-        p.split_row0 = full * n_clusters * CL * QT * TC_M;
-        p.piece_meta = piece_space + rows_split * k * (TC_GROUPS * TC_CAP);
-      } else {
-        rows_split = 0;
+      piece_tpp = gtb_cdiv(total_tiles, k);
+      k = gtb_cdiv(total_tiles, piece_tpp);
+      if (k >= 2 && rem * CL * QT * TC_M <= TC_SPLIT_ROWS_MAX) {
+        rem_units = rem; piece_k = k;
+        p.nrounds = full;                        // first launch: the full rounds only
       }
     }
   }
@@ -932,9 +913,26 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
   GTB_CUDA(cudaLaunchKernelEx(&cfg, kern, mBh, mBht, mBl, mBlt, q_hi, q_lo, p));
   GTB_CHECK_LAUNCH();
   if constexpr (MODE == 0 && FMT == 3) {
-    if (p.split_round >= 0) {
-      merge_pieces_kernel<2 * LS><<<(unsigned)gtb_cdiv(rows_split, TC_MERGE_WARPS), TC_MERGE_WARPS * 32, 0, st>>>(
-          p, rows_split);
+    if (rem_units > 0) {
+      // piece launch: cluster c = unit (c % rem_units) of the remaining ones, piece c / rem_units of the reference
+      // range (the mapping of the RADIUS launches), one round, no pacing; then the merge
+      TcParams q = p;
+      q.q_unit0 = p.nrounds * n_clusters;
+      q.nrounds = 1;
+      q.n_qclusters = rem_units;
+      q.tiles_per_split = piece_tpp;
+      q.sync_ctr = nullptr;
+      q.split_k = piece_k;
+      q.split_rows = rem_units * CL * QT * TC_M;
+      q.split_row0 = q.q_unit0 * CL * QT * TC_M;
+      q.piece_buf = piece_space;
+      q.piece_meta = piece_space + q.split_rows * piece_k * (TC_GROUPS * TC_CAP);
+      cfg.gridDim = dim3((unsigned)(rem_units * piece_k * CL));
+      auto pkern = search_tc_kernel<MODE, CL, FMT, LS, QT, true>;
+      GTB_CUDA(cudaFuncSetAttribute(pkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GTB_CUDA(cudaLaunchKernelEx(&cfg, pkern, mBh, mBht, mBl, mBlt, q_hi, q_lo, q));
+      GTB_CHECK_LAUNCH();
+      merge_pieces_kernel<2 * LS><<<(unsigned)gtb_cdiv(q.split_rows, TC_MERGE_WARPS), TC_MERGE_WARPS * 32, 0, st>>>(q);
       GTB_CHECK_LAUNCH();
     }
   }
@@ -1076,6 +1074,9 @@ extern "C" int gtb_knn_topk_tc_seeded(const void* q_hi, const void* q_lo, const 
   p.cand_idx = cand_idx; p.cand_buf = reinterpret_cast<uint2*>(scratch); p.tau = tau; p.sync_ctr = pace;
   p.seed_tau = seed_tau; p.tile_stride = tile_stride;
   p.piece_buf = p.cand_buf + nq_pad * TC_GROUPS * TC_CAP;   // second part of the scratch (gtb_tc_scratch_bytes)
+  if (const char* e = getenv("GTB_TC_SPLIT")) {              // kernel experiments: 0 = never split the last round
+    if (atoi(e) == 0) p.piece_buf = nullptr;
+  }
   return launch_tc<0>(q_hi, q_lo, r_hi, r_lo, Kp, dtype, list, cluster, qtiles, p, (cudaStream_t)stream);
 }
 
