@@ -218,7 +218,10 @@ __device__ __forceinline__ void tc_commit_mc_pred(uint32_t bar, uint16_t mask, u
 // drops to two products: 57 KB per stage and SM = 1340 clk against 896 clk of MMAs.)
 // PIECE: the second launch of a split top-k sweep (own instantiation: the ordinary sweep sits exactly at the register
 // budget ptxas grants this kernel, and one more live value in its epilogue costs 13 % of the sweep)
-template <int MODE, int CL, int FMT, int LS, int QT, bool PIECE = false>  // MODE 0 = TOPK, 1 = RADIUS, 2 = SEED
+// WIDE: operand rows longer than 8 k-steps (129 .. 512 float16 elements, i.e. d up to 510): the query tile still
+// lives in TMEM (hi parts only: 8 columns per k-step, up to 256 columns beside two accumulators), the reference tiles
+// stream in CHUNKS of 8 k-steps -- a stage is one (tile, chunk) pair and the accumulator collects all chunks of a tile.
+template <int MODE, int CL, int FMT, int LS, int QT, bool PIECE = false, bool WIDE = false>  // MODE 0 = TOPK, 1 = RADIUS, 2 = SEED
 __global__ void __launch_bounds__(TC_THREADS, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBht,
                  const __grid_constant__ CUtensorMap mBl, const __grid_constant__ CUtensorMap mBlt,
@@ -236,6 +239,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   static_assert(QT == 1 || (QT == 2 && FMT >= 2 && MODE != 1), "two query tiles per CTA: fp16 top-k / seed only");
   static_assert(MODE != 2 || (FMT == 3 && QT == 2), "seed sweeps use the one-product flavour");
   static_assert(FMT != 3 || QT == 2, "the one-product flavour runs two query tiles per CTA");
+  static_assert(!WIDE || (FMT == 2 && QT == 1 && !PIECE), "wide operand rows: fp16x2, one query tile per CTA");
   constexpr int LSO = (QT == 2) ? 2 * LS : LS;               // entries of one output list
   // candidate buffer of one list: a row owns TC_GROUPS * TC_CAP slots of scratch; the single long list of QT == 2 may
   // use all of them (fewer compactions between the seeded threshold and the final selection)
@@ -248,7 +252,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   const int nks = p.nks;                                     // 32-byte k-steps per operand row
   const int nfull = nks / 4, ntail = nks % 4;                // SWIZZLE_128B blocks (4 k-steps) + SWIZZLE_32B tail blocks
   const int a_lo_col = nks * 8;                              // TMEM column of A_lo (A_hi at 0)
-  const uint32_t sizeB = (uint32_t)TC_N * nks * 32;          // one part (hi or lo) of one stage
+  const int nch = WIDE ? (nks + 7) / 8 : 1;                  // chunks of 8 k-steps per reference tile (WIDE)
+  const uint32_t sizeB = (uint32_t)TC_N * (WIDE ? 8 : nks) * 32;   // one part (hi or lo) of one stage
   const char* q_hi = reinterpret_cast<const char*>(q_hi_v);
   const char* q_lo = reinterpret_cast<const char*>(q_lo_v);
   // shared-memory ring of NS reference stages (3 fit for bf16 operands, 2 for tf32); the two TMEM
@@ -256,8 +261,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   constexpr int NS = BF16 ? (NPART == 1 ? 4 : 3) : 2;
   // TMEM accumulator ring: bf16 query tiles need only 2 x 64 columns, leaving room for three 128-column
   // accumulators (the MMA warp can run two tiles ahead of a busy epilogue group); tf32 has room for two.
-  constexpr int NA = BF16 ? 3 : 2;
-  constexpr int ACC0 = BF16 ? 128 : 256;
+  constexpr int NA = (BF16 && !WIDE) ? 3 : 2;
+  constexpr int ACC0 = (BF16 && !WIDE) ? 128 : 256;
   const uint32_t B0 = base;                                  // stage s, part q at B0 + (NPART*s+q)*sizeB
   const uint32_t bar0 = B0 + NPART * NS * sizeB;
   const uint32_t bar_a = bar0, full_b = bar0 + 8, empty_b = bar0 + 40, tm_full = bar0 + 72, tm_empty = bar0 + 104;
@@ -315,7 +320,110 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 0 && WIDE) {
+    // ===================== TMA producer, chunked rows =====================
+    if (lane == 0) {
+      int64_t it = 0, sit = 0;                     // running tile / stage counters across rounds
+      for (int64_t round = 0; round < nrounds; ++round) {
+        for (int64_t t = 0; t < ntiles; ++t, ++it) {
+          if (p.sync_ctr != nullptr && (it % TC_SYNC_EVERY) == 0) {
+            const unsigned int target = (unsigned int)(it / TC_SYNC_EVERY + 1) * gridDim.x;
+            atomicAdd(p.sync_ctr, 1u);
+            for (int polls = 0; polls < (1 << 16); ++polls) {
+              unsigned int seen;
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sync_ctr) : "memory");
+              if (seen >= target) break;
+              __nanosleep(64);
+            }
+          }
+          const int row0 = (int)(btile(round, t) * TC_N) + (int)crank * ROWS;
+          for (int c = 0; c < nch; ++c, ++sit) {
+            const int s = (int)(sit % NS);
+            const uint32_t ph = (uint32_t)((sit / NS) & 1);
+            const int nk = (nks - 8 * c) < 8 ? (nks - 8 * c) : 8;      // k-steps of this chunk
+            const int nf = nk / 4, nt2 = nk % 4;
+            mbar_wait(empty_b + 8 * s, ph ^ 1);
+            mbar_arrive_expect_tx(full_b + 8 * s, (uint32_t)(NPART * TC_N * nk * 32));
+            for (int part = 0; part < NPART; ++part) {
+              const CUtensorMap* mm = part ? &mBl : &mBh;
+              const CUtensorMap* mt = part ? &mBlt : &mBht;
+              const uint32_t dst = B0 + (NPART * s + part) * sizeB;
+              for (int b = 0; b < nf; ++b) {
+                const uint32_t d = dst + b * (TC_N * 128) + crank * (ROWS * 128);
+                if (CL > 1) tma_load_2d_mc(d, mm, full_b + 8 * s, (c * 8 + b * 4) * EPK, row0, cmask);
+                else tma_load_2d(d, mm, full_b + 8 * s, (c * 8 + b * 4) * EPK, row0);
+              }
+              for (int t2 = 0; t2 < nt2; ++t2) {
+                const uint32_t d = dst + nf * (TC_N * 128) + t2 * (TC_N * 32) + crank * (ROWS * 32);
+                if (CL > 1) tma_load_2d_mc(d, mt, full_b + 8 * s, (c * 8 + nf * 4 + t2) * EPK, row0, cmask);
+                else tma_load_2d(d, mt, full_b + 8 * s, (c * 8 + nf * 4 + t2) * EPK, row0);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && WIDE) {
+    // ===================== MMA issuer, chunked rows =====================
+    const bool leader = elect_one();
+    const uint32_t lead = leader ? 1u : 0u;
+    constexpr uint32_t fmt = (FMT == 0) ? 2u : (FMT == 1 ? 1u : 0u);
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_N >> 3) << 17) |
+                           ((uint32_t)(TC_M >> 4) << 24);
+    const uint64_t bd_main0 = make_desc(B0, 1024, 2);
+    const uint32_t part_off = sizeB >> 4, stage_off = (NPART * sizeB) >> 4;
+    int64_t it = 0, sit = 0;
+    for (int64_t round = 0; round < nrounds; ++round) {
+      mbar_wait(bar_a, (uint32_t)(round & 1));
+      tc_fence_after();
+      for (int64_t tile = 0; tile < ntiles; ++tile, ++it) {
+        const int ac_i = (int)(it % NA);
+        const uint32_t aph = (uint32_t)((it / NA) & 1);
+        mbar_wait(tm_empty + 8 * ac_i, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ACC0 + ac_i * TC_N);
+        uint32_t accum = 0;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c, ++sit) {
+          const int s = (int)(sit % NS);
+          const uint32_t ph = (uint32_t)((sit / NS) & 1);
+          const int nk = (nks - 8 * c) < 8 ? (nks - 8 * c) : 8;
+          const int nf = nk / 4, nt2 = nk % 4;
+          mbar_wait(full_b + 8 * s, ph);
+          tc_fence_after();
+          const uint64_t bd_tail0 = make_desc(B0 + nf * (TC_N * 128), 256, 6);
+#pragma unroll 1
+          for (int prod = 0; prod < NPROD; ++prod) {   // (A_hi,B_hi), (A_hi,B_lo)
+            uint32_t ac = tmem_base + (uint32_t)(c * 64);
+            const uint64_t boff = (uint64_t)(s * stage_off + ((prod == 1) ? part_off : 0u));
+            uint64_t bd = bd_main0 + boff;
+#pragma unroll 1
+            for (int blk = 0; blk < nf; ++blk) {
+#pragma unroll
+              for (int sub = 0; sub < 4; ++sub) {
+                tc_mma_ts_pred(BF16, d_tmem, ac + sub * 8, bd + sub * 2, idesc, accum, lead);
+                accum = 1;
+              }
+              bd += (TC_N * 128) >> 4;
+              ac += 32;
+            }
+            bd = bd_tail0 + boff;
+#pragma unroll 1
+            for (int t = 0; t < nt2; ++t) {
+              tc_mma_ts_pred(BF16, d_tmem, ac, bd, idesc, accum, lead);
+              accum = 1;
+              bd += (TC_N * 32) >> 4;
+              ac += 8;
+            }
+          }
+          if (CL > 1) tc_commit_mc_pred(empty_b + 8 * s, cmask, lead);
+          else tc_commit_pred(empty_b + 8 * s, lead);
+        }
+        tc_commit_pred(tm_full + 8 * ac_i, lead);
+      }
+      tc_commit_pred(round_done, lead);
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int64_t it = 0;                              // running stage counter across rounds
@@ -838,7 +946,7 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int Kp, int box_k, i
   return GTB_OK;
 }
 
-template <int MODE, int CL, int FMT, int LS, int QT = 1>
+template <int MODE, int CL, int FMT, int LS, int QT = 1, bool WIDE = false>
 int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const void* r_lo, int Kp, TcParams& p,
                  cudaStream_t st) {
   CUtensorMap mBh, mBht, mBl, mBlt;
@@ -852,8 +960,8 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
   if ((rc = make_map(&mBlt, r_lo, p.nr_pad, Kp, EPK, TC_N / CL, false, FMT))) return rc;
   constexpr int NPART = (FMT == 3) ? 1 : 2;
   constexpr int NS = BF16 ? (NPART == 1 ? 4 : 3) : 2;
-  size_t smem = 1024 + (size_t)NPART * NS * TC_N * p.nks * 32 + 256 + 1024;
-  auto kern = search_tc_kernel<MODE, CL, FMT, LS, QT>;
+  size_t smem = 1024 + (size_t)NPART * NS * TC_N * (WIDE ? 8 : p.nks) * 32 + 256 + 1024;
+  auto kern = search_tc_kernel<MODE, CL, FMT, LS, QT, false, WIDE>;
   GTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, nsm = 0;
   GTB_CUDA(cudaGetDevice(&dev));
@@ -878,7 +986,7 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
   int64_t rem_units = 0, piece_k = 0, piece_tpp = 0;
   uint2* piece_space = p.piece_buf;
   p.q_unit0 = 0; p.split_k = 0;
-  if constexpr (MODE == 0 && FMT == 3) {
+  if constexpr (MODE == 0 && FMT == 3 && !WIDE) {
     const int64_t full = n_cluster_tiles / n_clusters, rem = n_cluster_tiles % n_clusters;
     if (piece_space != nullptr && full >= 1 && rem > 0 && rem * 2 <= n_clusters && total_tiles >= 64) {
       int64_t k = n_clusters / rem;
@@ -912,7 +1020,7 @@ int launch_tc_cl(const void* q_hi, const void* q_lo, const void* r_hi, const voi
   cfg.numAttrs = 1;
   GTB_CUDA(cudaLaunchKernelEx(&cfg, kern, mBh, mBht, mBl, mBlt, q_hi, q_lo, p));
   GTB_CHECK_LAUNCH();
-  if constexpr (MODE == 0 && FMT == 3) {
+  if constexpr (MODE == 0 && FMT == 3 && !WIDE) {
     if (rem_units > 0) {
       // piece launch: cluster c = unit (c % rem_units) of the remaining ones, piece c / rem_units of the reference
       // range (the mapping of the RADIUS launches), one round, no pacing; then the merge
@@ -962,6 +1070,23 @@ int launch_tc_fmt(const void* q_hi, const void* q_lo, const void* r_hi, const vo
     gtb_set_error("seed sweeps use the one-product flavour (dtype 3)");
     return GTB_ERR_ARG;
   } else {
+  if (Kp > 128) {
+    // operand rows beyond 8 k-steps: chunked reference stream (fp16x2 only, one query tile per CTA)
+    if constexpr (FMT == 2) {
+      if (qtiles != 1 || (cluster != 1 && cluster != 2)) {
+        gtb_set_error("wide operand rows (Kp > 128) need qtiles = 1 and cluster = 1 or 2");
+        return GTB_ERR_ARG;
+      }
+      if (cluster == 1)
+        return short_list ? launch_tc_cl<MODE, 1, 2, LS_SHORT, 1, true>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
+                          : launch_tc_cl<MODE, 1, 2, 32, 1, true>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+      return short_list ? launch_tc_cl<MODE, 2, 2, LS_SHORT, 1, true>(q_hi, q_lo, r_hi, r_lo, Kp, p, st)
+                        : launch_tc_cl<MODE, 2, 2, 32, 1, true>(q_hi, q_lo, r_hi, r_lo, Kp, p, st);
+    } else {
+      gtb_set_error("operand rows beyond 128 elements are supported by the fp16x2 flavour (dtype 2) only");
+      return GTB_ERR_ARG;
+    }
+  }
   if (qtiles == 2) {
     if constexpr (FMT == 2 && MODE == 0) {
       if (!short_list) { gtb_set_error("two query tiles per CTA need list = 16 (one list of 32 per row)"); return GTB_ERR_ARG; }
@@ -1025,8 +1150,8 @@ extern "C" int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const fl
   GTB_CHECK_ARG(n > 0 && d > 0 && n_pad >= n && n_pad % 128 == 0, "bad shape");
   GTB_CHECK_ARG(dtype >= 0 && dtype <= 2, "dtype must be 0 (tf32 pairs in float32), 1 (bfloat16 pairs) or 2 (float16 pairs)");
   const int epk = dtype ? 16 : 8;
-  GTB_CHECK_ARG(Kp % epk == 0 && Kp >= d + 1 + (dtype == 2) && Kp / epk <= (dtype ? 8 : 13),
-                "Kp must be a multiple of 8 (tf32, <= 104) / 16 (bf16 / fp16, <= 128) and >= d+1 (fp16: d+2)");
+  GTB_CHECK_ARG(Kp % epk == 0 && Kp >= d + 1 + (dtype == 2) && Kp / epk <= (dtype == 2 ? 32 : (dtype ? 8 : 13)),
+                "Kp must be a multiple of 8 (tf32, <= 104) / 16 (bf16 <= 128, fp16 <= 512) and >= d+1 (fp16: d+2)");
   GTB_CHECK_ARG(role == 0 || role == 1, "role must be 0 (query) or 1 (reference)");
   GTB_CHECK_ARG(dtype != 2 || scale > 0.f, "the fp16 flavour needs a positive scale");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1055,7 +1180,7 @@ static int tc_check(int64_t nq, int64_t nr, int64_t nq_pad, int64_t nr_pad, int 
   GTB_CHECK_ARG(nq > 0 && nr > 0 && nq_pad % TC_M == 0 && nr_pad % TC_N == 0, "bad shape (pads must be x128)");
   GTB_CHECK_ARG(dtype >= 0 && dtype <= 3, "dtype must be 0 (tf32), 1 (bf16), 2 (fp16, two products) or 3 (fp16, one)");
   const int epk = dtype ? 16 : 8;
-  GTB_CHECK_ARG(Kp % epk == 0 && Kp >= epk && Kp / epk <= (dtype ? 8 : 13), "Kp out of range");
+  GTB_CHECK_ARG(Kp % epk == 0 && Kp >= epk && Kp / epk <= (dtype == 2 ? 32 : (dtype ? 8 : 13)), "Kp out of range");
   GTB_CHECK_ARG(nr_pad < (1ll << 31) && nq_pad < (1ll << 31), "too many rows for 32-bit TMA coordinates");
   return GTB_OK;
 }

@@ -238,7 +238,8 @@ class SearchOperand:
     def tc_ok(self, dtype=0):
         if self.metric == "cityblock":
             return False                                  # no GEMM form: CUDA-core L1 kernel only
-        return self.kp(dtype) // (16 if dtype else 8) <= (8 if dtype else 13)
+        # resident query tile: 13 tf32 / 8 bf16 k-steps; the fp16x2 flavour streams longer rows in chunks (d <= 510)
+        return self.kp(dtype) // (16 if dtype else 8) <= {0: 13, 1: 8, 2: 32, 3: 8}[dtype]
 
     def l1_norms(self):
         """(per-row L1 norms float32 [n], max) of the search copy -- bound on its rounding for float64 inputs."""
@@ -500,7 +501,7 @@ def knn_kernel(Xq, ref, qry=None, *, knn, knn_max=None, decay=40, thresh=1e-4, b
         # rows whose kernel support is wider fail certification and are finished by the radius pass.
         want = max(knn, kmax)                                   # knn_max neighbours must fit the lists as well
         # (fp16x2 runs two query tiles per CTA and keeps ONE list of 32 per row, which covers want + 8 <= 32)
-        two_tiles = tcd == 2 and int(os.environ.get("GTB_TC_QTILES", "2")) == 2
+        two_tiles = tcd == 2 and int(os.environ.get("GTB_TC_QTILES", "2")) == 2 and ref.kp(2) <= 128
         short_ok = want + 8 <= (32 if two_tiles else 16)
         ls = int(os.environ.get("GTB_TC_LIST", "16" if short_ok else "32"))
         qtiles = 2 if (two_tiles and ls == 16) else 1

@@ -165,6 +165,33 @@ def test_tc_topk_candidates(n, d, dtype, ls):
             assert np.isinf(tau[i])
 
 
+@pytest.mark.parametrize("ls", [32, 16])
+@pytest.mark.parametrize("n,d", [(2000, 127), (3000, 129), (1500, 200), (900, 510), (2500, 333)])
+def test_tc_topk_wide_rows(n, d, ls):
+    """Operand rows beyond 128 float16 elements (d up to 510): the reference tiles stream in chunks of 8 k-steps, the
+    accumulator collects the chunks -- same contract as the resident-row kernel."""
+    X, _ = synth.gaussian_mixture(n, d, n_clusters=5, intrinsic_dim=8, seed=3)
+    cand, tau, qry, ref = _tc_topk(X, dtype=2, ls=ls)
+    assert ref.kp(2) > 128
+    X64 = X.astype(np.float64)
+    D2 = ((X64[:, None, :] - X64[None, :, :]) ** 2).sum(-1)
+    Xc = X64 - X64.mean(0)
+    nrm = (Xc ** 2).sum(1)
+    eps = pipeline.eps_rel_tch(d)
+    tile_par = (np.arange(n) // 128) % 2
+    n_even, n_odd = int((tile_par == 0).sum()), int((tile_par == 1).sum())
+    for i in range(0, n, max(1, n // 300)):
+        assert (cand[i] != -7).all(), "output slot never written"
+        c = cand[i][cand[i] >= 0]
+        assert (c < n).all() and len(np.unique(c)) == len(c)
+        assert len(c) == min(ls, n_even) + min(ls, n_odd), (i, len(c))
+        bound = eps * (nrm[i] + nrm.max())
+        non = np.setdiff1d(np.arange(n), c)
+        assert np.isfinite(tau[i])
+        assert D2[i, non].min() >= tau[i] - bound
+        assert set(np.flatnonzero(D2[i] < tau[i] - bound)).issubset(set(c))
+
+
 @pytest.mark.parametrize("n,d", [(1797, 64), (3000, 100), (300, 5), (40, 3), (1000, 31), (777, 103), (5000, 100)])
 def test_tc_topk_two_query_tiles(n, d):
     """fp16x2 with two query tiles per CTA: ONE list of 32 per row over the whole reference set."""

@@ -482,3 +482,25 @@ def test_host_result_pool_recycles_without_aliasing():
     finally:
         os.environ.pop("GTB_HOST_POOL")
     assert np.array_equal(K4.data, k2_copy) and np.array_equal(K4.indices, K3.indices)
+
+
+@pytest.mark.parametrize("d,iso", [(300, False), (200, True), (510, False)])
+def test_wide_data_runs_on_tensor_cores(d, iso):
+    """d beyond the resident query tile of the one-product flavour (d + 2 > 128): the fp16x2 flavour streams the
+    operand rows in chunks; kNN graph against the oracle, incl. an isotropic case that takes the radius pass."""
+    from oracle import graph_oracle as go
+    n = 4000
+    X, _ = synth.gaussian_mixture(n, d, n_clusters=4, intrinsic_dim=None if iso else 10, seed=17)
+    decay = 10 if iso else 40
+    K_ref, P_ref = go.knn_graph(X.astype(np.float64), knn=5, decay=decay, thresh=1e-4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G = gt.Graph(X, knn=5, decay=decay, thresh=1e-4, verbose=0)
+        K = G.kernel
+    st = pipeline.stats()
+    assert st["impl"] == "tch", st
+    if iso:
+        assert st["radius_rows"] > 0
+    r = compare_sparse(K, K_ref, thresh=1e-4, what="K (d=%d)" % d)
+    if r["n_exempt"] == 0:
+        compare_sparse(G.diff_op, P_ref, what="P (d=%d)" % d)
