@@ -1171,6 +1171,32 @@ extern "C" int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const fl
   return GTB_OK;
 }
 
+// The split alone, from norms that are already on hand (gtb_row_norms): both roles of an in-sample build share one pass
+// over the norms instead of recomputing them per role
+extern "C" int gtb_split_operand_tc(const float* X, int64_t n, int d, const float* mean, int role, void* hi, void* lo,
+                                    int64_t n_pad, int Kp, int dtype, float scale, const float* norm2, void* stream) {
+  GTB_CHECK_ARG(n > 0 && d > 0 && n_pad >= n && n_pad % 128 == 0, "bad shape");
+  GTB_CHECK_ARG(dtype >= 0 && dtype <= 2, "dtype must be 0 (tf32 pairs in float32), 1 (bfloat16 pairs) or 2 (float16 pairs)");
+  const int epk = dtype ? 16 : 8;
+  GTB_CHECK_ARG(Kp % epk == 0 && Kp >= d + 1 + (dtype == 2) && Kp / epk <= (dtype == 2 ? 32 : (dtype ? 8 : 13)),
+                "Kp must be a multiple of 8 (tf32, <= 104) / 16 (bf16 <= 128, fp16 <= 512) and >= d+1 (fp16: d+2)");
+  GTB_CHECK_ARG(role == 0 || role == 1, "role must be 0 (query) or 1 (reference)");
+  GTB_CHECK_ARG(dtype != 2 || scale > 0.f, "the fp16 flavour needs a positive scale");
+  GTB_CHECK_ARG(norm2 != nullptr, "norm2 (from gtb_row_norms) is required");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == 0)
+    tc_split_kernel<<<(unsigned)gtb_cdiv(n_pad * Kp, 256), 256, 0, st>>>(X, n, d, mean, role, norm2, n_pad, Kp,
+                                                                        (float*)hi, (float*)lo);
+  else if (dtype == 1)
+    tc_split16_kernel<<<(unsigned)gtb_cdiv(n_pad * Kp, 256), 256, 0, st>>>(X, n, d, mean, role, norm2, n_pad, Kp,
+                                                                          (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  else
+    tc_split16h_kernel<<<(unsigned)gtb_cdiv(n_pad * Kp, 256), 256, 0, st>>>(X, n, d, mean, role, norm2, n_pad, Kp, scale,
+                                                                           (__half*)hi, (__half*)lo);
+  GTB_CHECK_LAUNCH();
+  return GTB_OK;
+}
+
 // candidate buffers of every row + the piece buffers and piece records of a split last round
 extern "C" int64_t gtb_tc_scratch_bytes(int64_t nq_pad) {
   return (nq_pad * TC_GROUPS * TC_CAP + TC_SPLIT_ROWS_MAX * TC_SPLIT_MAX * (TC_GROUPS * TC_CAP + 1)) * (int64_t)sizeof(uint2);

@@ -196,6 +196,7 @@ class SearchOperand:
         self.mean = mean
         self._simt = None
         self._tc = {}
+        self._n2_tc = None
         self._maxnorm = None
         self._maxnorm_host = None
 
@@ -258,13 +259,20 @@ class SearchOperand:
             st = (torch.float32, torch.bfloat16, torch.float16)[dtype]
             hi = _empty((self.n_pad, Kp), st)
             lo = _empty((self.n_pad, Kp), st)
-            n2 = _empty((self.n_pad,), torch.float32)
-            mx = _empty((1,), torch.float32)
-            E.call("gtb_prepare_operand_tc", self.Xs, self.n, self.d, self._kmean, role, hi, lo, self.n_pad, Kp,
-                   dtype, float(scale), n2, mx)
+            if getattr(self, "_n2_tc", None) is not None:
+                # the norms are on hand (norm_max, or the other role): split only
+                n2 = self._n2_tc
+                E.call("gtb_split_operand_tc", self.Xs, self.n, self.d, self._kmean, role, hi, lo, self.n_pad, Kp,
+                       dtype, float(scale), n2)
+            else:
+                n2 = _empty((self.n_pad,), torch.float32)
+                mx = _empty((1,), torch.float32)
+                E.call("gtb_prepare_operand_tc", self.Xs, self.n, self.d, self._kmean, role, hi, lo, self.n_pad, Kp,
+                       dtype, float(scale), n2, mx)
+                self._n2_tc = n2
+                if self._maxnorm is None:
+                    self._maxnorm = mx
             self._tc[key] = (hi, lo, n2)
-            if self._maxnorm is None:
-                self._maxnorm = mx
         return self._tc[key]
 
     def norm_max(self):
@@ -275,6 +283,7 @@ class SearchOperand:
             mx = _empty((1,), torch.float32)
             E.call("gtb_row_norms", self.Xs, self.n, self.d, self._kmean, self.n_pad, n2, mx)
             self._maxnorm = mx
+            self._n2_tc = n2
         return self.maxnorm
 
     @property

@@ -91,6 +91,9 @@ int gtb_row_norms(const float* X, int64_t n, int d, const float* mean, int64_t n
                   void* stream);
 int gtb_prepare_operand_tc(const float* X, int64_t n, int d, const float* mean, int role, void* hi, void* lo,
                            int64_t n_pad, int Kp, int dtype, float scale, float* norm2, float* maxnorm, void* stream);
+/* the split of gtb_prepare_operand_tc alone, from norms computed by gtb_row_norms (norm2 is an INPUT here) */
+int gtb_split_operand_tc(const float* X, int64_t n, int d, const float* mean, int role, void* hi, void* lo,
+                         int64_t n_pad, int Kp, int dtype, float scale, const float* norm2, void* stream);
 int gtb_knn_topk_tc(const void* q_hi, const void* q_lo, const float* qn2, int64_t nq, int64_t nq_pad,
                     const void* r_hi, const void* r_lo, int64_t nr, int64_t nr_pad, int Kp, int dtype,
                     int list, int cluster, int qtiles, int32_t* cand_idx, void* scratch, float* tau,
