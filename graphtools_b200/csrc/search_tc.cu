@@ -158,6 +158,18 @@ __device__ __noinline__ float compact_row(uint2* buf, int cnt, int lane) {
   return ord2f((uint32_t)(T >> 32));
 }
 
+// minimum of 32 accumulator values as a balanced tree of 3-input minima (depth 4)
+__device__ __forceinline__ float tmin32(const uint32_t (&r)[32]) {
+  float b[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    b[i] = fminf(fminf(__uint_as_float(r[3 * i]), __uint_as_float(r[3 * i + 1])), __uint_as_float(r[3 * i + 2]));
+  b[10] = fminf(__uint_as_float(r[30]), __uint_as_float(r[31]));
+  const float c0 = fminf(fminf(b[0], b[1]), b[2]), c1 = fminf(fminf(b[3], b[4]), b[5]);
+  const float c2 = fminf(fminf(b[6], b[7]), b[8]), c3 = fminf(b[9], b[10]);
+  return fminf(fminf(fminf(c0, c1), c2), c3);
+}
+
 // ---------------------------------------------------------------- the kernel
 // TMEM column map (512 columns allocated): [0, 8*nks) A_hi, [8*nks, 16*nks) A_lo, then the accumulator
 // ring [ACC0 + a*TC_N, +TC_N): tf32 (nks <= 13) ACC0 = 256, 2 accumulators; bf16 (nks <= 8) ACC0 = 128, 3.
@@ -648,22 +660,30 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
         }
         continue;
       }
+      // Selection.  The minima of the four 32-column batches first -- balanced 3-input trees, four independent
+      // chains (a running fminf is a 31-deep dependent chain per batch, and the latency of this stretch is what decides
+      // how much hit servicing the accumulator ring can absorb before the MMA warp stalls) -- then one ballot per
+      // batch.  A tile in which no row has a qualifying column, the common case, ends at ONE warp-uniform branch.
+      const float bm0 = tmin32(r0), bm1 = tmin32(r1), bm2 = tmin32(r2), bm3 = tmin32(r3);
+      unsigned h0 = __ballot_sync(0xffffffffu, (MODE == 0) ? (bm0 < thr) : (bm0 <= thr));
+      unsigned h1 = __ballot_sync(0xffffffffu, (MODE == 0) ? (bm1 < thr) : (bm1 <= thr));
+      unsigned h2 = __ballot_sync(0xffffffffu, (MODE == 0) ? (bm2 < thr) : (bm2 <= thr));
+      unsigned h3 = __ballot_sync(0xffffffffu, (MODE == 0) ? (bm3 < thr) : (bm3 <= thr));
+#ifdef GTB_EXP_NOSERVICE
+      h0 = h1 = h2 = h3 = 0;
+#endif
+      if ((h0 | h1 | h2 | h3) == 0u) continue;
 #pragma unroll
       for (int part = 0; part < TC_N / 32; ++part) {
+        // (a compaction in an earlier batch of this tile may have tightened thr since the ballot: the pass test below
+        // uses the current threshold, a stale hot bit only costs an empty service)
+        unsigned hot = part == 0 ? h0 : part == 1 ? h1 : part == 2 ? h2 : h3;
+        if (hot == 0u) continue;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           v[j] = __uint_as_float(part == 0 ? r0[j] : part == 1 ? r1[j] : part == 2 ? r2[j] : r3[j]);
         const int32_t col0 = (int32_t)(tile * TC_N) + part * 32;
-        float vmin = v[0];
-#pragma unroll
-        for (int j = 1; j < 32; ++j) vmin = fminf(vmin, v[j]);
-        // Selection.  A batch in which no lane (= query row) has a qualifying column -- the common case once the
-        // thresholds have tightened -- costs the min tree and one ballot.
-        unsigned hot = __ballot_sync(0xffffffffu, (MODE == 0) ? (vmin < thr) : (vmin <= thr));
-#ifdef GTB_EXP_NOSERVICE
-        hot = 0;
-#endif
         if (MODE == 0) {
 #if GTB_TC_HYBRID > 0
           // Burst regime (round start: most rows hit in every batch): every lane appends its own hits to its own
