@@ -141,6 +141,7 @@ def stream_ptr():
 
 
 timing = None  # set to a dict to collect per-entry-point CUDA-event timings (bench.py / profiling)
+timing_only = None  # optional set of timing keys: only these entry points are bracketed with events
 
 
 def timings_ms():
@@ -163,12 +164,13 @@ def call(name, *args):
     for a, t in zip(args, argtypes):
         conv.append(_ptr(a) if t is _P else a)
     assert len(conv) == len(argtypes) - 1, (name, len(conv), len(argtypes))
-    if timing is not None:
+    timed = timing is not None and (timing_only is None or key in timing_only)
+    if timed:
         import torch
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     rc = getattr(L, name)(*conv, stream_ptr())
-    if timing is not None:
+    if timed:
         ev1.record()
         timing.setdefault(key, []).append((ev0, ev1))
     if rc != 0:
