@@ -642,16 +642,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap mBh, const __grid_constant_
       continue;                                   // experiment build: the sweep without any selection work
 #endif
       if (MODE == 2) {
-        float m0 = __uint_as_float(r0[0]), m1 = __uint_as_float(r1[0]), m2 = __uint_as_float(r2[0]),
-              m3 = __uint_as_float(r3[0]);
-#pragma unroll
-        for (int j = 1; j < 32; ++j) {
-          m0 = fminf(m0, __uint_as_float(r0[j]));
-          m1 = fminf(m1, __uint_as_float(r1[j]));
-          m2 = fminf(m2, __uint_as_float(r2[j]));
-          m3 = fminf(m3, __uint_as_float(r3[j]));
-        }
-        float v = fminf(fminf(m0, m1), fminf(m2, m3));
+        float v = fminf(fminf(tmin32(r0), tmin32(r1)), fminf(tmin32(r2), tmin32(r3)));
 #pragma unroll
         for (int i = 0; i < TC_SEED_K; ++i) {      // sorted insertion: best[] stays ascending, v carries the evicted value
           const float lo = fminf(best[i], v);
