@@ -33,6 +33,6 @@ for rep in range(a.reps):
     for k, (c, ms) in sorted(tm.items(), key=lambda kv: -kv[1][1]):
         print("   %-24s calls=%d %.3f ms" % (k, c, ms))
     flop = 2.0 * a.n * a.n * a.d
-    key = "gtb_knn_topk_tc" if "gtb_knn_topk_tc" in tm else "gtb_knn_topk_simt"
+    key = next(k for k in ("gtb_knn_topk_tc_seeded", "gtb_knn_topk_tc", "gtb_knn_topk_simt") if k in tm)
     ms = tm[key][1]
     print("   %s: %.2f TFLOP/s algorithmic (2*N*N*d)" % (key, flop / ms / 1e9))
