@@ -140,7 +140,9 @@ def take_shared(nbytes, group=None):
     if not enabled():
         return None
     rank = dist.get_rank(group)
-    dev = torch.device("cuda", torch.cuda.current_device())
+    # (a gloo group on CPU -- the host-logic tests -- agrees through CPU tensors and skips the page-locking)
+    on_gpu = torch.cuda.is_available() and "nccl" in str(dist.get_backend(group))
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
     # blocks are created collectively, so the lists agree across ranks; a block is usable when it is free EVERYWHERE
     if _shared:
         flags = torch.tensor([int(b.free and nbytes <= b.nbytes <= 2 * nbytes + (1 << 20)) for b in _shared],
@@ -188,18 +190,19 @@ def take_shared(nbytes, group=None):
     arr[rank * per: min(size, (rank + 1) * per)] = 0
     dist.barrier(group=group)
     registered = 1
-    try:
-        rc = torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, size, 0)
-        if int(rc) != 0:
+    if on_gpu:
+        try:
+            rc = torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, size, 0)
+            if int(rc) != 0:
+                registered = 0
+        except Exception:
             registered = 0
-    except Exception:
-        registered = 0
     del arr
     reg = torch.tensor([registered], dtype=torch.int32, device=dev)
     dist.all_reduce(reg, op=dist.ReduceOp.MIN, group=group)
     if rank == 0:
         os.unlink(path)                        # the mappings keep the segment alive; nothing is left behind
-    blk = _Block(size, mm=mm, registered=bool(registered))
+    blk = _Block(size, mm=mm, registered=bool(registered) and on_gpu)
     if not int(reg.item()):
         blk.close()
         return None

@@ -152,3 +152,51 @@ def test_owner_of_matches_bounds():
         for c, o in zip(cols.numpy(), own):
             lo, hi = bounds[o]
             assert lo <= c < hi, (n, world, c, o, bounds)
+
+
+def _pool_worker(rank, world, port, out):
+    """Collective block choice of the shared result pool (graphtools_b200/hostpool.take_shared) under gloo: every rank
+    maps the SAME segment, writes its slice, sees the others' slices; a segment is reused only when it is free on
+    every rank, and a second one is created while any rank still holds a view of the first."""
+    import gc
+    from graphtools_b200 import hostpool as hp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    n = 300_000
+    lay, total = hp.layout([("a", n, np.float64), ("b", n, np.int32)])
+    blk1 = hp.take_shared(total)
+    ok &= blk1 is not None
+    arr = blk1.carve(lay)
+    half = n // world
+    arr["a"][rank * half:(rank + 1) * half] = rank + 1.0
+    arr["b"][rank * half:(rank + 1) * half] = rank + 7
+    dist.barrier()
+    for r in range(world):                                  # every rank sees every slice: one segment
+        ok &= bool((arr["a"][r * half:(r + 1) * half] == r + 1.0).all())
+        ok &= bool((arr["b"][r * half:(r + 1) * half] == r + 7).all())
+    keep = arr["a"] if rank == 1 else None                  # rank 1 keeps a view: the segment is busy everywhere
+    del arr
+    gc.collect()
+    ok &= (blk1.free == (rank != 1))
+    blk2 = hp.take_shared(total)
+    ok &= blk2 is not None and blk2 is not blk1
+    a2 = blk2.carve(lay)
+    del keep, a2
+    gc.collect()
+    dist.barrier()
+    blk3 = hp.take_shared(total)                            # both free now: the first one is handed out again
+    ok &= blk3 is blk1
+    ok &= len(hp._shared) == 2
+    ok &= not any(os.path.exists(p) for p in ["/dev/shm/gtbpool%d_%s_%d" % (os.getppid(), str(port), k) for k in (1, 2)])
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_shared_result_pool_gloo_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_pool_worker, args=(world, port, out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world)), dict(out)
