@@ -63,7 +63,10 @@ constexpr float TC_BIG_H = 50000.f;
 constexpr float TC_PAD_NORM_H = 60000.f;
 constexpr float TC_H_MAXNORM = 8192.f;
 constexpr int64_t TC_SPLIT_ROWS_MAX = 40 * 4 * 128;   // rows of a piece launch: at most half of the (<= 80) clusters x 4 tiles
-constexpr int TC_SEED_K = 8;          // SEED mode: order statistic of the sampled tile minima that becomes the threshold
+#ifndef GTB_TC_SEED_K
+#define GTB_TC_SEED_K 8
+#endif
+constexpr int TC_SEED_K = GTB_TC_SEED_K;   // SEED mode: order statistic of the sampled tile minima that becomes the threshold
 
 using namespace gtbptx;
 
